@@ -1,0 +1,236 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (JADGardner/RENI).
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container, where the reference is mounted
+read-only at /root/reference:
+
+    python oracle/make_golden.py
+
+The reference modules are imported by path (nothing is copied); the fixtures hold
+seeded inputs plus the reference's fp32 outputs and an fp64 "truth" obtained from the
+same reference modules after ``.double()``.  Inputs that are cheap to regenerate are
+produced from ``numpy.random.default_rng(seed)`` by ``golden_inputs`` below (shared with
+the tests) so that only outputs need to be stored for the large case.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF = os.environ.get("RENI_REFERENCE_PATH", "/root/reference")
+
+
+def unit(v):
+    return v / np.linalg.norm(v, axis=-1, keepdims=True)
+
+
+def golden_inputs(seed: int, B: int, P: int, N: int, H: int, L: int, out_f: int, equivariance: str,
+                  omega: float = 30.0, grid_sidelen: int = 0):
+    """Deterministic inputs shared by make_golden.py and the tests (numpy RNG, fp32)."""
+    sys.path.insert(0, HERE)
+    import reni_oracle as O
+
+    rng = np.random.default_rng(seed)
+    p = O.siren_init(rng, N, equivariance, H, L, out_f, omega, omega)
+    Z = rng.standard_normal((B, N, 3)).astype(np.float32)
+    if grid_sidelen:
+        D = np.repeat(O.get_directions(grid_sidelen), B, 0)
+        sw = np.repeat(O.get_sineweight(grid_sidelen), B, 0)
+        assert D.shape[1] == P
+    else:
+        D = unit(rng.standard_normal((B, P, 3))).astype(np.float32)
+        sw = np.repeat(rng.uniform(0.0, 1.0, (B, P, 1)), 3, 2).astype(np.float32)
+    target = rng.uniform(-1, 1, (B, P, out_f)).astype(np.float32)
+    mask = (rng.uniform(0, 1, (1, P, 1)) < 0.6).astype(np.float32)
+    mask[0, 0, 0] = 1.0  # keep pixel 0 visible so the cosine term is not trivially zero
+    mask = np.repeat(mask, 3, 2)
+    return p, Z, D, target, sw, mask
+
+
+def _import_reference():
+    import torch  # noqa: F401
+
+    sys.modules.setdefault("gdown", types.ModuleType("gdown"))
+    sys.path.insert(0, REF)
+    from src.models import RENI as ref_model
+    from src.utils import loss_functions as ref_loss
+    from src.utils import utils as ref_utils
+
+    return ref_model, ref_loss, ref_utils
+
+
+def _load_params(model, p):
+    import torch
+
+    sd = {}
+    nl = len(p.weights)
+    for i in range(nl):
+        is_sine = (i < nl - 1) or (not p.last_layer_linear)
+        key = f"net.{i}.linear" if is_sine else f"net.{i}"
+        sd[f"{key}.weight"] = torch.from_numpy(p.weights[i])
+        sd[f"{key}.bias"] = torch.from_numpy(p.biases[i])
+    missing = model.net.load_state_dict({k[4:]: v for k, v in sd.items()}, strict=True)
+    return missing
+
+
+def _make_model(ref_model, N, H, L, out_f, equivariance, last_linear, out_act, dataset_size=4, fixed=False, omega=30.0):
+    return ref_model.RENIAutoDecoder(dataset_size, N, equivariance, H, L, out_f, last_linear, out_act, omega, omega, fixed)
+
+
+def run_reference_case(ref_model, ref_loss, p, Z, D, target, sw, dtype, alpha, beta):
+    import torch
+
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    N = Z.shape[1]
+    H = p.weights[1].shape[0]
+    L = len(p.weights) - 2
+    model = _make_model(ref_model, N, H, L, p.weights[-1].shape[0], p.equivariance, p.last_layer_linear,
+                        p.output_activation, omega=p.hidden_omega_0)
+    _load_params(model, p)
+    model = model.to(tdt)
+    res = {}
+    tZ = torch.tensor(Z, dtype=tdt, requires_grad=True)
+    tD = torch.tensor(D, dtype=tdt)
+    tt = torch.tensor(target, dtype=tdt)
+    tsw = torch.tensor(sw, dtype=tdt)
+    # --- FIT_DECODER step (RENITrainLoss), all grads
+    out = model(tZ, tD)
+    loss = ref_loss.RENITrainLoss()(out, tt, tsw)
+    loss.backward()
+    res["out"] = out.detach().numpy()
+    res["train_loss"] = loss.detach().numpy()
+    res["train_dZ"] = tZ.grad.detach().numpy().copy()
+    res["train_dW"] = [q.grad.detach().numpy().copy() for n, q in model.net.named_parameters() if n.endswith("weight")]
+    res["train_db"] = [q.grad.detach().numpy().copy() for n, q in model.net.named_parameters() if n.endswith("bias")]
+    # --- FIT_LATENT step (RENITestLoss), latent grads
+    model.zero_grad()
+    tZ2 = torch.tensor(Z, dtype=tdt, requires_grad=True)
+    out2 = model(tZ2, tD)
+    l, mse, prior, cos = ref_loss.RENITestLoss(alpha=alpha, beta=beta)(out2, tt, tsw, tZ2)
+    l.backward()
+    res["test_loss"] = np.array([l.item(), mse.item(), prior.item(), cos.item()])
+    res["test_dZ"] = tZ2.grad.detach().numpy().copy()
+    return res
+
+
+CASES = {
+    # name: (seed, B, P, N, H, L, out_f, equiv, last_linear, out_act, grid_sidelen, alpha, beta, store_full_dW)
+    "so2_small": (11, 3, 64, 5, 32, 2, 3, "SO2", True, "tanh", 0, 1e-3, 0.5, True),
+    "so2_small_noact": (12, 2, 48, 4, 32, 1, 3, "SO2", True, None, 0, 1e-7, 1e-4, True),
+    "so2_small_sinelast": (13, 2, 40, 3, 16, 2, 3, "SO2", False, None, 0, 1e-2, 1e-1, True),
+    "so3_small": (14, 2, 32, 4, 32, 2, 3, "SO3", True, "tanh", 0, 1e-3, 0.5, True),
+    "none_small": (15, 2, 32, 4, 32, 2, 3, "None", True, "tanh", 0, 1e-3, 0.5, True),
+    "so2_n9_h256": (16, 2, 128, 9, 256, 5, 3, "SO2", True, "tanh", 16, 1e-7, 1e-1, False),
+    "so2_n36_h256": (17, 2, 512, 36, 256, 5, 3, "SO2", True, "tanh", 32, 1e-7, 1e-1, False),
+    "so2_n36_h256_masked": (18, 3, 512, 36, 256, 5, 3, "SO2", True, "tanh", 32, 1e-7, 1e-4, False),
+}
+
+
+def sub_dw(i, w):
+    """Strided subsample stored for the large cases (full tensors would be MBs)."""
+    if w.shape[1] > 256:
+        return w[::8, ::29]
+    if w.shape[0] == 256:
+        return w[::8, ::8]
+    return w
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref_model, ref_loss, ref_utils = _import_reference()
+    import torch
+
+    torch.set_num_threads(8)
+    for name, (seed, B, P, N, H, L, out_f, eq, last_lin, act, grid, alpha, beta, full) in CASES.items():
+        p, Z, D, target, sw, mask = golden_inputs(seed, B, P, N, H, L, out_f, eq, grid_sidelen=grid)
+        p.last_layer_linear = last_lin
+        p.output_activation = act
+        if name.endswith("masked"):
+            sw = sw * mask
+        store = {}
+        for dt, tag in ((np.float32, "f32"), (np.float64, "f64")):
+            r = run_reference_case(ref_model, ref_loss, p, Z, D, target, sw, dt, alpha, beta)
+            store[f"out_{tag}"] = r["out"]
+            store[f"train_loss_{tag}"] = r["train_loss"]
+            store[f"train_dZ_{tag}"] = r["train_dZ"]
+            store[f"test_loss_{tag}"] = r["test_loss"]
+            store[f"test_dZ_{tag}"] = r["test_dZ"]
+            for i, (w, b) in enumerate(zip(r["train_dW"], r["train_db"])):
+                store[f"train_dW{i}_{tag}"] = w if full else sub_dw(i, w)
+                store[f"train_dW{i}_norm_{tag}"] = np.array(np.linalg.norm(w.astype(np.float64)))
+                store[f"train_db{i}_{tag}"] = b
+        # encoding itself (reference function called directly), fp32
+        enc = {"SO2": ref_model.SO2InvariantRepresentation, "SO3": ref_model.SO3InvariantRepresentation,
+               "None": ref_model.NoInvariance}[eq]
+        e = enc(torch.from_numpy(Z), torch.from_numpy(D)).numpy()
+        store["enc_checksum"] = np.array([e.astype(np.float64).sum(), np.abs(e.astype(np.float64)).sum()])
+        if full:
+            store["enc"] = e
+        store["meta"] = np.array([seed, B, P, N, H, L, out_f, grid], dtype=np.int64)
+        np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), **store)
+        print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in list(store.items())[:3]})
+
+    # ---- geometry helpers (utils.py:46-78) and reference constructor init statistics
+    geo = {}
+    for W in (16, 32, 128):
+        d = ref_utils.get_directions(W).numpy()
+        s = ref_utils.get_sineweight(W).numpy()
+        if W <= 32:
+            geo[f"dir_{W}"] = d
+            geo[f"sw_{W}"] = s
+        geo[f"dir_{W}_checksum"] = np.array([d.astype(np.float64).sum(), np.abs(d.astype(np.float64)).sum(),
+                                             (d.astype(np.float64) ** 2).sum()])
+        geo[f"sw_{W}_checksum"] = np.array([s.astype(np.float64).sum(), (s.astype(np.float64) ** 2).sum()])
+    np.savez_compressed(os.path.join(GOLDEN, "geometry.npz"), **geo)
+
+    # ---- module-level behaviour: constructor shapes/init ranges, dispatch, state-dict keys, VAD, KLD
+    torch.manual_seed(0)
+    m = ref_model.RENIAutoDecoder(7, 36, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False)
+    mod = {}
+    names, shapes, los, his = [], [], [], []
+    for k, v in m.state_dict().items():
+        names.append(k)
+        shapes.append(list(v.shape) + [0] * (3 - v.dim()))
+        los.append(float(v.min()))
+        his.append(float(v.max()))
+    mod["state_keys"] = np.array(names)
+    mod["state_shapes"] = np.array(shapes, dtype=np.int64)
+    mod["state_min"] = np.array(los)
+    mod["state_max"] = np.array(his)
+    mod["n_net_params"] = np.array(sum(q.numel() for q in m.net.parameters()))
+    for n_, cnt in ((9, None), (49, None), (100, None)):
+        mm = ref_model.RENIAutoDecoder(1, n_, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False)
+        mod[f"n_net_params_{n_}"] = np.array(sum(q.numel() for q in mm.net.parameters()))
+    mf = ref_model.RENIAutoDecoder(7, 36, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, True)
+    mod["fixed_Z_absmax"] = np.array(float(mf.Z.abs().max()))
+    mod["fixed_requires_grad"] = np.array([int(q.requires_grad) for q in mf.net.parameters()])
+    # dispatch (RENI.py:205-233) on a small model
+    torch.manual_seed(1)
+    ms = ref_model.RENIAutoDecoder(6, 4, "SO2", 32, 1, 3, True, "tanh", 30.0, 30.0, False)
+    Dd = torch.from_numpy(unit(np.random.default_rng(5).standard_normal((2, 16, 3))).astype(np.float32))
+    mod["disp_Z"] = ms.Z.detach().numpy()
+    for i, (k, v) in enumerate(ms.net.state_dict().items()):
+        mod[f"disp_param_{i}"] = v.numpy()
+    mod["disp_param_keys"] = np.array(list(ms.net.state_dict().keys()))
+    mod["disp_D"] = Dd.numpy()
+    mod["disp_out_int"] = ms(3, Dd[:1]).detach().numpy()
+    mod["disp_out_list"] = ms([1, 4], Dd).detach().numpy()
+    mod["disp_out_idx"] = ms(torch.tensor([5, 0]), Dd).detach().numpy()
+    mod["disp_out_lat"] = ms(ms.Z[[2, 3]], Dd).detach().numpy()
+    # KLD / VAD loss (loss_functions.py:16-22,47-58)
+    rng = np.random.default_rng(6)
+    mu = rng.standard_normal((3, 4, 3)).astype(np.float32)
+    lv = (rng.standard_normal((3, 4, 3)) - 5).astype(np.float32)
+    mod["kld_mu"], mod["kld_lv"] = mu, lv
+    mod["kld_val"] = ref_loss.KLD(torch.from_numpy(mu), torch.from_numpy(lv), Z_dims=12).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "module.npz"), **mod)
+    print("golden fixtures written to", GOLDEN)
+
+
+if __name__ == "__main__":
+    main()
