@@ -1,0 +1,101 @@
+/* reni_b200.h -- C ABI of the B200-native RENI decoder hot path (libreni_b200.so).
+ *
+ * The reference (JADGardner/RENI) is pure PyTorch: it has no FFI of its own.  Each entry point
+ * below replaces a span of reference Python that the drop-in module `reni_b200.models`
+ * (same class names / ctor args / parameter names as src/models/RENI.py) calls instead:
+ *
+ *   reni_prepare_weights        <- SineLayer / nn.Linear parameter use      src/models/RENI.py:63-87,132-178
+ *   reni_forward                <- InvariantRepresentation + self.net(x)    src/models/RENI.py:31-53,211-233
+ *                                  (+ WeightedMSE / cosine partial sums     src/utils/loss_functions.py:6-13,25-32)
+ *   reni_backward               <- autograd of the above (loss.backward())  src/lightning/RENI_module.py:105-118
+ *   reni_loss_forward_backward  <- training_step: model + RENITrainLoss /   src/lightning/RENI_module.py:80-146
+ *                                  RENITestLoss + backward                  src/utils/loss_functions.py:39-71
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the caller owns every buffer including the workspace (size from reni_workspace_bytes);
+ *     the library allocates nothing, keeps no state between calls and is re-entrant;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), no host synchronisation;
+ *   - return value: 0 on success, negative reni_status_t otherwise (reni_strerror for text);
+ *   - fp32 tensors are dense row-major exactly as the reference's torch tensors:
+ *       Z (B, N, 3), D (B or 1, P, 3), out (B, P, 3), weights as nn.Linear (out, in).
+ */
+#ifndef RENI_B200_H_
+#define RENI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RENI_ABI_VERSION 1
+
+typedef enum {
+  RENI_OK = 0,
+  RENI_ERR_BAD_CONFIG = -1,    /* unsupported hidden size / layer count / equivariance */
+  RENI_ERR_BAD_ARGUMENT = -2,  /* null pointer, non-positive size */
+  RENI_ERR_WORKSPACE = -3,     /* workspace too small or misaligned */
+  RENI_ERR_CUDA = -4,          /* a CUDA runtime call failed (launch configuration, ...) */
+  RENI_ERR_NO_DEVICE = -5      /* not running on an sm_100 device */
+} reni_status_t;
+
+typedef enum { RENI_EQ_NONE = 0, RENI_EQ_SO2 = 1, RENI_EQ_SO3 = 2 } reni_equivariance_t;
+
+/* Mirrors the constructor arguments of RENIAutoDecoder (src/models/RENI.py:91-104). */
+typedef struct {
+  int32_t ndims;             /* N: latent code is (N, 3)                                   */
+  int32_t equivariance;      /* reni_equivariance_t                                        */
+  int32_t hidden_features;   /* must be 256 on this path                                   */
+  int32_t hidden_layers;     /* number of 256->256 SineLayers after the first (1..6)       */
+  int32_t out_features;      /* <= 16 (3 for RGB)                                          */
+  int32_t last_layer_linear; /* 1: nn.Linear output layer, 0: SineLayer                    */
+  int32_t output_activation; /* 0: none, 1: tanh                                           */
+  float first_omega_0;
+  float hidden_omega_0;
+} reni_config_t;
+
+/* flags */
+#define RENI_FLAG_SAVE_FOR_BACKWARD 1 /* forward stashes cos(a_l) (and h_l if NEED_DW) for reni_backward */
+#define RENI_FLAG_NEED_DW 2           /* weight gradients wanted (otherwise latent gradients only)     */
+#define RENI_FLAG_LOSS 4              /* forward also produces per-map loss sums (target / sw given)   */
+
+int32_t reni_abi_version(void);
+const char* reni_strerror(int32_t code);
+
+/* in_features of the first layer for a config (src/models/RENI.py:118-126). */
+int64_t reni_in_features(const reni_config_t* cfg);
+
+/* Bytes of workspace needed for a batch of B maps x P directions under `flags`. */
+int64_t reni_workspace_bytes(const reni_config_t* cfg, int64_t B, int64_t P, int32_t flags);
+
+/* Convert the decoder parameters into the fp16 operand images the kernels stream.
+ * weights[i] / biases[i], i = 0 .. hidden_layers + 1, are HOST arrays of DEVICE pointers in
+ * the order of net.0.linear, ..., net.L.linear, net.(L+1) (state_dict order of the reference).
+ * Must be called again whenever the parameters change (i.e. once per optimiser step). */
+int32_t reni_prepare_weights(const reni_config_t* cfg, const float* const* host_weights,
+                             const float* const* host_biases, void* workspace, int64_t workspace_bytes,
+                             void* stream);
+
+/* Decoder forward: out[b,p,:] = net(encoding(Z[b], D[b,p])).
+ *   d_batch_stride : elements between consecutive maps in D (0 = one direction grid for all maps)
+ *   target, sw     : only with RENI_FLAG_LOSS; sw_batch_stride like d_batch_stride
+ *   weights0/bias0 : first-layer parameters (fp32, used by the per-map prologue)
+ * With RENI_FLAG_LOSS the per-map sums needed by the losses are left in the workspace for
+ * reni_loss_finish / reni_backward. */
+int32_t reni_forward(const reni_config_t* cfg, const float* Z, const float* D, int64_t d_batch_stride,
+                     const float* weight0, const float* bias0, int64_t B, int64_t P, float* out,
+                     const float* target, const float* sw, int64_t sw_batch_stride, void* workspace,
+                     int64_t workspace_bytes, int32_t flags, void* stream);
+
+/* Debug / test hook: one 128 x N x (16*ksteps) tcgen05.mma with caller-supplied operand images
+ * and descriptor fields; writes the fp32 accumulator tile (128 x N, row-major) to d_out. */
+int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes,
+                           uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t a_kstep,
+                           uint32_t b_kstep, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t n,
+                           uint32_t ksteps, float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RENI_B200_H_ */

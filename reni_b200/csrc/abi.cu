@@ -1,0 +1,242 @@
+// C ABI of libreni_b200.so -- see include/reni_b200.h.  Host-side glue only: argument
+// validation, workspace carving and kernel launches on the caller's stream.
+#include "../../include/reni_b200.h"
+
+#include <cuda_runtime.h>
+
+#include "fwd_kernel.cuh"
+#include "layout.cuh"
+#include "small_kernels.cuh"
+
+using namespace reni;
+
+namespace {
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+bool config_ok(const reni_config_t* c) {
+  if (c == nullptr) return false;
+  if (c->hidden_features != kH) return false;
+  if (c->hidden_layers < 1 || c->hidden_layers > kMaxHiddenLayers) return false;
+  if (c->out_features < 1 || c->out_features > 3) return false;
+  if (c->equivariance < 0 || c->equivariance > 2) return false;
+  if (c->ndims < 1 || c->ndims > 128) return false;
+  if (c->output_activation != 0 && c->output_activation != 1) return false;
+  return true;
+}
+
+int64_t tiles_per_map(int64_t P) { return (P + kTileRows - 1) / kTileRows; }
+
+WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_t flags) {
+  WorkspaceLayout w{};
+  const int64_t L = c->hidden_layers;
+  const int64_t ntiles = B * tiles_per_map(P);
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    int64_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  w.wf = take(L * kWImageBytes);
+  w.wb = take(L * kWImageBytes);
+  w.w6f = take(kW6ImageBytes);
+  w.w6b = take(kW6ImageBytes);
+  w.bias = take((L * kH + 16) * 4);
+  w.scalars = take(256 * 4);
+  w.mc = take(B * 5 * kH * 4);
+  w.dmc = take(B * 5 * kH * 4);
+  w.map_loss = take(B * 32 * 4);
+  w.loss_part = take(ntiles * 4 * kLossPartials * 4);
+  if (flags & RENI_FLAG_SAVE_FOR_BACKWARD) {
+    const bool dw = (flags & RENI_FLAG_NEED_DW) != 0;
+    w.stash_c = take(ntiles * (L + 1) * (int64_t)kTileImageBytes);
+    w.stash_h = dw ? take(ntiles * (L + 1) * (int64_t)kTileImageBytes) : -1;
+    w.stash_d = take(ntiles * (dw ? (L + 1) : 1) * (int64_t)kTileImageBytes);
+    w.stash_gy = take(ntiles * (int64_t)kGyImageBytes);
+  } else {
+    w.stash_c = w.stash_h = w.stash_d = w.stash_gy = -1;
+  }
+  w.total = off;
+  return w;
+}
+
+template <class T>
+T* at(void* ws, int64_t off) {
+  return off < 0 ? nullptr : reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(ws) + off);
+}
+
+int num_sms() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t reni_abi_version(void) { return RENI_ABI_VERSION; }
+
+const char* reni_strerror(int32_t code) {
+  switch (code) {
+    case RENI_OK: return "ok";
+    case RENI_ERR_BAD_CONFIG: return "unsupported decoder configuration (hidden_features must be 256, 1..6 hidden layers, out_features <= 3)";
+    case RENI_ERR_BAD_ARGUMENT: return "bad argument (null pointer or non-positive size)";
+    case RENI_ERR_WORKSPACE: return "workspace too small or not 1024-byte aligned";
+    case RENI_ERR_CUDA: return "CUDA runtime error";
+    case RENI_ERR_NO_DEVICE: return "no sm_100 device";
+    default: return "unknown error";
+  }
+}
+
+int64_t reni_in_features(const reni_config_t* c) {
+  if (c == nullptr) return RENI_ERR_BAD_ARGUMENT;
+  const int64_t N = c->ndims;
+  switch (c->equivariance) {
+    case RENI_EQ_SO2: return 2 * N + N * N + 2;
+    case RENI_EQ_SO3: return N + N * N;
+    case RENI_EQ_NONE: return 3 * N + N;
+    default: return RENI_ERR_BAD_CONFIG;
+  }
+}
+
+int64_t reni_workspace_bytes(const reni_config_t* c, int64_t B, int64_t P, int32_t flags) {
+  if (!config_ok(c)) return RENI_ERR_BAD_CONFIG;
+  if (B < 1 || P < 1) return RENI_ERR_BAD_ARGUMENT;
+  return make_layout(c, B, P, flags).total;
+}
+
+int32_t reni_prepare_weights(const reni_config_t* c, const float* const* host_weights,
+                             const float* const* host_biases, void* ws, int64_t ws_bytes, void* stream) {
+  if (!config_ok(c)) return RENI_ERR_BAD_CONFIG;
+  if (host_weights == nullptr || host_biases == nullptr || ws == nullptr) return RENI_ERR_BAD_ARGUMENT;
+  const WorkspaceLayout w = make_layout(c, 1, 1, 0);
+  if (ws_bytes < w.scalars || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
+  PrepParams p{};
+  const int L = c->hidden_layers;
+  for (int i = 0; i <= L + 1; ++i) {
+    if (host_weights[i] == nullptr || host_biases[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+    p.w[i] = host_weights[i];
+    p.b[i] = host_biases[i];
+  }
+  p.wf = at<__half>(ws, w.wf);
+  p.wb = at<__half>(ws, w.wb);
+  p.w6f = at<__half>(ws, w.w6f);
+  p.w6b = at<__half>(ws, w.w6b);
+  p.bias = at<float>(ws, w.bias);
+  p.L = L;
+  p.out_features = c->out_features;
+  p.last_sine = c->last_layer_linear ? 0 : 1;
+  p.first_omega = c->first_omega_0;
+  p.hidden_omega = c->hidden_omega_0;
+  reni_prep_weights_kernel<<<dim3(32, L + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return cudaGetLastError() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int64_t d_bstride,
+                     const float* weight0, const float* bias0, int64_t B, int64_t P, float* out,
+                     const float* target, const float* sw, int64_t sw_bstride, void* ws, int64_t ws_bytes,
+                     int32_t flags, void* stream_) {
+  if (!config_ok(c)) return RENI_ERR_BAD_CONFIG;
+  if (Z == nullptr || D == nullptr || weight0 == nullptr || bias0 == nullptr || out == nullptr || ws == nullptr ||
+      B < 1 || P < 1)
+    return RENI_ERR_BAD_ARGUMENT;
+  if ((flags & RENI_FLAG_LOSS) && (target == nullptr || sw == nullptr)) return RENI_ERR_BAD_ARGUMENT;
+  const WorkspaceLayout w = make_layout(c, B, P, flags);
+  if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int sms = num_sms();
+  if (sms <= 0) return RENI_ERR_NO_DEVICE;
+
+  // ---- per-map prologue: layer 0 hoisted to (M_b, c_b)
+  {
+    PrologueParams q{};
+    q.Z = Z;
+    q.W0 = weight0;
+    q.b0 = bias0;
+    q.mc = at<float>(ws, w.mc);
+    q.B = (int)B;
+    q.N = c->ndims;
+    q.in_features = (int)reni_in_features(c);
+    q.equivariance = c->equivariance;
+    q.omega0 = c->first_omega_0;
+    const size_t smem = (size_t)(q.in_features + 3 * q.N) * sizeof(float);
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(reni_prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reni_prologue_kernel<<<dim3(kH / 8, (unsigned)B), 256, smem, stream>>>(q);
+    if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+  }
+
+  // ---- fused decoder forward
+  FwdParams p{};
+  p.D = D;
+  p.d_bstride = d_bstride;
+  p.mc = at<float>(ws, w.mc);
+  p.wf = at<__half>(ws, w.wf);
+  p.w6f = at<__half>(ws, w.w6f);
+  p.bias = at<float>(ws, w.bias);
+  p.out = out;
+  p.stash_h = at<__half>(ws, w.stash_h);
+  p.stash_c = at<__half>(ws, w.stash_c);
+  p.target = (flags & RENI_FLAG_LOSS) ? target : nullptr;
+  p.sw = sw;
+  p.sw_bstride = sw_bstride;
+  p.loss_part = (flags & RENI_FLAG_LOSS) ? at<float>(ws, w.loss_part) : nullptr;
+  p.B = (int)B;
+  p.P = (int)P;
+  p.tiles_per_map = (int)tiles_per_map(P);
+  p.ntiles = (int)(B * tiles_per_map(P));
+  p.L = c->hidden_layers;
+  p.out_tanh = c->output_activation == 1;
+  p.last_sine = c->last_layer_linear ? 0 : 1;
+  p.so2 = c->equivariance == RENI_EQ_SO2;
+  const int npairs = (p.ntiles + 1) / 2;
+  const int grid = npairs < sms ? npairs : sms;
+  const bool train = (flags & RENI_FLAG_SAVE_FOR_BACKWARD) != 0;
+  const bool stash_h = train && (flags & RENI_FLAG_NEED_DW);
+  cudaError_t e;
+  if (train) {
+    if (!stash_h) p.stash_h = nullptr;
+    e = cudaFuncSetAttribute(reni_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal);
+    if (e != cudaSuccess) return RENI_ERR_CUDA;
+    reni_fwd_kernel<true><<<grid, kFwdThreads, FwdSmem::kTotal, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(reni_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal);
+    if (e != cudaSuccess) return RENI_ERR_CUDA;
+    reni_fwd_kernel<false><<<grid, kFwdThreads, FwdSmem::kTotal, stream>>>(p);
+  }
+  return cudaGetLastError() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, uint32_t a_lbo,
+                           uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t a_kstep, uint32_t b_kstep,
+                           uint32_t a_mn, uint32_t b_mn, uint32_t n, uint32_t ksteps, float* d_out, void* stream) {
+  if (a_img == nullptr || b_img == nullptr || d_out == nullptr) return RENI_ERR_BAD_ARGUMENT;
+  if (n < 16 || n > 256 || (n % 16) != 0 || (a_bytes % 16) != 0 || (b_bytes % 16) != 0) return RENI_ERR_BAD_ARGUMENT;
+  SelfTestParams p{};
+  p.a_img = static_cast<const uint8_t*>(a_img);
+  p.b_img = static_cast<const uint8_t*>(b_img);
+  p.d_out = d_out;
+  p.a_bytes = a_bytes;
+  p.b_bytes = b_bytes;
+  p.a_lbo = a_lbo;
+  p.a_sbo = a_sbo;
+  p.b_lbo = b_lbo;
+  p.b_sbo = b_sbo;
+  p.a_kstep = a_kstep;
+  p.b_kstep = b_kstep;
+  p.a_mn = a_mn;
+  p.b_mn = b_mn;
+  p.N = n;
+  p.ksteps = ksteps;
+  const size_t smem = ((a_bytes + 1023) & ~1023u) + b_bytes + 1024;
+  if (smem > 220 * 1024) return RENI_ERR_BAD_ARGUMENT;
+  if (cudaFuncSetAttribute(reni_selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return RENI_ERR_CUDA;
+  reni_selftest_umma_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return cudaGetLastError() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+}  // extern "C"

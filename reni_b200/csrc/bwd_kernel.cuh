@@ -1,0 +1,276 @@
+// Fused RENI decoder backward (delta chain) for sm_100a.
+//
+//   per 128-direction tile:
+//     g_y   = dLoss/dy                      fused loss (sine-weighted MSE + cosine term, loss_functions.py:6-32,60-71)
+//                                           or an external grad_out, times tanh' = 1 - o^2; scaled by S into fp16 range
+//     d_L   = (g_y  W_out'') * cos(a_L)     tcgen05.mma K = 16
+//     d_l-1 = (d_l  W_l'')   * cos(a_l-1)   tcgen05.mma 128 x 256 x 256, l = L..1, cos from the forward stash,
+//                                           omega of the consuming layer folded into W''
+//   d_l tiles stay in shared memory for the next GEMM; d_0 (and every d_l when weight gradients are wanted) is
+//   stashed as fp16 tile images for the weight-gradient GEMM / the per-map layer-0 reduction.
+//
+// Same CTA organisation as the forward kernel (producer warp, MMA warp, two ping-ponging epilogue groups).
+#pragma once
+#include "layout.cuh"
+#include "ptx.cuh"
+
+namespace reni {
+
+constexpr int kBwdThreads = 320;
+constexpr int kBwdStages = 4;
+
+struct BwdParams {
+  const float* out;       // (B, P, 3) forward output (after tanh)
+  const float* grad_out;  // (B, P, 3) external gradient, or null for the fused loss
+  const float* target;    // fused loss
+  const float* sw;
+  int64_t sw_bstride;
+  const float* map_loss;  // (B, 32): [16..18] = coefA_c, [19..21] = coefB_c (cosine term, pre-scaled by S)
+  const float* scalars;   // [0] = S (gradient scale)
+  const __half* wb;       // L backward weight images
+  const __half* w6b;      // [2][256][8]
+  const __half* stash_c;  // cos(a_l), per tile (L+1) images
+  __half* stash_d;        // delta stash: per tile nslots images (nslots = L+1 or 1)
+  __half* stash_gy;       // per tile [2 halves][2][64][8]
+  int B, P, tiles_per_map, ntiles, L;
+  int out_tanh, d_slots;
+};
+
+struct BwdSmem {
+  static constexpr int kA = 0;
+  static constexpr int kRing = kA + 2 * kTileImageBytes;
+  static constexpr int kW6 = kRing + kBwdStages * kWChunkBytes;
+  static constexpr int kBars = kW6 + kW6ImageBytes;
+  static constexpr int kNumBars = 2 * kBwdStages + 4;
+  static constexpr int kTmemPtr = kBars + kNumBars * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+};
+static_assert(BwdSmem::kTotal <= 232448, "backward kernel shared memory over budget");
+
+DEVINL uint32_t hmul2_u32(uint32_t a, uint32_t b) {
+  __half2 r = __hmul2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <bool kNeedDW>
+__global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::kBars);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = bars + kBwdStages;
+  uint64_t* a_ready = bars + 2 * kBwdStages;
+  uint64_t* acc_full = a_ready + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + BwdSmem::kTmemPtr);
+
+  const int L = p.L;
+  const int npairs = (p.ntiles + 1) >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBwdStages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(&a_ready[0], 128);
+    mbar_init(&a_ready[1], 128);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.w6b);
+    uint4* dst = reinterpret_cast<uint4*>(smem + BwdSmem::kW6);
+    for (int i = threadIdx.x; i < kW6ImageBytes / 16; i += kBwdThreads) dst[i] = src[i];
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ============================================================ weight-chunk producer (layers L..1)
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wb);
+      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
+        for (int l = L; l >= 1; --l) {
+          for (int g = 0; g < nsub; ++g) {
+            for (int c = 0; c < kChunksPerLayer; ++c) {
+              mbar_wait(&w_empty[st], ph ^ 1);
+              mbar_arrive_expect_tx(&w_full[st], kWChunkBytes);
+              bulk_g2s(smem + BwdSmem::kRing + st * kWChunkBytes,
+                       wsrc + (size_t)(l - 1) * kWImageBytes + (size_t)c * kWChunkBytes, kWChunkBytes, &w_full[st]);
+              if (++st == kBwdStages) { st = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_h = umma_idesc_f16(128, 256, 0, 0);
+      const uint32_t a_base = smem_u32(smem + BwdSmem::kA);
+      const uint32_t ring_base = smem_u32(smem + BwdSmem::kRing);
+      const uint32_t w6_base = smem_u32(smem + BwdSmem::kW6);
+      uint32_t st = 0, ph = 0;
+      uint32_t a_ph0 = 0, a_ph1 = 0;
+      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
+        for (int l = L + 1; l >= 1; --l) {  // l = L+1: output layer (K = 16); l <= L: hidden layer l
+          for (int g = 0; g < nsub; ++g) {
+            if (g == 0) { mbar_wait(&a_ready[0], a_ph0); a_ph0 ^= 1; }
+            else        { mbar_wait(&a_ready[1], a_ph1); a_ph1 ^= 1; }
+            tc_fence_after();
+            const uint32_t a_tile = a_base + g * kTileImageBytes;
+            const uint32_t d_tmem = tmem_base + g * 256;
+            if (l == L + 1) {
+              const uint64_t da = umma_smem_desc(a_tile, 2048, 128);
+              const uint64_t db = umma_smem_desc(w6_base, 4096, 128);
+              umma_f16_ss(d_tmem, da, db, idesc_h, 0);
+            } else {
+              for (int c = 0; c < kChunksPerLayer; ++c) {
+                mbar_wait(&w_full[st], ph);
+                tc_fence_after();
+                const uint32_t b_tile = ring_base + st * kWChunkBytes;
+#pragma unroll
+                for (int ks = 0; ks < kWChunkK / 16; ++ks) {
+                  const uint64_t da = umma_smem_desc(a_tile + (c * 4 + ks * 2) * 2048, 2048, 128);
+                  const uint64_t db = umma_smem_desc(b_tile + (ks * 2) * 4096, 4096, 128);
+                  umma_f16_ss(d_tmem, da, db, idesc_h, (c | ks) != 0);
+                }
+                umma_commit(&w_empty[st]);
+                if (++st == kBwdStages) { st = 0; ph ^= 1; }
+              }
+            }
+            umma_commit(&acc_full[g]);
+          }
+        }
+      }
+    }
+  } else {
+    // ============================================================ epilogue groups
+    const int g = (warp - 2) >> 2;
+    const uint32_t q = warp & 3;
+    const uint32_t row = q * 32 + lane;
+    uint8_t* a_tile = smem + BwdSmem::kA + g * kTileImageBytes;
+    const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256;
+    uint32_t acc_ph = 0;
+    const float S = __ldg(p.scalars);
+
+    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const int tile = 2 * pair + g;
+      if (tile >= p.ntiles) break;
+      const int b = tile / p.tiles_per_map;
+      const int pix = (tile - b * p.tiles_per_map) * kTileRows + row;
+      const bool rvalid = pix < p.P;
+      const uint8_t* st_c = reinterpret_cast<const uint8_t*>(p.stash_c) + (size_t)tile * (L + 1) * kTileImageBytes;
+      uint8_t* st_d = reinterpret_cast<uint8_t*>(p.stash_d) + (size_t)tile * p.d_slots * kTileImageBytes;
+
+      // ---- g_y (scaled by S) -> fp16 [128 x 16] operand at the head of the tile image
+      float gy[3] = {0.f, 0.f, 0.f};
+      if (rvalid) {
+        const size_t e = ((size_t)b * p.P + pix) * 3;
+        if (p.grad_out != nullptr) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float o = __ldg(p.out + e + c);
+            float gg = __ldg(p.grad_out + e + c) * S;
+            if (p.out_tanh) gg *= (1.f - o * o);
+            gy[c] = gg;
+          }
+        } else {
+          const float* wp = p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+          const float* ml = p.map_loss + (size_t)b * 32;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float o = __ldg(p.out + e + c);
+            const float t = __ldg(p.target + e + c);
+            // S*g_o = (o-t)*sw + coefA*t + coefB*o   with S = 3P/2
+            float gg = (o - t) * __ldg(wp + c) + __ldg(ml + 16 + c) * t + __ldg(ml + 19 + c) * o;
+            if (p.out_tanh) gg *= (1.f - o * o);
+            gy[c] = gg;
+          }
+        }
+      }
+      {
+        uint4 v0, v1;
+        v0.x = pack_half2(gy[0], gy[1]);
+        v0.y = pack_half2(gy[2], 0.f);
+        v0.z = 0u;
+        v0.w = 0u;
+        v1 = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, 0)) = v0;
+        *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, 1)) = v1;
+        if (kNeedDW) {
+          uint8_t* sg = reinterpret_cast<uint8_t*>(p.stash_gy) + (size_t)tile * kGyImageBytes;
+          *reinterpret_cast<uint4*>(sg + stash_off(row, 0, kW6N)) = v0;
+          *reinterpret_cast<uint4*>(sg + stash_off(row, 1, kW6N)) = v1;
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_ready[g]);
+
+      // ---- delta_l = acc * cos(a_l), l = L..0
+      for (int l = L; l >= 0; --l) {
+        const uint8_t* cl = st_c + (size_t)l * kTileImageBytes;
+        uint8_t* dl = nullptr;
+        if (kNeedDW) dl = st_d + (size_t)l * kTileImageBytes;
+        else if (l == 0) dl = st_d;
+        // prefetch the first chunk of cos values while the GEMM finishes
+        uint4 cc[4];
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) cc[q8] = __ldg(reinterpret_cast<const uint4*>(cl + stash_off(row, q8, kH)));
+        mbar_wait(&acc_full[g], acc_ph);
+        acc_ph ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < kH / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + ch * 32, v);
+          uint4 cn[4];
+          if (ch + 1 < kH / 32) {
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8)
+              cn[q8] = __ldg(reinterpret_cast<const uint4*>(cl + stash_off(row, (ch + 1) * 4 + q8, kH)));
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            const int kg = ch * 4 + q8;
+            uint4 dv;
+            dv.x = hmul2_u32(pack_half2(__uint_as_float(v[q8 * 8 + 0]), __uint_as_float(v[q8 * 8 + 1])), cc[q8].x);
+            dv.y = hmul2_u32(pack_half2(__uint_as_float(v[q8 * 8 + 2]), __uint_as_float(v[q8 * 8 + 3])), cc[q8].y);
+            dv.z = hmul2_u32(pack_half2(__uint_as_float(v[q8 * 8 + 4]), __uint_as_float(v[q8 * 8 + 5])), cc[q8].z);
+            dv.w = hmul2_u32(pack_half2(__uint_as_float(v[q8 * 8 + 6]), __uint_as_float(v[q8 * 8 + 7])), cc[q8].w);
+            if (l > 0) *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = dv;
+            if (dl != nullptr) *reinterpret_cast<uint4*>(dl + stash_off(row, kg, kH)) = dv;
+          }
+          if (ch + 1 < kH / 32) {
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) cc[q8] = cn[q8];
+          }
+        }
+        tc_fence_before();
+        if (l > 0) {
+          fence_proxy_async_smem();
+          mbar_arrive(&a_ready[g]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace reni

@@ -1,0 +1,379 @@
+// Fused RENI decoder forward for sm_100a.
+//
+//   per 128-direction tile:  f = [dx, dz, |d_xz|, dy]           (SO(2) invariants, registers only)
+//                            h0 = sin(f . M_b + c_b)            (layer 0 hoisted to a per-map 4x256 matrix)
+//                            h_l = sin(h_{l-1} W_l'^T + b_l')   (tcgen05.mma, fp16 operands, fp32 TMEM accumulators,
+//                                                                bias + sin (+cos) fused in the TMEM->register epilogue)
+//                            o = tanh(h_L W_out^T + b_out)      (tcgen05.mma N=16) + optional fused loss partial sums
+//
+// One persistent CTA per SM, 320 threads:
+//   warp 0      : weight-chunk producer (cp.async.bulk global->smem ring, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5  : epilogue group 0 (sub-tile 0, TMEM columns   0..255)
+//   warps 6..9  : epilogue group 1 (sub-tile 1, TMEM columns 256..511)
+// The two sub-tiles ping-pong: while group g runs the sin epilogue of layer l, the tensor pipe runs
+// layer l of the other sub-tile.  Activations never leave the SM (smem tile image, overwritten in place);
+// with kTrain they are additionally stashed (h and cos(a), fp16) for the backward kernels.
+//
+// Reference semantics: src/models/RENI.py:31-53 (encoding), :63-87 (SineLayer), :132-178 (net).
+#pragma once
+#include "layout.cuh"
+#include "ptx.cuh"
+
+namespace reni {
+
+constexpr int kFwdThreads = 320;
+constexpr int kFwdStages = 4;
+
+struct FwdParams {
+  const float* D;        // (B or 1, P, 3) unit directions
+  int64_t d_bstride;     // elements between maps (0: one grid shared by all maps)
+  const float* mc;       // (B, 5, 256): rows 0..3 = omega0*M_b, row 4 = omega0*c_b
+  const __half* wf;      // L weight images [k/8][n][8] of omega_l * W_l
+  const __half* w6f;     // [k/8 32][n 16][8] final-layer image
+  const float* bias;     // L*256 (omega_l * b_l) then 16 (final bias, zero padded)
+  float* out;            // (B, P, 3)
+  __half* stash_h;       // kTrain: per tile (L+1) half-image pairs of h_l
+  __half* stash_c;       // kTrain: same for cos(a_l)
+  const float* target;   // fused loss partial sums (optional, may be null)
+  const float* sw;       // (B or 1, P, 3)
+  int64_t sw_bstride;
+  float* loss_part;      // (ntiles, 4 warps, 10)
+  int B, P, tiles_per_map, ntiles, L;
+  int out_tanh, last_sine, so2;
+};
+
+struct FwdSmem {
+  static constexpr int kA = 0;                                        // 2 x 64 KB activation tile images
+  static constexpr int kRing = kA + 2 * kTileImageBytes;              // weight chunk ring
+  static constexpr int kW6 = kRing + kFwdStages * kWChunkBytes;       // final-layer image
+  static constexpr int kBias = kW6 + kW6ImageBytes;                   // (kMaxHiddenLayers*256 + 16) floats
+  static constexpr int kMc = kBias + (kMaxHiddenLayers * kH + 16) * 4;  // 2 x 5 x 256 floats
+  static constexpr int kBars = kMc + 2 * 5 * kH * 4;                  // mbarriers
+  static constexpr int kNumBars = 2 * kFwdStages + 4;
+  static constexpr int kTmemPtr = kBars + kNumBars * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+};
+static_assert(FwdSmem::kTotal <= 232448, "forward kernel shared memory over budget");
+
+template <bool kTrain>
+__global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBars);
+  uint64_t* w_full = bars;                      // [kFwdStages]
+  uint64_t* w_empty = bars + kFwdStages;        // [kFwdStages]
+  uint64_t* a_ready = bars + 2 * kFwdStages;    // [2]  epilogue group -> MMA (128 arrivals)
+  uint64_t* acc_full = a_ready + 2;             // [2]  MMA -> epilogue group (tcgen05.commit)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + FwdSmem::kTmemPtr);
+  float* s_bias = reinterpret_cast<float*>(smem + FwdSmem::kBias);
+
+  const int L = p.L;
+  const int npairs = (p.ntiles + 1) >> 1;
+
+  // ---------------------------------------------------------------- one-time setup
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kFwdStages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(&a_ready[0], 128);
+    mbar_init(&a_ready[1], 128);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  {  // resident small operands: final-layer weight image + all biases
+    const uint4* src = reinterpret_cast<const uint4*>(p.w6f);
+    uint4* dst = reinterpret_cast<uint4*>(smem + FwdSmem::kW6);
+    for (int i = threadIdx.x; i < kW6ImageBytes / 16; i += kFwdThreads) dst[i] = src[i];
+    const int nb = L * kH + 16;
+    for (int i = threadIdx.x; i < nb; i += kFwdThreads) s_bias[i] = p.bias[i];
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ============================================================ weight-chunk producer
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wf);
+      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
+        for (int l = 0; l < L; ++l) {
+          for (int g = 0; g < nsub; ++g) {
+            for (int c = 0; c < kChunksPerLayer; ++c) {
+              mbar_wait(&w_empty[st], ph ^ 1);
+              mbar_arrive_expect_tx(&w_full[st], kWChunkBytes);
+              bulk_g2s(smem + FwdSmem::kRing + st * kWChunkBytes,
+                       wsrc + (size_t)l * kWImageBytes + (size_t)c * kWChunkBytes, kWChunkBytes, &w_full[st]);
+              if (++st == kFwdStages) { st = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_h = umma_idesc_f16(128, 256, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, kW6N, 0, 0);
+      const uint32_t a_base = smem_u32(smem + FwdSmem::kA);
+      const uint32_t ring_base = smem_u32(smem + FwdSmem::kRing);
+      const uint32_t w6_base = smem_u32(smem + FwdSmem::kW6);
+      uint32_t st = 0, ph = 0;
+      uint32_t a_ph[2] = {0, 0};
+      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
+        for (int l = 1; l <= L + 1; ++l) {
+          for (int g = 0; g < nsub; ++g) {
+            mbar_wait(&a_ready[g], a_ph[g]);
+            a_ph[g] ^= 1;
+            tc_fence_after();
+            const uint32_t a_tile = a_base + g * kTileImageBytes;
+            const uint32_t d_tmem = tmem_base + g * 256;
+            if (l <= L) {
+              for (int c = 0; c < kChunksPerLayer; ++c) {
+                mbar_wait(&w_full[st], ph);
+                tc_fence_after();
+                const uint32_t b_tile = ring_base + st * kWChunkBytes;
+#pragma unroll
+                for (int ks = 0; ks < kWChunkK / 16; ++ks) {
+                  // A: [k/8][128][8] -> 2048 B per 8-column group; B: chunk [4][256][8] -> 4096 B per group
+                  const uint64_t da = umma_smem_desc(a_tile + (c * 4 + ks * 2) * 2048, 2048, 128);
+                  const uint64_t db = umma_smem_desc(b_tile + (ks * 2) * 4096, 4096, 128);
+                  umma_f16_ss(d_tmem, da, db, idesc_h, (c | ks) != 0);
+                }
+                umma_commit(&w_empty[st]);
+                if (++st == kFwdStages) { st = 0; ph ^= 1; }
+              }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < kH / 16; ++ks) {
+                const uint64_t da = umma_smem_desc(a_tile + (ks * 2) * 2048, 2048, 128);
+                const uint64_t db = umma_smem_desc(w6_base + (ks * 2) * (kW6N * 16), kW6N * 16, 128);
+                umma_f16_ss(d_tmem, da, db, idesc_o, ks != 0);
+              }
+            }
+            umma_commit(&acc_full[g]);
+          }
+        }
+      }
+    }
+  } else {
+    // ============================================================ epilogue groups
+    const int g = (warp - 2) >> 2;          // sub-tile handled by this group
+    const uint32_t q = warp & 3;            // TMEM lane quarter this warp may access
+    const uint32_t row = q * 32 + lane;     // row inside the tile == TMEM lane
+    const uint32_t gtid = (warp - 2 - 4 * g) * 32 + lane;  // 0..127 inside the group
+    uint8_t* a_tile = smem + FwdSmem::kA + g * kTileImageBytes;
+    float* s_mc = reinterpret_cast<float*>(smem + FwdSmem::kMc) + g * 5 * kH;
+    const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256;
+    uint32_t acc_ph = 0;
+
+    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const int tile = 2 * pair + g;
+      if (tile >= p.ntiles) break;
+      const int b = tile / p.tiles_per_map;
+      const int pix = (tile - b * p.tiles_per_map) * kTileRows + row;
+      const bool rvalid = pix < p.P;
+      __half* st_h = nullptr;
+      __half* st_c = nullptr;
+      if (kTrain) {
+        st_h = p.stash_h + (size_t)tile * (L + 1) * (kTileImageBytes / 2);
+        st_c = p.stash_c + (size_t)tile * (L + 1) * (kTileImageBytes / 2);
+      }
+
+      // ---- per-map layer-0 operands -> smem (group-private)
+      named_bar_sync(1 + g, 128);
+      {
+        const float4* src = reinterpret_cast<const float4*>(p.mc + (size_t)b * 5 * kH);
+        float4* dst = reinterpret_cast<float4*>(s_mc);
+        for (int i = gtid; i < 5 * kH / 4; i += 128) dst[i] = __ldg(src + i);
+      }
+      named_bar_sync(1 + g, 128);
+
+      // ---- SO(2)-invariant direction features, registers only (RENI.py:37-49)
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+      if (rvalid) {
+        const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
+        const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+        if (p.so2) {
+          f0 = dx;
+          f1 = dz;
+          f2 = sqrtf(dx * dx + dz * dz);
+          f3 = dy;
+        } else {  // SO3 / None: the three inner-product columns (RENI.py:25,57)
+          f0 = dx;
+          f1 = dy;
+          f2 = dz;
+        }
+      }
+
+      // ---- layer 0: h0 = sin(f . M' + c')  (omega folded into M', c')
+#pragma unroll 2
+      for (int kg = 0; kg < kH / 8; ++kg) {
+        float a[8];
+        {
+          const float4* m = reinterpret_cast<const float4*>(s_mc + kg * 8);
+          const float4 c0 = m[4 * kH / 4], c1 = m[4 * kH / 4 + 1];
+          a[0] = c0.x; a[1] = c0.y; a[2] = c0.z; a[3] = c0.w;
+          a[4] = c1.x; a[5] = c1.y; a[6] = c1.z; a[7] = c1.w;
+          const float fr[4] = {f0, f1, f2, f3};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 m0 = m[i * kH / 4], m1 = m[i * kH / 4 + 1];
+            a[0] = fmaf(fr[i], m0.x, a[0]); a[1] = fmaf(fr[i], m0.y, a[1]);
+            a[2] = fmaf(fr[i], m0.z, a[2]); a[3] = fmaf(fr[i], m0.w, a[3]);
+            a[4] = fmaf(fr[i], m1.x, a[4]); a[5] = fmaf(fr[i], m1.y, a[5]);
+            a[6] = fmaf(fr[i], m1.z, a[6]); a[7] = fmaf(fr[i], m1.w, a[7]);
+          }
+        }
+        uint4 hv;
+        hv.x = pack_half2(__sinf(a[0]), __sinf(a[1]));
+        hv.y = pack_half2(__sinf(a[2]), __sinf(a[3]));
+        hv.z = pack_half2(__sinf(a[4]), __sinf(a[5]));
+        hv.w = pack_half2(__sinf(a[6]), __sinf(a[7]));
+        *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
+        if (kTrain) {
+          uint4 cv;
+          cv.x = pack_half2(__cosf(a[0]), __cosf(a[1]));
+          cv.y = pack_half2(__cosf(a[2]), __cosf(a[3]));
+          cv.z = pack_half2(__cosf(a[4]), __cosf(a[5]));
+          cv.w = pack_half2(__cosf(a[6]), __cosf(a[7]));
+          const uint32_t so = stash_off(row, kg, kH);
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st_h) + so) = hv;
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st_c) + so) = cv;
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_ready[g]);
+
+      // ---- hidden layers: bias + sin (+cos) epilogue, TMEM -> registers -> smem tile image (in place)
+      for (int l = 1; l <= L; ++l) {
+        const float* bl = s_bias + (l - 1) * kH;
+        mbar_wait(&acc_full[g], acc_ph);
+        acc_ph ^= 1;
+        tc_fence_after();
+        uint8_t* sh = nullptr;
+        uint8_t* sc = nullptr;
+        if (kTrain) {
+          sh = reinterpret_cast<uint8_t*>(st_h) + (size_t)l * kTileImageBytes;
+          sc = reinterpret_cast<uint8_t*>(st_c) + (size_t)l * kTileImageBytes;
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < kH / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + ch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            const int kg = ch * 4 + q8;
+            const float4 b0 = *reinterpret_cast<const float4*>(bl + kg * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bl + kg * 8 + 4);
+            float a[8];
+            a[0] = __uint_as_float(v[q8 * 8 + 0]) + b0.x;
+            a[1] = __uint_as_float(v[q8 * 8 + 1]) + b0.y;
+            a[2] = __uint_as_float(v[q8 * 8 + 2]) + b0.z;
+            a[3] = __uint_as_float(v[q8 * 8 + 3]) + b0.w;
+            a[4] = __uint_as_float(v[q8 * 8 + 4]) + b1.x;
+            a[5] = __uint_as_float(v[q8 * 8 + 5]) + b1.y;
+            a[6] = __uint_as_float(v[q8 * 8 + 6]) + b1.z;
+            a[7] = __uint_as_float(v[q8 * 8 + 7]) + b1.w;
+            uint4 hv;
+            hv.x = pack_half2(__sinf(a[0]), __sinf(a[1]));
+            hv.y = pack_half2(__sinf(a[2]), __sinf(a[3]));
+            hv.z = pack_half2(__sinf(a[4]), __sinf(a[5]));
+            hv.w = pack_half2(__sinf(a[6]), __sinf(a[7]));
+            *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
+            if (kTrain) {
+              uint4 cv;
+              cv.x = pack_half2(__cosf(a[0]), __cosf(a[1]));
+              cv.y = pack_half2(__cosf(a[2]), __cosf(a[3]));
+              cv.z = pack_half2(__cosf(a[4]), __cosf(a[5]));
+              cv.w = pack_half2(__cosf(a[6]), __cosf(a[7]));
+              const uint32_t so = stash_off(row, kg, kH);
+              *reinterpret_cast<uint4*>(sh + so) = hv;
+              *reinterpret_cast<uint4*>(sc + so) = cv;
+            }
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(&a_ready[g]);
+      }
+
+      // ---- output layer (N = 16 padded): bias, optional sin, optional tanh, store, fused loss partials
+      mbar_wait(&acc_full[g], acc_ph);
+      acc_ph ^= 1;
+      tc_fence_after();
+      float o[3];
+      {
+        uint32_t v[16];
+        tmem_ld16(t_acc, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        const float* bo = s_bias + L * kH;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float y = __uint_as_float(v[c]) + bo[c];
+          if (p.last_sine) y = sinf(y);
+          if (p.out_tanh) y = tanhf(y);
+          o[c] = y;
+        }
+      }
+      if (rvalid) {
+        float* op = p.out + ((size_t)b * p.P + pix) * 3;
+        op[0] = o[0];
+        op[1] = o[1];
+        op[2] = o[2];
+      }
+      if (p.loss_part != nullptr) {
+        float part[kLossPartials];
+#pragma unroll
+        for (int i = 0; i < kLossPartials; ++i) part[i] = 0.f;
+        if (rvalid) {
+          const float* tp = p.target + ((size_t)b * p.P + pix) * 3;
+          const float* wp = p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float t = __ldg(tp + c), w = __ldg(wp + c);
+            const float e = o[c] - t;
+            part[0] = fmaf(e * e, w, part[0]);
+            part[1 + c] = o[c] * t;
+            part[4 + c] = o[c] * o[c];
+            part[7 + c] = t * t;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kLossPartials; ++i) {
+          float x = part[i];
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+          part[i] = x;
+        }
+        if (lane == 0) {
+          float* lp = p.loss_part + ((size_t)tile * 4 + q) * kLossPartials;
+#pragma unroll
+          for (int i = 0; i < kLossPartials; ++i) lp[i] = part[i];
+        }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace reni
