@@ -88,6 +88,35 @@ int32_t reni_forward(const reni_config_t* cfg, const float* Z, const float* D, i
                      const float* target, const float* sw, int64_t sw_batch_stride, void* workspace,
                      int64_t workspace_bytes, int32_t flags, void* stream);
 
+/* Backward of reni_forward for an external gradient (autograd contract, RENI_module.py:105 +
+ * loss.backward()).  Must follow a reni_forward call made with RENI_FLAG_SAVE_FOR_BACKWARD (and
+ * RENI_FLAG_NEED_DW if weight gradients are wanted) on the same workspace, B, P and stream order.
+ *   out, grad_out : (B, P, 3)   forward result and dLoss/dout
+ *   dZ            : (B, N, 3)   written
+ *   host_dW/db    : HOST arrays of hidden_layers + 2 DEVICE pointers shaped like the parameters; the
+ *                   gradients are ACCUMULATED (+=) into them (caller zero-fills); NULL without NEED_DW
+ *   host_weights  : as in reni_prepare_weights (only weights[0] is read, fp32) */
+int32_t reni_backward(const reni_config_t* cfg, const float* Z, const float* D, int64_t d_batch_stride,
+                      const float* const* host_weights, int64_t B, int64_t P, const float* out,
+                      const float* grad_out, float* dZ, float* const* host_dW, float* const* host_db,
+                      void* workspace, int64_t workspace_bytes, int32_t flags, void* stream);
+
+/* One fused training / latent-optimisation step (training_step of the reference without the
+ * optimiser): forward, loss, backward.
+ *   loss = sum_b mean_{p,c}((o-t)^2 sw) + alpha * sum Z^2 + beta * WeightedCosineSimilarity(o,t,sw)
+ *   (RENITrainLoss: alpha = beta = 0, use_cosine = 0;  RENITestLoss: loss_functions.py:60-71)
+ *   loss_out : 4 floats {loss, mse, prior, cosine} (device), overwritten
+ *   dZ       : (B, N, 3) written, includes the 2*alpha*Z prior gradient
+ *   host_dW/db as in reni_backward (NULL for latent-only optimisation, flags without NEED_DW)
+ * reni_prepare_weights must have been called on this workspace for the current parameters. */
+int32_t reni_loss_forward_backward(const reni_config_t* cfg, const float* Z, const float* D,
+                                   int64_t d_batch_stride, const float* const* host_weights,
+                                   const float* const* host_biases, int64_t B, int64_t P, const float* target,
+                                   const float* sw, int64_t sw_batch_stride, float alpha, float beta,
+                                   int32_t use_cosine, float* out, float* loss_out, float* dZ,
+                                   float* const* host_dW, float* const* host_db, void* workspace,
+                                   int64_t workspace_bytes, int32_t flags, void* stream);
+
 /* Debug / test hook: one 128 x N x (16*ksteps) tcgen05.mma with caller-supplied operand images
  * and descriptor fields; writes the fp32 accumulator tile (128 x N, row-major) to d_out. */
 int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes,

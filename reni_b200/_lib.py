@@ -51,6 +51,11 @@ SIGNATURES = {
     "reni_workspace_bytes": (_i64, [_cfgp, _i64, _i64, _i32]),
     "reni_prepare_weights": (_i32, [_cfgp, C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _vp]),
     "reni_forward": (_i32, [_cfgp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "reni_backward": (_i32, [_cfgp, _vp, _vp, _i64, C.POINTER(_vp), _i64, _i64, _vp, _vp, _vp, C.POINTER(_vp),
+                             C.POINTER(_vp), _vp, _i64, _i32, _vp]),
+    "reni_loss_forward_backward": (_i32, [_cfgp, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _vp,
+                                          _i64, C.c_float, C.c_float, _i32, _vp, _vp, _vp, C.POINTER(_vp),
+                                          C.POINTER(_vp), _vp, _i64, _i32, _vp]),
     "reni_selftest_umma": (_i32, [_vp, _u32, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]),
 }
 

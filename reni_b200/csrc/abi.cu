@@ -4,6 +4,8 @@
 
 #include <cuda_runtime.h>
 
+#include "bwd_kernel.cuh"
+#include "dw_kernel.cuh"
 #include "fwd_kernel.cuh"
 #include "layout.cuh"
 #include "small_kernels.cuh"
@@ -47,6 +49,10 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   w.dmc = take(B * 5 * kH * 4);
   w.map_loss = take(B * 32 * 4);
   w.loss_part = take(ntiles * 4 * kLossPartials * 4);
+  const int64_t nin = reni_in_features(c);
+  w.xc = take(B * nin * 4);
+  w.dxc = take(B * nin * 4);
+  w.dip = take(B * 3 * c->ndims * 4);
   if (flags & RENI_FLAG_SAVE_FOR_BACKWARD) {
     const bool dw = (flags & RENI_FLAG_NEED_DW) != 0;
     w.stash_c = take(ntiles * (L + 1) * (int64_t)kTileImageBytes);
@@ -156,6 +162,7 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
     q.W0 = weight0;
     q.b0 = bias0;
     q.mc = at<float>(ws, w.mc);
+    q.xc = at<float>(ws, w.xc);
     q.B = (int)B;
     q.N = c->ndims;
     q.in_features = (int)reni_in_features(c);
@@ -196,17 +203,202 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   const bool train = (flags & RENI_FLAG_SAVE_FOR_BACKWARD) != 0;
   const bool stash_h = train && (flags & RENI_FLAG_NEED_DW);
   cudaError_t e;
-  if (train) {
-    if (!stash_h) p.stash_h = nullptr;
-    e = cudaFuncSetAttribute(reni_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal);
-    if (e != cudaSuccess) return RENI_ERR_CUDA;
-    reni_fwd_kernel<true><<<grid, kFwdThreads, FwdSmem::kTotal, stream>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(reni_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal);
-    if (e != cudaSuccess) return RENI_ERR_CUDA;
-    reni_fwd_kernel<false><<<grid, kFwdThreads, FwdSmem::kTotal, stream>>>(p);
-  }
+  auto launch = [&](auto kernel) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal);
+    if (e != cudaSuccess) return;
+    kernel<<<grid, kFwdThreads, FwdSmem::kTotal, stream>>>(p);
+  };
+  if (stash_h) launch(reni_fwd_kernel<2>);
+  else if (train) launch(reni_fwd_kernel<1>);
+  else launch(reni_fwd_kernel<0>);
+  if (e != cudaSuccess) return RENI_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+// Shared tail of reni_backward / reni_loss_forward_backward: delta chain, weight-gradient GEMMs, layer-0 and
+// map-level reductions.  scalars[0..1] (gradient scale) must already be on the stream.
+static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w, const float* Z, const float* D,
+                               int64_t d_bstride, const float* weight0, int64_t B, int64_t P, const float* out,
+                               const float* grad_out, const float* target, const float* sw, int64_t sw_bstride,
+                               float alpha, float* dZ, float* const* host_dW, float* const* host_db, void* ws,
+                               int32_t flags, cudaStream_t stream) {
+  const int sms = num_sms();
+  if (sms <= 0) return RENI_ERR_NO_DEVICE;
+  const bool need_dw = (flags & RENI_FLAG_NEED_DW) != 0;
+  const int L = c->hidden_layers;
+  const int ntiles = (int)(B * tiles_per_map(P));
+  if (cudaMemsetAsync(at<float>(ws, w.dmc), 0, (size_t)B * 5 * kH * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
+
+  BwdParams p{};
+  p.out = out;
+  p.grad_out = grad_out;
+  p.target = target;
+  p.sw = sw;
+  p.sw_bstride = sw_bstride;
+  p.map_loss = at<float>(ws, w.map_loss);
+  p.scalars = at<float>(ws, w.scalars);
+  p.wb = at<__half>(ws, w.wb);
+  p.w6b = at<__half>(ws, w.w6b);
+  p.stash_c = at<__half>(ws, w.stash_c);
+  p.stash_d = at<__half>(ws, w.stash_d);
+  p.stash_gy = at<__half>(ws, w.stash_gy);
+  p.B = (int)B;
+  p.P = (int)P;
+  p.tiles_per_map = (int)tiles_per_map(P);
+  p.ntiles = ntiles;
+  p.L = L;
+  p.out_tanh = c->output_activation == 1;
+  p.d_slots = need_dw ? L + 1 : 1;
+  const int npairs = (ntiles + 1) / 2;
+  const int grid = npairs < sms ? npairs : sms;
+  if (need_dw) {
+    if (cudaFuncSetAttribute(reni_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal) !=
+        cudaSuccess)
+      return RENI_ERR_CUDA;
+    reni_bwd_kernel<true><<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(p);
+  } else {
+    if (cudaFuncSetAttribute(reni_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal) !=
+        cudaSuccess)
+      return RENI_ERR_CUDA;
+    reni_bwd_kernel<false><<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(p);
+  }
+  if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+
+  if (need_dw) {
+    DwParams q{};
+    q.stash_h = at<__half>(ws, w.stash_h);
+    q.stash_d = at<__half>(ws, w.stash_d);
+    q.stash_gy = at<__half>(ws, w.stash_gy);
+    for (int i = 1; i <= L + 1; ++i) {
+      if (host_dW[i] == nullptr || host_db[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+      q.dW[i] = host_dW[i];
+      q.db[i] = host_db[i];
+    }
+    q.scalars = at<float>(ws, w.scalars);
+    q.ntiles = ntiles;
+    q.L = L;
+    q.out_features = c->out_features;
+    if (cudaFuncSetAttribute(reni_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem::kTotal) !=
+        cudaSuccess)
+      return RENI_ERR_CUDA;
+    int g = sms;
+    const int max_useful = ntiles * 2 * (L + 1);
+    if (g > max_useful) g = max_useful;
+    if (g < L + 1) g = L + 1;
+    reni_dw_kernel<<<g, kDwThreads, DwSmem::kTotal, stream>>>(q);
+    if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+  }
+
+  {
+    L0ReduceParams r{};
+    r.stash_d = at<__half>(ws, w.stash_d);
+    r.D = D;
+    r.d_bstride = d_bstride;
+    r.scalars = at<float>(ws, w.scalars);
+    r.dmc = at<float>(ws, w.dmc);
+    r.P = (int)P;
+    r.tiles_per_map = (int)tiles_per_map(P);
+    r.d_slots = need_dw ? L + 1 : 1;
+    r.so2 = c->equivariance == RENI_EQ_SO2;
+    reni_layer0_reduce_kernel<<<ntiles, 256, 0, stream>>>(r);
+    if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+  }
+  {
+    MapBwdParams m{};
+    m.Z = Z;
+    m.W0 = weight0;
+    m.xc = at<float>(ws, w.xc);
+    m.dmc = at<float>(ws, w.dmc);
+    m.dW0 = need_dw ? host_dW[0] : nullptr;
+    m.db0 = need_dw ? host_db[0] : nullptr;
+    m.dxc = at<float>(ws, w.dxc);
+    m.dip = at<float>(ws, w.dip);
+    m.dZ = dZ;
+    m.B = (int)B;
+    m.N = c->ndims;
+    m.in_features = (int)reni_in_features(c);
+    m.equivariance = c->equivariance;
+    m.alpha2 = 2.f * alpha;
+    m.accumulate = 0;
+    if (dZ != nullptr) {
+      reni_dxc_kernel<<<dim3((m.in_features + 255) / 256, (unsigned)B), 256, 0, stream>>>(m);
+      reni_dz_kernel<<<(unsigned)B, 128, 0, stream>>>(m);
+    }
+    if (need_dw) {
+      if (m.dW0 == nullptr || m.db0 == nullptr) return RENI_ERR_BAD_ARGUMENT;
+      const int64_t n = (int64_t)kH * m.in_features;
+      reni_dw0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(m);
+    }
+    if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+  }
+  return RENI_OK;
+}
+
+int32_t reni_backward(const reni_config_t* c, const float* Z, const float* D, int64_t d_bstride,
+                      const float* const* host_weights, int64_t B, int64_t P, const float* out,
+                      const float* grad_out, float* dZ, float* const* host_dW, float* const* host_db, void* ws,
+                      int64_t ws_bytes, int32_t flags, void* stream_) {
+  if (!config_ok(c)) return RENI_ERR_BAD_CONFIG;
+  if (!c->last_layer_linear) return RENI_ERR_BAD_CONFIG;  // sine output layer: forward only on this path
+  if (Z == nullptr || D == nullptr || host_weights == nullptr || host_weights[0] == nullptr || out == nullptr ||
+      grad_out == nullptr || ws == nullptr || B < 1 || P < 1)
+    return RENI_ERR_BAD_ARGUMENT;
+  if (!(flags & RENI_FLAG_SAVE_FOR_BACKWARD)) return RENI_ERR_BAD_ARGUMENT;
+  if ((flags & RENI_FLAG_NEED_DW) && (host_dW == nullptr || host_db == nullptr)) return RENI_ERR_BAD_ARGUMENT;
+  const WorkspaceLayout w = make_layout(c, B, P, flags);
+  if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* scalars = at<float>(ws, w.scalars);
+  unsigned int* slot = reinterpret_cast<unsigned int*>(scalars + 2);
+  if (cudaMemsetAsync(slot, 0, 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
+  const int64_t n = B * P * 3;
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 1184) blocks = 1184;
+  reni_absmax_kernel<<<blocks, 256, 0, stream>>>(grad_out, n, slot);
+  reni_scale_from_absmax_kernel<<<1, 1, 0, stream>>>(slot, scalars);
+  if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+  return launch_backward(c, w, Z, D, d_bstride, host_weights[0], B, P, out, grad_out, nullptr, nullptr, 0, 0.f, dZ,
+                         host_dW, host_db, ws, flags, stream);
+}
+
+int32_t reni_loss_forward_backward(const reni_config_t* c, const float* Z, const float* D, int64_t d_bstride,
+                                   const float* const* host_weights, const float* const* host_biases, int64_t B,
+                                   int64_t P, const float* target, const float* sw, int64_t sw_bstride, float alpha,
+                                   float beta, int32_t use_cosine, float* out, float* loss_out, float* dZ,
+                                   float* const* host_dW, float* const* host_db, void* ws, int64_t ws_bytes,
+                                   int32_t flags, void* stream_) {
+  if (!config_ok(c)) return RENI_ERR_BAD_CONFIG;
+  if (!c->last_layer_linear) return RENI_ERR_BAD_CONFIG;
+  if (host_weights == nullptr || host_biases == nullptr || host_weights[0] == nullptr || host_biases[0] == nullptr ||
+      target == nullptr || sw == nullptr || out == nullptr || loss_out == nullptr)
+    return RENI_ERR_BAD_ARGUMENT;
+  flags |= RENI_FLAG_SAVE_FOR_BACKWARD | RENI_FLAG_LOSS;
+  if ((flags & RENI_FLAG_NEED_DW) && (host_dW == nullptr || host_db == nullptr)) return RENI_ERR_BAD_ARGUMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int32_t rc = reni_forward(c, Z, D, d_bstride, host_weights[0], host_biases[0], B, P, out, target, sw, sw_bstride, ws,
+                            ws_bytes, flags, stream_);
+  if (rc != RENI_OK) return rc;
+  const WorkspaceLayout w = make_layout(c, B, P, flags);
+  if (cudaMemsetAsync(loss_out, 0, 16, stream) != cudaSuccess) return RENI_ERR_CUDA;
+  LossFinishParams f{};
+  f.loss_part = at<float>(ws, w.loss_part);
+  f.sw = sw;
+  f.sw_bstride = sw_bstride;
+  f.Z = (alpha != 0.f) ? Z : nullptr;
+  f.map_loss = at<float>(ws, w.map_loss);
+  f.loss_out = loss_out;
+  f.scalars = at<float>(ws, w.scalars);
+  f.B = (int)B;
+  f.P = (int)P;
+  f.tiles_per_map = (int)tiles_per_map(P);
+  f.nz = c->ndims * 3;
+  f.alpha = alpha;
+  f.beta = beta;
+  f.use_cos = use_cosine;
+  reni_loss_finish_kernel<<<(unsigned)B, 128, 0, stream>>>(f);
+  if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+  return launch_backward(c, w, Z, D, d_bstride, host_weights[0], B, P, out, nullptr, target, sw, sw_bstride, alpha, dZ,
+                         host_dW, host_db, ws, flags, stream);
 }
 
 int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, uint32_t a_lbo,

@@ -1,0 +1,233 @@
+// Weight-gradient GEMMs of the RENI decoder for sm_100a (split-K over directions).
+//
+//   dW_l[j,k] = sum_r delta_l[r,j] * h_{l-1}[r,k]     l = 1..L      (256 x 256, K = all directions)
+//   db_l[j]   = sum_r delta_l[r,j]
+//   dW_out[c,k] = sum_r g_y[r,c] * h_L[r,k] ,  db_out[c] = sum_r g_y[r,c]
+//
+// Both operands are the fp16 tile images the forward / backward kernels stashed ([k/8][64 rows][8]); read as
+// MN-major UMMA operands the contraction runs over the rows, so no transpose is ever materialised.
+// CTA i works on layer job (i mod (L+1)) and a contiguous slice of the 64-row stash blocks; the 256 x 256 fp32
+// accumulator lives in TMEM (2 x 256 columns) for the whole slice and is flushed once with vector reductions.
+//   warp 0 : bulk-copy producer (3-stage ring, 64 KB per stage)     warp 1 : tcgen05.mma issuer
+//   warps 2..9 : column sums for the bias gradient (from the smem operand), then the TMEM -> HBM flush
+#pragma once
+#include "layout.cuh"
+#include "ptx.cuh"
+
+namespace reni {
+
+constexpr int kDwThreads = 320;
+constexpr int kDwStages = 3;
+constexpr int kDwStageBytes = 2 * kHalfImageBytes;  // 64 KB: A operand (32 KB) + B operand (up to 32 KB)
+
+struct DwParams {
+  const __half* stash_h;
+  const __half* stash_d;
+  const __half* stash_gy;
+  float* dW[kMaxHiddenLayers + 2];  // [1..L] hidden (256x256), [L+1] output (out_features x 256); [0] unused
+  float* db[kMaxHiddenLayers + 2];
+  const float* scalars;  // [1] = 1 / S
+  int ntiles, L, out_features;
+};
+
+struct DwSmem {
+  static constexpr int kRing = 0;
+  static constexpr int kBars = kRing + kDwStages * kDwStageBytes;
+  static constexpr int kNumBars = 2 * kDwStages + 1;
+  static constexpr int kTmemPtr = kBars + kNumBars * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+};
+static_assert(DwSmem::kTotal <= 232448, "dW kernel shared memory over budget");
+
+DEVINL void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DwSmem::kBars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kDwStages;
+  uint64_t* done = bars + 2 * kDwStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + DwSmem::kTmemPtr);
+
+  const int L = p.L;
+  const int njobs = L + 1;
+  const int job = blockIdx.x % njobs;   // 0..L-1 -> hidden layer job+1 ; L -> output layer
+  const int slice = blockIdx.x / njobs;
+  const int nslices = ((int)gridDim.x - 1 - job) / njobs + 1;
+  const int total = p.ntiles * 2;       // 64-row stash blocks
+  const int s_begin = (int)((int64_t)slice * total / nslices);
+  const int s_end = (int)((int64_t)(slice + 1) * total / nslices);
+  const int nst = s_end - s_begin;
+  const bool is_out = (job == L);
+  const int layer = job + 1;
+  const uint32_t b_bytes = is_out ? (kHalfRows * kW6N * 2) : kHalfImageBytes;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kDwStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 9);  // tcgen05.commit + 8 reader warps
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // operand sources for stash block s (tile = s/2, half = s%2)
+  auto a_src = [&](int s) -> const uint8_t* {
+    const int tile = s >> 1, half = s & 1;
+    if (is_out)
+      return reinterpret_cast<const uint8_t*>(p.stash_h) + ((size_t)tile * (L + 1) + L) * kTileImageBytes +
+             (size_t)half * kHalfImageBytes;
+    return reinterpret_cast<const uint8_t*>(p.stash_d) + ((size_t)tile * (L + 1) + layer) * kTileImageBytes +
+           (size_t)half * kHalfImageBytes;
+  };
+  auto b_src = [&](int s) -> const uint8_t* {
+    const int tile = s >> 1, half = s & 1;
+    if (is_out)
+      return reinterpret_cast<const uint8_t*>(p.stash_gy) + (size_t)tile * kGyImageBytes +
+             (size_t)half * (kHalfRows * kW6N * 2);
+    return reinterpret_cast<const uint8_t*>(p.stash_h) + ((size_t)tile * (L + 1) + (layer - 1)) * kTileImageBytes +
+           (size_t)half * kHalfImageBytes;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (int s = s_begin; s < s_end; ++s) {
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&full[st], kHalfImageBytes + b_bytes);
+        uint8_t* dst = smem + DwSmem::kRing + st * kDwStageBytes;
+        bulk_g2s(dst, a_src(s), kHalfImageBytes, &full[st]);
+        bulk_g2s(dst + kHalfImageBytes, b_src(s), b_bytes, &full[st]);
+        if (++st == kDwStages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = is_out ? umma_idesc_f16(128, kW6N, 1, 1) : umma_idesc_f16(128, 256, 1, 1);
+      const uint32_t ring_base = smem_u32(smem + DwSmem::kRing);
+      uint32_t st = 0, ph = 0;
+      for (int s = s_begin; s < s_end; ++s) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t sa = ring_base + st * kDwStageBytes;
+        const uint32_t sb = sa + kHalfImageBytes;
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh) {
+#pragma unroll
+          for (int ks = 0; ks < kHalfRows / 16; ++ks) {
+            // MN-major operands: 8-column groups are 64 rows x 16 B = 1024 B apart (SBO), 8-row groups 128 B (LBO)
+            const uint64_t da = umma_smem_desc(sa + mh * 16 * 1024 + ks * 256, 128, 1024);
+            const uint64_t db = umma_smem_desc(sb + ks * 256, 128, 1024);
+            umma_f16_ss(tmem_base + mh * 256, da, db, idesc, (s != s_begin) || (ks != 0));
+          }
+        }
+        umma_commit(&empty[st]);
+        if (++st == kDwStages) { st = 0; ph ^= 1; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    // ---- bias-gradient column sums straight from the smem operand (lane <-> row: conflict-free 16 B reads)
+    const uint32_t t = threadIdx.x - 64;  // 0..255
+    const uint32_t r = t & 63;            // row inside the 64-row block
+    const uint32_t kset = t >> 6;         // 8-column groups kset*8 .. kset*8+7
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    {
+      uint32_t st = 0, ph = 0;
+      for (int s = s_begin; s < s_end; ++s) {
+        mbar_wait(&full[st], ph);
+        const uint8_t* base = smem + DwSmem::kRing + st * kDwStageBytes + (is_out ? kHalfImageBytes : 0);
+        if (!is_out) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint4 v = *reinterpret_cast<const uint4*>(base + ((kset * 8 + kk) * kHalfRows + r) * 16);
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+            const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
+            const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+            acc[kk * 8 + 0] += f0.x; acc[kk * 8 + 1] += f0.y; acc[kk * 8 + 2] += f1.x; acc[kk * 8 + 3] += f1.y;
+            acc[kk * 8 + 4] += f2.x; acc[kk * 8 + 5] += f2.y; acc[kk * 8 + 6] += f3.x; acc[kk * 8 + 7] += f3.y;
+          }
+        } else if (kset == 0) {
+          const uint4 v = *reinterpret_cast<const uint4*>(base + r * 16);
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+          acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (++st == kDwStages) { st = 0; ph ^= 1; }
+      }
+    }
+
+    // ---- flush: all MMAs done -> ring is free for the cross-row reduction, TMEM holds dW
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const float inv_s = __ldg(p.scalars + 1);
+    float* s_red = reinterpret_cast<float*>(smem + DwSmem::kRing);  // [64 rows][257] floats
+    named_bar_sync(1, 256);  // every reader is done with the last stages before the ring is reused
+    if (nst > 0) {
+      if (!is_out) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) s_red[r * 257 + kset * 64 + i] = acc[i];
+      } else if (kset == 0) {
+        s_red[r * 257 + 0] = acc[0];
+        s_red[r * 257 + 1] = acc[1];
+        s_red[r * 257 + 2] = acc[2];
+      }
+    }
+    named_bar_sync(1, 256);
+    if (nst > 0) {
+      const int ncol = is_out ? p.out_features : kH;
+      if ((int)t < ncol) {
+        float s = 0.f;
+        for (int rr = 0; rr < 64; ++rr) s += s_red[rr * 257 + t];
+        atomicAdd(p.db[layer] + t, s * inv_s);
+      }
+      const uint32_t q = warp & 3;
+      const uint32_t mh = (warp - 2) >> 2;
+      const uint32_t j = mh * 128 + q * 32 + lane;  // accumulator row
+      const uint32_t t_acc = tmem_base + ((q * 32) << 16) + mh * 256;
+      if (!is_out) {
+        float* dst = p.dW[layer] + (size_t)j * kH;
+#pragma unroll 1
+        for (int ch = 0; ch < kH / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + ch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            red_add_v4(dst + ch * 32 + i, __uint_as_float(v[i]) * inv_s, __uint_as_float(v[i + 1]) * inv_s,
+                       __uint_as_float(v[i + 2]) * inv_s, __uint_as_float(v[i + 3]) * inv_s);
+        }
+      } else {
+        uint32_t v[16];
+        tmem_ld16(t_acc, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c < p.out_features) atomicAdd(p.dW[layer] + (size_t)c * kH + j, __uint_as_float(v[c]) * inv_s);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace reni

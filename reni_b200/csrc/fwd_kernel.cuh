@@ -56,9 +56,12 @@ struct FwdSmem {
 };
 static_assert(FwdSmem::kTotal <= 232448, "forward kernel shared memory over budget");
 
-template <bool kTrain>
+// kMode: 0 = inference, 1 = stash cos(a_l) (latent-only backward), 2 = stash cos(a_l) and h_l (full backward)
+template <int kMode>
 __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr bool kTrain = kMode != 0;
+  constexpr bool kStashH = kMode == 2;
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
 
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
       __half* st_h = nullptr;
       __half* st_c = nullptr;
       if (kTrain) {
-        st_h = p.stash_h + (size_t)tile * (L + 1) * (kTileImageBytes / 2);
+        if (kStashH) st_h = p.stash_h + (size_t)tile * (L + 1) * (kTileImageBytes / 2);
         st_c = p.stash_c + (size_t)tile * (L + 1) * (kTileImageBytes / 2);
       }
 
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
           cv.z = pack_half2(__cosf(a[4]), __cosf(a[5]));
           cv.w = pack_half2(__cosf(a[6]), __cosf(a[7]));
           const uint32_t so = stash_off(row, kg, kH);
-          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st_h) + so) = hv;
+          if (kStashH) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st_h) + so) = hv;
           *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st_c) + so) = cv;
         }
       }
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
         uint8_t* sh = nullptr;
         uint8_t* sc = nullptr;
         if (kTrain) {
-          sh = reinterpret_cast<uint8_t*>(st_h) + (size_t)l * kTileImageBytes;
+          if (kStashH) sh = reinterpret_cast<uint8_t*>(st_h) + (size_t)l * kTileImageBytes;
           sc = reinterpret_cast<uint8_t*>(st_c) + (size_t)l * kTileImageBytes;
         }
 #pragma unroll 1
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
               cv.z = pack_half2(__cosf(a[4]), __cosf(a[5]));
               cv.w = pack_half2(__cosf(a[6]), __cosf(a[7]));
               const uint32_t so = stash_off(row, kg, kH);
-              *reinterpret_cast<uint4*>(sh + so) = hv;
+              if (kStashH) *reinterpret_cast<uint4*>(sh + so) = hv;
               *reinterpret_cast<uint4*>(sc + so) = cv;
             }
           }

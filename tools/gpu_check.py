@@ -135,6 +135,96 @@ def forward_parity():
         OUT[f"prologue_{name}"] = O.rel_l2(mc, ref_mc)
 
 
+def ptr_array(ts):
+    return (C.c_void_p * len(ts))(*[(t.data_ptr() if t is not None else 0) for t in ts])
+
+
+def fused_step(dec, Z, D, target, sw, alpha, beta, use_cos, need_dw, ws=None, n=None):
+    B, P = Z.shape[0], D.shape[1]
+    flags = 1 | 4 | (2 if need_dw else 0)
+    if ws is None:
+        ws, n = dec.workspace(B, P, flags)
+        dec.prepare(ws, n)
+    out = torch.empty(B, P, 3, device=dev)
+    loss = torch.zeros(4, device=dev)
+    dZ = torch.zeros_like(Z)
+    dW = [torch.zeros_like(w) for w in dec.w] if need_dw else None
+    db = [torch.zeros_like(b) for b in dec.b] if need_dw else None
+    dbs = 0 if D.shape[0] == 1 else P * 3
+    sbs = 0 if sw.shape[0] == 1 else P * 3
+    rc = lib.reni_loss_forward_backward(
+        C.byref(dec.cfg), vp(Z), vp(D), dbs, ptr_array(dec.w), ptr_array(dec.b), B, P, vp(target), vp(sw), sbs,
+        alpha, beta, use_cos, vp(out), vp(loss), vp(dZ), ptr_array(dW) if need_dw else None,
+        ptr_array(db) if need_dw else None, vp(ws), n, flags, None)
+    _lib.check(rc, "loss_forward_backward")
+    return out, loss, dZ, dW, db, ws, n
+
+
+def backward_parity():
+    from make_golden import sub_dw
+    for name in ("so2_n9_h256", "so2_n36_h256", "so2_n36_h256_masked"):
+        seed, B, P, N, H, L, out_f, eq, last_lin, act, grid, alpha, beta, full = CASES[name]
+        p, Z, D, target, sw, mask = golden_inputs(seed, B, P, N, H, L, out_f, eq, grid_sidelen=grid)
+        p.last_layer_linear, p.output_activation = last_lin, act
+        if name.endswith("masked"):
+            sw = sw * mask
+        g = np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
+        dec = Decoder(p, N)
+        tZ, tD, tt, tsw = (torch.from_numpy(a).to(dev) for a in (Z, D, target, sw))
+        # FIT_DECODER step: RENITrainLoss, all gradients
+        out, loss, dZ, dW, db, ws, n = fused_step(dec, tZ, tD, tt, tsw, 0.0, 0.0, 0, True)
+        torch.cuda.synchronize()
+        print(f"[train {name}] loss={loss[0].item():.6f} ref={float(g['train_loss_f32']):.6f} "
+              f"dZ rel_l2={O.rel_l2(dZ.cpu().numpy(), g['train_dZ_f32']):.3e}")
+        OUT[f"train_{name}_dZ"] = O.rel_l2(dZ.cpu().numpy(), g["train_dZ_f32"])
+        for i in range(L + 2):
+            mine = dW[i].cpu().numpy()
+            e = O.rel_l2(sub_dw(i, mine), g[f"train_dW{i}_f32"])
+            nrm = float(np.linalg.norm(mine)) / float(g[f"train_dW{i}_norm_f32"])
+            eb = O.rel_l2(db[i].cpu().numpy(), g[f"train_db{i}_f32"])
+            print(f"   dW{i} rel_l2={e:.3e} norm_ratio={nrm:.5f}   db{i} rel_l2={eb:.3e}")
+            OUT[f"train_{name}_dW{i}"] = [e, nrm, eb]
+        # FIT_LATENT step: RENITestLoss, latent gradients only
+        out, loss, dZ, _, _, ws, n = fused_step(dec, tZ, tD, tt, tsw, alpha, beta, 1, False)
+        torch.cuda.synchronize()
+        print(f"[latent {name}] loss={loss.cpu().numpy()} ref={g['test_loss_f32']} "
+              f"dZ rel_l2={O.rel_l2(dZ.cpu().numpy(), g['test_dZ_f32']):.3e}")
+        OUT[f"latent_{name}_dZ"] = O.rel_l2(dZ.cpu().numpy(), g["test_dZ_f32"])
+
+
+def timing_step():
+    rng = np.random.default_rng(1)
+    N = 36
+    p = O.siren_init(rng, N)
+    dec = Decoder(p, N)
+    for (B, W, need_dw) in ((32, 128, True), (32, 128, False), (256, 128, True)):
+        P = W * W // 2
+        Z = torch.randn(B, N, 3, device=dev)
+        D = torch.from_numpy(O.get_directions(W)).to(dev)
+        sw = torch.from_numpy(O.get_sineweight(W)).to(dev)
+        target = torch.rand(B, P, 3, device=dev) * 2 - 1
+        flags = 1 | 4 | (2 if need_dw else 0)
+        ws, n = dec.workspace(B, P, flags)
+        dec.prepare(ws, n)
+        for _ in range(3):
+            fused_step(dec, Z, D, target, sw, 0.0, 0.0, 0, need_dw, ws, n)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 10
+        e0.record()
+        for _ in range(iters):
+            fused_step(dec, Z, D, target, sw, 0.0, 0.0, 0, need_dw, ws, n)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        rate = B * P / ms * 1e3
+        fl = 1976832 if need_dw else 1317888
+        print(f"[timing step B={B} P={P} need_dw={need_dw}] {ms:.3f} ms  {rate/1e6:.1f} M dirs/s  "
+              f"{rate*fl/1e12:.1f} TFLOP/s ({rate*fl/1e12/1674.5*100:.1f}% of burst peak)")
+        OUT[f"time_step_B{B}_dw{int(need_dw)}"] = [ms, rate]
+        del ws
+
+
 def timing():
     rng = np.random.default_rng(1)
     N = 36
@@ -167,10 +257,11 @@ def timing():
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), "missing symbols:", _lib.missing_symbols())
-    steps = sys.argv[1:] or ["selftest", "forward", "timing"]
+    steps = sys.argv[1:] or ["selftest", "forward", "backward", "timing", "timing_step"]
     for s in steps:
         try:
-            {"selftest": run_selftests, "forward": forward_parity, "timing": timing}[s]()
+            {"selftest": run_selftests, "forward": forward_parity, "timing": timing, "backward": backward_parity,
+             "timing_step": timing_step}[s]()
         except Exception as e:  # keep going: one GPU call should tell us as much as possible
             import traceback
 
