@@ -1,0 +1,325 @@
+"""Headline benchmark of the RENI decoder hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+Workload (BASELINE.json configs[1]): RENI N=36 SO(2)-invariant auto-decoder training step, batch of 32
+synthetic equirectangular maps at 64x128 per GPU (8192 directions each), random-init SIREN (5 x 256 hidden,
+omega 30, tanh output), RENITrainLoss.  One "step" = prepare weights + prologue + forward + loss + backward
+with every gradient (decoder weights, biases, latents) ready; with N > 1 ranks also the single NCCL
+all-reduce of the flat weight-gradient buffer (weak scaling: 32 maps per GPU).  The optimiser is excluded on
+both arms.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decoded directions/sec (fwd+bwd, N=36, 64x128)"
+UNIT = "directions/s"
+N_LATENT, SIDELEN, MAPS_PER_GPU = 36, 128, 32
+P = SIDELEN * SIDELEN // 2
+FLOPS_FWD = 2 * (4 * 256 + 5 * 256 * 256 + 256 * 3)  # algorithmic flops per direction
+FLOPS_TRAIN = 3 * FLOPS_FWD
+WORKLOAD = "cfg2: RENI N=36 autodecoder training step (fwd + RENITrainLoss + bwd, all grads), 32 maps x 64x128 per GPU"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(tflops=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained"), hbm=d["hbm_gbs"],
+                    source="measured (MEASURED_PEAKS.json, burst)")
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(steps: int, warmup: int, budget_s: float = 25.0, maps: int = 4):
+    """Times the reference's CPU path (eager PyTorch fp32, all host threads) on a bounded sample of the workload:
+    `maps` maps x 8192 directions per step (the reference materialises a 45 MB encoding per map).  Uses the
+    oracle port (oracle/reni_torch_port.py) because the Python reference cannot travel to the GPU box."""
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reni_oracle as O
+    import reni_torch_port as TP
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(0)
+    p = O.siren_init(rng, N_LATENT)
+    ws = [torch.from_numpy(w) for w in p.weights]
+    bs = [torch.from_numpy(b) for b in p.biases]
+    Z = torch.from_numpy(rng.standard_normal((maps, N_LATENT, 3)).astype(np.float32))
+    D = torch.from_numpy(np.repeat(O.get_directions(SIDELEN), maps, 0))
+    sw = torch.from_numpy(np.repeat(O.get_sineweight(SIDELEN), maps, 0))
+    tg = torch.from_numpy(rng.uniform(-1, 1, (maps, P, 3)).astype(np.float32))
+    for _ in range(max(1, min(warmup, 2))):
+        TP.training_step(Z, D, tg, sw, ws, bs)
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        TP.training_step(Z, D, tg, sw, ws, bs)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    sec = sum(times) / len(times)
+    return dict(value=maps * P / sec, unit=UNIT, cores=cores, kind="port",
+                sample=f"{maps} maps x {P} directions per step, {len(times)} timed steps, torch {torch.__version__} "
+                       f"eager fp32, {cores} threads"), sec, len(times)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, sec, nsteps = cpu_reference_run(args.steps, args.warmup, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": nsteps, "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": base["sample"]},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                       "-lms", "50", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples drawing more than half of the maximum observed power
+        thr = 0.5 * max(pw)
+        load = [s for s, w in zip(sm, pw) if w >= thr] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    from reni_b200 import RENIAutoDecoder, RENITrainer, _lib, get_directions, get_sineweight, shard_range
+    from reni_b200 import functional as F_
+    from reni_b200.training import FlatGradBuffer
+
+    lib = _lib.load()
+    B = MAPS_PER_GPU
+    total_maps = B * world
+    lo, hi = shard_range(total_maps, rank, world)  # maps shard across ranks; latents stay rank-local
+    torch.manual_seed(0)  # identical decoder weights on every rank (DDP broadcasts them from rank 0)
+    model = RENIAutoDecoder(total_maps, N_LATENT, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    target = (torch.rand(B, P, 3, generator=g) * 2 - 1).to(dev)
+    D = get_directions(SIDELEN).to(dev)
+    sw = get_sineweight(SIDELEN).to(dev)
+    Z = model.Z.detach()[lo:hi].contiguous()
+    weights, biases = model.decoder_weights(), model.decoder_biases()
+    flat = FlatGradBuffer(model.decoder_parameters())
+    ws = F_.Workspace()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        ws.prepared_key = None  # weights change every optimiser step: the conversion is part of the step
+        flat.zero_()
+        r = F_.loss_forward_backward(model.spec, ws, Z, D, target, sw, weights, biases, need_dw=True,
+                                     grad_weights=flat.views[0::2], grad_biases=flat.views[1::2])
+        flat.all_reduce_mean()
+        return r
+
+    # phase events: kernel-level timing on the launching stream
+    n_ev = 7
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
+    for e in evs:
+        e.record()  # forces creation of the cudaEvent_t handles
+    torch.cuda.synchronize()
+    handles = (C.c_void_p * n_ev)(*[e.cuda_event for e in evs])
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    # ---- timed region: exactly K steps, device-timed, L2 flushed between steps (flush outside the event pairs)
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    phase_ms = [[] for _ in range(n_ev - 1)]
+    _lib.check(lib.reni_debug_set_phase_events(handles, n_ev))
+    for i in range(args.steps):
+        flush.zero_()
+        e0[i].record()
+        step_resident()
+        e1[i].record()
+        e1[i].synchronize()
+        for k in range(n_ev - 1):
+            phase_ms[k].append(evs[k].elapsed_time(evs[k + 1]))
+    _lib.check(lib.reni_debug_set_phase_events(None, 0))
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end through the public API: pinned host batch -> H2D -> RENITrainer.training_step -> D2H loss
+    trainer = RENITrainer(model, "FIT_DECODER", SIDELEN, lr=1e-5)
+    host_imgs = (torch.rand(B, 3, SIDELEN // 2, SIDELEN, generator=g) * 2 - 1).pin_memory()
+    host_idx = torch.arange(lo, hi, dtype=torch.long).pin_memory()
+    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        imgs = host_imgs.to(dev, non_blocking=True)
+        idx = host_idx.to(dev, non_blocking=True)
+        trainer._ws.prepared_key = None
+        log = trainer.training_step((imgs, idx))
+        host_loss.copy_(log["loss"].reshape(1), non_blocking=True)
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    s1.record()
+    barrier()
+    e2e_ms = s0.elapsed_time(s1)
+
+    times = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        pk = peaks()
+        dirs_step = total_maps * P
+        value = dirs_step * args.steps / (total_ms * 1e-3)
+        e2e_value = dirs_step * args.steps / (e2e_ms * 1e-3)
+        names = ["prologue", "reni_fwd_kernel", "loss_finish", "reni_bwd_kernel", "reni_dw_kernel", "layer0+map_backward"]
+        kms = {n: statistics.mean(v) for n, v in zip(names, phase_ms)}
+        d = B * P  # directions one launch processes on this GPU
+        gemm_flops = {"reni_fwd_kernel": FLOPS_FWD * d, "reni_bwd_kernel": 2 * (5 * 256 * 256 + 256 * 3) * d,
+                      "reni_dw_kernel": 2 * (5 * 256 * 256 + 256 * 3) * d}
+        kernels = {}
+        for n, ms in kms.items():
+            kernels[n] = {"ms": round(ms, 4)}
+            if n in gemm_flops:
+                kernels[n]["tflops"] = round(gemm_flops[n] / (ms * 1e-3) / 1e12, 1)
+        # stash traffic of the weight-gradient GEMM: it re-reads h_{l-1} and delta_l (fp16) for 5 layers + h_L, g_y
+        kernels["reni_dw_kernel"]["hbm_gbs"] = round((5 * 1024 + 512 + 32) * d / (kms["reni_dw_kernel"] * 1e-3) / 1e9, 1)
+        dom = max(gemm_flops, key=lambda n: kms[n])
+        achieved = gemm_flops[dom] / (kms[dom] * 1e-3) / 1e12
+        step_tflops = FLOPS_TRAIN * dirs_step / world / (total_ms / args.steps * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "latent_dim": N_LATENT, "maps_per_gpu": B, "directions_per_map": P,
+                       "l2": "256 MB flush between timed steps (outside the event pairs)",
+                       "step": "weight prep + prologue + fwd + loss + bwd (dW, db, dZ)" + (" + NCCL all-reduce of 680707 fp32" if world > 1 else ""),
+                       "optimizer": "excluded on both arms", "parallelism": f"dp{world} (maps sharded, latents local)"},
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+                         "step_tflops_per_gpu": step_tflops, "step_frac": step_tflops / pk["tflops"]},
+            "kernels": kernels,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_imgs.numel() * 4 + host_idx.numel() * 8,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+                    "api": "RENITrainer.training_step((imgs, idx)) from pinned host memory"},
+            "gpu_launches": 10 * args.steps * 2,  # 10 kernels per step, K device-resident + K end-to-end steps
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            base, _, _ = cpu_reference_run(steps=1000, warmup=1, budget_s=20.0)
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -117,6 +117,13 @@ int32_t reni_loss_forward_backward(const reni_config_t* cfg, const float* Z, con
                                    float* const* host_dW, float* const* host_db, void* workspace,
                                    int64_t workspace_bytes, int32_t flags, void* stream);
 
+/* Debug / measurement hook: register up to 16 CUDA events (cudaEvent_t handles, HOST array) that the
+ * calling thread's subsequent reni_forward / reni_backward / reni_loss_forward_backward calls record on
+ * their stream between kernels: [0] start, [1] after the per-map prologue, [2] after the forward kernel,
+ * [3] after the loss reduction, [4] after the delta-chain kernel, [5] after the weight-gradient GEMM,
+ * [6] end of the step.  n = 0 clears.  Thread-local; this is the only state the library keeps. */
+int32_t reni_debug_set_phase_events(void* const* host_events, int32_t n);
+
 /* Debug / test hook: one 128 x N x (16*ksteps) tcgen05.mma with caller-supplied operand images
  * and descriptor fields; writes the fp32 accumulator tile (128 x N, row-major) to d_out. */
 int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes,

@@ -1,0 +1,25 @@
+"""reni_b200 -- B200-native (sm_100a) implementation of the RENI decoder hot path.
+
+Drop-in for the Cond-by-Concat decoder family of JADGardner/RENI (src/models/RENI.py) and the
+training / latent-optimisation step around it (src/lightning/RENI_module.py:80-146):
+
+    from reni_b200 import RENIAutoDecoder, RENIVariationalAutoDecoder, get_model   # same ctor args
+    from reni_b200 import RENITrainLoss, RENITestLoss, get_directions, get_sineweight
+    from reni_b200 import RENITrainer                                              # fused step + data parallel
+
+All decoder arithmetic runs in the hand-written CUDA library ``reni_b200/lib/libreni_b200.so``
+(C ABI: include/reni_b200.h), built by ``__graft_entry__.build()``.  There is no CPU fallback.
+"""
+from .geometry import get_directions, get_mask, get_sineweight, rectangle_mask
+from .losses import (KLD, CosineSimilarity, RENITestLoss, RENITrainLoss, RENIVADTrainLoss, WeightedCosineSimilarity,
+                     WeightedMSE)
+from .models import RENIAutoDecoder, RENIVariationalAutoDecoder, SineLayer, get_model
+from .training import FlatGradBuffer, RENITrainer, shard_range
+
+__all__ = [
+    "RENIAutoDecoder", "RENIVariationalAutoDecoder", "SineLayer", "get_model",
+    "WeightedMSE", "KLD", "WeightedCosineSimilarity", "CosineSimilarity",
+    "RENITrainLoss", "RENIVADTrainLoss", "RENITestLoss",
+    "get_directions", "get_sineweight", "get_mask", "rectangle_mask",
+    "RENITrainer", "FlatGradBuffer", "shard_range",
+]

@@ -56,6 +56,7 @@ SIGNATURES = {
     "reni_loss_forward_backward": (_i32, [_cfgp, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _vp,
                                           _i64, C.c_float, C.c_float, _i32, _vp, _vp, _vp, C.POINTER(_vp),
                                           C.POINTER(_vp), _vp, _i64, _i32, _vp]),
+    "reni_debug_set_phase_events": (_i32, [C.POINTER(_vp), _i32]),
     "reni_selftest_umma": (_i32, [_vp, _u32, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]),
 }
 

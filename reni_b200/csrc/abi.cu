@@ -71,6 +71,14 @@ T* at(void* ws, int64_t off) {
   return off < 0 ? nullptr : reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(ws) + off);
 }
 
+// Optional phase timing (debug hook, reni_debug_set_phase_events): CUDA events recorded between the kernels of a
+// step so a caller can time each kernel on the launching stream.  Thread-local; empty by default.
+thread_local cudaEvent_t g_phase_events[16];
+thread_local int g_num_phase_events = 0;
+inline void mark_phase(int i, cudaStream_t s) {
+  if (i < g_num_phase_events && g_phase_events[i] != nullptr) cudaEventRecord(g_phase_events[i], s);
+}
+
 int num_sms() {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -155,6 +163,7 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   const int sms = num_sms();
   if (sms <= 0) return RENI_ERR_NO_DEVICE;
 
+  mark_phase(0, stream);
   // ---- per-map prologue: layer 0 hoisted to (M_b, c_b)
   {
     PrologueParams q{};
@@ -174,6 +183,7 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
     reni_prologue_kernel<<<dim3(kH / 8, (unsigned)B), 256, smem, stream>>>(q);
     if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
   }
+  mark_phase(1, stream);
 
   // ---- fused decoder forward
   FwdParams p{};
@@ -212,6 +222,7 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   else if (train) launch(reni_fwd_kernel<1>);
   else launch(reni_fwd_kernel<0>);
   if (e != cudaSuccess) return RENI_ERR_CUDA;
+  mark_phase(2, stream);
   return cudaGetLastError() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
@@ -228,6 +239,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   const int L = c->hidden_layers;
   const int ntiles = (int)(B * tiles_per_map(P));
   if (cudaMemsetAsync(at<float>(ws, w.dmc), 0, (size_t)B * 5 * kH * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
+  mark_phase(3, stream);
 
   BwdParams p{};
   p.out = out;
@@ -263,6 +275,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     reni_bwd_kernel<false><<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(p);
   }
   if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+  mark_phase(4, stream);
 
   if (need_dw) {
     DwParams q{};
@@ -288,6 +301,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     reni_dw_kernel<<<g, kDwThreads, DwSmem::kTotal, stream>>>(q);
     if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
   }
+  mark_phase(5, stream);
 
   {
     L0ReduceParams r{};
@@ -331,6 +345,14 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     }
     if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
   }
+  mark_phase(6, stream);
+  return RENI_OK;
+}
+
+int32_t reni_debug_set_phase_events(void* const* events, int32_t n) {
+  if (n < 0 || n > 16 || (n > 0 && events == nullptr)) return RENI_ERR_BAD_ARGUMENT;
+  for (int i = 0; i < n; ++i) g_phase_events[i] = static_cast<cudaEvent_t>(events[i]);
+  g_num_phase_events = n;
   return RENI_OK;
 }
 

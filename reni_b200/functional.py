@@ -1,0 +1,296 @@
+"""Host-side mirror of the decoder call: torch tensors in, C-ABI kernels underneath.
+
+``decode`` is the autograd-aware replacement for ``self.net(self.InvariantRepresentation(Z, D))``
+(reference: src/models/RENI.py:211-233); ``loss_forward_backward`` is the fused
+``training_step`` body (src/lightning/RENI_module.py:80-146 with RENITrainLoss / RENITestLoss,
+src/utils/loss_functions.py:39-71).  PyTorch is used for device memory and streams only; all
+arithmetic happens in libreni_b200.so.  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import FLAG_LOSS, FLAG_NEED_DW, FLAG_SAVE_FOR_BACKWARD, RENIConfig
+
+HIDDEN_FEATURES = 256  # compile-time tile width of the tcgen05 kernels
+
+
+@dataclass(frozen=True)
+class DecoderSpec:
+    """Hyper-parameters of one decoder, as the reference constructor takes them (RENI.py:91-104)."""
+
+    ndims: int
+    equivariance: str
+    hidden_features: int
+    hidden_layers: int
+    out_features: int
+    last_layer_linear: bool
+    output_activation: Optional[str]
+    first_omega_0: float
+    hidden_omega_0: float
+
+    def validate(self) -> None:
+        if self.equivariance not in _lib.EQUIVARIANCE:
+            raise ValueError(f"equivariance must be one of {list(_lib.EQUIVARIANCE)}, got {self.equivariance!r}")
+        if self.output_activation == "exp":
+            # the reference raises here too: nn.Exp does not exist (RENI.py:173-174)
+            raise AttributeError("module 'torch.nn' has no attribute 'Exp'")
+        if self.output_activation not in (None, "tanh"):
+            raise ValueError(f"unsupported output_activation {self.output_activation!r}")
+        if self.hidden_features != HIDDEN_FEATURES:
+            raise NotImplementedError(
+                f"reni_b200 kernels are built for hidden_features={HIDDEN_FEATURES}, got {self.hidden_features}")
+        if not 1 <= self.hidden_layers <= 6:
+            raise NotImplementedError("reni_b200 kernels support 1..6 hidden layers")
+        if not 1 <= self.out_features <= 3:
+            raise NotImplementedError("reni_b200 kernels support out_features <= 3")
+
+    def c_config(self) -> RENIConfig:
+        self.validate()
+        return RENIConfig(
+            self.ndims, _lib.EQUIVARIANCE[self.equivariance], self.hidden_features, self.hidden_layers,
+            self.out_features, 1 if self.last_layer_linear else 0, 1 if self.output_activation == "tanh" else 0,
+            float(self.first_omega_0), float(self.hidden_omega_0))
+
+
+def _vp(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _ptr_array(ts: Sequence[Optional[torch.Tensor]]):
+    return (C.c_void_p * len(ts))(*[(t.data_ptr() if t is not None else 0) for t in ts])
+
+
+def _stream(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = tensors[0].device
+    for t in tensors:
+        if t.device.type != "cuda":
+            raise RuntimeError(
+                "reni_b200 runs on CUDA (sm_100a) only and has no CPU fallback; got a tensor on "
+                f"{t.device}.  Move the module and its inputs to a B200.")
+        if t.device != dev:
+            raise RuntimeError(f"all tensors must be on the same device ({dev} vs {t.device})")
+    return dev
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _batch_stride(t: torch.Tensor, B: int, what: str) -> Tuple[torch.Tensor, int]:
+    """(tensor to pass, elements between maps).  A (1,P,3) tensor or a stride-0 expand is shared by all maps."""
+    if t.dim() != 3 or t.shape[2] != 3:
+        raise ValueError(f"{what} must have shape (B, P, 3), got {tuple(t.shape)}")
+    if t.shape[0] == 1 or (t.stride(0) == 0 and t.shape[0] == B):
+        t0 = _f32c(t[:1])
+        return t0, 0
+    # the reference asserts len(idx) == directions.shape[0] (RENI.py:213,220)
+    assert t.shape[0] == B, f"{what} batch {t.shape[0]} != latent batch {B}"
+    t = _f32c(t)
+    return t, t.shape[1] * 3
+
+
+class Workspace:
+    """Caller-owned device workspace (grow-only), 1024-byte aligned, carved by the library."""
+
+    def __init__(self) -> None:
+        self.buf: Optional[torch.Tensor] = None
+        self.view: Optional[torch.Tensor] = None
+        self.nbytes = 0
+        self.prepared_key = None
+
+    def ensure(self, nbytes: int, device: torch.device) -> torch.Tensor:
+        if self.view is None or self.nbytes < nbytes or self.view.device != device:
+            self.buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            off = (-self.buf.data_ptr()) % 1024
+            self.view = self.buf[off:off + nbytes]
+            self.nbytes = nbytes
+            self.prepared_key = None
+        return self.view
+
+
+def workspace_bytes(cfg: RENIConfig, B: int, P: int, flags: int) -> int:
+    n = _lib.load().reni_workspace_bytes(C.byref(cfg), B, P, flags)
+    if n <= 0:
+        _lib.check(int(n), "reni_workspace_bytes")
+    return int(n)
+
+
+def _params_key(weights, biases):
+    return tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases))
+
+
+def prepare_weights(cfg: RENIConfig, weights, biases, ws: Workspace, device) -> None:
+    """fp32 parameters -> fp16 operand images inside the workspace (skipped if unchanged)."""
+    key = _params_key(weights, biases)
+    if ws.prepared_key == key:
+        return
+    lib = _lib.load()
+    rc = lib.reni_prepare_weights(C.byref(cfg), _ptr_array(weights), _ptr_array(biases), _vp(ws.view), ws.nbytes,
+                                  _stream(device))
+    _lib.check(rc, "reni_prepare_weights")
+    ws.prepared_key = key
+
+
+class _DecodeFunction(torch.autograd.Function):
+    """out = net(encoding(Z, D)) with gradients for Z and (optionally) the decoder parameters."""
+
+    @staticmethod
+    def forward(ctx, spec: DecoderSpec, inference_ws: Workspace, Z, D, *params):
+        lib = _lib.load()
+        cfg = spec.c_config()
+        nl = spec.hidden_layers + 2
+        weights = [_f32c(p) for p in params[0::2]]
+        biases = [_f32c(p) for p in params[1::2]]
+        assert len(weights) == nl and len(biases) == nl
+        dev = _require_cuda(Z, D, *weights, *biases)
+        if Z.dim() != 3 or Z.shape[1] != spec.ndims or Z.shape[2] != 3:
+            raise ValueError(f"latent codes must have shape (B, {spec.ndims}, 3), got {tuple(Z.shape)}")
+        Zc = _f32c(Z)
+        B = Zc.shape[0]
+        Dc, d_bs = _batch_stride(D, B, "directions")
+        P = Dc.shape[1]
+        need_dz = ctx.needs_input_grad[2]
+        need_dw = any(ctx.needs_input_grad[4:])
+        flags = 0
+        if need_dz or need_dw:
+            flags |= FLAG_SAVE_FOR_BACKWARD
+            if need_dw:
+                flags |= FLAG_NEED_DW
+        nbytes = workspace_bytes(cfg, B, P, flags)
+        # a forward that will be differentiated owns its stash until backward has run
+        ws = Workspace() if flags else inference_ws
+        ws.ensure(nbytes, dev)
+        prepare_weights(cfg, weights, biases, ws, dev)
+        out = torch.empty(B, P, 3, device=dev, dtype=torch.float32)
+        rc = lib.reni_forward(C.byref(cfg), _vp(Zc), _vp(Dc), d_bs, _vp(weights[0]), _vp(biases[0]), B, P, _vp(out),
+                              None, None, 0, _vp(ws.view), ws.nbytes, flags, _stream(dev))
+        _lib.check(rc, "reni_forward")
+        if flags:
+            ctx.spec, ctx.ws, ctx.flags, ctx.d_bs = spec, ws, flags, d_bs
+            ctx.save_for_backward(Zc, Dc, out, *weights, *biases)
+        if spec.out_features != 3:
+            return out[:, :, : spec.out_features]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        spec: DecoderSpec = ctx.spec
+        cfg = spec.c_config()
+        nl = spec.hidden_layers + 2
+        saved = ctx.saved_tensors
+        Zc, Dc, out = saved[0], saved[1], saved[2]
+        weights, biases = list(saved[3:3 + nl]), list(saved[3 + nl:3 + 2 * nl])
+        dev = Zc.device
+        B, P = Zc.shape[0], Dc.shape[1]
+        g = _f32c(grad_out)
+        if g.shape[2] != 3:
+            gp = torch.zeros(B, P, 3, device=dev)
+            gp[:, :, : g.shape[2]] = g
+            g = gp
+        need_dw = bool(ctx.flags & FLAG_NEED_DW)
+        dZ = torch.empty_like(Zc)
+        dW = [torch.zeros_like(w) for w in weights] if need_dw else None
+        db = [torch.zeros_like(b) for b in biases] if need_dw else None
+        rc = lib.reni_backward(C.byref(cfg), _vp(Zc), _vp(Dc), ctx.d_bs, _ptr_array(weights), B, P, _vp(out), _vp(g),
+                               _vp(dZ), _ptr_array(dW) if need_dw else None, _ptr_array(db) if need_dw else None,
+                               _vp(ctx.ws.view), ctx.ws.nbytes, ctx.flags, _stream(dev))
+        _lib.check(rc, "reni_backward")
+        ctx.ws = None  # release the stash
+        grads: List[Optional[torch.Tensor]] = []
+        for i in range(nl):
+            grads.append(dW[i] if need_dw and ctx.needs_input_grad[4 + 2 * i] else None)
+            grads.append(db[i] if need_dw and ctx.needs_input_grad[5 + 2 * i] else None)
+        return (None, None, dZ if ctx.needs_input_grad[2] else None, None, *grads)
+
+
+def decode(spec: DecoderSpec, inference_ws: Workspace, Z: torch.Tensor, D: torch.Tensor,
+           params: Sequence[torch.Tensor]) -> torch.Tensor:
+    """``params`` = [W0, b0, W1, b1, ..., W_out, b_out] (state_dict order of ``net``).
+
+    Differentiable w.r.t. Z and the parameters (never w.r.t. the directions, which the reference never
+    differentiates either).  Under ``torch.no_grad()`` or with nothing requiring grad this is the
+    inference kernel with no stash."""
+    spec.validate()
+    if torch.is_grad_enabled() and (Z.requires_grad or any(p.requires_grad for p in params)):
+        return _DecodeFunction.apply(spec, inference_ws, Z, D, *params)
+    with torch.no_grad():
+        return _DecodeFunction.forward(_NoGradCtx(len(params)), spec, inference_ws, Z, D, *params)
+
+
+class _NoGradCtx:
+    """Stand-in ctx for calling the forward outside autograd."""
+
+    def __init__(self, nparams: int) -> None:
+        self.needs_input_grad = (False,) * (4 + nparams)
+
+    def save_for_backward(self, *a) -> None:  # pragma: no cover - never reached (flags == 0)
+        raise AssertionError
+
+
+@dataclass
+class StepResult:
+    """What the reference's training_step returns (RENI_module.py:115-146) plus the gradients."""
+
+    loss: torch.Tensor         # scalar
+    mse_loss: torch.Tensor
+    prior_loss: torch.Tensor
+    cosine_loss: torch.Tensor
+    out: torch.Tensor          # (B, P, 3) model output
+    dZ: torch.Tensor           # (B, N, 3)
+    dW: Optional[List[torch.Tensor]]
+    db: Optional[List[torch.Tensor]]
+
+
+def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: torch.Tensor, target: torch.Tensor,
+                          sineweight: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+                          alpha: float = 0.0, beta: float = 0.0, use_cosine: bool = False, need_dw: bool = True,
+                          grad_weights: Optional[Sequence[torch.Tensor]] = None,
+                          grad_biases: Optional[Sequence[torch.Tensor]] = None) -> StepResult:
+    """Fused forward + loss + backward (one training / latent-fit step without the optimiser).
+
+    loss = WeightedMSE + alpha * sum Z^2 + beta * WeightedCosineSimilarity  (loss_functions.py:6-32,60-71);
+    RENITrainLoss is alpha = beta = 0.  ``grad_weights`` / ``grad_biases`` (e.g. views into one flat
+    all-reduce buffer) are ACCUMULATED into; fresh zero tensors are used when omitted."""
+    lib = _lib.load()
+    cfg = spec.c_config()
+    dev = _require_cuda(Z, D, target, sineweight, *weights, *biases)
+    Zc = _f32c(Z)
+    B = Zc.shape[0]
+    Dc, d_bs = _batch_stride(D, B, "directions")
+    swc, sw_bs = _batch_stride(sineweight, B, "sineweight")
+    P = Dc.shape[1]
+    tc = _f32c(target)
+    if tuple(tc.shape) != (B, P, 3):
+        raise ValueError(f"target must have shape {(B, P, 3)}, got {tuple(tc.shape)}")
+    weights = [_f32c(w) for w in weights]
+    biases = [_f32c(b) for b in biases]
+    flags = FLAG_SAVE_FOR_BACKWARD | FLAG_LOSS | (FLAG_NEED_DW if need_dw else 0)
+    ws.ensure(workspace_bytes(cfg, B, P, flags), dev)
+    prepare_weights(cfg, weights, biases, ws, dev)
+    out = torch.empty(B, P, 3, device=dev, dtype=torch.float32)
+    loss = torch.empty(4, device=dev, dtype=torch.float32)
+    dZ = torch.empty_like(Zc)
+    dW = db = None
+    if need_dw:
+        dW = list(grad_weights) if grad_weights is not None else [torch.zeros_like(w) for w in weights]
+        db = list(grad_biases) if grad_biases is not None else [torch.zeros_like(b) for b in biases]
+    rc = lib.reni_loss_forward_backward(
+        C.byref(cfg), _vp(Zc), _vp(Dc), d_bs, _ptr_array(weights), _ptr_array(biases), B, P, _vp(tc), _vp(swc), sw_bs,
+        float(alpha), float(beta), 1 if use_cosine else 0, _vp(out), _vp(loss), _vp(dZ),
+        _ptr_array(dW) if need_dw else None, _ptr_array(db) if need_dw else None, _vp(ws.view), ws.nbytes, flags,
+        _stream(dev))
+    _lib.check(rc, "reni_loss_forward_backward")
+    return StepResult(loss[0], loss[1], loss[2], loss[3], out, dZ, dW, db)

@@ -1,0 +1,177 @@
+"""Training / latent-optimisation step of the reference, on the fused kernels.
+
+Restates what one Lightning iteration does around the decoder (reference:
+src/lightning/RENI_module.py:80-146 ``training_step``, :168-195 optimiser, run.py:97-108
+DDPStrategy; examples.ipynb cell 4 is the same loop by hand):
+
+    imgs (B,3,H,W) -> (B,P,3);  Z = model.Z[idx] (or mu[idx] / sample_latent(idx));
+    out = model(Z, directions);  loss = criterion(out, imgs, sineweight [* mask], ...);
+    loss.backward();  [DDP: all-reduce(avg) of every gradient];  Adam.step()
+
+Here forward + loss + backward is ONE library call (``loss_forward_backward``); the decoder
+weight gradients land in a single flat fp32 buffer that is all-reduced with ONE NCCL call;
+latent gradients stay on the rank that owns the maps.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import functional as F_
+from .functional import Workspace
+from .geometry import get_directions, get_sineweight
+from .losses import KLD
+from .models import RENIAutoDecoder, RENIVariationalAutoDecoder, _DecoderBase
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block of maps owned by ``rank`` (maps are independent units; no data-path collective)."""
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class FlatGradBuffer:
+    """One contiguous fp32 buffer holding every decoder-weight gradient (680 707 floats at N=36), with
+    per-parameter views used both as the kernels' accumulation targets and as ``param.grad``."""
+
+    def __init__(self, params: Sequence[torch.Tensor]):
+        self.params = list(params)
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views: List[torch.Tensor] = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+
+    def attach(self) -> None:
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def all_reduce_mean(self, group=None) -> None:
+        """DDP semantics (run.py:97): average over ranks of the per-rank batch-summed gradients."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        world = dist.get_world_size(group)
+        if world == 1:
+            return
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(world)
+
+
+class RENITrainer:
+    """One task of the reference's ``RENI`` LightningModule, minus Lightning.
+
+    task: "FIT_DECODER" (all parameters, RENITrainLoss / RENIVADTrainLoss) or "FIT_LATENT"
+    (frozen decoder, RENITestLoss with optional mask; RENI_module.py:295-336)."""
+
+    def __init__(self, model: _DecoderBase, task: str, sidelen: int, lr: float = 1e-5,
+                 prior_loss_weight: float = 1e-7, cosine_similarity_weight: float = 1e-4,
+                 kld_weighting: float = 1e-4, mask: Optional[torch.Tensor] = None, process_group=None,
+                 ddp_latent_scaling: bool = True):
+        if task not in ("FIT_DECODER", "FIT_LATENT"):
+            raise NotImplementedError("FIT_INVERSE needs the PyTorch3D renderer and is out of scope for this path")
+        self.model = model
+        self.task = task
+        self.group = process_group
+        self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.ddp_latent_scaling = ddp_latent_scaling
+        dev = next(model.parameters()).device
+        self.device = dev
+        self.set_resolution(sidelen)
+        self.mask = mask.to(dev) if mask is not None else None
+        self.alpha = prior_loss_weight
+        self.beta = cosine_similarity_weight
+        self.kld_weighting = kld_weighting
+        self.is_vad = isinstance(model, RENIVariationalAutoDecoder)
+        self.fixed = task == "FIT_LATENT"
+        self._ws = Workspace()
+        # optimiser: Adam(lr) with default betas -- the cfg betas are never passed (RENI_module.py:191-192)
+        if self.fixed:
+            opt_params = [model.mu] if self.is_vad else [model.Z]  # RENI_module.py:178-183
+            self.flat = None
+        else:
+            opt_params = list(model.parameters())
+            self.flat = FlatGradBuffer(model.decoder_parameters())
+        self.optimizer = torch.optim.Adam(opt_params, lr=lr)
+
+    # -- multi-resolution curriculum hook (callbacks.py:11-29 doubles the resolution at curriculum epochs)
+    def set_resolution(self, sidelen: int) -> None:
+        self.sidelen = sidelen
+        self.directions = get_directions(sidelen).to(self.device)   # (1, P, 3), shared by every map
+        self.sineweight = get_sineweight(sidelen).to(self.device)   # (1, P, 3)
+
+    def exponential_lr(self, lr_start: float, lr_end: float, epochs: int):
+        """Per-epoch ExponentialLR with gamma = exp(ln(lr_end/lr_start)/epochs) (RENI_module.py:212-214)."""
+        gamma = math.exp(math.log(lr_end / lr_start) / epochs)
+        return torch.optim.lr_scheduler.ExponentialLR(self.optimizer, gamma=gamma)
+
+    def _latent_table(self) -> torch.nn.Parameter:
+        return self.model.mu if self.is_vad else self.model.Z
+
+    def training_step(self, batch, batch_idx: int = 0) -> Dict[str, torch.Tensor]:
+        """Same inputs and returned keys as RENI_module.training_step; gradients are left in ``.grad``."""
+        imgs, idx = batch
+        B = imgs.shape[0]
+        imgs = imgs.permute(0, 2, 3, 1).reshape(B, -1, 3)  # (B,C,H,W) -> (B,P,3)   RENI_module.py:83-84
+        sw = self.sineweight if self.mask is None else self.sineweight * self.mask  # :90-94
+        idx = torch.as_tensor(idx, device=self.device, dtype=torch.long)
+        model = self.model
+        table = self._latent_table()
+        sampled = self.is_vad and not self.fixed
+        if sampled:
+            Z, mu, log_var = model.sample_latent(idx)  # RENI_module.py:100-101 (torch RNG, autograd graph)
+            Zin = Z.detach()
+        else:
+            Zin = table.detach()[idx]  # :98,:103
+        need_dw = not self.fixed
+        if need_dw:
+            self.flat.zero_()
+        if self.task == "FIT_LATENT":
+            alpha, beta, use_cos = self.alpha, self.beta, True      # RENITestLoss  (:126-128)
+        else:
+            alpha, beta, use_cos = 0.0, 0.0, False                  # RENITrainLoss (:117)
+        res = F_.loss_forward_backward(
+            model.spec, self._ws, Zin, self.directions, imgs, sw, model.decoder_weights(), model.decoder_biases(),
+            alpha=alpha, beta=beta, use_cosine=use_cos, need_dw=need_dw,
+            grad_weights=self.flat.views[0::2] if need_dw else None,
+            grad_biases=self.flat.views[1::2] if need_dw else None)
+        dZ = res.dZ
+        if self.world_size > 1 and self.ddp_latent_scaling:
+            # the reference replicates the latent table and DDP averages its (mostly zero) gradient over ranks
+            dZ = dZ / self.world_size
+        log: Dict[str, torch.Tensor] = {"loss": res.loss}
+        if sampled:
+            kld = self.kld_weighting * KLD(mu, log_var, Z_dims=model.ndims * 3)  # :312-315
+            model.mu.grad = None
+            model.log_var.grad = None
+            torch.autograd.backward([Z, kld], [dZ, torch.ones_like(kld)])
+            log = {"loss": res.loss + kld.detach(), "mse_loss": res.mse_loss, "kld_loss": kld.detach()}
+        else:
+            g = torch.zeros_like(table)
+            g.index_add_(0, idx, dZ)
+            table.grad = g
+            if self.task == "FIT_LATENT":
+                log.update(mse_loss=res.mse_loss, prior_loss=res.prior_loss, cosine_loss=res.cosine_loss)
+        if need_dw:
+            self.flat.all_reduce_mean(self.group)  # the ONE exchange step of data-parallel training
+            self.flat.attach()
+        self.last_output = res.out
+        return log
+
+    def step(self, batch) -> Dict[str, torch.Tensor]:
+        """training_step + optimiser step (what trainer.fit does per iteration)."""
+        log = self.training_step(batch)
+        self.optimizer.step()
+        return log

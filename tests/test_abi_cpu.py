@@ -1,0 +1,89 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/reni_b200.h declares;
+host-side entry points that need no GPU behave (sizes, error codes)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from helpers import ROOT
+
+import __graft_entry__ as entry
+from reni_b200 import _lib
+
+
+@pytest.fixture(scope="module")
+def lib():
+    entry.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "reni_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(reni_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 9
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/reni_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in reni_b200/_lib.py"
+    assert _lib.missing_symbols() == []
+
+
+def test_version_and_strerror(lib):
+    assert lib.reni_abi_version() == 1
+    assert lib.reni_strerror(0) == b"ok"
+    for code in (-1, -2, -3, -4, -5):
+        assert len(lib.reni_strerror(code)) > 4
+
+
+def cfg(**kw):
+    d = dict(ndims=36, equivariance=1, hidden_features=256, hidden_layers=5, out_features=3, last_layer_linear=1,
+             output_activation=1, first_omega_0=30.0, hidden_omega_0=30.0)
+    d.update(kw)
+    return _lib.RENIConfig(**d)
+
+
+def test_in_features_matches_reference_formula(lib):
+    # src/models/RENI.py:118-126
+    for N in (9, 36, 49, 100):
+        assert lib.reni_in_features(C.byref(cfg(ndims=N, equivariance=1))) == 2 * N + N * N + 2
+        assert lib.reni_in_features(C.byref(cfg(ndims=N, equivariance=2))) == N + N * N
+        assert lib.reni_in_features(C.byref(cfg(ndims=N, equivariance=0))) == 4 * N
+
+
+def test_workspace_sizes(lib):
+    c = cfg()
+    inf = lib.reni_workspace_bytes(C.byref(c), 32, 8192, 0)
+    lat = lib.reni_workspace_bytes(C.byref(c), 32, 8192, 1)
+    full = lib.reni_workspace_bytes(C.byref(c), 32, 8192, 3)
+    assert 0 < inf < lat < full
+    ntiles = 32 * 64
+    # latent-only: cos stash (6 images) + delta_0 (1 image) per tile; full: cos + h + delta (6 each)
+    assert lat - inf >= ntiles * 7 * 65536
+    assert full - inf >= ntiles * 18 * 65536
+    assert full < 3.2e9
+    # ragged P rounds up to whole 128-direction tiles
+    assert lib.reni_workspace_bytes(C.byref(c), 1, 129, 1) > lib.reni_workspace_bytes(C.byref(c), 1, 128, 1)
+
+
+def test_bad_configs_are_rejected(lib):
+    assert lib.reni_workspace_bytes(C.byref(cfg(hidden_features=128)), 1, 128, 0) == -1
+    assert lib.reni_workspace_bytes(C.byref(cfg(hidden_layers=0)), 1, 128, 0) == -1
+    assert lib.reni_workspace_bytes(C.byref(cfg(hidden_layers=7)), 1, 128, 0) == -1
+    assert lib.reni_workspace_bytes(C.byref(cfg(equivariance=3)), 1, 128, 0) == -1
+    assert lib.reni_workspace_bytes(C.byref(cfg(out_features=4)), 1, 128, 0) == -1
+    assert lib.reni_workspace_bytes(C.byref(cfg()), 0, 128, 0) == -2
+    assert lib.reni_workspace_bytes(C.byref(cfg()), 1, 0, 0) == -2
+    with pytest.raises(_lib.RENILibraryError):
+        _lib.check(-3, "x")
+
+
+def test_null_arguments_return_error_codes_without_touching_the_gpu(lib):
+    c = cfg()
+    assert lib.reni_forward(C.byref(c), None, None, 0, None, None, 1, 128, None, None, None, 0, None, 0, 0, None) == -2
+    assert lib.reni_prepare_weights(C.byref(c), None, None, None, 0, None) == -2
+    assert lib.reni_selftest_umma(None, 0, None, 0, 0, 0, 0, 0, 0, 0, 0, 0, 16, 1, None, None) == -2

@@ -1,0 +1,296 @@
+"""Parity tests proper (run on a B200 with -m gpu): the CUDA path, called through the C ABI / the
+drop-in modules, against (a) golden fixtures produced by the reference itself and (b) the numpy
+oracle on the same seeded inputs.  Tolerances are BASELINE.json's: radiance 1e-3 relative,
+weight and latent gradients 1e-2 relative (rel-L2; max-abs is checked against a looser bar)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (O, TOL_GRAD, TOL_RADIANCE, TOL_RADIANCE_MAX, load_case, model_from_params, params_from_model,
+                     sub_dw)
+
+pytestmark = pytest.mark.gpu
+
+H256_CASES = ["so2_n9_h256", "so2_n36_h256", "so2_n36_h256_masked"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    import __graft_entry__ as entry
+
+    entry.build()
+    return torch.device("cuda:0")
+
+
+def t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def image_kmajor(mat):
+    R, K = mat.shape
+    return np.ascontiguousarray(mat.astype(np.float16).reshape(R, K // 8, 8).transpose(1, 0, 2))
+
+
+def test_umma_operand_layouts(dev):
+    """tcgen05 SWIZZLE_NONE descriptors: K-major (N=256, N=16) and MN-major operands from the tile image."""
+    from reni_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+
+    def run(a_img, b_img, args, N, ksteps):
+        ta, tb = t(a_img.view(np.uint8).reshape(-1), dev), t(b_img.view(np.uint8).reshape(-1), dev)
+        d = torch.zeros(128, N, device=dev)
+        rc = lib.reni_selftest_umma(C.c_void_p(ta.data_ptr()), ta.numel(), C.c_void_p(tb.data_ptr()), tb.numel(),
+                                    *args, N, ksteps, C.c_void_p(d.data_ptr()), None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        return d.cpu().numpy()
+
+    A = rng.uniform(-1, 1, (128, 256)).astype(np.float16)
+    Bw = rng.uniform(-1, 1, (256, 256)).astype(np.float16)
+    got = run(image_kmajor(A), image_kmajor(Bw), (2048, 128, 4096, 128, 4096, 8192, 0, 0), 256, 16)
+    np.testing.assert_allclose(got, A.astype(np.float32) @ Bw.astype(np.float32).T, atol=1e-4)
+    B16 = rng.uniform(-1, 1, (16, 256)).astype(np.float16)
+    got = run(image_kmajor(A), image_kmajor(B16), (2048, 128, 256, 128, 4096, 512, 0, 0), 16, 16)
+    np.testing.assert_allclose(got, A.astype(np.float32) @ B16.astype(np.float32).T, atol=1e-4)
+    At = rng.uniform(-1, 1, (64, 128)).astype(np.float16)
+    Bt = rng.uniform(-1, 1, (64, 256)).astype(np.float16)
+    got = run(image_kmajor(At), image_kmajor(Bt), (128, 1024, 128, 1024, 256, 256, 1, 1), 256, 4)
+    np.testing.assert_allclose(got, At.astype(np.float32).T @ Bt.astype(np.float32), atol=1e-4)
+
+
+@pytest.mark.parametrize("name", H256_CASES)
+def test_forward_matches_reference_golden(dev, name):
+    c = load_case(name)
+    m = model_from_params(c["p"], c["N"], dev)
+    with torch.no_grad():
+        out = m(t(c["Z"], dev), t(c["D"], dev)).cpu().numpy()
+    ref = c["g"]["out_f32"]  # the reference's own fp32 output
+    assert out.shape == ref.shape
+    assert O.rel_l2(out, ref) < TOL_RADIANCE
+    assert O.rel_max(out, ref) < TOL_RADIANCE_MAX
+
+
+@pytest.mark.parametrize("name", H256_CASES)
+def test_fused_training_step_matches_reference_golden(dev, name):
+    """FIT_DECODER: RENITrainLoss + all gradients; FIT_LATENT: RENITestLoss (prior + cosine [+ mask]) + dZ."""
+    from reni_b200 import functional as F_
+
+    c = load_case(name)
+    g = c["g"]
+    m = model_from_params(c["p"], c["N"], dev)
+    Z, D, tg, sw = (t(c[k], dev) for k in ("Z", "D", "target", "sw"))
+    ws = F_.Workspace()
+    r = F_.loss_forward_backward(m.spec, ws, Z, D, tg, sw, m.decoder_weights(), m.decoder_biases(), need_dw=True)
+    torch.cuda.synchronize()
+    assert abs(float(r.loss) - float(g["train_loss_f32"])) < 1e-4 * abs(float(g["train_loss_f32"]))
+    assert O.rel_l2(r.out.cpu().numpy(), g["out_f32"]) < TOL_RADIANCE
+    assert O.rel_l2(r.dZ.cpu().numpy(), g["train_dZ_f32"]) < TOL_GRAD
+    for i in range(c["L"] + 2):
+        dw = r.dW[i].cpu().numpy()
+        assert O.rel_l2(sub_dw(i, dw), g[f"train_dW{i}_f32"]) < TOL_GRAD, f"dW{i}"
+        assert abs(np.linalg.norm(dw) / float(g[f"train_dW{i}_norm_f32"]) - 1) < TOL_GRAD
+        assert O.rel_l2(r.db[i].cpu().numpy(), g[f"train_db{i}_f32"]) < TOL_GRAD, f"db{i}"
+    r2 = F_.loss_forward_backward(m.spec, ws, Z, D, tg, sw, m.decoder_weights(), m.decoder_biases(),
+                                  alpha=c["alpha"], beta=c["beta"], use_cosine=True, need_dw=False)
+    torch.cuda.synchronize()
+    got = np.array([float(r2.loss), float(r2.mse_loss), float(r2.prior_loss), float(r2.cosine_loss)])
+    np.testing.assert_allclose(got, g["test_loss_f32"], rtol=2e-4, atol=1e-8)
+    assert O.rel_l2(r2.dZ.cpu().numpy(), g["test_dZ_f32"]) < TOL_GRAD
+    assert r2.dW is None
+
+
+@pytest.mark.parametrize("name", ["so2_n36_h256"])
+def test_autograd_path_matches_reference_golden(dev, name):
+    """model(Z, D) + torch loss + loss.backward(): the reference's own calling pattern (RENI_module.py:105-118)."""
+    from reni_b200 import RENITestLoss, RENITrainLoss
+
+    c = load_case(name)
+    g = c["g"]
+    m = model_from_params(c["p"], c["N"], dev)
+    Z = t(c["Z"], dev).requires_grad_(True)
+    D, tg, sw = (t(c[k], dev) for k in ("D", "target", "sw"))
+    out = m(Z, D)
+    loss = RENITrainLoss()(out, tg, sw)
+    loss.backward()
+    assert O.rel_l2(Z.grad.cpu().numpy(), g["train_dZ_f32"]) < TOL_GRAD
+    for i, w in enumerate(m.decoder_weights()):
+        assert O.rel_l2(sub_dw(i, w.grad.cpu().numpy()), g[f"train_dW{i}_f32"]) < TOL_GRAD, f"dW{i}"
+    for i, b in enumerate(m.decoder_biases()):
+        assert O.rel_l2(b.grad.cpu().numpy(), g[f"train_db{i}_f32"]) < TOL_GRAD, f"db{i}"
+    # frozen decoder + RENITestLoss through autograd (examples.ipynb cell 4)
+    mf = model_from_params(c["p"], c["N"], dev, fixed=True)
+    Z2 = t(c["Z"], dev).requires_grad_(True)
+    l2, *_ = RENITestLoss(alpha=c["alpha"], beta=c["beta"])(mf(Z2, D), tg, sw, Z2)
+    l2.backward()
+    assert O.rel_l2(Z2.grad.cpu().numpy(), g["test_dZ_f32"]) < TOL_GRAD
+    assert all(p.grad is None for p in mf.net.parameters())
+
+
+def oracle_out(m, Z, D):
+    return O.decoder_forward(Z.astype(np.float64), D.astype(np.float64), params_from_model(m))
+
+
+def test_forward_dispatch_branches(dev):
+    """int / list / index tensor / latent tensor (RENI.py:211-233) all decode the right rows of Z."""
+    torch.manual_seed(1)
+    from reni_b200 import RENIAutoDecoder, get_directions
+
+    m = RENIAutoDecoder(6, 9, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+    Zt = m.Z.detach().cpu().numpy()
+    D1 = get_directions(16)
+    D2 = D1.repeat(2, 1, 1)
+    with torch.no_grad():
+        a = m(3, D1.to(dev)).cpu().numpy()
+        b = m([1, 4], D2.to(dev)).cpu().numpy()
+        c_ = m(torch.tensor([5, 0], device=dev), D2.to(dev)).cpu().numpy()
+        d = m(m.Z[[2, 3]], D2.to(dev)).cpu().numpy()
+        e = m(m.Z[[2, 3]], D1.to(dev)).cpu().numpy()  # one shared grid for all maps (stride-0 batch)
+    assert O.rel_l2(a, oracle_out(m, Zt[[3]], D1.numpy())) < TOL_RADIANCE
+    assert O.rel_l2(b, oracle_out(m, Zt[[1, 4]], D2.numpy())) < TOL_RADIANCE
+    assert O.rel_l2(c_, oracle_out(m, Zt[[5, 0]], D2.numpy())) < TOL_RADIANCE
+    assert O.rel_l2(d, oracle_out(m, Zt[[2, 3]], D2.numpy())) < TOL_RADIANCE
+    assert np.array_equal(d, e)
+
+
+@pytest.mark.parametrize("eq,act,last_linear", [("SO3", "tanh", True), ("None", "tanh", True), ("SO2", None, True),
+                                                ("SO2", None, False), ("SO2", "tanh", False)])
+def test_forward_other_variants_vs_oracle(dev, eq, act, last_linear):
+    """SO3 / None encodings (RENI.py:23-28,56-60), no output activation, sine output layer (RENI.py:164-171)."""
+    torch.manual_seed(2)
+    from reni_b200 import RENIAutoDecoder
+
+    m = RENIAutoDecoder(3, 7, eq, 256, 3, 3, last_linear, act, 30.0, 30.0, False).to(dev)
+    rng = np.random.default_rng(3)
+    D = rng.standard_normal((3, 200, 3))
+    D = (D / np.linalg.norm(D, axis=-1, keepdims=True)).astype(np.float32)  # per-map directions, ragged P
+    with torch.no_grad():
+        out = m(torch.tensor([0, 1, 2], device=dev), t(D, dev)).cpu().numpy()
+    ref = oracle_out(m, m.Z.detach().cpu().numpy(), D)
+    assert out.shape == (3, 200, 3)
+    assert O.rel_l2(out, ref) < TOL_RADIANCE
+
+
+@pytest.mark.parametrize("B,P", [(1, 1), (1, 127), (1, 129), (3, 128), (5, 300)])
+def test_ragged_and_tiny_shapes_training(dev, B, P):
+    """Edge cases: single direction, tiles that are not full, odd tile counts -- all gradients vs the oracle."""
+    torch.manual_seed(4)
+    from reni_b200 import RENIAutoDecoder
+    from reni_b200 import functional as F_
+
+    N = 5
+    m = RENIAutoDecoder(B, N, "SO2", 256, 2, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+    rng = np.random.default_rng(5)
+    D = rng.standard_normal((B, P, 3))
+    D = (D / np.linalg.norm(D, axis=-1, keepdims=True)).astype(np.float32)
+    tg = rng.uniform(-1, 1, (B, P, 3)).astype(np.float32)
+    sw = np.repeat(rng.uniform(0, 1, (B, P, 1)), 3, 2).astype(np.float32)
+    Z = m.Z.detach()
+    r = F_.loss_forward_backward(m.spec, F_.Workspace(), Z, t(D, dev), t(tg, dev), t(sw, dev), m.decoder_weights(),
+                                 m.decoder_biases(), alpha=1e-3, beta=0.3, use_cosine=True, need_dw=True)
+    torch.cuda.synchronize()
+    p = params_from_model(m)
+    Z64, D64, t64, s64 = (a.astype(np.float64) for a in (Z.cpu().numpy(), D, tg, sw))
+    o, tape = O.decoder_forward(Z64, D64, p, tape=True)
+    loss, mse, prior, cos = O.reni_test_loss(o, t64, s64, Z64, 1e-3, 0.3)
+    go = O.loss_grad_wrt_output(o, t64, s64, beta=0.3)
+    dWs, dbs, dZ = O.decoder_backward(Z64, D64, p, tape, go)
+    dZ = dZ + 2e-3 * Z64
+    assert abs(float(r.loss) - loss) < 2e-4 * abs(loss)
+    assert O.rel_l2(r.out.cpu().numpy(), o) < TOL_RADIANCE
+    assert O.rel_l2(r.dZ.cpu().numpy(), dZ) < TOL_GRAD
+    for i in range(4):
+        assert O.rel_l2(r.dW[i].cpu().numpy(), dWs[i]) < TOL_GRAD, f"dW{i}"
+        assert O.rel_l2(r.db[i].cpu().numpy(), dbs[i]) < TOL_GRAD, f"db{i}"
+
+
+def test_full_size_properties_config2(dev):
+    """BASELINE configs[1] (N=36, 32 maps x 64x128): size-independent properties instead of the oracle.
+    (1) SO(2) invariance: rotating Z and D about y leaves the radiance unchanged;
+    (2) additivity: weight gradients of the batch = sum of the gradients of its two halves, the loss too;
+    (3) forward is deterministic; (4) spot-check of 2 maps against the oracle."""
+    torch.manual_seed(6)
+    from reni_b200 import RENIAutoDecoder, get_directions, get_sineweight
+    from reni_b200 import functional as F_
+
+    B, N, W = 32, 36, 128
+    P = W * W // 2
+    m = RENIAutoDecoder(B, N, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+    D = get_directions(W).to(dev)
+    sw = get_sineweight(W).to(dev)
+    tg = torch.rand(B, P, 3, device=dev) * 2 - 1
+    Z = m.Z.detach()
+    with torch.no_grad():
+        o1 = m(Z, D)
+        o1b = m(Z, D)
+        th = 1.1
+        R = torch.tensor([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]], device=dev,
+                         dtype=torch.float32)
+        o2 = m(Z @ R.T, D @ R.T)
+    assert torch.equal(o1, o1b)
+    assert float((o1 - o2).norm() / o1.norm()) < TOL_RADIANCE
+    ws = F_.Workspace()
+    full = F_.loss_forward_backward(m.spec, ws, Z, D, tg, sw, m.decoder_weights(), m.decoder_biases())
+    h1 = F_.loss_forward_backward(m.spec, ws, Z[:16], D, tg[:16], sw, m.decoder_weights(), m.decoder_biases())
+    h2 = F_.loss_forward_backward(m.spec, ws, Z[16:], D, tg[16:], sw, m.decoder_weights(), m.decoder_biases())
+    assert abs(float(full.loss) - float(h1.loss) - float(h2.loss)) < 1e-4 * float(full.loss)
+    for a, b1, b2 in zip(full.dW + full.db, h1.dW + h1.db, h2.dW + h2.db):
+        assert float((a - b1 - b2).norm() / a.norm()) < 1e-3
+    assert torch.allclose(full.dZ[:16], h1.dZ, rtol=1e-3, atol=1e-7)
+    # spot check against the oracle, one map at a time (the encoding of one 64x128 map is 90 MB in fp64)
+    p64 = params_from_model(m)
+    D64, sw64 = D.cpu().numpy().astype(np.float64), sw.cpu().numpy().astype(np.float64)
+    outs, refs = [], []
+    for b in range(0, 32, 4):
+        ref = O.step_fit_decoder(Z[[b]].cpu().numpy().astype(np.float64), D64, tg[[b]].cpu().numpy().astype(np.float64),
+                                 sw64, p64)
+        outs.append(full.out[[b]].cpu().numpy())
+        refs.append(ref["out"])
+        assert O.rel_l2(full.dZ[[b]].cpu().numpy(), ref["dZ"]) < TOL_GRAD
+    outs, refs = np.concatenate(outs), np.concatenate(refs)
+    print("config-2 radiance over 8 maps: rel-L2", O.rel_l2(outs, refs), "rel-max", O.rel_max(outs, refs),
+          "max abs err", np.abs(outs - refs).max())
+    # a random-init decoder emits |o| ~ 0.05 (mostly the output bias), so the relative figure is taken over the
+    # whole set of maps, not per map; absolute radiance error stays ~1e-4 ("Precision")
+    assert O.rel_l2(outs, refs) < TOL_RADIANCE
+    assert O.rel_max(outs, refs) < TOL_RADIANCE_MAX
+
+
+def test_trainer_steps_autodecoder_and_vad(dev):
+    """RENITrainer mirrors training_step + Adam: losses fall, gradients land where the reference puts them."""
+    torch.manual_seed(7)
+    from reni_b200 import RENIAutoDecoder, RENITrainer, RENIVariationalAutoDecoder, rectangle_mask
+
+    W, B = 32, 4
+    imgs = torch.rand(B, 3, W // 2, W, device=dev) * 2 - 1
+    idx = torch.tensor([0, 2, 5, 7], device=dev)
+    m = RENIAutoDecoder(8, 9, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+    tr = RENITrainer(m, "FIT_DECODER", W, lr=1e-4)
+    l0 = float(tr.step((imgs, idx))["loss"])
+    assert m.Z.grad.shape == m.Z.shape and float(m.Z.grad[[1, 3, 4, 6]].abs().max()) == 0.0
+    assert all(p.grad is not None for p in m.net.parameters())
+    for _ in range(30):
+        log = tr.step((imgs, idx))
+    assert float(log["loss"]) < l0
+    # latent-only fit with mask (FIT_LATENT): decoder frozen, only Z moves
+    mf = RENIAutoDecoder(8, 9, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, True).to(dev)
+    mf.net.load_state_dict(m.net.state_dict())
+    w_before = mf.net[2].linear.weight.clone()
+    trf = RENITrainer(mf, "FIT_LATENT", W, lr=1e-2, mask=rectangle_mask(W, 2, 12, 8, 24))
+    first = trf.step((imgs, idx))
+    assert set(first) == {"loss", "mse_loss", "prior_loss", "cosine_loss"}
+    for _ in range(30):
+        last = trf.step((imgs, idx))
+    assert float(last["loss"]) < float(first["loss"])
+    assert torch.equal(mf.net[2].linear.weight, w_before) and float(mf.Z.abs().max()) > 0
+    # VAD, FIT_DECODER: sampled latents, KLD through torch autograd, decoder through the fused kernels
+    v = RENIVariationalAutoDecoder(8, 9, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+    trv = RENITrainer(v, "FIT_DECODER", W, lr=1e-4)
+    lg = trv.step((imgs, idx))
+    assert set(lg) == {"loss", "mse_loss", "kld_loss"}
+    assert v.mu.grad is not None and v.log_var.grad is not None
+    assert float(v.mu.grad[[1, 3, 4, 6]].abs().max()) == 0.0 and float(v.mu.grad[idx].abs().max()) > 0

@@ -153,3 +153,23 @@ def test_init_distribution_matches_reference_constructor():
         mine = np.abs(p.weights[i]).max()
         assert 0.9 * lim < mine < 1.1 * lim
     assert int(g["n_net_params"]) == sum(w.size for w in p.weights) + sum(b.size for b in p.biases) == 680707
+
+
+def test_torch_port_matches_reference_golden():
+    """oracle/reni_torch_port.py (the CPU baseline that bench.py times) == the reference's fp32 results."""
+    import torch
+
+    import reni_torch_port as TP
+
+    p, Z, D, target, sw, g, alpha, beta, full = load_case("so2_n9_h256")
+    ws = [torch.from_numpy(w) for w in p.weights]
+    bs = [torch.from_numpy(b) for b in p.biases]
+    loss, out, grads = TP.training_step(torch.from_numpy(Z), torch.from_numpy(D), torch.from_numpy(target),
+                                        torch.from_numpy(sw), ws, bs)
+    assert O.rel_max(out.numpy(), g["out_f32"]) < 2e-5
+    assert abs(float(loss) - float(g["train_loss_f32"])) < 1e-5 * abs(float(g["train_loss_f32"]))
+    assert O.rel_l2(grads[0].numpy(), g["train_dZ_f32"]) < 1e-4
+    nl = len(ws)
+    for i in range(nl):
+        assert O.rel_l2(sub_dw(i, grads[1 + i].numpy()), g[f"train_dW{i}_f32"]) < 1e-4
+        assert O.rel_l2(grads[1 + nl + i].numpy(), g[f"train_db{i}_f32"]) < 1e-4
