@@ -211,16 +211,14 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   const int npairs = (p.ntiles + 1) / 2;
   const int grid = npairs < sms ? npairs : sms;
   const bool train = (flags & RENI_FLAG_SAVE_FOR_BACKWARD) != 0;
-  const bool stash_h = train && (flags & RENI_FLAG_NEED_DW);
   cudaError_t e;
   auto launch = [&](auto kernel) {
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal);
     if (e != cudaSuccess) return;
     kernel<<<grid, kFwdThreads, FwdSmem::kTotal, stream>>>(p);
   };
-  if (stash_h) launch(reni_fwd_kernel<2>);
-  else if (train) launch(reni_fwd_kernel<1>);
-  else launch(reni_fwd_kernel<0>);
+  if (train) launch(reni_fwd_kernel<true>);
+  else launch(reni_fwd_kernel<false>);
   if (e != cudaSuccess) return RENI_ERR_CUDA;
   mark_phase(2, stream);
   return cudaGetLastError() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;

@@ -9,14 +9,17 @@
 //   d_l tiles stay in shared memory for the next GEMM; d_0 (and every d_l when weight gradients are wanted) is
 //   stashed as fp16 tile images for the weight-gradient GEMM / the per-map layer-0 reduction.
 //
-// Same CTA organisation as the forward kernel (producer warp, MMA warp, two ping-ponging epilogue groups).
+// Same CTA organisation as the forward kernel (producer warp, MMA warp, two ping-ponging epilogue groups of 8 warps).
+// Each epilogue thread owns (row, 128 columns): the 16 x 16-B stash loads of its whole layer slice are issued before it
+// waits for the GEMM, so their HBM/L2 latency hides under the tensor pipe; the producer warp additionally prefetches the
+// next layer's stash tiles into L2 (cp.async.bulk.prefetch.L2).
 #pragma once
 #include "layout.cuh"
 #include "ptx.cuh"
 
 namespace reni {
 
-constexpr int kBwdThreads = 320;
+constexpr int kBwdThreads = 576;
 constexpr int kBwdStages = 4;
 
 struct BwdParams {
@@ -47,8 +50,14 @@ struct BwdSmem {
 };
 static_assert(BwdSmem::kTotal <= 232448, "backward kernel shared memory over budget");
 
-DEVINL uint32_t hmul2_u32(uint32_t a, uint32_t b) {
-  __half2 r = __hmul2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+DEVINL void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+
+// delta = acc * cos(a) for two columns, packed fp16 arithmetic (cos comes packed from the stash)
+DEVINL uint32_t delta2(float acc0, float acc1, uint32_t c2) {
+  const uint32_t a2 = pack_half2(acc0, acc1);
+  __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&a2), *reinterpret_cast<const __half2*>(&c2));
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
@@ -73,8 +82,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(&a_ready[0], 128);
-    mbar_init(&a_ready[1], 128);
+    mbar_init(&a_ready[0], 256);
+    mbar_init(&a_ready[1], 256);
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
     fence_mbar_init();
@@ -98,8 +107,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wb);
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
         const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
+        for (int g = 0; g < nsub; ++g)
+          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_c) +
+                               ((size_t)(2 * pair + g) * (L + 1) + L) * kTileImageBytes,
+                           kTileImageBytes);
         for (int l = L; l >= 1; --l) {
           for (int g = 0; g < nsub; ++g) {
+            // the epilogue of this GEMM multiplies by cos(a_{l-1}): pull that stash tile towards L2 now
+            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_c) +
+                                 ((size_t)(2 * pair + g) * (L + 1) + (l - 1)) * kTileImageBytes,
+                             kTileImageBytes);
             for (int c = 0; c < kChunksPerLayer; ++c) {
               mbar_wait(&w_empty[st], ph ^ 1);
               mbar_arrive_expect_tx(&w_full[st], kWChunkBytes);
@@ -155,11 +172,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
     }
   } else {
     // ============================================================ epilogue groups
-    const int g = (warp - 2) >> 2;
+    const int g = (warp - 2) >> 3;
+    const uint32_t e = warp - 2 - 8 * g;
     const uint32_t q = warp & 3;
+    const uint32_t chalf = e >> 2;  // 128-column half handled by this warp
     const uint32_t row = q * 32 + lane;
     uint8_t* a_tile = smem + BwdSmem::kA + g * kTileImageBytes;
-    const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256;
+    const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256 + chalf * 128;
     uint32_t acc_ph = 0;
     const float S = __ldg(p.scalars);
 
@@ -198,7 +217,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
           }
         }
       }
-      {
+      if (chalf == 0) {
         uint4 v0, v1;
         v0.x = pack_half2(gy[0], gy[1]);
         v0.y = pack_half2(gy[2], 0.f);
@@ -216,44 +235,46 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
       fence_proxy_async_smem();
       mbar_arrive(&a_ready[g]);
 
-      // ---- delta_l = acc * cos(a_l), l = L..0
+      // ---- delta_l = acc * cos(a_l), l = L..0 ; this thread: (row, columns chalf*128 .. +127)
       for (int l = L; l >= 0; --l) {
-        const uint8_t* cl = st_c + (size_t)l * kTileImageBytes;
+        const uint8_t* hl = st_c + (size_t)l * kTileImageBytes;
         uint8_t* dl = nullptr;
         if (kNeedDW) dl = st_d + (size_t)l * kTileImageBytes;
         else if (l == 0) dl = st_d;
-        // prefetch the first chunk of cos values while the GEMM finishes
-        uint4 cc[4];
+        // the whole layer slice of the cos stash (16 x 16 B) is requested before waiting for the GEMM
+        uint4 hh[16];
 #pragma unroll
-        for (int q8 = 0; q8 < 4; ++q8) cc[q8] = __ldg(reinterpret_cast<const uint4*>(cl + stash_off(row, q8, kH)));
+        for (int k = 0; k < 16; ++k)
+          hh[k] = __ldg(reinterpret_cast<const uint4*>(hl + stash_off(row, chalf * 16 + k, kH)));
         mbar_wait(&acc_full[g], acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
-#pragma unroll 1
-        for (int ch = 0; ch < kH / 32; ++ch) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + ch * 32, v);
-          uint4 cn[4];
-          if (ch + 1 < kH / 32) {
+        auto process16 = [&](const uint32_t (&v)[16], int it) {
 #pragma unroll
-            for (int q8 = 0; q8 < 4; ++q8)
-              cn[q8] = __ldg(reinterpret_cast<const uint4*>(cl + stash_off(row, (ch + 1) * 4 + q8, kH)));
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int q8 = 0; q8 < 4; ++q8) {
-            const int kg = ch * 4 + q8;
+          for (int q8 = 0; q8 < 2; ++q8) {
+            const int kl = it * 2 + q8;
+            const int kg = chalf * 16 + kl;
+            const uint4 hw = hh[kl];
             uint4 dv;
-            dv.x = hmul2_u32(pack_half2(__uint_as_float(v[q8 * 8 + 0]), __uint_as_float(v[q8 * 8 + 1])), cc[q8].x);
-            dv.y = hmul2_u32(pack_half2(__uint_as_float(v[q8 * 8 + 2]), __uint_as_float(v[q8 * 8 + 3])), cc[q8].y);
-            dv.z = hmul2_u32(pack_half2(__uint_as_float(v[q8 * 8 + 4]), __uint_as_float(v[q8 * 8 + 5])), cc[q8].z);
-            dv.w = hmul2_u32(pack_half2(__uint_as_float(v[q8 * 8 + 6]), __uint_as_float(v[q8 * 8 + 7])), cc[q8].w);
+            dv.x = delta2(__uint_as_float(v[q8 * 8 + 0]), __uint_as_float(v[q8 * 8 + 1]), hw.x);
+            dv.y = delta2(__uint_as_float(v[q8 * 8 + 2]), __uint_as_float(v[q8 * 8 + 3]), hw.y);
+            dv.z = delta2(__uint_as_float(v[q8 * 8 + 4]), __uint_as_float(v[q8 * 8 + 5]), hw.z);
+            dv.w = delta2(__uint_as_float(v[q8 * 8 + 6]), __uint_as_float(v[q8 * 8 + 7]), hw.w);
             if (l > 0) *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = dv;
             if (dl != nullptr) *reinterpret_cast<uint4*>(dl + stash_off(row, kg, kH)) = dv;
           }
-          if (ch + 1 < kH / 32) {
+        };
+        {
+          uint32_t va[16], vb[16];
+          tmem_ld16(t_acc, va);
 #pragma unroll
-            for (int q8 = 0; q8 < 4; ++q8) cc[q8] = cn[q8];
+          for (int it = 0; it < 8; it += 2) {
+            tmem_ld_wait();
+            tmem_ld16(t_acc + (it + 1) * 16, vb);
+            process16(va, it);
+            tmem_ld_wait();
+            if (it + 2 < 8) tmem_ld16(t_acc + (it + 2) * 16, va);
+            process16(vb, it + 1);
           }
         }
         tc_fence_before();

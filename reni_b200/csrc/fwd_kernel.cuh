@@ -3,17 +3,20 @@
 //   per 128-direction tile:  f = [dx, dz, |d_xz|, dy]           (SO(2) invariants, registers only)
 //                            h0 = sin(f . M_b + c_b)            (layer 0 hoisted to a per-map 4x256 matrix)
 //                            h_l = sin(h_{l-1} W_l'^T + b_l')   (tcgen05.mma, fp16 operands, fp32 TMEM accumulators,
-//                                                                bias + sin (+cos) fused in the TMEM->register epilogue)
+//                                                                bias + sin fused in the TMEM->register epilogue)
 //                            o = tanh(h_L W_out^T + b_out)      (tcgen05.mma N=16) + optional fused loss partial sums
 //
-// One persistent CTA per SM, 320 threads:
-//   warp 0      : weight-chunk producer (cp.async.bulk global->smem ring, mbarrier complete_tx)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2..5  : epilogue group 0 (sub-tile 0, TMEM columns   0..255)
-//   warps 6..9  : epilogue group 1 (sub-tile 1, TMEM columns 256..511)
+// One persistent CTA per SM, 576 threads:
+//   warp 0        : weight-chunk producer (cp.async.bulk global->smem ring, mbarrier complete_tx)
+//   warp 1        : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..9    : epilogue group 0 (sub-tile 0, TMEM columns   0..255)
+//   warps 10..17  : epilogue group 1 (sub-tile 1, TMEM columns 256..511)
+// Inside a group two warps share each TMEM lane quarter and split the 256 columns in halves.
 // The two sub-tiles ping-pong: while group g runs the sin epilogue of layer l, the tensor pipe runs
-// layer l of the other sub-tile.  Activations never leave the SM (smem tile image, overwritten in place);
-// with kTrain they are additionally stashed (h and cos(a), fp16) for the backward kernels.
+// layer l of the other sub-tile.  Activations never leave the SM (smem tile image, overwritten in place).
+// With kTrain h_l (operand of the weight-gradient GEMM) and cos(a_l) (factor of the delta chain) are additionally
+// stashed as fp16 tile images.  (Rebuilding cos as +-sqrt(1 - h^2) from the fp16 h was tried and measured: the
+// gradient error grows to 0.6-1.6e-2, outside the 1e-2 bar, so the cosine is stored.)
 //
 // Reference semantics: src/models/RENI.py:31-53 (encoding), :63-87 (SineLayer), :132-178 (net).
 #pragma once
@@ -22,8 +25,12 @@
 
 namespace reni {
 
-constexpr int kFwdThreads = 320;
-constexpr int kFwdStages = 4;
+constexpr int kFwdThreads = 576;
+#ifndef RENI_FWD_STAGES
+#define RENI_FWD_STAGES 4
+#endif
+constexpr int kFwdStages = RENI_FWD_STAGES;
+constexpr int kGroupThreads = 256;  // epilogue threads per sub-tile
 
 struct FwdParams {
   const float* D;        // (B or 1, P, 3) unit directions
@@ -33,8 +40,8 @@ struct FwdParams {
   const __half* w6f;     // [k/8 32][n 16][8] final-layer image
   const float* bias;     // L*256 (omega_l * b_l) then 16 (final bias, zero padded)
   float* out;            // (B, P, 3)
-  __half* stash_h;       // kTrain: per tile (L+1) half-image pairs of h_l
-  __half* stash_c;       // kTrain: same for cos(a_l)
+  __half* stash_h;       // kTrain (weight gradients wanted): per tile (L+1) images of h_l; may be null
+  __half* stash_c;       // kTrain: per tile (L+1) images of cos(a_l)
   const float* target;   // fused loss partial sums (optional, may be null)
   const float* sw;       // (B or 1, P, 3)
   int64_t sw_bstride;
@@ -56,19 +63,31 @@ struct FwdSmem {
 };
 static_assert(FwdSmem::kTotal <= 232448, "forward kernel shared memory over budget");
 
-// kMode: 0 = inference, 1 = stash cos(a_l) (latent-only backward), 2 = stash cos(a_l) and h_l (full backward)
-template <int kMode>
+// sin (and, if kCos, cos) of 8 pre-activations -> packed fp16
+template <bool kCos>
+DEVINL void sincos8(const float (&a)[8], uint4& hv, uint4& cv) {
+  hv.x = pack_half2(__sinf(a[0]), __sinf(a[1]));
+  hv.y = pack_half2(__sinf(a[2]), __sinf(a[3]));
+  hv.z = pack_half2(__sinf(a[4]), __sinf(a[5]));
+  hv.w = pack_half2(__sinf(a[6]), __sinf(a[7]));
+  if (kCos) {
+    cv.x = pack_half2(__cosf(a[0]), __cosf(a[1]));
+    cv.y = pack_half2(__cosf(a[2]), __cosf(a[3]));
+    cv.z = pack_half2(__cosf(a[4]), __cosf(a[5]));
+    cv.w = pack_half2(__cosf(a[6]), __cosf(a[7]));
+  }
+}
+
+template <bool kTrain>
 __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr bool kTrain = kMode != 0;
-  constexpr bool kStashH = kMode == 2;
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBars);
   uint64_t* w_full = bars;                      // [kFwdStages]
   uint64_t* w_empty = bars + kFwdStages;        // [kFwdStages]
-  uint64_t* a_ready = bars + 2 * kFwdStages;    // [2]  epilogue group -> MMA (128 arrivals)
+  uint64_t* a_ready = bars + 2 * kFwdStages;    // [2]  epilogue group -> MMA (256 arrivals)
   uint64_t* acc_full = a_ready + 2;             // [2]  MMA -> epilogue group (tcgen05.commit)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + FwdSmem::kTmemPtr);
   float* s_bias = reinterpret_cast<float*>(smem + FwdSmem::kBias);
@@ -82,8 +101,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(&a_ready[0], 128);
-    mbar_init(&a_ready[1], 128);
+    mbar_init(&a_ready[0], kGroupThreads);
+    mbar_init(&a_ready[1], kGroupThreads);
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
     fence_mbar_init();
@@ -131,13 +150,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
       const uint32_t ring_base = smem_u32(smem + FwdSmem::kRing);
       const uint32_t w6_base = smem_u32(smem + FwdSmem::kW6);
       uint32_t st = 0, ph = 0;
-      uint32_t a_ph[2] = {0, 0};
+      uint32_t a_ph0 = 0, a_ph1 = 0;
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
         const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
         for (int l = 1; l <= L + 1; ++l) {
           for (int g = 0; g < nsub; ++g) {
-            mbar_wait(&a_ready[g], a_ph[g]);
-            a_ph[g] ^= 1;
+            if (g == 0) { mbar_wait(&a_ready[0], a_ph0); a_ph0 ^= 1; }
+            else        { mbar_wait(&a_ready[1], a_ph1); a_ph1 ^= 1; }
             tc_fence_after();
             const uint32_t a_tile = a_base + g * kTileImageBytes;
             const uint32_t d_tmem = tmem_base + g * 256;
@@ -171,13 +190,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
     }
   } else {
     // ============================================================ epilogue groups
-    const int g = (warp - 2) >> 2;          // sub-tile handled by this group
-    const uint32_t q = warp & 3;            // TMEM lane quarter this warp may access
-    const uint32_t row = q * 32 + lane;     // row inside the tile == TMEM lane
-    const uint32_t gtid = (warp - 2 - 4 * g) * 32 + lane;  // 0..127 inside the group
+    const int g = (warp - 2) >> 3;                  // sub-tile handled by this group
+    const uint32_t e = warp - 2 - 8 * g;            // warp inside the group, 0..7
+    const uint32_t q = warp & 3;                    // TMEM lane quarter this warp may access
+    const uint32_t chalf = e >> 2;                  // which 128-column half this warp handles
+    const uint32_t row = q * 32 + lane;             // row inside the tile == TMEM lane
+    const uint32_t gtid = e * 32 + lane;            // 0..255 inside the group
     uint8_t* a_tile = smem + FwdSmem::kA + g * kTileImageBytes;
     float* s_mc = reinterpret_cast<float*>(smem + FwdSmem::kMc) + g * 5 * kH;
-    const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256;
+    const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256 + chalf * 128;
     uint32_t acc_ph = 0;
 
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
@@ -186,23 +207,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
       const int b = tile / p.tiles_per_map;
       const int pix = (tile - b * p.tiles_per_map) * kTileRows + row;
       const bool rvalid = pix < p.P;
-      __half* st_h = nullptr;
-      __half* st_c = nullptr;
+      uint8_t* st_h = nullptr;
+      uint8_t* st_c = nullptr;
       if (kTrain) {
-        if (kStashH) st_h = p.stash_h + (size_t)tile * (L + 1) * (kTileImageBytes / 2);
-        st_c = p.stash_c + (size_t)tile * (L + 1) * (kTileImageBytes / 2);
+        st_c = reinterpret_cast<uint8_t*>(p.stash_c) + (size_t)tile * (L + 1) * kTileImageBytes;
+        if (p.stash_h != nullptr) st_h = reinterpret_cast<uint8_t*>(p.stash_h) + (size_t)tile * (L + 1) * kTileImageBytes;
       }
 
       // ---- per-map layer-0 operands -> smem (group-private)
-      named_bar_sync(1 + g, 128);
+      named_bar_sync(1 + g, kGroupThreads);
       {
         const float4* src = reinterpret_cast<const float4*>(p.mc + (size_t)b * 5 * kH);
         float4* dst = reinterpret_cast<float4*>(s_mc);
-        for (int i = gtid; i < 5 * kH / 4; i += 128) dst[i] = __ldg(src + i);
+        for (int i = gtid; i < 5 * kH / 4; i += kGroupThreads) dst[i] = __ldg(src + i);
       }
-      named_bar_sync(1 + g, 128);
+      named_bar_sync(1 + g, kGroupThreads);
 
-      // ---- SO(2)-invariant direction features, registers only (RENI.py:37-49)
+      // ---- invariant direction features, registers only (RENI.py:37-49)
       float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
       if (rvalid) {
         const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
@@ -219,67 +240,55 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
         }
       }
 
-      // ---- layer 0: h0 = sin(f . M' + c')  (omega folded into M', c')
+      // ---- layer 0: h0 = sin(f . M' + c')  (omega folded into M', c'); this warp's 128 columns
 #pragma unroll 2
-      for (int kg = 0; kg < kH / 8; ++kg) {
+      for (int k8 = 0; k8 < 16; ++k8) {
+        const int kg = chalf * 16 + k8;
         float a[8];
         {
           const float4* m = reinterpret_cast<const float4*>(s_mc + kg * 8);
-          const float4 c0 = m[4 * kH / 4], c1 = m[4 * kH / 4 + 1];
+          const float4 c0 = m[4 * (kH / 4)], c1 = m[4 * (kH / 4) + 1];
           a[0] = c0.x; a[1] = c0.y; a[2] = c0.z; a[3] = c0.w;
           a[4] = c1.x; a[5] = c1.y; a[6] = c1.z; a[7] = c1.w;
-          const float fr[4] = {f0, f1, f2, f3};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 m0 = m[i * kH / 4], m1 = m[i * kH / 4 + 1];
-            a[0] = fmaf(fr[i], m0.x, a[0]); a[1] = fmaf(fr[i], m0.y, a[1]);
-            a[2] = fmaf(fr[i], m0.z, a[2]); a[3] = fmaf(fr[i], m0.w, a[3]);
-            a[4] = fmaf(fr[i], m1.x, a[4]); a[5] = fmaf(fr[i], m1.y, a[5]);
-            a[6] = fmaf(fr[i], m1.z, a[6]); a[7] = fmaf(fr[i], m1.w, a[7]);
+            const float fi = (i == 0) ? f0 : (i == 1) ? f1 : (i == 2) ? f2 : f3;
+            const float4 m0 = m[i * (kH / 4)], m1 = m[i * (kH / 4) + 1];
+            a[0] = fmaf(fi, m0.x, a[0]); a[1] = fmaf(fi, m0.y, a[1]);
+            a[2] = fmaf(fi, m0.z, a[2]); a[3] = fmaf(fi, m0.w, a[3]);
+            a[4] = fmaf(fi, m1.x, a[4]); a[5] = fmaf(fi, m1.y, a[5]);
+            a[6] = fmaf(fi, m1.z, a[6]); a[7] = fmaf(fi, m1.w, a[7]);
           }
         }
-        uint4 hv;
-        hv.x = pack_half2(__sinf(a[0]), __sinf(a[1]));
-        hv.y = pack_half2(__sinf(a[2]), __sinf(a[3]));
-        hv.z = pack_half2(__sinf(a[4]), __sinf(a[5]));
-        hv.w = pack_half2(__sinf(a[6]), __sinf(a[7]));
+        uint4 hv, cv;
+        sincos8<kTrain>(a, hv, cv);
         *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
         if (kTrain) {
-          uint4 cv;
-          cv.x = pack_half2(__cosf(a[0]), __cosf(a[1]));
-          cv.y = pack_half2(__cosf(a[2]), __cosf(a[3]));
-          cv.z = pack_half2(__cosf(a[4]), __cosf(a[5]));
-          cv.w = pack_half2(__cosf(a[6]), __cosf(a[7]));
           const uint32_t so = stash_off(row, kg, kH);
-          if (kStashH) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st_h) + so) = hv;
-          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(st_c) + so) = cv;
+          *reinterpret_cast<uint4*>(st_c + so) = cv;
+          if (st_h != nullptr) *reinterpret_cast<uint4*>(st_h + so) = hv;
         }
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_ready[g]);
 
-      // ---- hidden layers: bias + sin (+cos) epilogue, TMEM -> registers -> smem tile image (in place)
+      // ---- hidden layers: bias + sin epilogue, TMEM -> registers -> smem tile image (in place)
       for (int l = 1; l <= L; ++l) {
-        const float* bl = s_bias + (l - 1) * kH;
+        const float* bl = s_bias + (l - 1) * kH + chalf * 128;
+        uint8_t* sc = kTrain ? st_c + (size_t)l * kTileImageBytes : nullptr;
+        uint8_t* sh = (kTrain && st_h != nullptr) ? st_h + (size_t)l * kTileImageBytes : nullptr;
         mbar_wait(&acc_full[g], acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
-        uint8_t* sh = nullptr;
-        uint8_t* sc = nullptr;
-        if (kTrain) {
-          if (kStashH) sh = reinterpret_cast<uint8_t*>(st_h) + (size_t)l * kTileImageBytes;
-          sc = reinterpret_cast<uint8_t*>(st_c) + (size_t)l * kTileImageBytes;
-        }
-#pragma unroll 1
-        for (int ch = 0; ch < kH / 32; ++ch) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + ch * 32, v);
-          tmem_ld_wait();
+        // TMEM -> registers in 16-column slices, double buffered: the next tcgen05.ld is in flight while this
+        // slice goes through bias + sin + pack + store
+        auto process16 = [&](const uint32_t (&v)[16], int it) {
 #pragma unroll
-          for (int q8 = 0; q8 < 4; ++q8) {
-            const int kg = ch * 4 + q8;
-            const float4 b0 = *reinterpret_cast<const float4*>(bl + kg * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bl + kg * 8 + 4);
+          for (int q8 = 0; q8 < 2; ++q8) {
+            const int kl = it * 2 + q8;          // 8-column group inside this warp's half
+            const int kg = chalf * 16 + kl;      // ... inside the tile
+            const float4 b0 = *reinterpret_cast<const float4*>(bl + kl * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bl + kl * 8 + 4);
             float a[8];
             a[0] = __uint_as_float(v[q8 * 8 + 0]) + b0.x;
             a[1] = __uint_as_float(v[q8 * 8 + 1]) + b0.y;
@@ -289,22 +298,27 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
             a[5] = __uint_as_float(v[q8 * 8 + 5]) + b1.y;
             a[6] = __uint_as_float(v[q8 * 8 + 6]) + b1.z;
             a[7] = __uint_as_float(v[q8 * 8 + 7]) + b1.w;
-            uint4 hv;
-            hv.x = pack_half2(__sinf(a[0]), __sinf(a[1]));
-            hv.y = pack_half2(__sinf(a[2]), __sinf(a[3]));
-            hv.z = pack_half2(__sinf(a[4]), __sinf(a[5]));
-            hv.w = pack_half2(__sinf(a[6]), __sinf(a[7]));
+            uint4 hv, cv;
+            sincos8<kTrain>(a, hv, cv);
             *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
             if (kTrain) {
-              uint4 cv;
-              cv.x = pack_half2(__cosf(a[0]), __cosf(a[1]));
-              cv.y = pack_half2(__cosf(a[2]), __cosf(a[3]));
-              cv.z = pack_half2(__cosf(a[4]), __cosf(a[5]));
-              cv.w = pack_half2(__cosf(a[6]), __cosf(a[7]));
               const uint32_t so = stash_off(row, kg, kH);
-              if (kStashH) *reinterpret_cast<uint4*>(sh + so) = hv;
               *reinterpret_cast<uint4*>(sc + so) = cv;
+              if (sh != nullptr) *reinterpret_cast<uint4*>(sh + so) = hv;
             }
+          }
+        };
+        {
+          uint32_t va[16], vb[16];
+          tmem_ld16(t_acc, va);
+#pragma unroll 1
+          for (int it = 0; it < 8; it += 2) {
+            tmem_ld_wait();
+            tmem_ld16(t_acc + (it + 1) * 16, vb);
+            process16(va, it);
+            tmem_ld_wait();
+            if (it + 2 < 8) tmem_ld16(t_acc + (it + 2) * 16, va);
+            process16(vb, it + 1);
           }
         }
         tc_fence_before();
@@ -316,57 +330,59 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
       mbar_wait(&acc_full[g], acc_ph);
       acc_ph ^= 1;
       tc_fence_after();
-      float o[3];
-      {
-        uint32_t v[16];
-        tmem_ld16(t_acc, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        const float* bo = s_bias + L * kH;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float y = __uint_as_float(v[c]) + bo[c];
-          if (p.last_sine) y = sinf(y);
-          if (p.out_tanh) y = tanhf(y);
-          o[c] = y;
-        }
-      }
-      if (rvalid) {
-        float* op = p.out + ((size_t)b * p.P + pix) * 3;
-        op[0] = o[0];
-        op[1] = o[1];
-        op[2] = o[2];
-      }
-      if (p.loss_part != nullptr) {
-        float part[kLossPartials];
-#pragma unroll
-        for (int i = 0; i < kLossPartials; ++i) part[i] = 0.f;
-        if (rvalid) {
-          const float* tp = p.target + ((size_t)b * p.P + pix) * 3;
-          const float* wp = p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+      if (chalf == 0) {
+        float o[3];
+        {
+          uint32_t v[16];
+          tmem_ld16(t_acc, v);
+          tmem_ld_wait();
+          const float* bo = s_bias + L * kH;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float t = __ldg(tp + c), w = __ldg(wp + c);
-            const float e = o[c] - t;
-            part[0] = fmaf(e * e, w, part[0]);
-            part[1 + c] = o[c] * t;
-            part[4 + c] = o[c] * o[c];
-            part[7 + c] = t * t;
+            float y = __uint_as_float(v[c]) + bo[c];
+            if (p.last_sine) y = sinf(y);
+            if (p.out_tanh) y = tanhf(y);
+            o[c] = y;
           }
         }
-#pragma unroll
-        for (int i = 0; i < kLossPartials; ++i) {
-          float x = part[i];
-#pragma unroll
-          for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
-          part[i] = x;
+        if (rvalid) {
+          float* op = p.out + ((size_t)b * p.P + pix) * 3;
+          op[0] = o[0];
+          op[1] = o[1];
+          op[2] = o[2];
         }
-        if (lane == 0) {
-          float* lp = p.loss_part + ((size_t)tile * 4 + q) * kLossPartials;
+        if (p.loss_part != nullptr) {
+          float part[kLossPartials];
 #pragma unroll
-          for (int i = 0; i < kLossPartials; ++i) lp[i] = part[i];
+          for (int i = 0; i < kLossPartials; ++i) part[i] = 0.f;
+          if (rvalid) {
+            const float* tp = p.target + ((size_t)b * p.P + pix) * 3;
+            const float* wp = p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float t = __ldg(tp + c), w = __ldg(wp + c);
+              const float er = o[c] - t;
+              part[0] = fmaf(er * er, w, part[0]);
+              part[1 + c] = o[c] * t;
+              part[4 + c] = o[c] * o[c];
+              part[7 + c] = t * t;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kLossPartials; ++i) {
+            float x = part[i];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+            part[i] = x;
+          }
+          if (lane == 0) {
+            float* lp = p.loss_part + ((size_t)tile * 4 + q) * kLossPartials;
+#pragma unroll
+            for (int i = 0; i < kLossPartials; ++i) lp[i] = part[i];
+          }
         }
       }
+      tc_fence_before();
     }
   }
 
