@@ -50,14 +50,14 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   w.map_loss = take(B * 32 * 4);
   w.loss_part = take(ntiles * 4 * kLossPartials * 4);
   const int64_t nin = reni_in_features(c);
-  w.xc = take(B * nin * 4);
-  w.dxc = take(B * nin * 4);
-  w.dip = take(B * 3 * c->ndims * 4);
+  w.xc = take(B * 5 * nin * 4);   // xfull: input columns paired with [dM0..dM3, dc]
+  w.dxc = take(B * 5 * nin * 4);  // E: gradient w.r.t. xfull
+  w.dip = -1;
   if (flags & RENI_FLAG_SAVE_FOR_BACKWARD) {
     const bool dw = (flags & RENI_FLAG_NEED_DW) != 0;
     w.stash_c = take(ntiles * (L + 1) * (int64_t)kTileImageBytes);
     w.stash_h = dw ? take(ntiles * (L + 1) * (int64_t)kTileImageBytes) : -1;
-    w.stash_d = take(ntiles * (dw ? (L + 1) : 1) * (int64_t)kTileImageBytes);
+    w.stash_d = dw ? take(ntiles * (L + 1) * (int64_t)kTileImageBytes) : -1;  // slot 0 unused (delta_0 stays on chip)
     w.stash_gy = take(ntiles * (int64_t)kGyImageBytes);
   } else {
     w.stash_c = w.stash_h = w.stash_d = w.stash_gy = -1;
@@ -171,7 +171,7 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
     q.W0 = weight0;
     q.b0 = bias0;
     q.mc = at<float>(ws, w.mc);
-    q.xc = at<float>(ws, w.xc);
+    q.xfull = at<float>(ws, w.xc);
     q.B = (int)B;
     q.N = c->ndims;
     q.in_features = (int)reni_in_features(c);
@@ -252,6 +252,10 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   p.stash_c = at<__half>(ws, w.stash_c);
   p.stash_d = at<__half>(ws, w.stash_d);
   p.stash_gy = at<__half>(ws, w.stash_gy);
+  p.D = D;
+  p.d_bstride = d_bstride;
+  p.dmc = at<float>(ws, w.dmc);
+  p.so2 = c->equivariance == RENI_EQ_SO2;
   p.B = (int)B;
   p.P = (int)P;
   p.tiles_per_map = (int)tiles_per_map(P);
@@ -302,44 +306,37 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   mark_phase(5, stream);
 
   {
-    L0ReduceParams r{};
-    r.stash_d = at<__half>(ws, w.stash_d);
-    r.D = D;
-    r.d_bstride = d_bstride;
-    r.scalars = at<float>(ws, w.scalars);
-    r.dmc = at<float>(ws, w.dmc);
-    r.P = (int)P;
-    r.tiles_per_map = (int)tiles_per_map(P);
-    r.d_slots = need_dw ? L + 1 : 1;
-    r.so2 = c->equivariance == RENI_EQ_SO2;
-    reni_layer0_reduce_kernel<<<ntiles, 256, 0, stream>>>(r);
-    if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
-  }
-  {
-    MapBwdParams m{};
-    m.Z = Z;
-    m.W0 = weight0;
-    m.xc = at<float>(ws, w.xc);
-    m.dmc = at<float>(ws, w.dmc);
-    m.dW0 = need_dw ? host_dW[0] : nullptr;
-    m.db0 = need_dw ? host_db[0] : nullptr;
-    m.dxc = at<float>(ws, w.dxc);
-    m.dip = at<float>(ws, w.dip);
-    m.dZ = dZ;
-    m.B = (int)B;
-    m.N = c->ndims;
-    m.in_features = (int)reni_in_features(c);
-    m.equivariance = c->equivariance;
-    m.alpha2 = 2.f * alpha;
-    m.accumulate = 0;
+    const int nin = (int)reni_in_features(c);
+    const int K5 = 5 * (int)B;
     if (dZ != nullptr) {
-      reni_dxc_kernel<<<dim3((m.in_features + 255) / 256, (unsigned)B), 256, 0, stream>>>(m);
+      SmallGemmParams g{};  // E[(b,r), i] = sum_j dmc[(b,r), j] W0[j, i]
+      g.A = at<float>(ws, w.dmc);
+      g.B = weight0;
+      g.C = at<float>(ws, w.dxc);
+      g.M = K5; g.N = nin; g.K = kH; g.a_sk = 1; g.a_sm = kH; g.ldb = nin; g.ldc = nin;
+      if (cudaMemsetAsync(g.C, 0, (size_t)K5 * nin * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
+      reni_small_gemm_kernel<<<dim3((nin + 63) / 64, (K5 + 63) / 64, kH / kSmallGemmK), 256, 0, stream>>>(g);
+      MapBwdParams m{};
+      m.Z = Z;
+      m.E = at<float>(ws, w.dxc);
+      m.dZ = dZ;
+      m.B = (int)B;
+      m.N = c->ndims;
+      m.in_features = nin;
+      m.equivariance = c->equivariance;
+      m.alpha2 = 2.f * alpha;
+      m.accumulate = 0;
       reni_dz_kernel<<<(unsigned)B, 128, 0, stream>>>(m);
     }
     if (need_dw) {
-      if (m.dW0 == nullptr || m.db0 == nullptr) return RENI_ERR_BAD_ARGUMENT;
-      const int64_t n = (int64_t)kH * m.in_features;
-      reni_dw0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(m);
+      if (host_dW[0] == nullptr || host_db[0] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+      SmallGemmParams g{};  // dW0[j, i] += sum_{(b,r)} dmc[(b,r), j] xfull[(b,r), i]
+      g.A = at<float>(ws, w.dmc);
+      g.B = at<float>(ws, w.xc);
+      g.C = host_dW[0];
+      g.M = kH; g.N = nin; g.K = K5; g.a_sk = kH; g.a_sm = 1; g.ldb = nin; g.ldc = nin;
+      reni_small_gemm_kernel<<<dim3((nin + 63) / 64, kH / 64, (K5 + kSmallGemmK - 1) / kSmallGemmK), 256, 0, stream>>>(g);
+      reni_db0_kernel<<<1, 256, 0, stream>>>(at<float>(ws, w.dmc), host_db[0], (int)B);
     }
     if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
   }

@@ -6,8 +6,10 @@
 //     d_L   = (g_y  W_out'') * cos(a_L)     tcgen05.mma K = 16
 //     d_l-1 = (d_l  W_l'')   * cos(a_l-1)   tcgen05.mma 128 x 256 x 256, l = L..1, cos from the forward stash,
 //                                           omega of the consuming layer folded into W''
-//   d_l tiles stay in shared memory for the next GEMM; d_0 (and every d_l when weight gradients are wanted) is
-//   stashed as fp16 tile images for the weight-gradient GEMM / the per-map layer-0 reduction.
+//     dM_b, dc_b += [f | 1]^T d_0           tcgen05.mma N = 16 with d_0 read as an MN-major operand (contraction over the
+//                                           tile's rows): the per-map layer-0 reduction costs 16 tiny MMAs per tile
+//   d_l tiles stay in shared memory for the next GEMM; when weight gradients are wanted d_1..d_L are also stashed as
+//   fp16 tile images for the weight-gradient GEMM.  d_0 never leaves the SM.
 //
 // Same CTA organisation as the forward kernel (producer warp, MMA warp, two ping-ponging epilogue groups of 8 warps).
 // Each epilogue thread owns (row, 128 columns): the 16 x 16-B stash loads of its whole layer slice are issued before it
@@ -35,15 +37,19 @@ struct BwdParams {
   const __half* stash_c;  // cos(a_l), per tile (L+1) images
   __half* stash_d;        // delta stash: per tile nslots images (nslots = L+1 or 1)
   __half* stash_gy;       // per tile [2 halves][2][64][8]
+  const float* D;         // directions (for the layer-0 feature columns f)
+  int64_t d_bstride;
+  float* dmc;             // (B, 5, 256): dM_b rows 0..3, dc_b row 4; accumulated with atomics (caller zeroes)
   int B, P, tiles_per_map, ntiles, L;
-  int out_tanh, d_slots;
+  int out_tanh, d_slots, so2;
 };
 
 struct BwdSmem {
   static constexpr int kA = 0;
   static constexpr int kRing = kA + 2 * kTileImageBytes;
   static constexpr int kW6 = kRing + kBwdStages * kWChunkBytes;
-  static constexpr int kBars = kW6 + kW6ImageBytes;
+  static constexpr int kF = kW6 + kW6ImageBytes;               // 2 x [2][128][8] fp16 feature tiles [f0..f3, 1, 0..]
+  static constexpr int kBars = kF + 2 * kGyImageBytes;
   static constexpr int kNumBars = 2 * kBwdStages + 4;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemPtr + 16;
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
       uint32_t a_ph0 = 0, a_ph1 = 0;
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
         const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
-        for (int l = L + 1; l >= 1; --l) {  // l = L+1: output layer (K = 16); l <= L: hidden layer l
+        for (int l = L + 1; l >= 0; --l) {  // l = L+1: output layer (K = 16); L..1: hidden layer l; 0: layer-0 reduction
           for (int g = 0; g < nsub; ++g) {
             if (g == 0) { mbar_wait(&a_ready[0], a_ph0); a_ph0 ^= 1; }
             else        { mbar_wait(&a_ready[1], a_ph1); a_ph1 ^= 1; }
@@ -150,6 +156,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
               const uint64_t da = umma_smem_desc(a_tile, 2048, 128);
               const uint64_t db = umma_smem_desc(w6_base, 4096, 128);
               umma_f16_ss(d_tmem, da, db, idesc_h, 0);
+            } else if (l == 0) {
+              // D[j, i] = sum_r delta0[r, j] * F[r, i]: both operands MN-major views of [k/8][128][8] images
+              // (8-column groups 2048 B apart = SBO, 8-row groups 128 B apart = LBO, 16 rows per K step = 256 B)
+              constexpr uint32_t idesc_r = umma_idesc_f16(128, kW6N, 1, 1);
+              const uint32_t f_tile = smem_u32(smem + BwdSmem::kF) + g * kGyImageBytes;
+#pragma unroll
+              for (int mh = 0; mh < 2; ++mh) {
+#pragma unroll
+                for (int ks = 0; ks < kTileRows / 16; ++ks) {
+                  const uint64_t da = umma_smem_desc(a_tile + mh * 16 * 2048 + ks * 256, 128, 2048);
+                  const uint64_t db = umma_smem_desc(f_tile + ks * 256, 128, 2048);
+                  umma_f16_ss(d_tmem + mh * kW6N, da, db, idesc_r, ks != 0);
+                }
+              }
             } else {
               for (int c = 0; c < kChunksPerLayer; ++c) {
                 mbar_wait(&w_full[st], ph);
@@ -218,6 +238,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
         }
       }
       if (chalf == 0) {
+        // feature row [f0, f1, f2, f3, 1, 0, ...] for the layer-0 reduction GEMM (zero for rows beyond P)
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, one = 0.f;
+        if (rvalid) {
+          const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
+          const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+          if (p.so2) { f0 = dx; f1 = dz; f2 = sqrtf(dx * dx + dz * dz); f3 = dy; }
+          else       { f0 = dx; f1 = dy; f2 = dz; }
+          one = 1.f;
+        }
+        uint8_t* f_tile = smem + BwdSmem::kF + g * kGyImageBytes;
+        *reinterpret_cast<uint4*>(f_tile + tile_image_off(kTileRows, row, 0)) =
+            make_uint4(pack_half2(f0, f1), pack_half2(f2, f3), pack_half2(one, 0.f), 0u);
+        *reinterpret_cast<uint4*>(f_tile + tile_image_off(kTileRows, row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (chalf == 0) {
         uint4 v0, v1;
         v0.x = pack_half2(gy[0], gy[1]);
         v0.y = pack_half2(gy[2], 0.f);
@@ -239,8 +274,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
       for (int l = L; l >= 0; --l) {
         const uint8_t* hl = st_c + (size_t)l * kTileImageBytes;
         uint8_t* dl = nullptr;
-        if (kNeedDW) dl = st_d + (size_t)l * kTileImageBytes;
-        else if (l == 0) dl = st_d;
+        if (kNeedDW && l > 0) dl = st_d + (size_t)l * kTileImageBytes;
         // the whole layer slice of the cos stash (16 x 16 B) is requested before waiting for the GEMM
         uint4 hh[16];
 #pragma unroll
@@ -260,7 +294,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
             dv.y = delta2(__uint_as_float(v[q8 * 8 + 2]), __uint_as_float(v[q8 * 8 + 3]), hw.y);
             dv.z = delta2(__uint_as_float(v[q8 * 8 + 4]), __uint_as_float(v[q8 * 8 + 5]), hw.z);
             dv.w = delta2(__uint_as_float(v[q8 * 8 + 6]), __uint_as_float(v[q8 * 8 + 7]), hw.w);
-            if (l > 0) *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = dv;
+            *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = dv;
             if (dl != nullptr) *reinterpret_cast<uint4*>(dl + stash_off(row, kg, kH)) = dv;
           }
         };
@@ -278,11 +312,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
           }
         }
         tc_fence_before();
-        if (l > 0) {
-          fence_proxy_async_smem();
-          mbar_arrive(&a_ready[g]);
-        }
+        fence_proxy_async_smem();
+        mbar_arrive(&a_ready[g]);
       }
+
+      // ---- layer-0 reduction result: D[j, 0..4] for j = row (columns 0..15) and j = 128 + row (columns 16..31)
+      mbar_wait(&acc_full[g], acc_ph);
+      acc_ph ^= 1;
+      tc_fence_after();
+      if (chalf == 0) {
+        uint32_t v[32];
+        tmem_ld32(t_acc, v);
+        tmem_ld_wait();
+        const float inv_s = __ldg(p.scalars + 1);
+        float* dst = p.dmc + (size_t)b * 5 * kH;
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+          for (int i = 0; i < 5; ++i)
+            atomicAdd(dst + i * kH + mh * 128 + row, __uint_as_float(v[mh * kW6N + i]) * inv_s);
+      }
+      tc_fence_before();
     }
   }
 

@@ -74,7 +74,7 @@ struct PrologueParams {
   const float* W0;  // (256, in_features)
   const float* b0;  // (256)
   float* mc;        // (B, 5, 256)
-  float* xc;        // (B, in_features) per-map constant columns (optional, for the dW0 kernel)
+  float* xfull;     // (B, 5, in_features): per-map input columns paired with [dM0..dM3, dc] for the dW0 GEMM (optional)
   int B, N, in_features, equivariance;  // 0 None, 1 SO2, 2 SO3
   float omega0;
 };
@@ -105,7 +105,20 @@ __global__ void __launch_bounds__(256) reni_prologue_kernel(const PrologueParams
       if (i >= N) v = s_z[i - N];
     }
     s_x[i] = v;
-    if (p.xc != nullptr && blockIdx.x == 0) p.xc[(size_t)b * p.in_features + i] = v;
+    if (p.xfull != nullptr && blockIdx.x == 0) {
+      // rows 0..3 multiply dM_b[0..3] (direction features), row 4 multiplies dc_b (constant columns)
+      float* xf = p.xfull + (size_t)b * 5 * p.in_features + i;
+      const int in = p.in_features;
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+      if (p.equivariance == 1) {
+        if (i < N) { r0 = s_z[i * 3]; r1 = s_z[i * 3 + 2]; }
+        if (i == N + N * N) r2 = 1.f;
+        if (i == 2 * N + N * N + 1) r3 = 1.f;
+      } else if (i < N) {
+        r0 = s_z[i * 3]; r1 = s_z[i * 3 + 1]; r2 = s_z[i * 3 + 2];
+      }
+      xf[0] = r0; xf[in] = r1; xf[2 * in] = r2; xf[3 * in] = r3; xf[4 * in] = v;
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -320,168 +333,94 @@ __global__ void reni_scale_from_absmax_kernel(const unsigned int* slot, float* s
 }
 
 // ------------------------------------------------------------------------------------------------
-// Layer-0 reduction (one block per tile): dM_b[i][j] += sum_p f_i delta0[p,j], dc_b[j] += sum_p delta0[p,j]
-// from the fp16 delta_0 stash; f recomputed from the directions (never stored).
+// Map-level backward of the hoisted first layer, as two small GEMMs + a per-map kernel.
+//   dmc   (B,5,256) : rows 0..3 = dM_b, row 4 = dc_b          xfull (B,5,in): the input columns they multiply
+//   (1) dW0[j,i] += sum_{(b,r)} dmc[b,r,j] * xfull[b,r,i]      (M=256, N=in, K=5B)   ; db0[j] += sum_b dc_b[j]
+//   (2) E[(b,r),i] = sum_j dmc[b,r,j] * W0[j,i]                (M=5B, N=in, K=256)   = d(loss)/d(xfull)
+//   (3) dZ from E (chain rule through G = Z Z^T etc.) + 2 alpha Z
 // ------------------------------------------------------------------------------------------------
-struct L0ReduceParams {
-  const __half* stash_d;
-  const float* D;
-  int64_t d_bstride;
-  const float* scalars;
-  float* dmc;  // (B, 5, 256), caller zeroes
-  int P, tiles_per_map, d_slots, so2;
+struct SmallGemmParams {
+  const float* A;  // A(k, m) = A[k * a_sk + m * a_sm]
+  const float* B;  // B(k, n) = B[k * ldb + n]
+  float* C;        // C(m, n) = C[m * ldc + n]
+  int M, N, K, a_sk, a_sm, ldb, ldc;
 };
 
-__global__ void __launch_bounds__(256) reni_layer0_reduce_kernel(const L0ReduceParams p) {
-  __shared__ float s_f[kTileRows][4];
-  __shared__ float s_red[8][5][kH];  // 40 KB
-  const int tile = blockIdx.x;
-  const int b = tile / p.tiles_per_map;
-  const int p0 = (tile - b * p.tiles_per_map) * kTileRows;
-  if (threadIdx.x < kTileRows) {
-    const int pix = p0 + threadIdx.x;
-    float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-    if (pix < p.P) {
-      const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
-      const float dx = d[0], dy = d[1], dz = d[2];
-      if (p.so2) { f0 = dx; f1 = dz; f2 = sqrtf(dx * dx + dz * dz); f3 = dy; }
-      else       { f0 = dx; f1 = dy; f2 = dz; }
-    }
-    s_f[threadIdx.x][0] = f0; s_f[threadIdx.x][1] = f1; s_f[threadIdx.x][2] = f2; s_f[threadIdx.x][3] = f3;
+// 64 x 64 output tile x 32-deep K slice per block (grid.z = K slices), 256 threads, 4 x 4 outputs per thread; every
+// block does ONE round of loads (latency paid once) and adds its partial result with atomics, so C must be
+// zero-filled (or hold the value to accumulate into).  These GEMMs are <= 0.7 GFLOP even at N=100, B=256.
+constexpr int kSmallGemmK = 32;
+__global__ void __launch_bounds__(256) reni_small_gemm_kernel(const SmallGemmParams p) {
+  __shared__ float As[kSmallGemmK][64 + 4];
+  __shared__ float Bs[kSmallGemmK][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64, k0 = blockIdx.z * kSmallGemmK;
+  for (int e = threadIdx.x; e < kSmallGemmK * 64; e += 256) {
+    int ka = e >> 6, ma = e & 63;  // A tile: follow whichever index is contiguous in memory
+    if (p.a_sk == 1) { ka = e % kSmallGemmK; ma = e / kSmallGemmK; }
+    const int kA = k0 + ka, mA = m0 + ma;
+    As[ka][ma] = (kA < p.K && mA < p.M) ? __ldg(p.A + (size_t)kA * p.a_sk + (size_t)mA * p.a_sm) : 0.f;
+    const int kk = e >> 6, c = e & 63;
+    const int k = k0 + kk, n = n0 + c;
+    Bs[kk][c] = (k < p.K && n < p.N) ? __ldg(p.B + (size_t)k * p.ldb + n) : 0.f;
   }
   __syncthreads();
-  const uint8_t* src = reinterpret_cast<const uint8_t*>(p.stash_d) + (size_t)tile * p.d_slots * kTileImageBytes;
-  // thread -> (8-column group kg, group rg of 16 rows); rows are read in pairs (32 contiguous bytes = one sector)
-  const int kg = threadIdx.x & 31;
-  const int rg = threadIdx.x >> 5;
-  float acc[5][8];
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
-  for (int rr = 0; rr < 16; rr += 2) {
-    const int r = rg * 16 + rr;
-    const uint4* ptr = reinterpret_cast<const uint4*>(src + stash_off(r, kg, kH));
-    const uint4 vv[2] = {__ldg(ptr), __ldg(ptr + 1)};
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint4 v = vv[h];
-      float d[8];
-      float2 t2;
-      t2 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)); d[0] = t2.x; d[1] = t2.y;
-      t2 = __half22float2(*reinterpret_cast<const __half2*>(&v.y)); d[2] = t2.x; d[3] = t2.y;
-      t2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)); d[4] = t2.x; d[5] = t2.y;
-      t2 = __half22float2(*reinterpret_cast<const __half2*>(&v.w)); d[6] = t2.x; d[7] = t2.y;
-      const float f0 = s_f[r + h][0], f1 = s_f[r + h][1], f2 = s_f[r + h][2], f3 = s_f[r + h][3];
+  for (int kk = 0; kk < kSmallGemmK; ++kk) {
+    float a[4], b[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        acc[0][k] = fmaf(f0, d[k], acc[0][k]);
-        acc[1][k] = fmaf(f1, d[k], acc[1][k]);
-        acc[2][k] = fmaf(f2, d[k], acc[2][k]);
-        acc[3][k] = fmaf(f3, d[k], acc[3][k]);
-        acc[4][k] += d[k];
-      }
-    }
+    for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
   }
 #pragma unroll
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s_red[rg][i][kg * 8 + k] = acc[i][k];
-  __syncthreads();
-  const float inv_s = p.scalars[1];
-  float* dst = p.dmc + (size_t)b * 5 * kH;
-  for (int i = threadIdx.x; i < 5 * kH; i += blockDim.x) {
-    const int a = i / kH, j = i % kH;
-    float s = 0.f;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) s += s_red[g][a][j];
-    atomicAdd(dst + i, s * inv_s);
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < p.N) atomicAdd(p.C + (size_t)m * p.ldc + n, acc[i][j]);
+    }
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Map-level backward of the hoisted first layer.
-//   xc (B, in)   : per-map constant input columns (written by the prologue)
-//   dmc (B,5,256): rows 0..3 = dM_b, row 4 = dc_b
-//   (1) dW0[j,i] += sum_b dc_b[j] xc_b[i] + [i<N] sum_b dM_b[.][j] Z_b[i,.] + direction columns ; db0 += sum_b dc_b
-//   (2) dxc[b,i]  = sum_j dc_b[j] W0[j,i]      ;  dip[b,c,n] = sum_j dM_b[c][j] W0[j,n]
-//   (3) dZ from dxc / dip (chain rule through G = Z Z^T etc.) + 2 alpha Z
-// ------------------------------------------------------------------------------------------------
+// db0[j] += sum_b dc_b[j]
+__global__ void reni_db0_kernel(const float* dmc, float* db0, int B) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= kH) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += dmc[((size_t)b * 5 + 4) * kH + j];
+  db0[j] += s;
+}
+
 struct MapBwdParams {
   const float* Z;
-  const float* W0;
-  const float* xc;
-  const float* dmc;
-  float* dW0;   // (256, in) accumulated
-  float* db0;   // (256) accumulated
-  float* dxc;   // (B, in) scratch
-  float* dip;   // (B, 3, N) scratch
-  float* dZ;    // (B, N, 3) written (+= if accumulate)
+  const float* E;   // (B, 5, in): gradient w.r.t. xfull
+  float* dZ;        // (B, N, 3) written (+= if accumulate)
   int B, N, in_features, equivariance;
   float alpha2;  // 2*alpha (prior gradient), 0 if none
   int accumulate;
 };
 
-__global__ void __launch_bounds__(256) reni_dw0_kernel(const MapBwdParams p) {
-  // one thread per dW0 element, i fastest (coalesced); loops over the maps
-  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int in = p.in_features, N = p.N;
-  if (idx >= (int64_t)kH * in) return;
-  const int j = (int)(idx / in), i = (int)(idx % in);
-  float s = 0.f, sb = 0.f;
-  const int col_dn = N + N * N, col_dy = 2 * N + N * N + 1;
-  for (int b = 0; b < p.B; ++b) {
-    const float* m = p.dmc + (size_t)b * 5 * kH;
-    const float dc = m[4 * kH + j];
-    s = fmaf(dc, p.xc[(size_t)b * in + i], s);
-    if (i < N) {
-      const float* z = p.Z + ((size_t)b * N + i) * 3;
-      if (p.equivariance == 1) s += m[j] * z[0] + m[kH + j] * z[2];
-      else s += m[j] * z[0] + m[kH + j] * z[1] + m[2 * kH + j] * z[2];
-    } else if (p.equivariance == 1) {
-      if (i == col_dn) s += m[2 * kH + j];
-      if (i == col_dy) s += m[3 * kH + j];
-    }
-    if (i == 0) sb += dc;
-  }
-  p.dW0[idx] += s;
-  if (i == 0) p.db0[j] += sb;
-}
-
-__global__ void __launch_bounds__(256) reni_dxc_kernel(const MapBwdParams p) {
-  // grid (ceil(in/256), B): dxc[b,i] = sum_j dc_b[j] W0[j,i]; dip[b,c,n] = sum_j dM_b[c][j] W0[j,n]
-  __shared__ float s_m[5 * kH];
-  const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int k = threadIdx.x; k < 5 * kH; k += blockDim.x) s_m[k] = p.dmc[(size_t)b * 5 * kH + k];
-  __syncthreads();
-  if (i >= p.in_features) return;
-  float s = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
-  const bool ip = i < p.N;
-  for (int j = 0; j < kH; ++j) {
-    const float w = __ldg(p.W0 + (size_t)j * p.in_features + i);
-    s = fmaf(s_m[4 * kH + j], w, s);
-    if (ip) {
-      d0 = fmaf(s_m[j], w, d0);
-      d1 = fmaf(s_m[kH + j], w, d1);
-      d2 = fmaf(s_m[2 * kH + j], w, d2);
-    }
-  }
-  p.dxc[(size_t)b * p.in_features + i] = s;
-  if (ip) {
-    float* o = p.dip + (size_t)b * 3 * p.N;
-    o[i] = d0;
-    o[p.N + i] = d1;
-    o[2 * p.N + i] = d2;
-  }
-}
-
 __global__ void __launch_bounds__(128) reni_dz_kernel(const MapBwdParams p) {
   // grid (B): one thread per latent row n
   const int b = blockIdx.x, N = p.N;
   const float* Z = p.Z + (size_t)b * N * 3;
-  const float* dxc = p.dxc + (size_t)b * p.in_features;
-  const float* dip = p.dip + (size_t)b * 3 * N;
+  const float* Eb = p.E + (size_t)b * 5 * p.in_features;
+  const float* dxc = Eb + (size_t)4 * p.in_features;  // gradient of the constant columns
+  const float* dip0 = Eb;                             // gradients of the inner-product columns, per feature row
+  const float* dip1 = Eb + p.in_features;
+  const float* dip2 = Eb + 2 * (size_t)p.in_features;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
     if (p.equivariance == 1) {
@@ -491,8 +430,8 @@ __global__ void __launch_bounds__(128) reni_dz_kernel(const MapBwdParams p) {
         g0 = fmaf(s, Z[m * 3], g0);
         g2 = fmaf(s, Z[m * 3 + 2], g2);
       }
-      g0 += dip[n];
-      g2 += dip[N + n];
+      g0 += dip0[n];
+      g2 += dip1[n];
       g1 = dxc[N + N * N + 1 + n];
     } else if (p.equivariance == 2) {
       const float* dG = dxc + N;
@@ -502,13 +441,13 @@ __global__ void __launch_bounds__(128) reni_dz_kernel(const MapBwdParams p) {
         g1 = fmaf(s, Z[m * 3 + 1], g1);
         g2 = fmaf(s, Z[m * 3 + 2], g2);
       }
-      g0 += dip[n];
-      g1 += dip[N + n];
-      g2 += dip[2 * N + n];
+      g0 += dip0[n];
+      g1 += dip1[n];
+      g2 += dip2[n];
     } else {
-      g0 = dxc[N + n * 3] + dip[n];
-      g1 = dxc[N + n * 3 + 1] + dip[N + n];
-      g2 = dxc[N + n * 3 + 2] + dip[2 * N + n];
+      g0 = dxc[N + n * 3] + dip0[n];
+      g1 = dxc[N + n * 3 + 1] + dip1[n];
+      g2 = dxc[N + n * 3 + 2] + dip2[n];
     }
     g0 = fmaf(p.alpha2, Z[n * 3], g0);
     g1 = fmaf(p.alpha2, Z[n * 3 + 1], g1);

@@ -62,8 +62,8 @@ def test_workspace_sizes(lib):
     full = lib.reni_workspace_bytes(C.byref(c), 32, 8192, 3)
     assert 0 < inf < lat < full
     ntiles = 32 * 64
-    # latent-only: cos stash (6 images) + delta_0 (1 image) per tile; full: cos + h + delta (6 each) + g_y
-    assert lat - inf >= ntiles * 7 * 65536
+    # latent-only: cos stash (6 images) per tile; full: cos + h + delta (6 each) + g_y
+    assert lat - inf >= ntiles * 6 * 65536
     assert full - inf >= ntiles * 18 * 65536
     assert full < 3.2e9
     # ragged P rounds up to whole 128-direction tiles
