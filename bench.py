@@ -281,6 +281,10 @@ def run_gpu_arm(args):
         dom = max(gemm_flops, key=lambda n: kms[n])
         achieved = gemm_flops[dom] / (kms[dom] * 1e-3) / 1e12
         step_tflops = FLOPS_TRAIN * dirs_step / world / (total_ms / args.steps * 1e-3) / 1e12
+        traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))["bytes_per_launch"].get(dom)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -290,7 +294,7 @@ def run_gpu_arm(args):
                        "step": "weight prep + prologue + fwd + loss + bwd (dW, db, dZ)" + (" + NCCL all-reduce of 680707 fp32" if world > 1 else ""),
                        "optimizer": "excluded on both arms", "parallelism": f"dp{world} (maps sharded, latents local)"},
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+                         "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": pk["source"],
                          "step_tflops_per_gpu": step_tflops, "step_frac": step_tflops / pk["tflops"]},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_imgs.numel() * 4 + host_idx.numel() * 8,

@@ -9,7 +9,7 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 mode = sys.argv[2] if len(sys.argv) > 2 else "train"
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-B, N, W = 32, 36, 128
+B, N, W = int(os.environ.get("RENI_B", "32")), 36, 128
 P = W * W // 2
 m = RENIAutoDecoder(B, N, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, mode == "latent").to(dev)
 D, sw = get_directions(W).to(dev), get_sineweight(W).to(dev)
