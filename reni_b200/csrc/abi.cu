@@ -55,8 +55,8 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   w.dip = -1;
   if (flags & RENI_FLAG_SAVE_FOR_BACKWARD) {
     const bool dw = (flags & RENI_FLAG_NEED_DW) != 0;
-    w.stash_c = take(ntiles * (L + 1) * (int64_t)kTileImageBytes);
-    w.stash_h = dw ? take(ntiles * (L + 1) * (int64_t)kTileImageBytes) : -1;
+    w.stash_c = take(ntiles * (L + 1) * (int64_t)kTileImageBytes);  // 16-bit phase stash (rebuilds both h and cos)
+    w.stash_h = -1;
     w.stash_d = dw ? take(ntiles * (L + 1) * (int64_t)kTileImageBytes) : -1;  // slot 0 unused (delta_0 stays on chip)
     w.stash_gy = take(ntiles * (int64_t)kGyImageBytes);
   } else {
@@ -194,8 +194,7 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   p.w6f = at<__half>(ws, w.w6f);
   p.bias = at<float>(ws, w.bias);
   p.out = out;
-  p.stash_h = at<__half>(ws, w.stash_h);
-  p.stash_c = at<__half>(ws, w.stash_c);
+  p.stash_u = at<uint16_t>(ws, w.stash_c);
   p.target = (flags & RENI_FLAG_LOSS) ? target : nullptr;
   p.sw = sw;
   p.sw_bstride = sw_bstride;
@@ -249,7 +248,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   p.scalars = at<float>(ws, w.scalars);
   p.wb = at<__half>(ws, w.wb);
   p.w6b = at<__half>(ws, w.w6b);
-  p.stash_c = at<__half>(ws, w.stash_c);
+  p.stash_u = at<uint16_t>(ws, w.stash_c);
   p.stash_d = at<__half>(ws, w.stash_d);
   p.stash_gy = at<__half>(ws, w.stash_gy);
   p.D = D;
@@ -281,7 +280,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
 
   if (need_dw) {
     DwParams q{};
-    q.stash_h = at<__half>(ws, w.stash_h);
+    q.stash_u = at<uint16_t>(ws, w.stash_c);
     q.stash_d = at<__half>(ws, w.stash_d);
     q.stash_gy = at<__half>(ws, w.stash_gy);
     for (int i = 1; i <= L + 1; ++i) {

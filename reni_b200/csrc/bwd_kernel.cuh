@@ -4,8 +4,8 @@
 //     g_y   = dLoss/dy                      fused loss (sine-weighted MSE + cosine term, loss_functions.py:6-32,60-71)
 //                                           or an external grad_out, times tanh' = 1 - o^2; scaled by S into fp16 range
 //     d_L   = (g_y  W_out'') * cos(a_L)     tcgen05.mma K = 16
-//     d_l-1 = (d_l  W_l'')   * cos(a_l-1)   tcgen05.mma 128 x 256 x 256, l = L..1, cos from the forward stash,
-//                                           omega of the consuming layer folded into W''
+//     d_l-1 = (d_l  W_l'')   * cos(a_l-1)   tcgen05.mma 128 x 256 x 256, l = L..1; cos rebuilt (MUFU) from the forward's
+//                                           16-bit phase stash; omega of the consuming layer folded into W''
 //     dM_b, dc_b += [f | 1]^T d_0           tcgen05.mma N = 16 with d_0 read as an MN-major operand (contraction over the
 //                                           tile's rows): the per-map layer-0 reduction costs 16 tiny MMAs per tile
 //   d_l tiles stay in shared memory for the next GEMM; when weight gradients are wanted d_1..d_L are also stashed as
@@ -34,7 +34,7 @@ struct BwdParams {
   const float* scalars;   // [0] = S (gradient scale)
   const __half* wb;       // L backward weight images
   const __half* w6b;      // [2][256][8]
-  const __half* stash_c;  // cos(a_l), per tile (L+1) images
+  const uint16_t* stash_u;  // 16-bit phases of a_l, per tile (L+1) tile images
   __half* stash_d;        // delta stash: per tile nslots images (nslots = L+1 or 1)
   __half* stash_gy;       // per tile [2 halves][2][64][8]
   const float* D;         // directions (for the layer-0 feature columns f)
@@ -60,11 +60,9 @@ DEVINL void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
 
-// delta = acc * cos(a) for two columns, packed fp16 arithmetic (cos comes packed from the stash)
-DEVINL uint32_t delta2(float acc0, float acc1, uint32_t c2) {
-  const uint32_t a2 = pack_half2(acc0, acc1);
-  __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&a2), *reinterpret_cast<const __half2*>(&c2));
-  return *reinterpret_cast<uint32_t*>(&r);
+// delta = acc * cos(a) for two columns; w holds the two 16-bit phases of a
+DEVINL uint32_t delta2(float acc0, float acc1, uint32_t w) {
+  return pack_half2(acc0 * __cosf(phase_angle_lo(w)), acc1 * __cosf(phase_angle_hi(w)));
 }
 
 template <bool kNeedDW>
@@ -114,13 +112,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
         const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
         for (int g = 0; g < nsub; ++g)
-          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_c) +
+          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
                                ((size_t)(2 * pair + g) * (L + 1) + L) * kTileImageBytes,
                            kTileImageBytes);
         for (int l = L; l >= 1; --l) {
           for (int g = 0; g < nsub; ++g) {
             // the epilogue of this GEMM multiplies by cos(a_{l-1}): pull that stash tile towards L2 now
-            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_c) +
+            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
                                  ((size_t)(2 * pair + g) * (L + 1) + (l - 1)) * kTileImageBytes,
                              kTileImageBytes);
             for (int c = 0; c < kChunksPerLayer; ++c) {
@@ -208,7 +206,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
       const int b = tile / p.tiles_per_map;
       const int pix = (tile - b * p.tiles_per_map) * kTileRows + row;
       const bool rvalid = pix < p.P;
-      const uint8_t* st_c = reinterpret_cast<const uint8_t*>(p.stash_c) + (size_t)tile * (L + 1) * kTileImageBytes;
+      const uint8_t* st_u = reinterpret_cast<const uint8_t*>(p.stash_u) + (size_t)tile * (L + 1) * kTileImageBytes;
       uint8_t* st_d = reinterpret_cast<uint8_t*>(p.stash_d) + (size_t)tile * p.d_slots * kTileImageBytes;
 
       // ---- g_y (scaled by S) -> fp16 [128 x 16] operand at the head of the tile image
@@ -272,10 +270,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
 
       // ---- delta_l = acc * cos(a_l), l = L..0 ; this thread: (row, columns chalf*128 .. +127)
       for (int l = L; l >= 0; --l) {
-        const uint8_t* hl = st_c + (size_t)l * kTileImageBytes;
+        const uint8_t* hl = st_u + (size_t)l * kTileImageBytes;
         uint8_t* dl = nullptr;
         if (kNeedDW && l > 0) dl = st_d + (size_t)l * kTileImageBytes;
-        // the whole layer slice of the cos stash (16 x 16 B) is requested before waiting for the GEMM
+        // the whole layer slice of the phase stash (16 x 16 B) is requested before waiting for the GEMM
         uint4 hh[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k)

@@ -4,12 +4,13 @@
 //   db_l[j]   = sum_r delta_l[r,j]
 //   dW_out[c,k] = sum_r g_y[r,c] * h_L[r,k] ,  db_out[c] = sum_r g_y[r,c]
 //
-// Both operands are the fp16 tile images the forward / backward kernels stashed ([k/8][64 rows][8]); read as
-// MN-major UMMA operands the contraction runs over the rows, so no transpose is ever materialised.
+// delta_l / g_y are the fp16 tile images the delta-chain kernel stashed ([k/8][64 rows][8]); h_l is rebuilt here from
+// the forward's 16-bit phase stash (sin via MUFU on the otherwise idle CUDA cores, written straight into the operand
+// image).  Read as MN-major UMMA operands the contraction runs over the rows, so no transpose is ever materialised.
 // CTA i works on layer job (i mod (L+1)) and a contiguous slice of the 64-row stash blocks; the 256 x 256 fp32
 // accumulator lives in TMEM (2 x 256 columns) for the whole slice and is flushed once with vector reductions.
-//   warp 0 : bulk-copy producer (3-stage ring, 64 KB per stage)     warp 1 : tcgen05.mma issuer
-//   warps 2..9 : column sums for the bias gradient (from the smem operand), then the TMEM -> HBM flush
+//   warp 0 : bulk-copy producer (3-stage ring: delta block + phase block)     warp 1 : tcgen05.mma issuer
+//   warps 2..9 : phase -> h operand image (in place), column sums for the bias gradient, then the TMEM -> HBM flush
 #pragma once
 #include "layout.cuh"
 #include "ptx.cuh"
@@ -18,10 +19,11 @@ namespace reni {
 
 constexpr int kDwThreads = 320;
 constexpr int kDwStages = 3;
-constexpr int kDwStageBytes = 2 * kHalfImageBytes;  // 64 KB: A operand (32 KB) + B operand (up to 32 KB)
+constexpr int kDwStageBytes = 2 * kHalfImageBytes;  // 64 KB: A operand + B operand; the phase block lands in the
+                                                    // operand slot of h and is converted in place
 
 struct DwParams {
-  const __half* stash_h;
+  const uint16_t* stash_u;
   const __half* stash_d;
   const __half* stash_gy;
   float* dW[kMaxHiddenLayers + 2];  // [1..L] hidden (256x256), [L+1] output (out_features x 256); [0] unused
@@ -33,7 +35,7 @@ struct DwParams {
 struct DwSmem {
   static constexpr int kRing = 0;
   static constexpr int kBars = kRing + kDwStages * kDwStageBytes;
-  static constexpr int kNumBars = 2 * kDwStages + 1;
+  static constexpr int kNumBars = 3 * kDwStages + 1;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemPtr + 16;
 };
@@ -50,7 +52,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DwSmem::kBars);
   uint64_t* full = bars;
   uint64_t* empty = bars + kDwStages;
-  uint64_t* done = bars + 2 * kDwStages;
+  uint64_t* conv = bars + 2 * kDwStages;  // converters -> MMA: operand images ready
+  uint64_t* done = bars + 3 * kDwStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + DwSmem::kTmemPtr);
 
   const int L = p.L;
@@ -64,12 +67,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
   const int nst = s_end - s_begin;
   const bool is_out = (job == L);
   const int layer = job + 1;
-  const uint32_t b_bytes = is_out ? (kHalfRows * kW6N * 2) : kHalfImageBytes;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kDwStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 9);  // tcgen05.commit + 8 reader warps
+      mbar_init(&empty[i], 1);  // tcgen05.commit
+      mbar_init(&conv[i], 8);   // one arrival per converter warp
     }
     mbar_init(done, 1);
     fence_mbar_init();
@@ -80,33 +83,36 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // operand sources for stash block s (tile = s/2, half = s%2)
-  auto a_src = [&](int s) -> const uint8_t* {
-    const int tile = s >> 1, half = s & 1;
-    if (is_out)
-      return reinterpret_cast<const uint8_t*>(p.stash_h) + ((size_t)tile * (L + 1) + L) * kTileImageBytes +
-             (size_t)half * kHalfImageBytes;
-    return reinterpret_cast<const uint8_t*>(p.stash_d) + ((size_t)tile * (L + 1) + layer) * kTileImageBytes +
-           (size_t)half * kHalfImageBytes;
-  };
-  auto b_src = [&](int s) -> const uint8_t* {
+  // sources for stash block s (tile = s/2, half = s%2): the fp16 image that is used as it is, and the phase block
+  // from which the h operand is rebuilt
+  auto img_src = [&](int s) -> const uint8_t* {
     const int tile = s >> 1, half = s & 1;
     if (is_out)
       return reinterpret_cast<const uint8_t*>(p.stash_gy) + (size_t)tile * kGyImageBytes +
              (size_t)half * (kHalfRows * kW6N * 2);
-    return reinterpret_cast<const uint8_t*>(p.stash_h) + ((size_t)tile * (L + 1) + (layer - 1)) * kTileImageBytes +
+    return reinterpret_cast<const uint8_t*>(p.stash_d) + ((size_t)tile * (L + 1) + layer) * kTileImageBytes +
            (size_t)half * kHalfImageBytes;
   };
+  auto phase_src = [&](int s) -> const uint8_t* {
+    const int tile = s >> 1, half = s & 1;
+    const int lh = is_out ? L : layer - 1;  // h_L for the output layer, h_{l-1} for hidden layer l
+    return reinterpret_cast<const uint8_t*>(p.stash_u) + ((size_t)tile * (L + 1) + lh) * kTileImageBytes +
+           (size_t)half * kHalfImageBytes;
+  };
+  // hidden job: A = delta_l (copied), B = h_{l-1} (converted).  output job: A = h_L (converted), B = g_y (copied)
+  const uint32_t img_off = is_out ? kHalfImageBytes : 0;
+  const uint32_t cvt_off = is_out ? 0 : kHalfImageBytes;
+  const uint32_t img_bytes = is_out ? (kHalfRows * kW6N * 2) : kHalfImageBytes;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
       for (int s = s_begin; s < s_end; ++s) {
         mbar_wait(&empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&full[st], kHalfImageBytes + b_bytes);
+        mbar_arrive_expect_tx(&full[st], img_bytes + kHalfImageBytes);
         uint8_t* dst = smem + DwSmem::kRing + st * kDwStageBytes;
-        bulk_g2s(dst, a_src(s), kHalfImageBytes, &full[st]);
-        bulk_g2s(dst + kHalfImageBytes, b_src(s), b_bytes, &full[st]);
+        bulk_g2s(dst + img_off, img_src(s), img_bytes, &full[st]);
+        bulk_g2s(dst + cvt_off, phase_src(s), kHalfImageBytes, &full[st]);
         if (++st == kDwStages) { st = 0; ph ^= 1; }
       }
     }
@@ -116,7 +122,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
       const uint32_t ring_base = smem_u32(smem + DwSmem::kRing);
       uint32_t st = 0, ph = 0;
       for (int s = s_begin; s < s_end; ++s) {
-        mbar_wait(&full[st], ph);
+        mbar_wait(&conv[st], ph);
         tc_fence_after();
         const uint32_t sa = ring_base + st * kDwStageBytes;
         const uint32_t sb = sa + kHalfImageBytes;
@@ -147,7 +153,25 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
       uint32_t st = 0, ph = 0;
       for (int s = s_begin; s < s_end; ++s) {
         mbar_wait(&full[st], ph);
-        const uint8_t* base = smem + DwSmem::kRing + st * kDwStageBytes + (is_out ? kHalfImageBytes : 0);
+        uint8_t* stage = smem + DwSmem::kRing + st * kDwStageBytes;
+        // (1) phase block -> h = sin(angle) operand image, in place (same [k/8][64][8] geometry, 16 B per thread/group)
+        {
+          uint8_t* hd = stage + cvt_off;
+          const uint8_t* us = hd;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t off = ((kset * 8 + kk) * kHalfRows + r) * 16;
+            const uint4 u = *reinterpret_cast<const uint4*>(us + off);
+            uint4 h;
+            h.x = pack_half2(__sinf(phase_angle_lo(u.x)), __sinf(phase_angle_hi(u.x)));
+            h.y = pack_half2(__sinf(phase_angle_lo(u.y)), __sinf(phase_angle_hi(u.y)));
+            h.z = pack_half2(__sinf(phase_angle_lo(u.z)), __sinf(phase_angle_hi(u.z)));
+            h.w = pack_half2(__sinf(phase_angle_lo(u.w)), __sinf(phase_angle_hi(u.w)));
+            *reinterpret_cast<uint4*>(hd + off) = h;
+          }
+        }
+        // (2) bias-gradient column sums from the delta / g_y image
+        const uint8_t* base = stage + img_off;
         if (!is_out) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
@@ -165,8 +189,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
           const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
           acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x;
         }
+        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
+        if (lane == 0) mbar_arrive(&conv[st]);
         if (++st == kDwStages) { st = 0; ph ^= 1; }
       }
     }

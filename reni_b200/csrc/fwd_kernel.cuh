@@ -14,9 +14,10 @@
 // Inside a group two warps share each TMEM lane quarter and split the 256 columns in halves.
 // The two sub-tiles ping-pong: while group g runs the sin epilogue of layer l, the tensor pipe runs
 // layer l of the other sub-tile.  Activations never leave the SM (smem tile image, overwritten in place).
-// With kTrain h_l (operand of the weight-gradient GEMM) and cos(a_l) (factor of the delta chain) are additionally
-// stashed as fp16 tile images.  (Rebuilding cos as +-sqrt(1 - h^2) from the fp16 h was tried and measured: the
-// gradient error grows to 0.6-1.6e-2, outside the 1e-2 bar, so the cosine is stored.)
+// With kTrain the 16-bit phase of every pre-activation (ptx.cuh: phase_encode2) is additionally stashed in the
+// tile-image geometry: the backward kernels rebuild cos(a_l) (delta chain) and h_l = sin(a_l) (weight-gradient GEMM
+// operand) from it to ~5e-5, so one 2-byte stash replaces an h stash plus a cos stash and costs no second MUFU here.
+// (Rebuilding cos as +-sqrt(1 - h^2) from an fp16 h was tried and measured: gradient error 0.6-1.6e-2, rejected.)
 //
 // Reference semantics: src/models/RENI.py:31-53 (encoding), :63-87 (SineLayer), :132-178 (net).
 #pragma once
@@ -40,8 +41,7 @@ struct FwdParams {
   const __half* w6f;     // [k/8 32][n 16][8] final-layer image
   const float* bias;     // L*256 (omega_l * b_l) then 16 (final bias, zero padded)
   float* out;            // (B, P, 3)
-  __half* stash_h;       // kTrain (weight gradients wanted): per tile (L+1) images of h_l; may be null
-  __half* stash_c;       // kTrain: per tile (L+1) images of cos(a_l)
+  uint16_t* stash_u;     // kTrain: per tile (L+1) tile images of the 16-bit phases of a_l
   const float* target;   // fused loss partial sums (optional, may be null)
   const float* sw;       // (B or 1, P, 3)
   int64_t sw_bstride;
@@ -63,18 +63,18 @@ struct FwdSmem {
 };
 static_assert(FwdSmem::kTotal <= 232448, "forward kernel shared memory over budget");
 
-// sin (and, if kCos, cos) of 8 pre-activations -> packed fp16
-template <bool kCos>
-DEVINL void sincos8(const float (&a)[8], uint4& hv, uint4& cv) {
+// sin of 8 pre-activations -> packed fp16 and, if kPhase, their packed 16-bit phases
+template <bool kPhase>
+DEVINL void sin8(const float (&a)[8], uint4& hv, uint4& uv) {
   hv.x = pack_half2(__sinf(a[0]), __sinf(a[1]));
   hv.y = pack_half2(__sinf(a[2]), __sinf(a[3]));
   hv.z = pack_half2(__sinf(a[4]), __sinf(a[5]));
   hv.w = pack_half2(__sinf(a[6]), __sinf(a[7]));
-  if (kCos) {
-    cv.x = pack_half2(__cosf(a[0]), __cosf(a[1]));
-    cv.y = pack_half2(__cosf(a[2]), __cosf(a[3]));
-    cv.z = pack_half2(__cosf(a[4]), __cosf(a[5]));
-    cv.w = pack_half2(__cosf(a[6]), __cosf(a[7]));
+  if (kPhase) {
+    uv.x = phase_encode2(a[0], a[1]);
+    uv.y = phase_encode2(a[2], a[3]);
+    uv.z = phase_encode2(a[4], a[5]);
+    uv.w = phase_encode2(a[6], a[7]);
   }
 }
 
@@ -207,12 +207,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
       const int b = tile / p.tiles_per_map;
       const int pix = (tile - b * p.tiles_per_map) * kTileRows + row;
       const bool rvalid = pix < p.P;
-      uint8_t* st_h = nullptr;
-      uint8_t* st_c = nullptr;
-      if (kTrain) {
-        st_c = reinterpret_cast<uint8_t*>(p.stash_c) + (size_t)tile * (L + 1) * kTileImageBytes;
-        if (p.stash_h != nullptr) st_h = reinterpret_cast<uint8_t*>(p.stash_h) + (size_t)tile * (L + 1) * kTileImageBytes;
-      }
+      uint8_t* st_u = nullptr;
+      if (kTrain) st_u = reinterpret_cast<uint8_t*>(p.stash_u) + (size_t)tile * (L + 1) * kTileImageBytes;
 
       // ---- per-map layer-0 operands -> smem (group-private)
       named_bar_sync(1 + g, kGroupThreads);
@@ -260,14 +256,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
             a[6] = fmaf(fi, m1.z, a[6]); a[7] = fmaf(fi, m1.w, a[7]);
           }
         }
-        uint4 hv, cv;
-        sincos8<kTrain>(a, hv, cv);
+        uint4 hv, uv;
+        sin8<kTrain>(a, hv, uv);
         *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
-        if (kTrain) {
-          const uint32_t so = stash_off(row, kg, kH);
-          *reinterpret_cast<uint4*>(st_c + so) = cv;
-          if (st_h != nullptr) *reinterpret_cast<uint4*>(st_h + so) = hv;
-        }
+        if (kTrain) *reinterpret_cast<uint4*>(st_u + stash_off(row, kg, kH)) = uv;
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_ready[g]);
@@ -275,8 +267,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
       // ---- hidden layers: bias + sin epilogue, TMEM -> registers -> smem tile image (in place)
       for (int l = 1; l <= L; ++l) {
         const float* bl = s_bias + (l - 1) * kH + chalf * 128;
-        uint8_t* sc = kTrain ? st_c + (size_t)l * kTileImageBytes : nullptr;
-        uint8_t* sh = (kTrain && st_h != nullptr) ? st_h + (size_t)l * kTileImageBytes : nullptr;
+        uint8_t* su = kTrain ? st_u + (size_t)l * kTileImageBytes : nullptr;
         mbar_wait(&acc_full[g], acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
@@ -298,14 +289,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
             a[5] = __uint_as_float(v[q8 * 8 + 5]) + b1.y;
             a[6] = __uint_as_float(v[q8 * 8 + 6]) + b1.z;
             a[7] = __uint_as_float(v[q8 * 8 + 7]) + b1.w;
-            uint4 hv, cv;
-            sincos8<kTrain>(a, hv, cv);
+            uint4 hv, uv;
+            sin8<kTrain>(a, hv, uv);
             *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
-            if (kTrain) {
-              const uint32_t so = stash_off(row, kg, kH);
-              *reinterpret_cast<uint4*>(sc + so) = cv;
-              if (sh != nullptr) *reinterpret_cast<uint4*>(sh + so) = hv;
-            }
+            if (kTrain) *reinterpret_cast<uint4*>(su + stash_off(row, kg, kH)) = uv;
           }
         };
         {

@@ -166,6 +166,27 @@ DEVINL uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// ------------------------------------------------------------------ 16-bit phase stash
+// The forward kernel stashes ONE 16-bit number per activation: the phase u = frac(a / 2pi) * 65536 of the
+// pre-activation a.  sin and cos are both rebuilt from it to ~5e-5 (better than an fp16 rounding of either), so the
+// backward kernels need neither an h stash nor a cos stash.
+//   encode: mantissa of (a * 65536/2pi + 1.5*2^23) holds round(a * 65536/2pi) in two's complement -> low 16 bits
+//   decode: bytes {u, 0x00, 0x4B} are the float 2^23 + u; one FFMA maps it to the angle 2pi*u/65536 in [0, 2pi)
+DEVINL uint32_t phase_encode2(float a0, float a1) {
+  const uint32_t z0 = __float_as_uint(fmaf(a0, 10430.378350470453f, 12582912.f));
+  const uint32_t z1 = __float_as_uint(fmaf(a1, 10430.378350470453f, 12582912.f));
+  return __byte_perm(z0, z1, 0x5410);
+}
+constexpr float kPhaseToAngle = 9.587379924285257e-05f;  // 2pi / 65536 (the offset below is its exact 2^23 multiple)
+DEVINL float phase_angle_lo(uint32_t w) {  // angle of the low 16-bit phase of w
+  const float f = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610));
+  return fmaf(f, kPhaseToAngle, -8388608.f * kPhaseToAngle);
+}
+DEVINL float phase_angle_hi(uint32_t w) {  // angle of the high 16-bit phase of w
+  const float f = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632));
+  return fmaf(f, kPhaseToAngle, -8388608.f * kPhaseToAngle);
+}
+
 DEVINL float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -62,10 +62,10 @@ def test_workspace_sizes(lib):
     full = lib.reni_workspace_bytes(C.byref(c), 32, 8192, 3)
     assert 0 < inf < lat < full
     ntiles = 32 * 64
-    # latent-only: cos stash (6 images) per tile; full: cos + h + delta (6 each) + g_y
+    # latent-only: 16-bit phase stash (6 images) per tile; full: phase + delta (6 each) + g_y
     assert lat - inf >= ntiles * 6 * 65536
-    assert full - inf >= ntiles * 18 * 65536
-    assert full < 3.2e9
+    assert full - inf >= ntiles * 12 * 65536
+    assert full < 2.0e9
     # ragged P rounds up to whole 128-direction tiles
     assert lib.reni_workspace_bytes(C.byref(c), 1, 129, 1) > lib.reni_workspace_bytes(C.byref(c), 1, 128, 1)
 
