@@ -195,16 +195,21 @@ def run_gpu_arm(args):
         flat.all_reduce_mean()
         return r
 
-    # phase events: kernel-level timing on the launching stream
-    n_ev = 7
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
-    for e in evs:
-        e.record()  # forces creation of the cudaEvent_t handles
-    torch.cuda.synchronize()
-    handles = (C.c_void_p * n_ev)(*[e.cuda_event for e in evs])
-
     for _ in range(max(3, args.warmup)):
         step_resident()
+    torch.cuda.synchronize()
+
+    # the step is ~12 launches for < 1 ms of GPU work: capture it once, replay it (CUDA graph; NCCL all-reduce included)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step_resident()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step_resident()
+    for _ in range(max(3, args.warmup)):
+        graph.replay()
     torch.cuda.synchronize()
 
     def barrier():
@@ -217,32 +222,43 @@ def run_gpu_arm(args):
     # ---- timed region: exactly K steps, device-timed, L2 flushed between steps (flush outside the event pairs)
     e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    phase_ms = [[] for _ in range(n_ev - 1)]
-    _lib.check(lib.reni_debug_set_phase_events(handles, n_ev))
     for i in range(args.steps):
         flush.zero_()
         e0[i].record()
-        step_resident()
+        graph.replay()
         e1[i].record()
-        e1[i].synchronize()
-        for k in range(n_ev - 1):
-            phase_ms[k].append(evs[k].elapsed_time(evs[k + 1]))
-    _lib.check(lib.reni_debug_set_phase_events(None, 0))
     barrier()
     total_ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
     clocks = sampler.stop() if sampler else None
 
+    # ---- per-kernel breakdown: the same step launched eagerly with CUDA events recorded between its kernels on the
+    # launching stream (library debug hook; the map-level backward then stays on the main stream instead of
+    # overlapping the weight-gradient GEMM, so the parts add up to slightly more than the graph-replayed step)
+    n_ev = 7
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
+    for e in evs:
+        e.record()  # forces creation of the cudaEvent_t handles
+    torch.cuda.synchronize()
+    handles = (C.c_void_p * n_ev)(*[e.cuda_event for e in evs])
+    phase_ms = [[] for _ in range(n_ev - 1)]
+    _lib.check(lib.reni_debug_set_phase_events(handles, n_ev))
+    for i in range(min(args.steps, 50)):
+        flush.zero_()
+        step_resident()
+        torch.cuda.synchronize()
+        for k in range(n_ev - 1):
+            phase_ms[k].append(evs[k].elapsed_time(evs[k + 1]))
+    _lib.check(lib.reni_debug_set_phase_events(None, 0))
+    barrier()
+
     # ---- end-to-end through the public API: pinned host batch -> H2D -> RENITrainer.training_step -> D2H loss
-    trainer = RENITrainer(model, "FIT_DECODER", SIDELEN, lr=1e-5)
+    trainer = RENITrainer(model, "FIT_DECODER", SIDELEN, lr=1e-5, cuda_graph=True)
     host_imgs = (torch.rand(B, 3, SIDELEN // 2, SIDELEN, generator=g) * 2 - 1).pin_memory()
     host_idx = torch.arange(lo, hi, dtype=torch.long).pin_memory()
     host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        imgs = host_imgs.to(dev, non_blocking=True)
-        idx = host_idx.to(dev, non_blocking=True)
-        trainer._ws.prepared_key = None
-        log = trainer.training_step((imgs, idx))
+        log = trainer.training_step((host_imgs, host_idx))  # pinned host -> static device buffers -> graph replay
         host_loss.copy_(log["loss"].reshape(1), non_blocking=True)
 
     for _ in range(3):
@@ -291,6 +307,7 @@ def run_gpu_arm(args):
             "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD, "latent_dim": N_LATENT, "maps_per_gpu": B, "directions_per_map": P,
                        "l2": "256 MB flush between timed steps (outside the event pairs)",
+                       "launch": "whole step captured once in a CUDA graph and replayed; per-kernel times from a separate eager pass with events between kernels",
                        "step": "weight prep + prologue + fwd + loss + bwd (dW, db, dZ)" + (" + NCCL all-reduce of 680707 fp32" if world > 1 else ""),
                        "optimizer": "excluded on both arms", "parallelism": f"dp{world} (maps sharded, latents local)"},
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
@@ -299,7 +316,7 @@ def run_gpu_arm(args):
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_imgs.numel() * 4 + host_idx.numel() * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
-                    "api": "RENITrainer.training_step((imgs, idx)) from pinned host memory"},
+                    "api": "RENITrainer(cuda_graph=True).training_step((imgs, idx)) from pinned host memory"},
             "gpu_launches": 10 * args.steps * 2,  # 10 kernels per step, K device-resident + K end-to-end steps
             "clocks": clocks,
         }

@@ -124,6 +124,10 @@ int32_t reni_loss_forward_backward(const reni_config_t* cfg, const float* Z, con
  * [6] end of the step.  n = 0 clears.  Thread-local; this is the only state the library keeps. */
 int32_t reni_debug_set_phase_events(void* const* host_events, int32_t n);
 
+/* Debug hook: cudaGetErrorString of the last CUDA runtime error this thread saw inside the library
+ * ("no error" if none); lets a caller turn RENI_ERR_CUDA into a readable message. */
+const char* reni_debug_last_cuda_error(void);
+
 /* Debug / test hook: one 128 x N x (16*ksteps) tcgen05.mma with caller-supplied operand images
  * and descriptor fields; writes the fp32 accumulator tile (128 x N, row-major) to d_out. */
 int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes,

@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libreni_b200.so")
+# RENI_B200_LIB overrides the path (tools/variant_time.py times alternative builds of the same ABI)
+LIB_PATH = os.environ.get("RENI_B200_LIB") or os.path.join(_HERE, "lib", "libreni_b200.so")
 
 FLAG_SAVE_FOR_BACKWARD = 1
 FLAG_NEED_DW = 2
@@ -57,6 +58,7 @@ SIGNATURES = {
                                           _i64, C.c_float, C.c_float, _i32, _vp, _vp, _vp, C.POINTER(_vp),
                                           C.POINTER(_vp), _vp, _i64, _i32, _vp]),
     "reni_debug_set_phase_events": (_i32, [C.POINTER(_vp), _i32]),
+    "reni_debug_last_cuda_error": (C.c_char_p, []),
     "reni_selftest_umma": (_i32, [_vp, _u32, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]),
 }
 
@@ -90,4 +92,6 @@ def missing_symbols():
 def check(code: int, what: str = "reni_b200") -> None:
     if code != 0:
         msg = load().reni_strerror(int(code)).decode()
+        if int(code) == -4:  # RENI_ERR_CUDA: say which runtime error
+            msg += ": " + load().reni_debug_last_cuda_error().decode()
         raise RENILibraryError(f"{what} failed: {msg} (code {code})")

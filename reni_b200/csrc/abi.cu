@@ -79,6 +79,38 @@ inline void mark_phase(int i, cudaStream_t s) {
   if (i < g_num_phase_events && g_phase_events[i] != nullptr) cudaEventRecord(g_phase_events[i], s);
 }
 
+// last CUDA runtime error seen by this thread inside the library (debug hook reni_debug_last_cuda_error)
+thread_local cudaError_t g_last_cuda = cudaSuccess;
+inline cudaError_t note(cudaError_t e) {
+  if (e != cudaSuccess) g_last_cuda = e;
+  return e;
+}
+inline cudaError_t last_err() { return note(cudaGetLastError()); }
+
+// Side stream for the map-level backward (tiny latency-bound kernels that only depend on the delta chain): forked
+// after the delta-chain kernel, joined at the end of the step, so it runs under the weight-gradient GEMM.  One per
+// host thread and device, created on first use; event-based fork/join is legal inside CUDA-graph capture.
+struct SideStream {
+  int dev = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+thread_local SideStream g_side;
+bool side_stream(SideStream** out) {
+  int dev = 0;
+  if (note(cudaGetDevice(&dev)) != cudaSuccess) return false;
+  if (g_side.dev != dev) {
+    SideStream s;
+    if (note(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return false;
+    if (note(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming)) != cudaSuccess) return false;
+    if (note(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming)) != cudaSuccess) return false;
+    s.dev = dev;
+    g_side = s;  // (a thread that hops devices leaks one stream + two events per hop; callers are one-process-per-GPU)
+  }
+  *out = &g_side;
+  return true;
+}
+
 int num_sms() {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -145,7 +177,7 @@ int32_t reni_prepare_weights(const reni_config_t* c, const float* const* host_we
   p.first_omega = c->first_omega_0;
   p.hidden_omega = c->hidden_omega_0;
   reni_prep_weights_kernel<<<dim3(32, L + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  return cudaGetLastError() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
 int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int64_t d_bstride,
@@ -179,9 +211,9 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
     q.omega0 = c->first_omega_0;
     const size_t smem = (size_t)(q.in_features + 3 * q.N) * sizeof(float);
     if (smem > 48 * 1024)
-      cudaFuncSetAttribute(reni_prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      note(cudaFuncSetAttribute(reni_prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     reni_prologue_kernel<<<dim3(kH / 8, (unsigned)B), 256, smem, stream>>>(q);
-    if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+    if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   }
   mark_phase(1, stream);
 
@@ -212,15 +244,15 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   const bool train = (flags & RENI_FLAG_SAVE_FOR_BACKWARD) != 0;
   cudaError_t e;
   auto launch = [&](auto kernel) {
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal);
+    e = note(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal));
     if (e != cudaSuccess) return;
     kernel<<<grid, kFwdThreads, FwdSmem::kTotal, stream>>>(p);
   };
-  if (train) launch(reni_fwd_kernel<true>);
-  else launch(reni_fwd_kernel<false>);
+  if (train) launch(reni_fwd_kernel<true, false>);
+  else launch(reni_fwd_kernel<false, true>);
   if (e != cudaSuccess) return RENI_ERR_CUDA;
   mark_phase(2, stream);
-  return cudaGetLastError() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
 // Shared tail of reni_backward / reni_loss_forward_backward: delta chain, weight-gradient GEMMs, layer-0 and
@@ -265,18 +297,29 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   const int npairs = (ntiles + 1) / 2;
   const int grid = npairs < sms ? npairs : sms;
   if (need_dw) {
-    if (cudaFuncSetAttribute(reni_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal) !=
+    if (note(cudaFuncSetAttribute(reni_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal)) !=
         cudaSuccess)
       return RENI_ERR_CUDA;
     reni_bwd_kernel<true><<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(p);
   } else {
-    if (cudaFuncSetAttribute(reni_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal) !=
+    if (note(cudaFuncSetAttribute(reni_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal)) !=
         cudaSuccess)
       return RENI_ERR_CUDA;
     reni_bwd_kernel<false><<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(p);
   }
-  if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+  if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   mark_phase(4, stream);
+
+  // fork: the map-level backward below only needs dmc from the delta chain; with the per-kernel timing hook active
+  // everything stays on the caller's stream so the phase events keep their meaning
+  cudaStream_t mstream = stream;
+  SideStream* side = nullptr;
+  if (need_dw && g_num_phase_events == 0) {
+    if (!side_stream(&side)) return RENI_ERR_CUDA;
+    if (note(cudaEventRecord(side->fork, stream)) != cudaSuccess) return RENI_ERR_CUDA;
+    if (note(cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return RENI_ERR_CUDA;
+    mstream = side->stream;
+  }
 
   if (need_dw) {
     DwParams q{};
@@ -292,7 +335,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     q.ntiles = ntiles;
     q.L = L;
     q.out_features = c->out_features;
-    if (cudaFuncSetAttribute(reni_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem::kTotal) !=
+    if (note(cudaFuncSetAttribute(reni_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem::kTotal)) !=
         cudaSuccess)
       return RENI_ERR_CUDA;
     int g = sms;
@@ -300,7 +343,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     if (g > max_useful) g = max_useful;
     if (g < L + 1) g = L + 1;
     reni_dw_kernel<<<g, kDwThreads, DwSmem::kTotal, stream>>>(q);
-    if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+    if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   }
   mark_phase(5, stream);
 
@@ -313,8 +356,8 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
       g.B = weight0;
       g.C = at<float>(ws, w.dxc);
       g.M = K5; g.N = nin; g.K = kH; g.a_sk = 1; g.a_sm = kH; g.ldb = nin; g.ldc = nin;
-      if (cudaMemsetAsync(g.C, 0, (size_t)K5 * nin * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
-      reni_small_gemm_kernel<<<dim3((nin + 63) / 64, (K5 + 63) / 64, kH / kSmallGemmK), 256, 0, stream>>>(g);
+      if (cudaMemsetAsync(g.C, 0, (size_t)K5 * nin * 4, mstream) != cudaSuccess) return RENI_ERR_CUDA;
+      reni_small_gemm_kernel<<<dim3((nin + 63) / 64, (K5 + 63) / 64, kH / kSmallGemmK), 256, 0, mstream>>>(g);
       MapBwdParams m{};
       m.Z = Z;
       m.E = at<float>(ws, w.dxc);
@@ -325,7 +368,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
       m.equivariance = c->equivariance;
       m.alpha2 = 2.f * alpha;
       m.accumulate = 0;
-      reni_dz_kernel<<<(unsigned)B, 128, 0, stream>>>(m);
+      reni_dz_kernel<<<(unsigned)B, 128, 0, mstream>>>(m);
     }
     if (need_dw) {
       if (host_dW[0] == nullptr || host_db[0] == nullptr) return RENI_ERR_BAD_ARGUMENT;
@@ -334,14 +377,20 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
       g.B = at<float>(ws, w.xc);
       g.C = host_dW[0];
       g.M = kH; g.N = nin; g.K = K5; g.a_sk = kH; g.a_sm = 1; g.ldb = nin; g.ldc = nin;
-      reni_small_gemm_kernel<<<dim3((nin + 63) / 64, kH / 64, (K5 + kSmallGemmK - 1) / kSmallGemmK), 256, 0, stream>>>(g);
-      reni_db0_kernel<<<1, 256, 0, stream>>>(at<float>(ws, w.dmc), host_db[0], (int)B);
+      reni_small_gemm_kernel<<<dim3((nin + 63) / 64, kH / 64, (K5 + kSmallGemmK - 1) / kSmallGemmK), 256, 0, mstream>>>(g);
+      reni_db0_kernel<<<1, 256, 0, mstream>>>(at<float>(ws, w.dmc), host_db[0], (int)B);
     }
-    if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+    if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
+  }
+  if (side != nullptr) {  // join
+    if (note(cudaEventRecord(side->join, side->stream)) != cudaSuccess) return RENI_ERR_CUDA;
+    if (note(cudaStreamWaitEvent(stream, side->join, 0)) != cudaSuccess) return RENI_ERR_CUDA;
   }
   mark_phase(6, stream);
   return RENI_OK;
 }
+
+const char* reni_debug_last_cuda_error(void) { return cudaGetErrorString(g_last_cuda); }
 
 int32_t reni_debug_set_phase_events(void* const* events, int32_t n) {
   if (n < 0 || n > 16 || (n > 0 && events == nullptr)) return RENI_ERR_BAD_ARGUMENT;
@@ -372,7 +421,7 @@ int32_t reni_backward(const reni_config_t* c, const float* Z, const float* D, in
   if (blocks > 1184) blocks = 1184;
   reni_absmax_kernel<<<blocks, 256, 0, stream>>>(grad_out, n, slot);
   reni_scale_from_absmax_kernel<<<1, 1, 0, stream>>>(slot, scalars);
-  if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+  if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   return launch_backward(c, w, Z, D, d_bstride, host_weights[0], B, P, out, grad_out, nullptr, nullptr, 0, 0.f, dZ,
                          host_dW, host_db, ws, flags, stream);
 }
@@ -412,7 +461,7 @@ int32_t reni_loss_forward_backward(const reni_config_t* c, const float* Z, const
   f.beta = beta;
   f.use_cos = use_cosine;
   reni_loss_finish_kernel<<<(unsigned)B, 128, 0, stream>>>(f);
-  if (cudaGetLastError() != cudaSuccess) return RENI_ERR_CUDA;
+  if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   return launch_backward(c, w, Z, D, d_bstride, host_weights[0], B, P, out, nullptr, target, sw, sw_bstride, alpha, dZ,
                          host_dW, host_db, ws, flags, stream);
 }
@@ -440,11 +489,11 @@ int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_im
   p.ksteps = ksteps;
   const size_t smem = ((a_bytes + 1023) & ~1023u) + b_bytes + 1024;
   if (smem > 220 * 1024) return RENI_ERR_BAD_ARGUMENT;
-  if (cudaFuncSetAttribute(reni_selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+  if (note(cudaFuncSetAttribute(reni_selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=
       cudaSuccess)
     return RENI_ERR_CUDA;
   reni_selftest_umma_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
-  return cudaGetLastError() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
 }  // extern "C"

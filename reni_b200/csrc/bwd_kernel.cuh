@@ -62,7 +62,7 @@ DEVINL void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
 
 // delta = acc * cos(a) for two columns; w holds the two 16-bit phases of a
 DEVINL uint32_t delta2(float acc0, float acc1, uint32_t w) {
-  return pack_half2(acc0 * __cosf(phase_angle_lo(w)), acc1 * __cosf(phase_angle_hi(w)));
+  return pack_half2(acc0 * abl_cos(phase_angle_lo(w)), acc1 * abl_cos(phase_angle_hi(w)));
 }
 
 template <bool kNeedDW>
@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
         uint4 hh[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k)
-          hh[k] = __ldg(reinterpret_cast<const uint4*>(hl + stash_off(row, chalf * 16 + k, kH)));
+          hh[k] = (RENI_ABL & 8) ? make_uint4(k, row, l, g)
+                                 : __ldg(reinterpret_cast<const uint4*>(hl + stash_off(row, chalf * 16 + k, kH)));
         mbar_wait(&acc_full[g], acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
             dv.z = delta2(__uint_as_float(v[q8 * 8 + 4]), __uint_as_float(v[q8 * 8 + 5]), hw.z);
             dv.w = delta2(__uint_as_float(v[q8 * 8 + 6]), __uint_as_float(v[q8 * 8 + 7]), hw.w);
             *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = dv;
-            if (dl != nullptr) *reinterpret_cast<uint4*>(dl + stash_off(row, kg, kH)) = dv;
+            if (dl != nullptr && !(RENI_ABL & 1)) *reinterpret_cast<uint4*>(dl + stash_off(row, kg, kH)) = dv;
           }
         };
         {

@@ -163,10 +163,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
             const uint32_t off = ((kset * 8 + kk) * kHalfRows + r) * 16;
             const uint4 u = *reinterpret_cast<const uint4*>(us + off);
             uint4 h;
-            h.x = pack_half2(__sinf(phase_angle_lo(u.x)), __sinf(phase_angle_hi(u.x)));
-            h.y = pack_half2(__sinf(phase_angle_lo(u.y)), __sinf(phase_angle_hi(u.y)));
-            h.z = pack_half2(__sinf(phase_angle_lo(u.z)), __sinf(phase_angle_hi(u.z)));
-            h.w = pack_half2(__sinf(phase_angle_lo(u.w)), __sinf(phase_angle_hi(u.w)));
+            h.x = pack_half2(abl_sin(phase_angle_lo(u.x)), abl_sin(phase_angle_hi(u.x)));
+            h.y = pack_half2(abl_sin(phase_angle_lo(u.y)), abl_sin(phase_angle_hi(u.y)));
+            h.z = pack_half2(abl_sin(phase_angle_lo(u.z)), abl_sin(phase_angle_hi(u.z)));
+            h.w = pack_half2(abl_sin(phase_angle_lo(u.w)), abl_sin(phase_angle_hi(u.w)));
             *reinterpret_cast<uint4*>(hd + off) = h;
           }
         }

@@ -9,11 +9,15 @@
 // One persistent CTA per SM, 576 threads:
 //   warp 0        : weight-chunk producer (cp.async.bulk global->smem ring, mbarrier complete_tx)
 //   warp 1        : TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2..9    : epilogue group 0 (sub-tile 0, TMEM columns   0..255)
-//   warps 10..17  : epilogue group 1 (sub-tile 1, TMEM columns 256..511)
-// Inside a group two warps share each TMEM lane quarter and split the 256 columns in halves.
-// The two sub-tiles ping-pong: while group g runs the sin epilogue of layer l, the tensor pipe runs
-// layer l of the other sub-tile.  Activations never leave the SM (smem tile image, overwritten in place).
+//   warps 2..17   : sixteen epilogue warps over two 128-row sub-tiles (TMEM columns 0..255 / 256..511) that ping-pong:
+//                   while the sin epilogue of layer l runs for one sub-tile the tensor pipe runs layer l of the other.
+//     grouped mode (training): warps 2..9 own sub-tile 0, warps 10..17 own sub-tile 1; two warps share a TMEM lane
+//                   quarter and split the 256 columns in halves.  A store-stalled group only delays its own sub-tile.
+//     all-hands mode (inference): all sixteen warps work on one sub-tile at a time (four per lane quarter, 64 columns
+//                   each), so no warp idles through a GEMM.  Measured on B200 (tools/variant_time.py): all-hands wins
+//                   without stash stores (63.5 % vs 61 % of the bf16 peak at cfg 5), grouped wins with them
+//                   (234 vs 262 us at cfg 2) -- hence one mode per use.
+// Activations never leave the SM (smem tile image, overwritten in place).
 // With kTrain the 16-bit phase of every pre-activation (ptx.cuh: phase_encode2) is additionally stashed in the
 // tile-image geometry: the backward kernels rebuild cos(a_l) (delta chain) and h_l = sin(a_l) (weight-gradient GEMM
 // operand) from it to ~5e-5, so one 2-byte stash replaces an h stash plus a cos stash and costs no second MUFU here.
@@ -31,7 +35,8 @@ constexpr int kFwdThreads = 576;
 #define RENI_FWD_STAGES 4
 #endif
 constexpr int kFwdStages = RENI_FWD_STAGES;
-constexpr int kGroupThreads = 256;  // epilogue threads per sub-tile
+constexpr int kGroupThreads = 256;  // epilogue threads per sub-tile (grouped mode)
+constexpr int kEpiThreads = 512;    // all epilogue threads (all-hands mode)
 
 struct FwdParams {
   const float* D;        // (B or 1, P, 3) unit directions
@@ -66,10 +71,10 @@ static_assert(FwdSmem::kTotal <= 232448, "forward kernel shared memory over budg
 // sin of 8 pre-activations -> packed fp16 and, if kPhase, their packed 16-bit phases
 template <bool kPhase>
 DEVINL void sin8(const float (&a)[8], uint4& hv, uint4& uv) {
-  hv.x = pack_half2(__sinf(a[0]), __sinf(a[1]));
-  hv.y = pack_half2(__sinf(a[2]), __sinf(a[3]));
-  hv.z = pack_half2(__sinf(a[4]), __sinf(a[5]));
-  hv.w = pack_half2(__sinf(a[6]), __sinf(a[7]));
+  hv.x = pack_half2(abl_sin(a[0]), abl_sin(a[1]));
+  hv.y = pack_half2(abl_sin(a[2]), abl_sin(a[3]));
+  hv.z = pack_half2(abl_sin(a[4]), abl_sin(a[5]));
+  hv.w = pack_half2(abl_sin(a[6]), abl_sin(a[7]));
   if (kPhase) {
     uv.x = phase_encode2(a[0], a[1]);
     uv.y = phase_encode2(a[2], a[3]);
@@ -78,7 +83,7 @@ DEVINL void sin8(const float (&a)[8], uint4& hv, uint4& uv) {
   }
 }
 
-template <bool kTrain>
+template <bool kTrain, bool kAllHands>
 __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5;
@@ -101,8 +106,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(&a_ready[0], kGroupThreads);
-    mbar_init(&a_ready[1], kGroupThreads);
+    mbar_init(&a_ready[0], kAllHands ? kEpiThreads : kGroupThreads);
+    mbar_init(&a_ready[1], kAllHands ? kEpiThreads : kGroupThreads);
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
     fence_mbar_init();
@@ -188,6 +193,203 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
         }
       }
     }
+  } else if (kAllHands) {
+    // ============================================================ epilogue warps
+    const uint32_t e = warp - 2;                    // 0..15
+    const uint32_t q = warp & 3;                    // TMEM lane quarter this warp may access
+    const uint32_t cq = e >> 2;                     // which 64-column quarter this warp handles
+    const uint32_t row = q * 32 + lane;             // row inside a sub-tile == TMEM lane
+    const uint32_t etid = threadIdx.x - 64;         // 0..511
+    float* s_mc_all = reinterpret_cast<float*>(smem + FwdSmem::kMc);
+    uint32_t acc_ph = 0;  // bit g = phase parity of acc_full[g]
+
+    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
+      const int tile0 = 2 * pair, tile1 = min(2 * pair + 1, p.ntiles - 1);
+      const int bmap0 = tile0 / p.tiles_per_map, bmap1 = tile1 / p.tiles_per_map;
+      const int pix0 = (tile0 - bmap0 * p.tiles_per_map) * kTileRows + row;
+      const int pix1 = (tile1 - bmap1 * p.tiles_per_map) * kTileRows + row;
+
+      // ---- per-map layer-0 operands of both sub-tiles -> smem
+      named_bar_sync(1, kEpiThreads);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const float4* src = reinterpret_cast<const float4*>(p.mc + (size_t)(g ? bmap1 : bmap0) * 5 * kH);
+        float4* dst = reinterpret_cast<float4*>(s_mc_all + g * 5 * kH);
+        for (int i = etid; i < 5 * kH / 4; i += kEpiThreads) dst[i] = __ldg(src + i);
+      }
+      named_bar_sync(1, kEpiThreads);
+
+      // ---- layer 0: h0 = sin(f . M' + c')  (omega folded into M', c'); this warp's 64 columns of each sub-tile
+      for (int g = 0; g < nsub; ++g) {
+        const int b = g ? bmap1 : bmap0, pix = g ? pix1 : pix0;
+        // invariant direction features, registers only (RENI.py:37-49)
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+        if (pix < p.P) {
+          const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
+          const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+          if (p.so2) {
+            f0 = dx;
+            f1 = dz;
+            f2 = sqrtf(dx * dx + dz * dz);
+            f3 = dy;
+          } else {  // SO3 / None: the three inner-product columns (RENI.py:25,57)
+            f0 = dx;
+            f1 = dy;
+            f2 = dz;
+          }
+        }
+        uint8_t* a_tile = smem + FwdSmem::kA + g * kTileImageBytes;
+        const float* s_mc = s_mc_all + g * 5 * kH;
+        uint8_t* st_u = nullptr;
+        if (kTrain) st_u = reinterpret_cast<uint8_t*>(p.stash_u) + (size_t)(2 * pair + g) * (L + 1) * kTileImageBytes;
+#pragma unroll 2
+        for (int k8 = 0; k8 < 8; ++k8) {
+          const int kg = cq * 8 + k8;
+          float a[8];
+          {
+            const float4* m = reinterpret_cast<const float4*>(s_mc + kg * 8);
+            const float4 c0 = m[4 * (kH / 4)], c1 = m[4 * (kH / 4) + 1];
+            a[0] = c0.x; a[1] = c0.y; a[2] = c0.z; a[3] = c0.w;
+            a[4] = c1.x; a[5] = c1.y; a[6] = c1.z; a[7] = c1.w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float fi = (i == 0) ? f0 : (i == 1) ? f1 : (i == 2) ? f2 : f3;
+              const float4 m0 = m[i * (kH / 4)], m1 = m[i * (kH / 4) + 1];
+              a[0] = fmaf(fi, m0.x, a[0]); a[1] = fmaf(fi, m0.y, a[1]);
+              a[2] = fmaf(fi, m0.z, a[2]); a[3] = fmaf(fi, m0.w, a[3]);
+              a[4] = fmaf(fi, m1.x, a[4]); a[5] = fmaf(fi, m1.y, a[5]);
+              a[6] = fmaf(fi, m1.z, a[6]); a[7] = fmaf(fi, m1.w, a[7]);
+            }
+          }
+          uint4 hv, uv;
+          sin8<kTrain>(a, hv, uv);
+          *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
+          if (kTrain && !(RENI_ABL & 1)) *reinterpret_cast<uint4*>(st_u + stash_off(row, kg, kH)) = uv;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&a_ready[g]);
+      }
+
+      // ---- hidden layers: bias + sin epilogue, TMEM -> registers -> smem tile image (in place); the sub-tiles alternate
+      for (int l = 1; l <= L; ++l) {
+        const float* bl = s_bias + (l - 1) * kH + cq * 64;
+        for (int g = 0; g < nsub; ++g) {
+          uint8_t* a_tile = smem + FwdSmem::kA + g * kTileImageBytes;
+          uint8_t* su = nullptr;
+          if (kTrain)
+            su = reinterpret_cast<uint8_t*>(p.stash_u) + ((size_t)(2 * pair + g) * (L + 1) + l) * kTileImageBytes;
+          const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256 + cq * 64;
+          mbar_wait(&acc_full[g], (acc_ph >> g) & 1);
+          acc_ph ^= 1u << g;
+          tc_fence_after();
+          // TMEM -> registers in 16-column slices, double buffered: the next tcgen05.ld is in flight while this
+          // slice goes through bias + sin + pack + store
+          auto process16 = [&](const uint32_t (&v)[16], int it) {
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8) {
+              const int kl = it * 2 + q8;          // 8-column group inside this warp's quarter
+              const int kg = cq * 8 + kl;          // ... inside the tile
+              const float4 b0 = *reinterpret_cast<const float4*>(bl + kl * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bl + kl * 8 + 4);
+              float a[8];
+              a[0] = __uint_as_float(v[q8 * 8 + 0]) + b0.x;
+              a[1] = __uint_as_float(v[q8 * 8 + 1]) + b0.y;
+              a[2] = __uint_as_float(v[q8 * 8 + 2]) + b0.z;
+              a[3] = __uint_as_float(v[q8 * 8 + 3]) + b0.w;
+              a[4] = __uint_as_float(v[q8 * 8 + 4]) + b1.x;
+              a[5] = __uint_as_float(v[q8 * 8 + 5]) + b1.y;
+              a[6] = __uint_as_float(v[q8 * 8 + 6]) + b1.z;
+              a[7] = __uint_as_float(v[q8 * 8 + 7]) + b1.w;
+              uint4 hv, uv;
+              sin8<kTrain>(a, hv, uv);
+              *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
+              if (kTrain && !(RENI_ABL & 1)) *reinterpret_cast<uint4*>(su + stash_off(row, kg, kH)) = uv;
+            }
+          };
+          {
+            uint32_t va[16], vb[16];
+            tmem_ld16(t_acc, va);
+#pragma unroll
+            for (int it = 0; it < 4; it += 2) {
+              tmem_ld_wait();
+              tmem_ld16(t_acc + (it + 1) * 16, vb);
+              process16(va, it);
+              tmem_ld_wait();
+              if (it + 2 < 4) tmem_ld16(t_acc + (it + 2) * 16, va);
+              process16(vb, it + 1);
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async_smem();
+          mbar_arrive(&a_ready[g]);
+        }
+      }
+
+      // ---- output layer (N = 16 padded): bias, optional sin, optional tanh, store, fused loss partials
+      for (int g = 0; g < nsub; ++g) {
+        mbar_wait(&acc_full[g], (acc_ph >> g) & 1);
+        acc_ph ^= 1u << g;
+        tc_fence_after();
+        if (cq == 0) {
+          const int tile = 2 * pair + g;
+          const int b = g ? bmap1 : bmap0, pix = g ? pix1 : pix0;
+          const bool rvalid = pix < p.P;
+          const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256;
+          float o[3];
+          {
+            uint32_t v[16];
+            tmem_ld16(t_acc, v);
+            tmem_ld_wait();
+            const float* bo = s_bias + L * kH;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float y = __uint_as_float(v[c]) + bo[c];
+              if (p.last_sine) y = sinf(y);
+              if (p.out_tanh) y = tanhf(y);
+              o[c] = y;
+            }
+          }
+          if (rvalid) {
+            float* op = p.out + ((size_t)b * p.P + pix) * 3;
+            op[0] = o[0];
+            op[1] = o[1];
+            op[2] = o[2];
+          }
+          if (p.loss_part != nullptr) {
+            float part[kLossPartials];
+#pragma unroll
+            for (int i = 0; i < kLossPartials; ++i) part[i] = 0.f;
+            if (rvalid) {
+              const float* tp = p.target + ((size_t)b * p.P + pix) * 3;
+              const float* wp = p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const float t = __ldg(tp + c), w = __ldg(wp + c);
+                const float er = o[c] - t;
+                part[0] = fmaf(er * er, w, part[0]);
+                part[1 + c] = o[c] * t;
+                part[4 + c] = o[c] * o[c];
+                part[7 + c] = t * t;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < kLossPartials; ++i) {
+              float x = part[i];
+#pragma unroll
+              for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+              part[i] = x;
+            }
+            if (lane == 0) {
+              float* lp = p.loss_part + ((size_t)tile * 4 + q) * kLossPartials;
+#pragma unroll
+              for (int i = 0; i < kLossPartials; ++i) lp[i] = part[i];
+            }
+          }
+        }
+        tc_fence_before();
+      }
+    }
   } else {
     // ============================================================ epilogue groups
     const int g = (warp - 2) >> 3;                  // sub-tile handled by this group
@@ -259,7 +461,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
         uint4 hv, uv;
         sin8<kTrain>(a, hv, uv);
         *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
-        if (kTrain) *reinterpret_cast<uint4*>(st_u + stash_off(row, kg, kH)) = uv;
+        if (kTrain && !(RENI_ABL & 1)) *reinterpret_cast<uint4*>(st_u + stash_off(row, kg, kH)) = uv;
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_ready[g]);
@@ -292,7 +494,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
             uint4 hv, uv;
             sin8<kTrain>(a, hv, uv);
             *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
-            if (kTrain) *reinterpret_cast<uint4*>(su + stash_off(row, kg, kH)) = uv;
+            if (kTrain && !(RENI_ABL & 1)) *reinterpret_cast<uint4*>(su + stash_off(row, kg, kH)) = uv;
           }
         };
         {

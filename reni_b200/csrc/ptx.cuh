@@ -9,6 +9,15 @@ namespace reni {
 
 #define DEVINL __device__ __forceinline__
 
+// Ablation switches for bottleneck attribution (tools/build_variants.sh builds timing-only variants; results are
+// wrong by construction): 1 = no stash stores, 2 = no MUFU (sin/cos replaced by a multiply), 4 = no tcgen05.mma issue,
+// 8 = no phase-stash loads in the delta chain.
+#ifndef RENI_ABL
+#define RENI_ABL 0
+#endif
+DEVINL float abl_sin(float x) { return (RENI_ABL & 2) ? x * 0.5f : __sinf(x); }
+DEVINL float abl_cos(float x) { return (RENI_ABL & 2) ? x * 0.5f : __cosf(x); }
+
 DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 DEVINL uint32_t lane_id() {
@@ -90,6 +99,7 @@ DEVINL void tmem_dealloc(uint32_t taddr) {  // whole warp (the allocating one)
 
 // D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16/bf16 in, fp32 accumulate), one thread issues.
 DEVINL void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (RENI_ABL & 4) return;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"

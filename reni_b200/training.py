@@ -79,7 +79,7 @@ class RENITrainer:
     def __init__(self, model: _DecoderBase, task: str, sidelen: int, lr: float = 1e-5,
                  prior_loss_weight: float = 1e-7, cosine_similarity_weight: float = 1e-4,
                  kld_weighting: float = 1e-4, mask: Optional[torch.Tensor] = None, process_group=None,
-                 ddp_latent_scaling: bool = True):
+                 ddp_latent_scaling: bool = True, cuda_graph: bool = False):
         if task not in ("FIT_DECODER", "FIT_LATENT"):
             raise NotImplementedError("FIT_INVERSE needs the PyTorch3D renderer and is out of scope for this path")
         self.model = model
@@ -97,6 +97,10 @@ class RENITrainer:
         self.is_vad = isinstance(model, RENIVariationalAutoDecoder)
         self.fixed = task == "FIT_LATENT"
         self._ws = Workspace()
+        # cuda_graph=True: the whole step (weight images, prologue, fwd, loss, bwd, grad exchange) is captured once per
+        # batch shape and replayed from static input buffers -- ~12 launches become one, which matters for a <1 ms step
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs: Dict[tuple, tuple] = {}
         # optimiser: Adam(lr) with default betas -- the cfg betas are never passed (RENI_module.py:191-192)
         if self.fixed:
             opt_params = [model.mu] if self.is_vad else [model.Z]  # RENI_module.py:178-183
@@ -122,6 +126,40 @@ class RENITrainer:
 
     def training_step(self, batch, batch_idx: int = 0) -> Dict[str, torch.Tensor]:
         """Same inputs and returned keys as RENI_module.training_step; gradients are left in ``.grad``."""
+        if self.cuda_graph and not (self.is_vad and not self.fixed):  # (the VAD sampler draws from torch's RNG: eager)
+            return self._graphed_step(batch)
+        return self._eager_step(batch)
+
+    def _graphed_step(self, batch) -> Dict[str, torch.Tensor]:
+        imgs, idx = batch
+        idx = torch.as_tensor(idx, dtype=torch.long)
+        key = (tuple(imgs.shape), imgs.dtype, int(idx.numel()))
+        entry = self._graphs.get(key)
+        if entry is None:
+            s_imgs = torch.empty(imgs.shape, dtype=imgs.dtype, device=self.device)
+            s_idx = torch.empty(idx.shape, dtype=torch.long, device=self.device)
+            s_imgs.copy_(imgs)
+            s_idx.copy_(idx)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):  # warm-up outside capture: lazy allocations, function attributes, NCCL
+                for _ in range(2):
+                    self._ws.prepared_key = None
+                    self._eager_step((s_imgs, s_idx))
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            self._ws.prepared_key = None  # the fp32 -> fp16 weight conversion is part of every replayed step
+            with torch.cuda.graph(graph):
+                log = self._eager_step((s_imgs, s_idx))
+            entry = (graph, s_imgs, s_idx, log)
+            self._graphs[key] = entry
+        graph, s_imgs, s_idx, log = entry
+        s_imgs.copy_(imgs, non_blocking=True)
+        s_idx.copy_(idx, non_blocking=True)
+        graph.replay()
+        return log
+
+    def _eager_step(self, batch) -> Dict[str, torch.Tensor]:
         imgs, idx = batch
         B = imgs.shape[0]
         imgs = imgs.permute(0, 2, 3, 1).reshape(B, -1, 3)  # (B,C,H,W) -> (B,P,3)   RENI_module.py:83-84
