@@ -124,6 +124,11 @@ int32_t reni_loss_forward_backward(const reni_config_t* cfg, const float* Z, con
  * [6] end of the step.  n = 0 clears.  Thread-local; this is the only state the library keeps. */
 int32_t reni_debug_set_phase_events(void* const* host_events, int32_t n);
 
+/* Debug hook: device buffer of 3 x 4096 uint64 into which CTA 0 of the calling thread's next forward kernels
+ * writes a clock64 timeline (event code << 48 | clock) per role: [0] MMA issuer, [1], [2] epilogue groups.
+ * NULL clears.  Used by tools/trace_fwd.py to read the pipeline's critical path. */
+int32_t reni_debug_set_trace(void* device_buffer);
+
 /* Debug hook: cudaGetErrorString of the last CUDA runtime error this thread saw inside the library
  * ("no error" if none); lets a caller turn RENI_ERR_CUDA into a readable message. */
 const char* reni_debug_last_cuda_error(void);
@@ -134,6 +139,18 @@ int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_im
                            uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t a_kstep,
                            uint32_t b_kstep, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t n,
                            uint32_t ksteps, float* d_out, void* stream);
+
+/* Same, for a CTA pair: one cluster of two CTAs, tcgen05.mma.cta_group::2 with M = 256.  a_img holds two
+ * operand images back to back (rows 0..127, rows 128..255), b_img the two N/2-row halves of B; the descriptor
+ * fields apply to each CTA's own image.  d_out is 256 x N, row-major. */
+int32_t reni_selftest_umma2(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes,
+                           uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t a_kstep,
+                           uint32_t b_kstep, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t n,
+                           uint32_t ksteps, float* d_out, void* stream);
+
+/* Debug probe: does a bulk copy into a CTA's own shared memory complete on an mbarrier of its cluster peer?
+ * result[0] = 1 if the leader's barrier completed, result[1], result[2] = byte sums each CTA read back. */
+int32_t reni_probe_remote_tx(const void* src, uint32_t bytes, uint32_t* result, void* stream);
 
 #ifdef __cplusplus
 }

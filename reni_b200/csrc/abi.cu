@@ -10,6 +10,13 @@
 #include "layout.cuh"
 #include "small_kernels.cuh"
 
+#ifndef RENI_NO_FORK
+#define RENI_NO_FORK 0  // 1: keep every kernel of the step on the caller's stream (A/B switch for the fork/join)
+#endif
+#ifndef RENI_FWD_PAIR
+#define RENI_FWD_PAIR 0
+#endif
+
 using namespace reni;
 
 namespace {
@@ -41,6 +48,7 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   };
   w.wf = take(L * kWImageBytes);
   w.wb = take(L * kWImageBytes);
+  w.wf2 = take(L * kWImageBytes);
   w.w6f = take(kW6ImageBytes);
   w.w6b = take(kW6ImageBytes);
   w.bias = take((L * kH + 16) * 4);
@@ -75,6 +83,7 @@ T* at(void* ws, int64_t off) {
 // step so a caller can time each kernel on the launching stream.  Thread-local; empty by default.
 thread_local cudaEvent_t g_phase_events[16];
 thread_local int g_num_phase_events = 0;
+thread_local unsigned long long* g_trace = nullptr;  // reni_debug_set_trace
 inline void mark_phase(int i, cudaStream_t s) {
   if (i < g_num_phase_events && g_phase_events[i] != nullptr) cudaEventRecord(g_phase_events[i], s);
 }
@@ -168,6 +177,7 @@ int32_t reni_prepare_weights(const reni_config_t* c, const float* const* host_we
   }
   p.wf = at<__half>(ws, w.wf);
   p.wb = at<__half>(ws, w.wb);
+  p.wf2 = at<__half>(ws, w.wf2);
   p.w6f = at<__half>(ws, w.w6f);
   p.w6b = at<__half>(ws, w.w6b);
   p.bias = at<float>(ws, w.bias);
@@ -209,6 +219,8 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
     q.in_features = (int)reni_in_features(c);
     q.equivariance = c->equivariance;
     q.omega0 = c->first_omega_0;
+    q.scalars = (flags & RENI_FLAG_LOSS) ? at<float>(ws, w.scalars) : nullptr;
+    q.fused_S = 1.5f * (float)P;  // gradient scale of the fused loss: S = 3P/2 (see reni_loss_finish_kernel)
     const size_t smem = (size_t)(q.in_features + 3 * q.N) * sizeof(float);
     if (smem > 48 * 1024)
       note(cudaFuncSetAttribute(reni_prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -223,6 +235,7 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   p.d_bstride = d_bstride;
   p.mc = at<float>(ws, w.mc);
   p.wf = at<__half>(ws, w.wf);
+  p.wf2 = at<__half>(ws, w.wf2);
   p.w6f = at<__half>(ws, w.w6f);
   p.bias = at<float>(ws, w.bias);
   p.out = out;
@@ -239,17 +252,42 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   p.out_tanh = c->output_activation == 1;
   p.last_sine = c->last_layer_linear ? 0 : 1;
   p.so2 = c->equivariance == RENI_EQ_SO2;
+  p.trace = g_trace;
   const int npairs = (p.ntiles + 1) / 2;
-  const int grid = npairs < sms ? npairs : sms;
   const bool train = (flags & RENI_FLAG_SAVE_FOR_BACKWARD) != 0;
+  // CTA pairs (cluster of 2) share the weight stream: half the L2 -> SM weight traffic per SM
+  const bool pair_mode = RENI_FWD_PAIR != 0;
+  int grid = npairs < sms ? npairs : sms;
+  if (pair_mode) {  // one cluster of two CTAs per tile quad
+    const int nquads = (p.ntiles + 3) / 4;
+    const int nclusters = nquads < sms / 2 ? nquads : sms / 2;
+    grid = 2 * nclusters;
+  }
   cudaError_t e;
   auto launch = [&](auto kernel) {
     e = note(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kTotal));
     if (e != cudaSuccess) return;
-    kernel<<<grid, kFwdThreads, FwdSmem::kTotal, stream>>>(p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kFwdThreads);
+    cfg.dynamicSmemBytes = FwdSmem::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair_mode ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = note(cudaLaunchKernelEx(&cfg, kernel, p));
   };
-  if (train) launch(reni_fwd_kernel<true, false>);
-  else launch(reni_fwd_kernel<false, true>);
+  if (pair_mode) {
+    if (train) launch(reni_fwd_kernel<true, false, true>);
+    else launch(reni_fwd_kernel<false, true, true>);
+  } else {
+    if (train) launch(reni_fwd_kernel<true, false, false>);
+    else launch(reni_fwd_kernel<false, true, false>);
+  }
   if (e != cudaSuccess) return RENI_ERR_CUDA;
   mark_phase(2, stream);
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
@@ -261,7 +299,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
                                int64_t d_bstride, const float* weight0, int64_t B, int64_t P, const float* out,
                                const float* grad_out, const float* target, const float* sw, int64_t sw_bstride,
                                float alpha, float* dZ, float* const* host_dW, float* const* host_db, void* ws,
-                               int32_t flags, cudaStream_t stream) {
+                               int32_t flags, cudaStream_t stream, int use_cos = 1, SideStream* side = nullptr) {
   const int sms = num_sms();
   if (sms <= 0) return RENI_ERR_NO_DEVICE;
   const bool need_dw = (flags & RENI_FLAG_NEED_DW) != 0;
@@ -294,6 +332,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   p.L = L;
   p.out_tanh = c->output_activation == 1;
   p.d_slots = need_dw ? L + 1 : 1;
+  p.use_cos = use_cos;
   const int npairs = (ntiles + 1) / 2;
   const int grid = npairs < sms ? npairs : sms;
   if (need_dw) {
@@ -313,9 +352,8 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   // fork: the map-level backward below only needs dmc from the delta chain; with the per-kernel timing hook active
   // everything stays on the caller's stream so the phase events keep their meaning
   cudaStream_t mstream = stream;
-  SideStream* side = nullptr;
-  if (need_dw && g_num_phase_events == 0) {
-    if (!side_stream(&side)) return RENI_ERR_CUDA;
+  if (need_dw && g_num_phase_events == 0 && !RENI_NO_FORK) {
+    if (side == nullptr && !side_stream(&side)) return RENI_ERR_CUDA;
     if (note(cudaEventRecord(side->fork, stream)) != cudaSuccess) return RENI_ERR_CUDA;
     if (note(cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return RENI_ERR_CUDA;
     mstream = side->stream;
@@ -390,6 +428,11 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   return RENI_OK;
 }
 
+int32_t reni_debug_set_trace(void* device_buffer) {
+  g_trace = static_cast<unsigned long long*>(device_buffer);
+  return RENI_OK;
+}
+
 const char* reni_debug_last_cuda_error(void) { return cudaGetErrorString(g_last_cuda); }
 
 int32_t reni_debug_set_phase_events(void* const* events, int32_t n) {
@@ -444,7 +487,17 @@ int32_t reni_loss_forward_backward(const reni_config_t* c, const float* Z, const
                             ws_bytes, flags, stream_);
   if (rc != RENI_OK) return rc;
   const WorkspaceLayout w = make_layout(c, B, P, flags);
-  if (cudaMemsetAsync(loss_out, 0, 16, stream) != cudaSuccess) return RENI_ERR_CUDA;
+  // Without the cosine term the backward needs nothing from the loss reduction (S = 3P/2 is written by the prologue,
+  // the per-map cosine coefficients are not read): the reduction then runs on the side stream under the delta chain.
+  SideStream* side = nullptr;
+  cudaStream_t lstream = stream;
+  if (!use_cosine && g_num_phase_events == 0 && !RENI_NO_FORK) {
+    if (!side_stream(&side)) return RENI_ERR_CUDA;
+    if (note(cudaEventRecord(side->fork, stream)) != cudaSuccess) return RENI_ERR_CUDA;
+    if (note(cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return RENI_ERR_CUDA;
+    lstream = side->stream;
+  }
+  if (cudaMemsetAsync(loss_out, 0, 16, lstream) != cudaSuccess) return RENI_ERR_CUDA;
   LossFinishParams f{};
   f.loss_part = at<float>(ws, w.loss_part);
   f.sw = sw;
@@ -460,10 +513,11 @@ int32_t reni_loss_forward_backward(const reni_config_t* c, const float* Z, const
   f.alpha = alpha;
   f.beta = beta;
   f.use_cos = use_cosine;
-  reni_loss_finish_kernel<<<(unsigned)B, 128, 0, stream>>>(f);
+  reni_loss_finish_kernel<<<(unsigned)B, 128, 0, lstream>>>(f);
   if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
-  return launch_backward(c, w, Z, D, d_bstride, host_weights[0], B, P, out, nullptr, target, sw, sw_bstride, alpha, dZ,
-                         host_dW, host_db, ws, flags, stream);
+  rc = launch_backward(c, w, Z, D, d_bstride, host_weights[0], B, P, out, nullptr, target, sw, sw_bstride, alpha, dZ,
+                       host_dW, host_db, ws, flags, stream, use_cosine, side);
+  return rc;  // (launch_backward joins the side stream before it returns)
 }
 
 int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, uint32_t a_lbo,
@@ -493,6 +547,71 @@ int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_im
       cudaSuccess)
     return RENI_ERR_CUDA;
   reni_selftest_umma_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+int32_t reni_selftest_umma2(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, uint32_t a_lbo,
+                            uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t a_kstep, uint32_t b_kstep,
+                            uint32_t a_mn, uint32_t b_mn, uint32_t n, uint32_t ksteps, float* d_out, void* stream) {
+  if (a_img == nullptr || b_img == nullptr || d_out == nullptr) return RENI_ERR_BAD_ARGUMENT;
+  if (n < 16 || n > 256 || (n % 16) != 0 || (a_bytes % 16) != 0 || (b_bytes % 16) != 0) return RENI_ERR_BAD_ARGUMENT;
+  SelfTestParams p{};
+  p.a_img = static_cast<const uint8_t*>(a_img);
+  p.b_img = static_cast<const uint8_t*>(b_img);
+  p.d_out = d_out;
+  p.a_bytes = a_bytes;
+  p.b_bytes = b_bytes;
+  p.a_lbo = a_lbo;
+  p.a_sbo = a_sbo;
+  p.b_lbo = b_lbo;
+  p.b_sbo = b_sbo;
+  p.a_kstep = a_kstep;
+  p.b_kstep = b_kstep;
+  p.a_mn = a_mn;
+  p.b_mn = b_mn;
+  p.N = n;
+  p.ksteps = ksteps;
+  const size_t smem = ((a_bytes + 1023) & ~1023u) + b_bytes + 1024;
+  if (smem > 220 * 1024) return RENI_ERR_BAD_ARGUMENT;
+  if (note(cudaFuncSetAttribute(reni_selftest_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=
+      cudaSuccess)
+    return RENI_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (note(cudaLaunchKernelEx(&cfg, reni_selftest_umma2_kernel, p)) != cudaSuccess) return RENI_ERR_CUDA;
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+int32_t reni_probe_remote_tx(const void* src, uint32_t bytes, uint32_t* result, void* stream) {
+  if (src == nullptr || result == nullptr || bytes == 0 || (bytes % 16) != 0 || bytes > 65536) return RENI_ERR_BAD_ARGUMENT;
+  if (note(cudaFuncSetAttribute(reni_probe_remote_tx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560)) !=
+      cudaSuccess)
+    return RENI_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = 66560;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (note(cudaLaunchKernelEx(&cfg, reni_probe_remote_tx_kernel, static_cast<const uint8_t*>(src), bytes, result)) !=
+      cudaSuccess)
+    return RENI_ERR_CUDA;
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 

@@ -42,6 +42,7 @@ struct BwdParams {
   float* dmc;             // (B, 5, 256): dM_b rows 0..3, dc_b row 4; accumulated with atomics (caller zeroes)
   int B, P, tiles_per_map, ntiles, L;
   int out_tanh, d_slots, so2;
+  int use_cos;            // fused loss: 0 = no cosine term (map_loss is not read, it may still be in flight)
 };
 
 struct BwdSmem {
@@ -109,7 +110,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wb);
-      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
+      // descending tile order: the forward kernel's last tiles are the freshest in L2 (measured: -37 us at cfg 2)
+      const int pair = npairs - 1 - pi;
         const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
         for (int g = 0; g < nsub; ++g)
           bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
@@ -141,7 +144,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
       const uint32_t w6_base = smem_u32(smem + BwdSmem::kW6);
       uint32_t st = 0, ph = 0;
       uint32_t a_ph0 = 0, a_ph1 = 0;
-      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
+      // descending tile order: the forward kernel's last tiles are the freshest in L2 (measured: -37 us at cfg 2)
+      const int pair = npairs - 1 - pi;
         const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
         for (int l = L + 1; l >= 0; --l) {  // l = L+1: output layer (K = 16); L..1: hidden layer l; 0: layer-0 reduction
           for (int g = 0; g < nsub; ++g) {
@@ -200,9 +205,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
     uint32_t acc_ph = 0;
     const float S = __ldg(p.scalars);
 
-    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
+      // descending tile order: the forward kernel's last tiles are the freshest in L2 (measured: -37 us at cfg 2)
+      const int pair = npairs - 1 - pi;
       const int tile = 2 * pair + g;
-      if (tile >= p.ntiles) break;
+      if (tile >= p.ntiles) continue;  // (the ragged last pair is visited first)
       const int b = tile / p.tiles_per_map;
       const int pix = (tile - b * p.tiles_per_map) * kTileRows + row;
       const bool rvalid = pix < p.P;
@@ -229,7 +236,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
             const float o = __ldg(p.out + e + c);
             const float t = __ldg(p.target + e + c);
             // S*g_o = (o-t)*sw + coefA*t + coefB*o   with S = 3P/2
-            float gg = (o - t) * __ldg(wp + c) + __ldg(ml + 16 + c) * t + __ldg(ml + 19 + c) * o;
+            float gg = (o - t) * __ldg(wp + c);
+            if (p.use_cos) gg += __ldg(ml + 16 + c) * t + __ldg(ml + 19 + c) * o;
             if (p.out_tanh) gg *= (1.f - o * o);
             gy[c] = gg;
           }

@@ -43,6 +43,7 @@ struct FwdParams {
   int64_t d_bstride;     // elements between maps (0: one grid shared by all maps)
   const float* mc;       // (B, 5, 256): rows 0..3 = omega0*M_b, row 4 = omega0*c_b
   const __half* wf;      // L weight images [k/8][n][8] of omega_l * W_l
+  const __half* wf2;     // the same, split for CTA pairs: [l][n half][k/8][128][8]
   const __half* w6f;     // [k/8 32][n 16][8] final-layer image
   const float* bias;     // L*256 (omega_l * b_l) then 16 (final bias, zero padded)
   float* out;            // (B, P, 3)
@@ -53,20 +54,32 @@ struct FwdParams {
   float* loss_part;      // (ntiles, 4 warps, 10)
   int B, P, tiles_per_map, ntiles, L;
   int out_tanh, last_sine, so2;
+  unsigned long long* trace;  // debug: per-role clock64 timeline of CTA 0 (reni_debug_set_trace), else null
 };
 
 struct FwdSmem {
   static constexpr int kA = 0;                                        // 2 x 64 KB activation tile images
   static constexpr int kRing = kA + 2 * kTileImageBytes;              // weight chunk ring
-  static constexpr int kW6 = kRing + kFwdStages * kWChunkBytes;       // final-layer image
+  static constexpr int kMaxStages = 9;                                // paired mode: 9 x 8 KB half chunks
+  static constexpr int kRingBytes = kMaxStages * 8192 > kFwdStages * kWChunkBytes ? kMaxStages * 8192
+                                                                                   : kFwdStages * kWChunkBytes;
+  static constexpr int kW6 = kRing + kRingBytes;                      // final-layer image
   static constexpr int kBias = kW6 + kW6ImageBytes;                   // (kMaxHiddenLayers*256 + 16) floats
   static constexpr int kMc = kBias + (kMaxHiddenLayers * kH + 16) * 4;  // 2 x 5 x 256 floats
   static constexpr int kBars = kMc + 2 * 5 * kH * 4;                  // mbarriers
-  static constexpr int kNumBars = 2 * kFwdStages + 4;
+  static constexpr int kNumBars = 3 * kMaxStages + 6;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemPtr + 16;
 };
 static_assert(FwdSmem::kTotal <= 232448, "forward kernel shared memory over budget");
+
+// debug timeline: role r (0 MMA issuer, 1/2 epilogue group 0/1) appends (code << 48 | clock) to its 4096-entry lane
+DEVINL void trace_ev(const FwdParams& p, int role, uint32_t& n, uint32_t code) {
+  if (p.trace != nullptr && blockIdx.x == 0 && n < 4096) {
+    p.trace[role * 4096 + n] = ((unsigned long long)code << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+    ++n;
+  }
+}
 
 // sin of 8 pre-activations -> packed fp16 and, if kPhase, their packed 16-bit phases
 template <bool kPhase>
@@ -83,112 +96,191 @@ DEVINL void sin8(const float (&a)[8], uint4& hv, uint4& uv) {
   }
 }
 
-template <bool kTrain, bool kAllHands>
+template <bool kTrain, bool kAllHands, bool kPair>
 __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBars);
-  uint64_t* w_full = bars;                      // [kFwdStages]
-  uint64_t* w_empty = bars + kFwdStages;        // [kFwdStages]
-  uint64_t* a_ready = bars + 2 * kFwdStages;    // [2]  epilogue group -> MMA (256 arrivals)
+  constexpr int kStages = kPair ? FwdSmem::kMaxStages : kFwdStages;
+  uint64_t* w_full = bars;                                 // [kStages]
+  uint64_t* w_empty = bars + FwdSmem::kMaxStages;          // [kStages]
+  uint64_t* w_full_peer = bars + 2 * FwdSmem::kMaxStages;  // [kStages] leader only: the peer's half chunk has landed
+  uint64_t* a_ready = bars + 3 * FwdSmem::kMaxStages;      // [2]  epilogue -> MMA (one arrival per thread)
   uint64_t* acc_full = a_ready + 2;             // [2]  MMA -> epilogue group (tcgen05.commit)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + FwdSmem::kTmemPtr);
   float* s_bias = reinterpret_cast<float*>(smem + FwdSmem::kBias);
 
   const int L = p.L;
-  const int npairs = (p.ntiles + 1) >> 1;
+  // Work distribution.  Unpaired: CTA c owns tiles {2u, 2u+1}, u = c, c + grid, ...  Paired (cluster of 2,
+  // tcgen05.mma.cta_group::2): cluster k owns tile quads q = k, k + nclusters, ...; the leader (rank 0) owns tiles
+  // {4q, 4q+1}, its peer {4q+2, 4q+3}.  One M = 256 MMA covers sub-tile g of both CTAs, each CTA holds (and streams
+  // from L2) only its 128-column half of every weight matrix: half the weight bytes enter each SM.
+  const uint32_t crank = kPair ? cluster_ctarank() : 0;
+  const int unit_tiles = kPair ? 4 : 2;
+  const int nunits = (p.ntiles + unit_tiles - 1) / unit_tiles;
+  const int nworkers = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int worker = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int iters = (nunits - worker + nworkers - 1) / nworkers;  // same for both CTAs of a pair
+  auto clamp02 = [](int x) { return x < 0 ? 0 : (x > 2 ? 2 : x); };
+  constexpr int kChunkBytes = kPair ? 8192 : kWChunkBytes;  // paired: [4 k-groups][128 n][8] = K 32 of one N half
+  constexpr int kChunks = kChunksPerLayer;
+  uint64_t* a_ready_peer = acc_full + 2;  // [2] leader only: the peer's sub-tile g is ready (one arrival per warp)
+  constexpr uint32_t kPeerWarps = kAllHands ? 16 : 8;
 
   // ---------------------------------------------------------------- one-time setup
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kFwdStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
+      mbar_init(&w_full_peer[i], 1);
     }
     mbar_init(&a_ready[0], kAllHands ? kEpiThreads : kGroupThreads);
     mbar_init(&a_ready[1], kAllHands ? kEpiThreads : kGroupThreads);
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
+    mbar_init(&a_ready_peer[0], kPeerWarps);
+    mbar_init(&a_ready_peer[1], kPeerWarps);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  if (warp == 1) {
+    if (kPair) tmem_alloc2<512>(tmem_ptr);
+    else tmem_alloc<512>(tmem_ptr);
+  }
   {  // resident small operands: final-layer weight image + all biases
     const uint4* src = reinterpret_cast<const uint4*>(p.w6f);
     uint4* dst = reinterpret_cast<uint4*>(smem + FwdSmem::kW6);
-    for (int i = threadIdx.x; i < kW6ImageBytes / 16; i += kFwdThreads) dst[i] = src[i];
+    if (kPair) {  // this CTA's 8 of the 16 padded output rows: [k/8][8][8]
+      for (int i = threadIdx.x; i < kW6ImageBytes / 32; i += kFwdThreads)
+        dst[i] = src[(i >> 3) * kW6N + crank * 8 + (i & 7)];
+    } else {
+      for (int i = threadIdx.x; i < kW6ImageBytes / 16; i += kFwdThreads) dst[i] = src[i];
+    }
     const int nb = L * kH + 16;
     for (int i = threadIdx.x; i < nb; i += kFwdThreads) s_bias[i] = p.bias[i];
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // both CTAs' barriers and TMEM exist before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // "sub-tile g of this CTA is in shared memory": the leader's (or an unpaired CTA's) epilogue threads arrive on the
+  // local barrier; the peer's warps arrive on the leader's a_ready_peer, one remote arrival per warp
+  const uint32_t ra_peer = kPair ? mapa_u32(smem_u32(a_ready_peer), 0) : 0;
+  auto signal_ready = [&](int g) {
+    if (kPair && crank == 1) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(ra_peer + g * 8);
+    } else {
+      mbar_arrive(&a_ready[g]);
+    }
+  };
 
   if (warp == 0) {
     // ============================================================ weight-chunk producer
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wf);
-      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-        const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(kPair ? p.wf2 : p.wf);
+      for (int it = 0; it < iters; ++it) {
+        const int ubase = (worker + it * nworkers) * unit_tiles;
+        const int nstream = clamp02(p.ntiles - ubase);  // passes the (leader's) MMA issuer makes over each layer
         for (int l = 0; l < L; ++l) {
-          for (int g = 0; g < nsub; ++g) {
-            for (int c = 0; c < kChunksPerLayer; ++c) {
+          for (int g = 0; g < nstream; ++g) {
+            for (int c = 0; c < kChunks; ++c) {
               mbar_wait(&w_empty[st], ph ^ 1);
-              mbar_arrive_expect_tx(&w_full[st], kWChunkBytes);
-              bulk_g2s(smem + FwdSmem::kRing + st * kWChunkBytes,
-                       wsrc + (size_t)l * kWImageBytes + (size_t)c * kWChunkBytes, kWChunkBytes, &w_full[st]);
-              if (++st == kFwdStages) { st = 0; ph ^= 1; }
+              mbar_arrive_expect_tx(&w_full[st], kChunkBytes);
+              const size_t off = kPair ? ((size_t)(l * 2 + crank) * (kWImageBytes / 2) + (size_t)c * kChunkBytes)
+                                       : ((size_t)l * kWImageBytes + (size_t)c * kChunkBytes);
+              bulk_g2s(smem + FwdSmem::kRing + st * kChunkBytes, wsrc + off, kChunkBytes, &w_full[st]);
+              if (++st == kStages) { st = 0; ph ^= 1; }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_h = umma_idesc_f16(128, 256, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_f16(128, kW6N, 0, 0);
+    if (lane == 0 && crank == 0) {
+      // ============================================================ MMA issuer (paired: the leader issues for both)
+      constexpr uint32_t idesc_h = umma_idesc_f16(kPair ? 256 : 128, 256, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_f16(kPair ? 256 : 128, kW6N, 0, 0);
+      constexpr uint32_t kBRows = kPair ? 128 : 256;   // rows of B in this CTA's chunk
+      constexpr uint32_t kW6Rows = kPair ? 8 : kW6N;
       const uint32_t a_base = smem_u32(smem + FwdSmem::kA);
       const uint32_t ring_base = smem_u32(smem + FwdSmem::kRing);
       const uint32_t w6_base = smem_u32(smem + FwdSmem::kW6);
       uint32_t st = 0, ph = 0;
-      uint32_t a_ph0 = 0, a_ph1 = 0;
-      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-        const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
+      uint32_t a_ph = 0, ap_ph = 0;  // bit g: parity of a_ready[g] / a_ready_peer[g]
+      uint32_t tn = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int ubase = (worker + it * nworkers) * unit_tiles;
+        const int nsub = clamp02(p.ntiles - ubase);                      // live sub-tiles of this (the leader) CTA
+        const int nsub_peer = kPair ? clamp02(p.ntiles - ubase - 2) : 0;  // ... of the peer
         for (int l = 1; l <= L + 1; ++l) {
           for (int g = 0; g < nsub; ++g) {
-            if (g == 0) { mbar_wait(&a_ready[0], a_ph0); a_ph0 ^= 1; }
-            else        { mbar_wait(&a_ready[1], a_ph1); a_ph1 ^= 1; }
+            mbar_wait(&a_ready[g], (a_ph >> g) & 1);
+            a_ph ^= 1u << g;
+            if (g < nsub_peer) {
+              mbar_wait(&a_ready_peer[g], (ap_ph >> g) & 1);
+              ap_ph ^= 1u << g;
+            }
             tc_fence_after();
+            trace_ev(p, 0, tn, 0x100 | (l << 4) | g);  // operand ready seen
             const uint32_t a_tile = a_base + g * kTileImageBytes;
             const uint32_t d_tmem = tmem_base + g * 256;
+            const uint16_t live_mask = (g < nsub_peer) ? 0x3 : 0x1;
             if (l <= L) {
-              for (int c = 0; c < kChunksPerLayer; ++c) {
+              for (int c = 0; c < kChunks; ++c) {
                 mbar_wait(&w_full[st], ph);
+                if (kPair) mbar_wait(&w_full_peer[st], ph);
                 tc_fence_after();
-                const uint32_t b_tile = ring_base + st * kWChunkBytes;
+                const uint32_t b_tile = ring_base + st * kChunkBytes;
+                constexpr int kSteps = kChunkBytes / (kBRows * 32);  // K = 16 steps per chunk
 #pragma unroll
-                for (int ks = 0; ks < kWChunkK / 16; ++ks) {
-                  // A: [k/8][128][8] -> 2048 B per 8-column group; B: chunk [4][256][8] -> 4096 B per group
-                  const uint64_t da = umma_smem_desc(a_tile + (c * 4 + ks * 2) * 2048, 2048, 128);
-                  const uint64_t db = umma_smem_desc(b_tile + (ks * 2) * 4096, 4096, 128);
-                  umma_f16_ss(d_tmem, da, db, idesc_h, (c | ks) != 0);
+                for (int ks = 0; ks < kSteps; ++ks) {
+                  // A: [k/8][128][8] -> 2048 B per 8-column group; B: [k/8][kBRows][8] -> kBRows*16 B per group
+                  const uint64_t da = umma_smem_desc(a_tile + (c * kSteps + ks) * 4096, 2048, 128);
+                  const uint64_t db = umma_smem_desc(b_tile + ks * (kBRows * 32), kBRows * 16, 128);
+                  if (kPair) umma2_f16_ss(d_tmem, da, db, idesc_h, (c | ks) != 0);
+                  else umma_f16_ss(d_tmem, da, db, idesc_h, (c | ks) != 0);
                 }
-                umma_commit(&w_empty[st]);
-                if (++st == kFwdStages) { st = 0; ph ^= 1; }
+                if (kPair) umma2_commit_multicast(&w_empty[st], 0x3);
+                else umma_commit(&w_empty[st]);
+                if (++st == kStages) { st = 0; ph ^= 1; }
               }
             } else {
 #pragma unroll
               for (int ks = 0; ks < kH / 16; ++ks) {
-                const uint64_t da = umma_smem_desc(a_tile + (ks * 2) * 2048, 2048, 128);
-                const uint64_t db = umma_smem_desc(w6_base + (ks * 2) * (kW6N * 16), kW6N * 16, 128);
-                umma_f16_ss(d_tmem, da, db, idesc_o, ks != 0);
+                const uint64_t da = umma_smem_desc(a_tile + ks * 4096, 2048, 128);
+                const uint64_t db = umma_smem_desc(w6_base + ks * (kW6Rows * 32), kW6Rows * 16, 128);
+                if (kPair) umma2_f16_ss(d_tmem, da, db, idesc_o, ks != 0);
+                else umma_f16_ss(d_tmem, da, db, idesc_o, ks != 0);
               }
             }
-            umma_commit(&acc_full[g]);
+            if (kPair) umma2_commit_multicast(&acc_full[g], live_mask);
+            else umma_commit(&acc_full[g]);
+            trace_ev(p, 0, tn, 0x200 | (l << 4) | g);  // all MMAs of this pass issued
+          }
+        }
+      }
+    } else if (kPair && lane == 0) {
+      // ============================================================ peer relay: forwards "my half chunk has landed" to
+      // the leader's barriers (a bulk copy can only complete on an mbarrier of its destination CTA: probed on B200)
+      const uint32_t rw = mapa_u32(smem_u32(w_full_peer), 0);
+      uint32_t st = 0, ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int ubase = (worker + it * nworkers) * unit_tiles;
+        const int nsub_lead = clamp02(p.ntiles - ubase);
+        for (int l = 1; l <= L + 1; ++l) {
+          for (int g = 0; g < nsub_lead; ++g) {
+            if (l <= L) {
+              for (int c = 0; c < kChunks; ++c) {
+                mbar_wait(&w_full[st], ph);
+                mbar_arrive_remote(rw + st * 8);
+                if (++st == kStages) { st = 0; ph ^= 1; }
+              }
+            }
           }
         }
       }
@@ -203,9 +295,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
     float* s_mc_all = reinterpret_cast<float*>(smem + FwdSmem::kMc);
     uint32_t acc_ph = 0;  // bit g = phase parity of acc_full[g]
 
-    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
-      const int tile0 = 2 * pair, tile1 = min(2 * pair + 1, p.ntiles - 1);
+    for (int it = 0; it < iters; ++it) {
+      const int tbase = (worker + it * nworkers) * unit_tiles + 2 * (int)crank;  // this CTA's first tile
+      const int nsub = clamp02(p.ntiles - tbase);
+      if (nsub == 0) break;
+      const int tile0 = tbase, tile1 = min(tbase + 1, p.ntiles - 1);
       const int bmap0 = tile0 / p.tiles_per_map, bmap1 = tile1 / p.tiles_per_map;
       const int pix0 = (tile0 - bmap0 * p.tiles_per_map) * kTileRows + row;
       const int pix1 = (tile1 - bmap1 * p.tiles_per_map) * kTileRows + row;
@@ -242,7 +336,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
         uint8_t* a_tile = smem + FwdSmem::kA + g * kTileImageBytes;
         const float* s_mc = s_mc_all + g * 5 * kH;
         uint8_t* st_u = nullptr;
-        if (kTrain) st_u = reinterpret_cast<uint8_t*>(p.stash_u) + (size_t)(2 * pair + g) * (L + 1) * kTileImageBytes;
+        if (kTrain) st_u = reinterpret_cast<uint8_t*>(p.stash_u) + (size_t)(tbase + g) * (L + 1) * kTileImageBytes;
 #pragma unroll 2
         for (int k8 = 0; k8 < 8; ++k8) {
           const int kg = cq * 8 + k8;
@@ -268,7 +362,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
           if (kTrain && !(RENI_ABL & 1)) *reinterpret_cast<uint4*>(st_u + stash_off(row, kg, kH)) = uv;
         }
         fence_proxy_async_smem();
-        mbar_arrive(&a_ready[g]);
+        signal_ready(g);
       }
 
       // ---- hidden layers: bias + sin epilogue, TMEM -> registers -> smem tile image (in place); the sub-tiles alternate
@@ -278,7 +372,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
           uint8_t* a_tile = smem + FwdSmem::kA + g * kTileImageBytes;
           uint8_t* su = nullptr;
           if (kTrain)
-            su = reinterpret_cast<uint8_t*>(p.stash_u) + ((size_t)(2 * pair + g) * (L + 1) + l) * kTileImageBytes;
+            su = reinterpret_cast<uint8_t*>(p.stash_u) + ((size_t)(tbase + g) * (L + 1) + l) * kTileImageBytes;
           const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256 + cq * 64;
           mbar_wait(&acc_full[g], (acc_ph >> g) & 1);
           acc_ph ^= 1u << g;
@@ -322,7 +416,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
           }
           tc_fence_before();
           fence_proxy_async_smem();
-          mbar_arrive(&a_ready[g]);
+          signal_ready(g);
         }
       }
 
@@ -332,7 +426,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
         acc_ph ^= 1u << g;
         tc_fence_after();
         if (cq == 0) {
-          const int tile = 2 * pair + g;
+          const int tile = tbase + g;
           const int b = g ? bmap1 : bmap0, pix = g ? pix1 : pix0;
           const bool rvalid = pix < p.P;
           const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256;
@@ -402,9 +496,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
     float* s_mc = reinterpret_cast<float*>(smem + FwdSmem::kMc) + g * 5 * kH;
     const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256 + chalf * 128;
     uint32_t acc_ph = 0;
+    uint32_t tn = 0;
 
-    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      const int tile = 2 * pair + g;
+    for (int it = 0; it < iters; ++it) {
+      const int tile = (worker + it * nworkers) * unit_tiles + 2 * (int)crank + g;
       if (tile >= p.ntiles) break;
       const int b = tile / p.tiles_per_map;
       const int pix = (tile - b * p.tiles_per_map) * kTileRows + row;
@@ -464,15 +559,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
         if (kTrain && !(RENI_ABL & 1)) *reinterpret_cast<uint4*>(st_u + stash_off(row, kg, kH)) = uv;
       }
       fence_proxy_async_smem();
-      mbar_arrive(&a_ready[g]);
+      signal_ready(g);
 
       // ---- hidden layers: bias + sin epilogue, TMEM -> registers -> smem tile image (in place)
       for (int l = 1; l <= L; ++l) {
         const float* bl = s_bias + (l - 1) * kH + chalf * 128;
         uint8_t* su = kTrain ? st_u + (size_t)l * kTileImageBytes : nullptr;
+        if (e == 0 && lane == 0) trace_ev(p, 1 + g, tn, 0x300 | (l << 4) | g);  // waiting for the accumulator
         mbar_wait(&acc_full[g], acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
+        if (e == 0 && lane == 0) trace_ev(p, 1 + g, tn, 0x400 | (l << 4) | g);  // accumulator seen
         // TMEM -> registers in 16-column slices, double buffered: the next tcgen05.ld is in flight while this
         // slice goes through bias + sin + pack + store
         auto process16 = [&](const uint32_t (&v)[16], int it) {
@@ -512,7 +609,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
         }
         tc_fence_before();
         fence_proxy_async_smem();
-        mbar_arrive(&a_ready[g]);
+        signal_ready(g);
+        if (e == 0 && lane == 0) trace_ev(p, 1 + g, tn, 0x500 | (l << 4) | g);  // this warp's epilogue done
       }
 
       // ---- output layer (N = 16 padded): bias, optional sin, optional tanh, store, fused loss partials
@@ -578,9 +676,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // the pair's MMAs, multicast commits and remote arrivals are all behind us
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (kPair) tmem_dealloc2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 

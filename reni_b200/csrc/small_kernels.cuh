@@ -10,6 +10,8 @@ namespace reni {
 // Weight preparation: fp32 nn.Linear parameters -> fp16 tile images with omega folded in.
 //   wf[l]  (l = 1..L)  [k/8][n][8]  = omega_l     * W_l[n][k]          forward  B operand (N = out, K = in)
 //   wb[l]              [j/8][k][8]  = omega_{l-1} * W_l[j][k]          backward B operand (N = in,  K = out)
+//   wf2[l] [n/128][k/8][n%128][8]   = omega_l     * W_l[n][k]          forward B operand split in two N halves for
+//                                                                     CTA pairs (tcgen05.mma.cta_group::2)
 //   w6f                [k/8][16][8] = s * W_out[n][k]   (n < out_features, else 0);  s = omega if sine-last
 //   w6b                [c/8][256][8]= omega_L * s * W_out[c][k]
 //   bias               L*256: omega_l * b_l ; then 16: s * b_out
@@ -20,6 +22,7 @@ struct PrepParams {
   const float* b[kMaxHiddenLayers + 2];
   __half* wf;
   __half* wb;
+  __half* wf2;
   __half* w6f;
   __half* w6b;
   float* bias;
@@ -37,11 +40,13 @@ __global__ void reni_prep_weights_kernel(const PrepParams p) {
     const float om_b = (l == 0) ? p.first_omega : p.hidden_omega;  // omega of the layer feeding it
     __half* wf = p.wf + (size_t)l * kH * kH;
     __half* wb = p.wb + (size_t)l * kH * kH;
+    __half* wf2 = p.wf2 + (size_t)l * kH * kH;
     for (int i = tid; i < kH * kH; i += nthreads) {
       const int n = i / kH, k = i % kH;  // W[n][k], coalesced read
       const float w = W[i];
       wf[((k >> 3) * kH + n) * 8 + (k & 7)] = __float2half_rn(om_f * w);
       wb[((n >> 3) * kH + k) * 8 + (n & 7)] = __float2half_rn(om_b * w);
+      wf2[(((n >> 7) * (kH / 8) + (k >> 3)) * 128 + (n & 127)) * 8 + (k & 7)] = __float2half_rn(om_f * w);
     }
     for (int i = tid; i < kH; i += nthreads) p.bias[l * kH + i] = om_f * p.b[l + 1][i];
   } else {
@@ -77,12 +82,18 @@ struct PrologueParams {
   float* xfull;     // (B, 5, in_features): per-map input columns paired with [dM0..dM3, dc] for the dW0 GEMM (optional)
   int B, N, in_features, equivariance;  // 0 None, 1 SO2, 2 SO3
   float omega0;
+  float* scalars;  // fused loss: [0] = S, [1] = 1/S written here so the backward does not wait for the loss reduction
+  float fused_S;
 };
 
 __global__ void __launch_bounds__(256) reni_prologue_kernel(const PrologueParams p) {
   extern __shared__ float s_x[];  // in_features constants (0 where the column depends on the direction) + 3N latents
   const int b = blockIdx.y;
   const int N = p.N;
+  if (p.scalars != nullptr && blockIdx.x == 0 && b == 0 && threadIdx.x == 0) {
+    p.scalars[0] = p.fused_S;
+    p.scalars[1] = 1.f / p.fused_S;
+  }
   float* s_z = s_x + p.in_features;
   const float* Zb = p.Z + (size_t)b * N * 3;
   for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_z[i] = Zb[i];
@@ -225,6 +236,107 @@ __global__ void __launch_bounds__(128, 1) reni_selftest_umma_kernel(const SelfTe
   if (threadIdx.x < 32) tmem_dealloc<256>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Probe: can a (non-tensor) bulk copy into THIS CTA's shared memory complete its bytes on an mbarrier that lives in
+// the PEER CTA?  (cp.async.bulk.shared::cluster.global with a mapa'd mbarrier address.)  Both CTAs of a cluster copy
+// `bytes` from global into their own smem and signal the leader's barrier, which expects 2 x bytes.  The leader polls
+// a bounded number of times and reports: result[0] = 1 completed / 0 timed out, result[1 + rank] = byte sum seen by
+// each CTA in its own buffer.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) reni_probe_remote_tx_kernel(const uint8_t* src, uint32_t bytes,
+                                                                      uint32_t* result) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x == 0) {
+    if (rank == 0) mbar_arrive_expect_tx(&bar, 2 * bytes);
+    const uint32_t leader_bar = mapa_u32(smem_u32(&bar), 0);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem)),
+                 "l"(src + (size_t)rank * bytes), "r"(bytes), "r"(leader_bar)
+                 : "memory");
+    if (rank == 0) {
+      uint32_t ok = 0;
+      for (int i = 0; i < 2000000 && !ok; ++i) ok = mbar_try_wait(&bar, 0) ? 1u : 0u;
+      result[0] = ok;
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();  // (the leader's poll loop bounds how long the peer waits here)
+  if (threadIdx.x == 0) {
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < bytes; ++i) sum += smem[i];
+    result[1 + rank] = sum;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant of the self-test: one cluster of two CTAs, D[256 x N] = [A0; A1] * [B0; B1]^T with
+// tcgen05.mma.cta_group::2 -- CTA r supplies A_r (its 128 rows) and B_r (its N/2 rows of B), the leader (rank 0)
+// issues, the multicast commit releases both CTAs, each reads its own 128 accumulator rows.  Also exercises the
+// cross-CTA hand-shake the pipelined kernels use (remote mbarrier arrive + cluster-scope acquire).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) reni_selftest_umma2_kernel(const SelfTestParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_done, bar_peer;
+  __shared__ uint32_t tmem_ptr;
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + ((p.a_bytes + 1023) & ~1023u);
+  const uint8_t* ga = p.a_img + (size_t)rank * p.a_bytes;
+  const uint8_t* gb = p.b_img + (size_t)rank * p.b_bytes;
+  for (uint32_t i = threadIdx.x * 16; i < p.a_bytes; i += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(sa + i) = *reinterpret_cast<const uint4*>(ga + i);
+  for (uint32_t i = threadIdx.x * 16; i < p.b_bytes; i += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(sb + i) = *reinterpret_cast<const uint4*>(gb + i);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_done, 1);
+    mbar_init(&bar_peer, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc2<256>(&tmem_ptr);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr;
+  if (rank == 1 && threadIdx.x == 0) mbar_arrive_remote(mapa_u32(smem_u32(&bar_peer), 0));
+  if (rank == 0 && threadIdx.x == 0) {
+    mbar_wait_cluster(&bar_peer, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_f16(256, p.N, p.a_mn, p.b_mn);
+    for (uint32_t k = 0; k < p.ksteps; ++k) {
+      const uint64_t da = umma_smem_desc(smem_u32(sa) + k * p.a_kstep, p.a_lbo, p.a_sbo);
+      const uint64_t db = umma_smem_desc(smem_u32(sb) + k * p.b_kstep, p.b_lbo, p.b_sbo);
+      umma2_f16_ss(tmem_base, da, db, idesc, k != 0);
+    }
+    umma2_commit_multicast(&bar_done, 0x3);
+  }
+  __syncwarp();
+  mbar_wait(&bar_done, 0);
+  tc_fence_after();
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row = rank * 128 + warp * 32 + lane;
+  for (uint32_t c = 0; c < p.N; c += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem_base + ((warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p.d_out[row * p.N + c + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x < 32) tmem_dealloc2<256>(tmem_base);
+}
+
 }  // namespace reni
 
 namespace reni {
@@ -309,10 +421,6 @@ __global__ void __launch_bounds__(128) reni_loss_finish_kernel(const LossFinishP
     atomicAdd(p.loss_out + 1, mse);
     atomicAdd(p.loss_out + 2, prior);
     atomicAdd(p.loss_out + 3, cosl);
-    if (b == 0) {
-      p.scalars[0] = S;
-      p.scalars[1] = 1.f / S;
-    }
   }
 }
 

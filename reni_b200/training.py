@@ -101,6 +101,12 @@ class RENITrainer:
         # batch shape and replayed from static input buffers -- ~12 launches become one, which matters for a <1 ms step
         self.cuda_graph = bool(cuda_graph)
         self._graphs: Dict[tuple, tuple] = {}
+        # prefetch(): double-buffered device staging filled on a copy stream, so the host->device copy of batch i+1
+        # runs under the step of batch i (what a pinned-memory DataLoader with prefetching gives the reference)
+        self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._stage: Dict[tuple, list] = {}
+        self._stage_next = 0
+        self._pending: Optional[tuple] = None
         # optimiser: Adam(lr) with default betas -- the cfg betas are never passed (RENI_module.py:191-192)
         if self.fixed:
             opt_params = [model.mu] if self.is_vad else [model.Z]  # RENI_module.py:178-183
@@ -130,7 +136,44 @@ class RENITrainer:
             return self._graphed_step(batch)
         return self._eager_step(batch)
 
+    def prefetch(self, batch) -> None:
+        """Start copying ``batch`` (pinned host tensors) to the device on a side stream.  The next
+        ``training_step(batch)`` called with the same tensors consumes the staged copy instead of copying itself."""
+        imgs, idx = batch
+        idx = torch.as_tensor(idx, dtype=torch.long)
+        key = (tuple(imgs.shape), imgs.dtype, int(idx.numel()))
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        slots = self._stage.get(key)
+        if slots is None:
+            slots = []
+            for _ in range(2):
+                slots.append({"imgs": torch.empty(imgs.shape, dtype=imgs.dtype, device=self.device),
+                              "idx": torch.empty(idx.shape, dtype=torch.long, device=self.device),
+                              "ready": torch.cuda.Event(), "free": torch.cuda.Event()})
+                slots[-1]["free"].record(torch.cuda.current_stream(self.device))
+            self._stage[key] = slots
+        slot = slots[self._stage_next]
+        self._stage_next ^= 1
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(slot["free"])  # the step that last read this slot has consumed it
+            slot["imgs"].copy_(imgs, non_blocking=True)
+            slot["idx"].copy_(idx, non_blocking=True)
+            slot["ready"].record(self._copy_stream)
+        self._pending = (batch[0], batch[1], slot)
+
+    def _take_prefetched(self, batch):
+        """Device tensors of ``batch`` if it is the pending prefetch (waits for the copy on the current stream)."""
+        pend = self._pending
+        if pend is None or pend[0] is not batch[0] or pend[1] is not batch[1]:
+            return None
+        self._pending = None
+        slot = pend[2]
+        torch.cuda.current_stream(self.device).wait_event(slot["ready"])
+        return slot
+
     def _graphed_step(self, batch) -> Dict[str, torch.Tensor]:
+        slot = self._take_prefetched(batch)
         imgs, idx = batch
         idx = torch.as_tensor(idx, dtype=torch.long)
         key = (tuple(imgs.shape), imgs.dtype, int(idx.numel()))
@@ -151,16 +194,30 @@ class RENITrainer:
             self._ws.prepared_key = None  # the fp32 -> fp16 weight conversion is part of every replayed step
             with torch.cuda.graph(graph):
                 log = self._eager_step((s_imgs, s_idx))
-            entry = (graph, s_imgs, s_idx, log)
+            entry = (graph, s_imgs, s_idx, log, self._latent_table().grad)
             self._graphs[key] = entry
-        graph, s_imgs, s_idx, log = entry
-        s_imgs.copy_(imgs, non_blocking=True)
-        s_idx.copy_(idx, non_blocking=True)
+        graph, s_imgs, s_idx, log, table_grad = entry
+        if slot is not None:  # staged by prefetch(): device -> device into the graph's static inputs
+            s_imgs.copy_(slot["imgs"], non_blocking=True)
+            s_idx.copy_(slot["idx"], non_blocking=True)
+            slot["free"].record(torch.cuda.current_stream(self.device))
+        else:
+            s_imgs.copy_(imgs, non_blocking=True)
+            s_idx.copy_(idx, non_blocking=True)
         graph.replay()
+        # the replay refreshed the captured gradient tensors in place; make sure the parameters still point at them
+        self._latent_table().grad = table_grad
+        if self.flat is not None:
+            self.flat.attach()
         return log
 
     def _eager_step(self, batch) -> Dict[str, torch.Tensor]:
+        slot = self._take_prefetched(batch)
         imgs, idx = batch
+        if slot is not None:
+            imgs, idx = slot["imgs"].clone(), slot["idx"].clone()
+            slot["free"].record(torch.cuda.current_stream(self.device))
+        imgs = imgs.to(self.device, non_blocking=True)
         B = imgs.shape[0]
         imgs = imgs.permute(0, 2, 3, 1).reshape(B, -1, 3)  # (B,C,H,W) -> (B,P,3)   RENI_module.py:83-84
         sw = self.sineweight if self.mask is None else self.sineweight * self.mask  # :90-94
