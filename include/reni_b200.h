@@ -149,8 +149,10 @@ int32_t reni_selftest_umma2(const void* a_img, uint32_t a_bytes, const void* b_i
                            uint32_t ksteps, float* d_out, void* stream);
 
 /* Debug probe: does a bulk copy into a CTA's own shared memory complete on an mbarrier of its cluster peer?
- * result[0] = 1 if the leader's barrier completed, result[1], result[2] = byte sums each CTA read back. */
-int32_t reni_probe_remote_tx(const void* src, uint32_t bytes, uint32_t* result, void* stream);
+ * result[0] = 1 if the leader's barrier completed, result[1], result[2] = byte sums each CTA read back.
+ * use_tma = 0: plain cp.async.bulk (measured: completes on the destination CTA only); 1: TMA tile load with
+ * .cta_group::2 through a tensor map (completes on the leader's barrier). */
+int32_t reni_probe_remote_tx(const void* src, uint32_t bytes, uint32_t* result, int32_t use_tma, void* stream);
 
 #ifdef __cplusplus
 }

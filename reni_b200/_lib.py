@@ -60,7 +60,7 @@ SIGNATURES = {
     "reni_debug_set_phase_events": (_i32, [C.POINTER(_vp), _i32]),
     "reni_debug_last_cuda_error": (C.c_char_p, []),
     "reni_debug_set_trace": (_i32, [_vp]),
-    "reni_probe_remote_tx": (_i32, [_vp, _u32, _vp, _vp]),
+    "reni_probe_remote_tx": (_i32, [_vp, _u32, _vp, _i32, _vp]),
     "reni_selftest_umma": (_i32, [_vp, _u32, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]),
     "reni_selftest_umma2": (_i32, [_vp, _u32, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]),
 }

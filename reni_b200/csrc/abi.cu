@@ -2,7 +2,9 @@
 // validation, workspace carving and kernel launches on the caller's stream.
 #include "../../include/reni_b200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "bwd_kernel.cuh"
 #include "dw_kernel.cuh"
@@ -13,8 +15,11 @@
 #ifndef RENI_NO_FORK
 #define RENI_NO_FORK 0  // 1: keep every kernel of the step on the caller's stream (A/B switch for the fork/join)
 #endif
+#ifndef RENI_FWD_TRAIN_ALLHANDS
+#define RENI_FWD_TRAIN_ALLHANDS 1
+#endif
 #ifndef RENI_FWD_PAIR
-#define RENI_FWD_PAIR 0
+#define RENI_FWD_PAIR 1
 #endif
 
 using namespace reni;
@@ -118,6 +123,30 @@ bool side_stream(SideStream** out) {
   }
   *out = &g_side;
   return true;
+}
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda): a 2-D uint8 view of `bytes` of
+// global memory as rows of 256 B, box = rows_per_box rows -> one TMA load moves rows_per_box * 256 contiguous bytes.
+bool encode_rows256(CUtensorMap* map, const void* base, uint64_t bytes, uint32_t rows_per_box) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (note(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q)) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || ptr == nullptr)
+      return false;
+    fn = reinterpret_cast<EncodeFn>(ptr);
+  }
+  const cuuint64_t dims[2] = {256, bytes / 256};
+  const cuuint64_t strides[1] = {256};
+  const cuuint32_t box[2] = {256, rows_per_box};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int num_sms() {
@@ -253,12 +282,14 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   p.last_sine = c->last_layer_linear ? 0 : 1;
   p.so2 = c->equivariance == RENI_EQ_SO2;
   p.trace = g_trace;
+  memset(&p.wmap, 0, sizeof(p.wmap));
   const int npairs = (p.ntiles + 1) / 2;
   const bool train = (flags & RENI_FLAG_SAVE_FOR_BACKWARD) != 0;
   // CTA pairs (cluster of 2) share the weight stream: half the L2 -> SM weight traffic per SM
   const bool pair_mode = RENI_FWD_PAIR != 0;
   int grid = npairs < sms ? npairs : sms;
   if (pair_mode) {  // one cluster of two CTAs per tile quad
+    if (!encode_rows256(&p.wmap, p.wf2, (uint64_t)p.L * kWImageBytes, kWChunkBytes / 256)) return RENI_ERR_CUDA;
     const int nquads = (p.ntiles + 3) / 4;
     const int nclusters = nquads < sms / 2 ? nquads : sms / 2;
     grid = 2 * nclusters;
@@ -282,7 +313,8 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
     e = note(cudaLaunchKernelEx(&cfg, kernel, p));
   };
   if (pair_mode) {
-    if (train) launch(reni_fwd_kernel<true, false, true>);
+    if (train && RENI_FWD_TRAIN_ALLHANDS) launch(reni_fwd_kernel<true, true, true>);
+    else if (train) launch(reni_fwd_kernel<true, false, true>);
     else launch(reni_fwd_kernel<false, true, true>);
   } else {
     if (train) launch(reni_fwd_kernel<true, false, false>);
@@ -592,8 +624,11 @@ int32_t reni_selftest_umma2(const void* a_img, uint32_t a_bytes, const void* b_i
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
-int32_t reni_probe_remote_tx(const void* src, uint32_t bytes, uint32_t* result, void* stream) {
-  if (src == nullptr || result == nullptr || bytes == 0 || (bytes % 16) != 0 || bytes > 65536) return RENI_ERR_BAD_ARGUMENT;
+int32_t reni_probe_remote_tx(const void* src, uint32_t bytes, uint32_t* result, int32_t use_tma, void* stream) {
+  if (src == nullptr || result == nullptr || bytes == 0 || (bytes % 256) != 0 || bytes > 65536) return RENI_ERR_BAD_ARGUMENT;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (use_tma && !encode_rows256(&tmap, src, 2ull * bytes, bytes / 256)) return RENI_ERR_CUDA;
   if (note(cudaFuncSetAttribute(reni_probe_remote_tx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560)) !=
       cudaSuccess)
     return RENI_ERR_CUDA;
@@ -609,7 +644,8 @@ int32_t reni_probe_remote_tx(const void* src, uint32_t bytes, uint32_t* result, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (note(cudaLaunchKernelEx(&cfg, reni_probe_remote_tx_kernel, static_cast<const uint8_t*>(src), bytes, result)) !=
+  if (note(cudaLaunchKernelEx(&cfg, reni_probe_remote_tx_kernel, static_cast<const uint8_t*>(src), bytes, result, tmap,
+                              (int)use_tma)) !=
       cudaSuccess)
     return RENI_ERR_CUDA;
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;

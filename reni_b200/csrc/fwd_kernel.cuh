@@ -25,6 +25,8 @@
 //
 // Reference semantics: src/models/RENI.py:31-53 (encoding), :63-87 (SineLayer), :132-178 (net).
 #pragma once
+#include <cuda.h>  // CUtensorMap
+
 #include "layout.cuh"
 #include "ptx.cuh"
 
@@ -55,19 +57,19 @@ struct FwdParams {
   int B, P, tiles_per_map, ntiles, L;
   int out_tanh, last_sine, so2;
   unsigned long long* trace;  // debug: per-role clock64 timeline of CTA 0 (reni_debug_set_trace), else null
+  alignas(64) CUtensorMap wmap;  // paired mode: wf2 as rows of 256 B, box = one 16 KB half chunk (TMA tile loads)
 };
 
 struct FwdSmem {
   static constexpr int kA = 0;                                        // 2 x 64 KB activation tile images
   static constexpr int kRing = kA + 2 * kTileImageBytes;              // weight chunk ring
-  static constexpr int kMaxStages = 9;                                // paired mode: 9 x 8 KB half chunks
-  static constexpr int kRingBytes = kMaxStages * 8192 > kFwdStages * kWChunkBytes ? kMaxStages * 8192
-                                                                                   : kFwdStages * kWChunkBytes;
+  static constexpr int kMaxStages = kFwdStages;
+  static constexpr int kRingBytes = kFwdStages * kWChunkBytes;
   static constexpr int kW6 = kRing + kRingBytes;                      // final-layer image
   static constexpr int kBias = kW6 + kW6ImageBytes;                   // (kMaxHiddenLayers*256 + 16) floats
   static constexpr int kMc = kBias + (kMaxHiddenLayers * kH + 16) * 4;  // 2 x 5 x 256 floats
   static constexpr int kBars = kMc + 2 * 5 * kH * 4;                  // mbarriers
-  static constexpr int kNumBars = 3 * kMaxStages + 6;
+  static constexpr int kNumBars = 2 * kMaxStages + 6;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemPtr + 16;
 };
@@ -97,17 +99,16 @@ DEVINL void sin8(const float (&a)[8], uint4& hv, uint4& uv) {
 }
 
 template <bool kTrain, bool kAllHands, bool kPair>
-__global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBars);
-  constexpr int kStages = kPair ? FwdSmem::kMaxStages : kFwdStages;
+  constexpr int kStages = kFwdStages;
   uint64_t* w_full = bars;                                 // [kStages]
   uint64_t* w_empty = bars + FwdSmem::kMaxStages;          // [kStages]
-  uint64_t* w_full_peer = bars + 2 * FwdSmem::kMaxStages;  // [kStages] leader only: the peer's half chunk has landed
-  uint64_t* a_ready = bars + 3 * FwdSmem::kMaxStages;      // [2]  epilogue -> MMA (one arrival per thread)
+  uint64_t* a_ready = bars + 2 * FwdSmem::kMaxStages;      // [2]  epilogue -> MMA (one arrival per thread)
   uint64_t* acc_full = a_ready + 2;             // [2]  MMA -> epilogue group (tcgen05.commit)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + FwdSmem::kTmemPtr);
   float* s_bias = reinterpret_cast<float*>(smem + FwdSmem::kBias);
@@ -124,8 +125,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
   const int worker = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int iters = (nunits - worker + nworkers - 1) / nworkers;  // same for both CTAs of a pair
   auto clamp02 = [](int x) { return x < 0 ? 0 : (x > 2 ? 2 : x); };
-  constexpr int kChunkBytes = kPair ? 8192 : kWChunkBytes;  // paired: [4 k-groups][128 n][8] = K 32 of one N half
-  constexpr int kChunks = kChunksPerLayer;
+  constexpr int kChunkBytes = kWChunkBytes;            // paired: [8 k-groups][128 n][8] = K 64 of this CTA's N half
+  constexpr int kChunks = kPair ? 4 : kChunksPerLayer;
   uint64_t* a_ready_peer = acc_full + 2;  // [2] leader only: the peer's sub-tile g is ready (one arrival per warp)
   constexpr uint32_t kPeerWarps = kAllHands ? 16 : 8;
 
@@ -134,7 +135,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
-      mbar_init(&w_full_peer[i], 1);
     }
     mbar_init(&a_ready[0], kAllHands ? kEpiThreads : kGroupThreads);
     mbar_init(&a_ready[1], kAllHands ? kEpiThreads : kGroupThreads);
@@ -190,10 +190,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
           for (int g = 0; g < nstream; ++g) {
             for (int c = 0; c < kChunks; ++c) {
               mbar_wait(&w_empty[st], ph ^ 1);
-              mbar_arrive_expect_tx(&w_full[st], kChunkBytes);
-              const size_t off = kPair ? ((size_t)(l * 2 + crank) * (kWImageBytes / 2) + (size_t)c * kChunkBytes)
-                                       : ((size_t)l * kWImageBytes + (size_t)c * kChunkBytes);
-              bulk_g2s(smem + FwdSmem::kRing + st * kChunkBytes, wsrc + off, kChunkBytes, &w_full[st]);
+              if (kPair) {
+                // both halves complete on the LEADER's barrier (TMA tile load with .cta_group::2): no relay, one wait
+                if (crank == 0) mbar_arrive_expect_tx(&w_full[st], 2 * kChunkBytes);
+                const int32_t row = (int32_t)(((size_t)(l * 2 + crank) * (kWImageBytes / 2) + (size_t)c * kChunkBytes) / 256);
+                tma2_load_2d(smem + FwdSmem::kRing + st * kChunkBytes, &p.wmap, 0, row,
+                             mapa_u32(smem_u32(&w_full[st]), 0));
+              } else {
+                mbar_arrive_expect_tx(&w_full[st], kChunkBytes);
+                bulk_g2s(smem + FwdSmem::kRing + st * kChunkBytes, wsrc + (size_t)l * kWImageBytes + (size_t)c * kChunkBytes,
+                         kChunkBytes, &w_full[st]);
+              }
               if (++st == kStages) { st = 0; ph ^= 1; }
             }
           }
@@ -233,7 +240,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
             if (l <= L) {
               for (int c = 0; c < kChunks; ++c) {
                 mbar_wait(&w_full[st], ph);
-                if (kPair) mbar_wait(&w_full_peer[st], ph);
                 tc_fence_after();
                 const uint32_t b_tile = ring_base + st * kChunkBytes;
                 constexpr int kSteps = kChunkBytes / (kBRows * 32);  // K = 16 steps per chunk
@@ -261,26 +267,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const FwdParam
             if (kPair) umma2_commit_multicast(&acc_full[g], live_mask);
             else umma_commit(&acc_full[g]);
             trace_ev(p, 0, tn, 0x200 | (l << 4) | g);  // all MMAs of this pass issued
-          }
-        }
-      }
-    } else if (kPair && lane == 0) {
-      // ============================================================ peer relay: forwards "my half chunk has landed" to
-      // the leader's barriers (a bulk copy can only complete on an mbarrier of its destination CTA: probed on B200)
-      const uint32_t rw = mapa_u32(smem_u32(w_full_peer), 0);
-      uint32_t st = 0, ph = 0;
-      for (int it = 0; it < iters; ++it) {
-        const int ubase = (worker + it * nworkers) * unit_tiles;
-        const int nsub_lead = clamp02(p.ntiles - ubase);
-        for (int l = 1; l <= L + 1; ++l) {
-          for (int g = 0; g < nsub_lead; ++g) {
-            if (l <= L) {
-              for (int c = 0; c < kChunks; ++c) {
-                mbar_wait(&w_full[st], ph);
-                mbar_arrive_remote(rw + st * 8);
-                if (++st == kStages) { st = 0; ph ^= 1; }
-              }
-            }
           }
         }
       }

@@ -15,6 +15,9 @@ namespace reni {
 #ifndef RENI_ABL
 #define RENI_ABL 0
 #endif
+#ifndef RENI_REMOTE_RELAXED
+#define RENI_REMOTE_RELAXED 1
+#endif
 DEVINL float abl_sin(float x) { return (RENI_ABL & 2) ? x * 0.5f : __sinf(x); }
 DEVINL float abl_cos(float x) { return (RENI_ABL & 2) ? x * 0.5f : __cosf(x); }
 
@@ -106,7 +109,14 @@ DEVINL uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
 }
 // arrive on an mbarrier of another CTA of the cluster (release at cluster scope)
 DEVINL void mbar_arrive_remote(uint32_t cluster_addr) {
+#if RENI_REMOTE_RELAXED
+  // the only data the consumer touches after this signal is read by the tensor core (async proxy) from THIS CTA's
+  // shared memory, and fence.proxy.async has already ordered those writes; a cluster-scope release would in addition
+  // wait for every earlier global store of the warp (the stash) to be acknowledged
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 // wait on a local mbarrier that a peer CTA arrives on (acquire at cluster scope)
 DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -122,6 +132,16 @@ DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   } while (!ok);
+}
+
+// TMA tile load of a CTA pair: box (x, y) of `tmap` -> this CTA's smem; the bytes complete on `bar_cluster_addr`,
+// which may be an mbarrier of the pair's OTHER CTA (that is what .cta_group::2 adds over the plain bulk copy)
+DEVINL void tma2_load_2d(void* smem_dst, const void* tmap, int32_t x, int32_t y, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(x), "r"(y), "r"(bar_cluster_addr)
+      : "memory");
 }
 
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)

@@ -244,7 +244,9 @@ __global__ void __launch_bounds__(128, 1) reni_selftest_umma_kernel(const SelfTe
 // each CTA in its own buffer.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) reni_probe_remote_tx_kernel(const uint8_t* src, uint32_t bytes,
-                                                                      uint32_t* result) {
+                                                                      uint32_t* result,
+                                                                      const __grid_constant__ CUtensorMap tmap,
+                                                                      int use_tma) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   const uint32_t rank = cluster_ctarank();
@@ -257,10 +259,14 @@ __global__ void __launch_bounds__(128, 1) reni_probe_remote_tx_kernel(const uint
   if (threadIdx.x == 0) {
     if (rank == 0) mbar_arrive_expect_tx(&bar, 2 * bytes);
     const uint32_t leader_bar = mapa_u32(smem_u32(&bar), 0);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem)),
-                 "l"(src + (size_t)rank * bytes), "r"(bytes), "r"(leader_bar)
-                 : "memory");
+    if (use_tma) {  // tensor map: rows of 256 B; this CTA's box starts at row rank * bytes / 256
+      tma2_load_2d(smem, &tmap, 0, (int32_t)(rank * bytes / 256), leader_bar);
+    } else {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(smem)),
+                   "l"(src + (size_t)rank * bytes), "r"(bytes), "r"(leader_bar)
+                   : "memory");
+    }
     if (rank == 0) {
       uint32_t ok = 0;
       for (int i = 0; i < 2000000 && !ok; ++i) ok = mbar_try_wait(&bar, 0) ? 1u : 0u;

@@ -31,13 +31,14 @@ B16 = rng.uniform(-1, 1, (16, 64)).astype(np.float16)
 ref = A.astype(np.float32) @ B16.astype(np.float32).T
 got = run(A, B16, (2048, 128, 128, 128, 4096, 256, 0, 0), 16, 4)
 print("selftest2 N=16 max err", np.abs(got - ref).max())
-# probe: bulk copy completing on the peer CTA's mbarrier
-src = torch.randint(0, 255, (2 * 16384,), dtype=torch.uint8, device=dev)
-res = torch.zeros(4, dtype=torch.int32, device=dev)
-rc = lib.reni_probe_remote_tx(C.c_void_p(src.data_ptr()), 16384, C.c_void_p(res.data_ptr()), None)
-try:
-    _lib.check(rc, "probe"); torch.cuda.synchronize()
-    r = res.cpu().numpy()
-    print("probe remote complete_tx: completed", r[0], "sums", r[1], r[2], "expected", int(src[:16384].sum()), int(src[16384:].sum()))
-except Exception as ex:
-    print("probe failed:", ex)
+# probe: bulk copy completing on the peer CTA's mbarrier (plain bulk copy vs TMA tile load with .cta_group::2)
+for use_tma in (0, 1):
+    src = torch.randint(0, 255, (2 * 16384,), dtype=torch.uint8, device=dev)
+    res = torch.zeros(4, dtype=torch.int32, device=dev)
+    rc = lib.reni_probe_remote_tx(C.c_void_p(src.data_ptr()), 16384, C.c_void_p(res.data_ptr()), use_tma, None)
+    try:
+        _lib.check(rc, "probe"); torch.cuda.synchronize()
+        r = res.cpu().numpy()
+        print("probe remote complete_tx use_tma", use_tma, ": completed", r[0], "sums", r[1], r[2], "expected", int(src[:16384].sum()), int(src[16384:].sum()))
+    except Exception as ex:
+        print("probe failed:", ex)
