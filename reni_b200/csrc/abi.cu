@@ -54,6 +54,7 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   w.wf = take(L * kWImageBytes);
   w.wb = take(L * kWImageBytes);
   w.wf2 = take(L * kWImageBytes);
+  w.wb2 = take(L * kWImageBytes);
   w.w6f = take(kW6ImageBytes);
   w.w6b = take(kW6ImageBytes);
   w.bias = take((L * kH + 16) * 4);
@@ -207,6 +208,7 @@ int32_t reni_prepare_weights(const reni_config_t* c, const float* const* host_we
   p.wf = at<__half>(ws, w.wf);
   p.wb = at<__half>(ws, w.wb);
   p.wf2 = at<__half>(ws, w.wf2);
+  p.wb2 = at<__half>(ws, w.wb2);
   p.w6f = at<__half>(ws, w.w6f);
   p.w6b = at<__half>(ws, w.w6b);
   p.bias = at<float>(ws, w.bias);
@@ -348,7 +350,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   p.sw_bstride = sw_bstride;
   p.map_loss = at<float>(ws, w.map_loss);
   p.scalars = at<float>(ws, w.scalars);
-  p.wb = at<__half>(ws, w.wb);
+  p.wb2 = at<__half>(ws, w.wb2);
   p.w6b = at<__half>(ws, w.w6b);
   p.stash_u = at<uint16_t>(ws, w.stash_c);
   p.stash_d = at<__half>(ws, w.stash_d);
@@ -365,18 +367,35 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   p.out_tanh = c->output_activation == 1;
   p.d_slots = need_dw ? L + 1 : 1;
   p.use_cos = use_cos;
-  const int npairs = (ntiles + 1) / 2;
-  const int grid = npairs < sms ? npairs : sms;
-  if (need_dw) {
-    if (note(cudaFuncSetAttribute(reni_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal)) !=
-        cudaSuccess)
-      return RENI_ERR_CUDA;
-    reni_bwd_kernel<true><<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(p);
-  } else {
-    if (note(cudaFuncSetAttribute(reni_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal)) !=
-        cudaSuccess)
-      return RENI_ERR_CUDA;
-    reni_bwd_kernel<false><<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(p);
+  // one cluster of two CTAs per tile quad (tcgen05.mma.cta_group::2)
+  const int nquads = (ntiles + 3) / 4;
+  const int nclusters = nquads < sms / 2 ? nquads : sms / 2;
+  memset(&p.wmap, 0, sizeof(p.wmap));
+  if (!encode_rows256(&p.wmap, p.wb2, (uint64_t)L * kWImageBytes, kWChunkBytes / 256)) return RENI_ERR_CUDA;
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * nclusters));
+    cfg.blockDim = dim3(kBwdThreads);
+    cfg.dynamicSmemBytes = BwdSmem::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (need_dw) {
+      if (note(cudaFuncSetAttribute(reni_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal)) !=
+          cudaSuccess)
+        return RENI_ERR_CUDA;
+      if (note(cudaLaunchKernelEx(&cfg, reni_bwd_kernel<true>, p)) != cudaSuccess) return RENI_ERR_CUDA;
+    } else {
+      if (note(cudaFuncSetAttribute(reni_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal)) !=
+          cudaSuccess)
+        return RENI_ERR_CUDA;
+      if (note(cudaLaunchKernelEx(&cfg, reni_bwd_kernel<false>, p)) != cudaSuccess) return RENI_ERR_CUDA;
+    }
   }
   if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   mark_phase(4, stream);

@@ -11,11 +11,18 @@
 //   d_l tiles stay in shared memory for the next GEMM; when weight gradients are wanted d_1..d_L are also stashed as
 //   fp16 tile images for the weight-gradient GEMM.  d_0 never leaves the SM.
 //
-// Same CTA organisation as the forward kernel (producer warp, MMA warp, two ping-ponging epilogue groups of 8 warps).
+// CTA pairs (cluster of 2, tcgen05.mma.cta_group::2, M = 256) like the forward kernel: the leader issues every MMA for
+// sub-tile g of BOTH CTAs, each CTA streams only its 128-column half of every backward weight image (TMA tile loads
+// that complete on the leader's mbarrier) and holds its own accumulators.  The per-tile reductions ride along: the
+// K = 16 head GEMM splits W_out'' by columns, and the layer-0 reduction (MN-major operands) gives each CTA 8 of the
+// 16 accumulator columns for its own [f | 1] features.
+// Per CTA: producer warp, MMA warp (leader only), two ping-ponging epilogue groups of 8 warps.
 // Each epilogue thread owns (row, 128 columns): the 16 x 16-B stash loads of its whole layer slice are issued before it
 // waits for the GEMM, so their HBM/L2 latency hides under the tensor pipe; the producer warp additionally prefetches the
 // next layer's stash tiles into L2 (cp.async.bulk.prefetch.L2).
 #pragma once
+#include <cuda.h>  // CUtensorMap
+
 #include "layout.cuh"
 #include "ptx.cuh"
 
@@ -32,7 +39,7 @@ struct BwdParams {
   int64_t sw_bstride;
   const float* map_loss;  // (B, 32): [16..18] = coefA_c, [19..21] = coefB_c (cosine term, pre-scaled by S)
   const float* scalars;   // [0] = S (gradient scale)
-  const __half* wb;       // L backward weight images
+  const __half* wb2;      // L backward weight images split for CTA pairs: [l][k half][j/8][128][8]
   const __half* w6b;      // [2][256][8]
   const uint16_t* stash_u;  // 16-bit phases of a_l, per tile (L+1) tile images
   __half* stash_d;        // delta stash: per tile nslots images (nslots = L+1 or 1)
@@ -43,6 +50,7 @@ struct BwdParams {
   int B, P, tiles_per_map, ntiles, L;
   int out_tanh, d_slots, so2;
   int use_cos;            // fused loss: 0 = no cosine term (map_loss is not read, it may still be in flight)
+  alignas(64) CUtensorMap wmap;  // wb2 as rows of 256 B, box = one 16 KB half chunk
 };
 
 struct BwdSmem {
@@ -51,7 +59,7 @@ struct BwdSmem {
   static constexpr int kW6 = kRing + kBwdStages * kWChunkBytes;
   static constexpr int kF = kW6 + kW6ImageBytes;               // 2 x [2][128][8] fp16 feature tiles [f0..f3, 1, 0..]
   static constexpr int kBars = kF + 2 * kGyImageBytes;
-  static constexpr int kNumBars = 2 * kBwdStages + 4;
+  static constexpr int kNumBars = 2 * kBwdStages + 6;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemPtr + 16;
 };
@@ -67,20 +75,30 @@ DEVINL uint32_t delta2(float acc0, float acc1, uint32_t w) {
 }
 
 template <bool kNeedDW>
-__global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::kBars);
-  uint64_t* w_full = bars;
-  uint64_t* w_empty = bars + kBwdStages;
-  uint64_t* a_ready = bars + 2 * kBwdStages;
-  uint64_t* acc_full = a_ready + 2;
+  uint64_t* w_full = bars;                        // [kBwdStages] leader: both halves of a chunk have landed
+  uint64_t* w_empty = bars + kBwdStages;          // [kBwdStages] multicast commit: the slot is free in both CTAs
+  uint64_t* a_ready = bars + 2 * kBwdStages;      // [2] this CTA's epilogue group g -> (leader's) MMA issuer
+  uint64_t* acc_full = a_ready + 2;               // [2] multicast commit -> epilogue group g of both CTAs
+  uint64_t* a_ready_peer = acc_full + 2;          // [2] leader only: the peer's group g (one arrival per warp)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + BwdSmem::kTmemPtr);
 
   const int L = p.L;
-  const int npairs = (p.ntiles + 1) >> 1;
+  // cluster k owns tile quads q = k, k + nclusters, ... taken in DESCENDING tile order (the forward kernel's last
+  // tiles are the freshest in L2); leader: tiles {4q, 4q+1}, peer: {4q+2, 4q+3}
+  const uint32_t crank = cluster_ctarank();
+  const int nunits = (p.ntiles + 3) / 4;
+  const int nworkers = (int)(gridDim.x >> 1);
+  const int worker = (int)(blockIdx.x >> 1);
+  const int iters = (nunits - worker + nworkers - 1) / nworkers;
+  auto clamp02 = [](int x) { return x < 0 ? 0 : (x > 2 ? 2 : x); };
+  auto unit_base = [&](int it) { return (nunits - 1 - (worker + it * nworkers)) * 4; };  // first tile of the quad
+  constexpr int kChunks = 4;  // per layer pass: 4 x [8 j-groups][128 k][8] = K 64 of this CTA's N half
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kBwdStages; ++i) {
@@ -91,44 +109,59 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
     mbar_init(&a_ready[1], 256);
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
+    mbar_init(&a_ready_peer[0], 8);
+    mbar_init(&a_ready_peer[1], 8);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
-  {
+  if (warp == 1) tmem_alloc2<512>(tmem_ptr);
+  {  // this CTA's 128 of the 256 columns of W_out'': [c/8 2][128 k][8]
     const uint4* src = reinterpret_cast<const uint4*>(p.w6b);
     uint4* dst = reinterpret_cast<uint4*>(smem + BwdSmem::kW6);
-    for (int i = threadIdx.x; i < kW6ImageBytes / 16; i += kBwdThreads) dst[i] = src[i];
+    for (int i = threadIdx.x; i < kW6ImageBytes / 32; i += kBwdThreads)
+      dst[i] = src[(i >> 7) * kH + crank * 128 + (i & 127)];
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers and TMEM exist before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t ra_peer = mapa_u32(smem_u32(a_ready_peer), 0);
+  auto signal_ready = [&](int g) {  // "sub-tile g of this CTA is in shared memory"
+    if (crank == 1) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(ra_peer + g * 8);
+    } else {
+      mbar_arrive(&a_ready[g]);
+    }
+  };
 
   if (warp == 0) {
-    // ============================================================ weight-chunk producer (layers L..1)
+    // ============================================================ weight-chunk producer (layers L..1, this CTA's half)
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wb);
-      for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
-      // descending tile order: the forward kernel's last tiles are the freshest in L2 (measured: -37 us at cfg 2)
-      const int pair = npairs - 1 - pi;
-        const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
+      for (int it = 0; it < iters; ++it) {
+        const int ubase = unit_base(it);
+        const int tbase = ubase + 2 * (int)crank;
+        const int nsub = clamp02(p.ntiles - tbase);          // this CTA's live sub-tiles
+        const int nstream = clamp02(p.ntiles - ubase);       // passes the leader makes over each layer
         for (int g = 0; g < nsub; ++g)
           bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
-                               ((size_t)(2 * pair + g) * (L + 1) + L) * kTileImageBytes,
+                               ((size_t)(tbase + g) * (L + 1) + L) * kTileImageBytes,
                            kTileImageBytes);
         for (int l = L; l >= 1; --l) {
-          for (int g = 0; g < nsub; ++g) {
+          for (int g = 0; g < nstream; ++g) {
             // the epilogue of this GEMM multiplies by cos(a_{l-1}): pull that stash tile towards L2 now
-            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
-                                 ((size_t)(2 * pair + g) * (L + 1) + (l - 1)) * kTileImageBytes,
-                             kTileImageBytes);
-            for (int c = 0; c < kChunksPerLayer; ++c) {
+            if (g < nsub)
+              bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
+                                   ((size_t)(tbase + g) * (L + 1) + (l - 1)) * kTileImageBytes,
+                               kTileImageBytes);
+            for (int c = 0; c < kChunks; ++c) {
               mbar_wait(&w_empty[st], ph ^ 1);
-              mbar_arrive_expect_tx(&w_full[st], kWChunkBytes);
-              bulk_g2s(smem + BwdSmem::kRing + st * kWChunkBytes,
-                       wsrc + (size_t)(l - 1) * kWImageBytes + (size_t)c * kWChunkBytes, kWChunkBytes, &w_full[st]);
+              if (crank == 0) mbar_arrive_expect_tx(&w_full[st], 2 * kWChunkBytes);
+              const int32_t row =
+                  (int32_t)(((size_t)((l - 1) * 2 + crank) * (kWImageBytes / 2) + (size_t)c * kWChunkBytes) / 256);
+              tma2_load_2d(smem + BwdSmem::kRing + st * kWChunkBytes, &p.wmap, 0, row, mapa_u32(smem_u32(&w_full[st]), 0));
               if (++st == kBwdStages) { st = 0; ph ^= 1; }
             }
           }
@@ -136,33 +169,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_h = umma_idesc_f16(128, 256, 0, 0);
+    // ============================================================ MMA issuer (leader CTA: issues for the pair)
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc_h = umma_idesc_f16(256, 256, 0, 0);
+      constexpr uint32_t idesc_r = umma_idesc_f16(256, kW6N, 1, 1);
       const uint32_t a_base = smem_u32(smem + BwdSmem::kA);
       const uint32_t ring_base = smem_u32(smem + BwdSmem::kRing);
       const uint32_t w6_base = smem_u32(smem + BwdSmem::kW6);
       uint32_t st = 0, ph = 0;
-      uint32_t a_ph0 = 0, a_ph1 = 0;
-      for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
-      // descending tile order: the forward kernel's last tiles are the freshest in L2 (measured: -37 us at cfg 2)
-      const int pair = npairs - 1 - pi;
-        const int nsub = (2 * pair + 1 < p.ntiles) ? 2 : 1;
+      uint32_t a_ph = 0, ap_ph = 0;  // bit g: parity of a_ready[g] / a_ready_peer[g]
+      for (int it = 0; it < iters; ++it) {
+        const int ubase = unit_base(it);
+        const int nsub = clamp02(p.ntiles - ubase);           // live sub-tiles of the leader
+        const int nsub_peer = clamp02(p.ntiles - ubase - 2);  // ... of the peer
         for (int l = L + 1; l >= 0; --l) {  // l = L+1: output layer (K = 16); L..1: hidden layer l; 0: layer-0 reduction
           for (int g = 0; g < nsub; ++g) {
-            if (g == 0) { mbar_wait(&a_ready[0], a_ph0); a_ph0 ^= 1; }
-            else        { mbar_wait(&a_ready[1], a_ph1); a_ph1 ^= 1; }
+            mbar_wait(&a_ready[g], (a_ph >> g) & 1);
+            a_ph ^= 1u << g;
+            if (g < nsub_peer) {
+              mbar_wait(&a_ready_peer[g], (ap_ph >> g) & 1);
+              ap_ph ^= 1u << g;
+            }
             tc_fence_after();
             const uint32_t a_tile = a_base + g * kTileImageBytes;
             const uint32_t d_tmem = tmem_base + g * 256;
             if (l == L + 1) {
+              // A: g_y [128 x 16] of each CTA; B: each CTA's [2][128 k][8] half of W_out''
               const uint64_t da = umma_smem_desc(a_tile, 2048, 128);
-              const uint64_t db = umma_smem_desc(w6_base, 4096, 128);
-              umma_f16_ss(d_tmem, da, db, idesc_h, 0);
+              const uint64_t db = umma_smem_desc(w6_base, 2048, 128);
+              umma2_f16_ss(d_tmem, da, db, idesc_h, 0);
             } else if (l == 0) {
-              // D[j, i] = sum_r delta0[r, j] * F[r, i]: both operands MN-major views of [k/8][128][8] images
-              // (8-column groups 2048 B apart = SBO, 8-row groups 128 B apart = LBO, 16 rows per K step = 256 B)
-              constexpr uint32_t idesc_r = umma_idesc_f16(128, kW6N, 1, 1);
+              // D_r[j, i] = sum_rows delta0_r[row, j] * F[row, i]: MN-major views of [k/8][128][8] images; CTA r
+              // contributes columns 8r..8r+7 of B (its own [f | 1] features), so it reads back columns 8r.. of D
               const uint32_t f_tile = smem_u32(smem + BwdSmem::kF) + g * kGyImageBytes;
 #pragma unroll
               for (int mh = 0; mh < 2; ++mh) {
@@ -170,25 +208,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
                 for (int ks = 0; ks < kTileRows / 16; ++ks) {
                   const uint64_t da = umma_smem_desc(a_tile + mh * 16 * 2048 + ks * 256, 128, 2048);
                   const uint64_t db = umma_smem_desc(f_tile + ks * 256, 128, 2048);
-                  umma_f16_ss(d_tmem + mh * kW6N, da, db, idesc_r, ks != 0);
+                  umma2_f16_ss(d_tmem + mh * kW6N, da, db, idesc_r, ks != 0);
                 }
               }
             } else {
-              for (int c = 0; c < kChunksPerLayer; ++c) {
+              for (int c = 0; c < kChunks; ++c) {
                 mbar_wait(&w_full[st], ph);
                 tc_fence_after();
                 const uint32_t b_tile = ring_base + st * kWChunkBytes;
 #pragma unroll
-                for (int ks = 0; ks < kWChunkK / 16; ++ks) {
-                  const uint64_t da = umma_smem_desc(a_tile + (c * 4 + ks * 2) * 2048, 2048, 128);
-                  const uint64_t db = umma_smem_desc(b_tile + (ks * 2) * 4096, 4096, 128);
-                  umma_f16_ss(d_tmem, da, db, idesc_h, (c | ks) != 0);
+                for (int ks = 0; ks < 4; ++ks) {
+                  // A: [j/8][128][8] -> 2048 B per 8-column group; B: [j/8][128 k][8] -> 2048 B per group
+                  const uint64_t da = umma_smem_desc(a_tile + (c * 4 + ks) * 4096, 2048, 128);
+                  const uint64_t db = umma_smem_desc(b_tile + ks * 4096, 2048, 128);
+                  umma2_f16_ss(d_tmem, da, db, idesc_h, (c | ks) != 0);
                 }
-                umma_commit(&w_empty[st]);
+                umma2_commit_multicast(&w_empty[st], 0x3);
                 if (++st == kBwdStages) { st = 0; ph ^= 1; }
               }
             }
-            umma_commit(&acc_full[g]);
+            umma2_commit_multicast(&acc_full[g], (g < nsub_peer) ? 0x3 : 0x1);
           }
         }
       }
@@ -205,11 +244,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
     uint32_t acc_ph = 0;
     const float S = __ldg(p.scalars);
 
-    for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
-      // descending tile order: the forward kernel's last tiles are the freshest in L2 (measured: -37 us at cfg 2)
-      const int pair = npairs - 1 - pi;
-      const int tile = 2 * pair + g;
-      if (tile >= p.ntiles) continue;  // (the ragged last pair is visited first)
+    for (int it = 0; it < iters; ++it) {
+      const int tile = unit_base(it) + 2 * (int)crank + g;
+      if (tile >= p.ntiles) continue;  // (the ragged last quad is visited first)
       const int b = tile / p.tiles_per_map;
       const int pix = (tile - b * p.tiles_per_map) * kTileRows + row;
       const bool rvalid = pix < p.P;
@@ -274,7 +311,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(&a_ready[g]);
+      signal_ready(g);
 
       // ---- delta_l = acc * cos(a_l), l = L..0 ; this thread: (row, columns chalf*128 .. +127)
       for (int l = L; l >= 0; --l) {
@@ -320,7 +357,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
         }
         tc_fence_before();
         fence_proxy_async_smem();
-        mbar_arrive(&a_ready[g]);
+        signal_ready(g);
       }
 
       // ---- layer-0 reduction result: D[j, 0..4] for j = row (columns 0..15) and j = 128 + row (columns 16..31)
@@ -337,7 +374,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
         for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
           for (int i = 0; i < 5; ++i)
-            atomicAdd(dst + i * kH + mh * 128 + row, __uint_as_float(v[mh * kW6N + i]) * inv_s);
+            atomicAdd(dst + i * kH + mh * 128 + row, __uint_as_float(v[mh * kW6N + crank * 8 + i]) * inv_s);
       }
       tc_fence_before();
     }
@@ -345,9 +382,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const BwdParam
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the pair's MMAs, multicast commits and remote arrivals are all behind us
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc2<512>(tmem_base);
   }
 }
 

@@ -12,6 +12,7 @@ namespace reni {
 //   wb[l]              [j/8][k][8]  = omega_{l-1} * W_l[j][k]          backward B operand (N = in,  K = out)
 //   wf2[l] [n/128][k/8][n%128][8]   = omega_l     * W_l[n][k]          forward B operand split in two N halves for
 //                                                                     CTA pairs (tcgen05.mma.cta_group::2)
+//   wb2[l] [k/128][j/8][k%128][8]   = omega_{l-1} * W_l[j][k]          backward B operand, same split
 //   w6f                [k/8][16][8] = s * W_out[n][k]   (n < out_features, else 0);  s = omega if sine-last
 //   w6b                [c/8][256][8]= omega_L * s * W_out[c][k]
 //   bias               L*256: omega_l * b_l ; then 16: s * b_out
@@ -23,6 +24,7 @@ struct PrepParams {
   __half* wf;
   __half* wb;
   __half* wf2;
+  __half* wb2;
   __half* w6f;
   __half* w6b;
   float* bias;
@@ -41,12 +43,14 @@ __global__ void reni_prep_weights_kernel(const PrepParams p) {
     __half* wf = p.wf + (size_t)l * kH * kH;
     __half* wb = p.wb + (size_t)l * kH * kH;
     __half* wf2 = p.wf2 + (size_t)l * kH * kH;
+    __half* wb2 = p.wb2 + (size_t)l * kH * kH;
     for (int i = tid; i < kH * kH; i += nthreads) {
       const int n = i / kH, k = i % kH;  // W[n][k], coalesced read
       const float w = W[i];
       wf[((k >> 3) * kH + n) * 8 + (k & 7)] = __float2half_rn(om_f * w);
       wb[((n >> 3) * kH + k) * 8 + (n & 7)] = __float2half_rn(om_b * w);
       wf2[(((n >> 7) * (kH / 8) + (k >> 3)) * 128 + (n & 127)) * 8 + (k & 7)] = __float2half_rn(om_f * w);
+      wb2[(((k >> 7) * (kH / 8) + (n >> 3)) * 128 + (k & 127)) * 8 + (n & 7)] = __float2half_rn(om_b * w);
     }
     for (int i = tid; i < kH; i += nthreads) p.bias[l * kH + i] = om_f * p.b[l + 1][i];
   } else {

@@ -42,3 +42,18 @@ for use_tma in (0, 1):
         print("probe remote complete_tx use_tma", use_tma, ": completed", r[0], "sums", r[1], r[2], "expected", int(src[:16384].sum()), int(src[16384:].sum()))
     except Exception as ex:
         print("probe failed:", ex)
+# MN-major operands on a CTA pair, N = 16 (8 columns of B per CTA): the layer-0 reduction of the paired delta chain
+At = [rng.uniform(-1, 1, (64, 128)).astype(np.float16) for _ in range(2)]
+Bt = [rng.uniform(-1, 1, (64, 8)).astype(np.float16) for _ in range(2)]
+a = np.concatenate([image_kmajor(x).reshape(-1) for x in At]).view(np.uint8)
+b = np.concatenate([image_kmajor(x).reshape(-1) for x in Bt]).view(np.uint8)
+ta, tb = torch.from_numpy(a.copy()).to(dev), torch.from_numpy(b.copy()).to(dev)
+d = torch.zeros(256, 16, device=dev)
+rc = lib.reni_selftest_umma2(C.c_void_p(ta.data_ptr()), ta.numel() // 2, C.c_void_p(tb.data_ptr()), tb.numel() // 2,
+                             128, 1024, 128, 1024, 256, 256, 1, 1, 16, 4, C.c_void_p(d.data_ptr()), None)
+_lib.check(rc, "selftest2 mn"); torch.cuda.synchronize()
+got = d.cpu().numpy()
+Bcat = np.concatenate([Bt[0], Bt[1]], axis=1).astype(np.float32)
+ref = np.concatenate([At[0].astype(np.float32).T @ Bcat, At[1].astype(np.float32).T @ Bcat])
+print("selftest2 MN-major N=16 max err", np.abs(got - ref).max(), "(own-columns only:",
+      max(np.abs(got[:128, :8] - ref[:128, :8]).max(), np.abs(got[128:, 8:] - ref[128:, 8:]).max()), ")")
