@@ -350,6 +350,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   p.sw_bstride = sw_bstride;
   p.map_loss = at<float>(ws, w.map_loss);
   p.scalars = at<float>(ws, w.scalars);
+  p.wb = at<__half>(ws, w.wb);
   p.wb2 = at<__half>(ws, w.wb2);
   p.w6b = at<__half>(ws, w.w6b);
   p.stash_u = at<uint16_t>(ws, w.stash_c);
@@ -367,34 +368,41 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   p.out_tanh = c->output_activation == 1;
   p.d_slots = need_dw ? L + 1 : 1;
   p.use_cos = use_cos;
-  // one cluster of two CTAs per tile quad (tcgen05.mma.cta_group::2)
-  const int nquads = (ntiles + 3) / 4;
-  const int nclusters = nquads < sms / 2 ? nquads : sms / 2;
+  // Latent-only (no weight gradients): CTA pairs, one cluster of two CTAs per tile quad (tcgen05.mma.cta_group::2).
+  // With weight gradients the delta-stash stores make the pair wait for its slower half: one CTA per tile pair.
+  const bool pair_mode = !need_dw;
   memset(&p.wmap, 0, sizeof(p.wmap));
-  if (!encode_rows256(&p.wmap, p.wb2, (uint64_t)L * kWImageBytes, kWChunkBytes / 256)) return RENI_ERR_CUDA;
   {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(2 * nclusters));
+    if (pair_mode) {
+      const int nquads = (ntiles + 3) / 4;
+      const int nclusters = nquads < sms / 2 ? nquads : sms / 2;
+      cfg.gridDim = dim3((unsigned)(2 * nclusters));
+      if (!encode_rows256(&p.wmap, p.wb2, (uint64_t)L * kWImageBytes, kWChunkBytes / 256)) return RENI_ERR_CUDA;
+    } else {
+      const int npairs = (ntiles + 1) / 2;
+      cfg.gridDim = dim3((unsigned)(npairs < sms ? npairs : sms));
+    }
     cfg.blockDim = dim3(kBwdThreads);
     cfg.dynamicSmemBytes = BwdSmem::kTotal;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = pair_mode ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (need_dw) {
-      if (note(cudaFuncSetAttribute(reni_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal)) !=
-          cudaSuccess)
+      if (note(cudaFuncSetAttribute(reni_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    BwdSmem::kTotal)) != cudaSuccess)
         return RENI_ERR_CUDA;
-      if (note(cudaLaunchKernelEx(&cfg, reni_bwd_kernel<true>, p)) != cudaSuccess) return RENI_ERR_CUDA;
+      if (note(cudaLaunchKernelEx(&cfg, reni_bwd_kernel<true, false>, p)) != cudaSuccess) return RENI_ERR_CUDA;
     } else {
-      if (note(cudaFuncSetAttribute(reni_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::kTotal)) !=
-          cudaSuccess)
+      if (note(cudaFuncSetAttribute(reni_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    BwdSmem::kTotal)) != cudaSuccess)
         return RENI_ERR_CUDA;
-      if (note(cudaLaunchKernelEx(&cfg, reni_bwd_kernel<false>, p)) != cudaSuccess) return RENI_ERR_CUDA;
+      if (note(cudaLaunchKernelEx(&cfg, reni_bwd_kernel<false, true>, p)) != cudaSuccess) return RENI_ERR_CUDA;
     }
   }
   if (last_err() != cudaSuccess) return RENI_ERR_CUDA;

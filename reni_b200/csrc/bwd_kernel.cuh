@@ -39,7 +39,8 @@ struct BwdParams {
   int64_t sw_bstride;
   const float* map_loss;  // (B, 32): [16..18] = coefA_c, [19..21] = coefB_c (cosine term, pre-scaled by S)
   const float* scalars;   // [0] = S (gradient scale)
-  const __half* wb2;      // L backward weight images split for CTA pairs: [l][k half][j/8][128][8]
+  const __half* wb;       // L backward weight images [j/8][k][8] (unpaired mode)
+  const __half* wb2;      // ... split for CTA pairs: [l][k half][j/8][128][8]
   const __half* w6b;      // [2][256][8]
   const uint16_t* stash_u;  // 16-bit phases of a_l, per tile (L+1) tile images
   __half* stash_d;        // delta stash: per tile nslots images (nslots = L+1 or 1)
@@ -74,7 +75,7 @@ DEVINL uint32_t delta2(float acc0, float acc1, uint32_t w) {
   return pack_half2(acc0 * abl_cos(phase_angle_lo(w)), acc1 * abl_cos(phase_angle_hi(w)));
 }
 
-template <bool kNeedDW>
+template <bool kNeedDW, bool kPair>
 __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5;
@@ -89,16 +90,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + BwdSmem::kTmemPtr);
 
   const int L = p.L;
-  // cluster k owns tile quads q = k, k + nclusters, ... taken in DESCENDING tile order (the forward kernel's last
-  // tiles are the freshest in L2); leader: tiles {4q, 4q+1}, peer: {4q+2, 4q+3}
-  const uint32_t crank = cluster_ctarank();
-  const int nunits = (p.ntiles + 3) / 4;
-  const int nworkers = (int)(gridDim.x >> 1);
-  const int worker = (int)(blockIdx.x >> 1);
+  // Work units are taken in DESCENDING tile order (the forward kernel's last tiles are the freshest in L2).
+  // kPair (cluster of 2, used without weight gradients): cluster k owns tile quads; leader: tiles {4q, 4q+1}, peer:
+  // {4q+2, 4q+3}.  Unpaired (with weight gradients: the stash traffic makes the coupled pair wait for its slower half,
+  // measured 327 vs 307 us at cfg 2): CTA c owns tile pairs.
+  const uint32_t crank = kPair ? cluster_ctarank() : 0;
+  constexpr int kUnitTiles = kPair ? 4 : 2;
+  const int nunits = (p.ntiles + kUnitTiles - 1) / kUnitTiles;
+  const int nworkers = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int worker = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int iters = (nunits - worker + nworkers - 1) / nworkers;
   auto clamp02 = [](int x) { return x < 0 ? 0 : (x > 2 ? 2 : x); };
-  auto unit_base = [&](int it) { return (nunits - 1 - (worker + it * nworkers)) * 4; };  // first tile of the quad
-  constexpr int kChunks = 4;  // per layer pass: 4 x [8 j-groups][128 k][8] = K 64 of this CTA's N half
+  auto unit_base = [&](int it) { return (nunits - 1 - (worker + it * nworkers)) * kUnitTiles; };  // first tile of the unit
+  // per layer pass: paired 4 x [8 j-groups][128 k][8] (K 64 of this CTA's N half), unpaired 8 x [4 j-groups][256 k][8]
+  constexpr int kChunks = kPair ? 4 : 8;
+  constexpr int kSteps = kPair ? 4 : 2;          // K = 16 steps per chunk
+  constexpr uint32_t kBRows = kPair ? 128 : 256;  // rows of B in this CTA's chunk
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kBwdStages; ++i) {
@@ -113,22 +120,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
     mbar_init(&a_ready_peer[1], 8);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc2<512>(tmem_ptr);
+  if (warp == 1) {
+    if (kPair) tmem_alloc2<512>(tmem_ptr);
+    else tmem_alloc<512>(tmem_ptr);
+  }
   {  // this CTA's 128 of the 256 columns of W_out'': [c/8 2][128 k][8]
     const uint4* src = reinterpret_cast<const uint4*>(p.w6b);
     uint4* dst = reinterpret_cast<uint4*>(smem + BwdSmem::kW6);
-    for (int i = threadIdx.x; i < kW6ImageBytes / 32; i += kBwdThreads)
-      dst[i] = src[(i >> 7) * kH + crank * 128 + (i & 127)];
+    if (kPair) {
+      for (int i = threadIdx.x; i < kW6ImageBytes / 32; i += kBwdThreads)
+        dst[i] = src[(i >> 7) * kH + crank * 128 + (i & 127)];
+    } else {
+      for (int i = threadIdx.x; i < kW6ImageBytes / 16; i += kBwdThreads) dst[i] = src[i];
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // both CTAs' barriers and TMEM exist before anything crosses the pair
+  if (kPair) cluster_sync_all();  // both CTAs' barriers and TMEM exist before anything crosses the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t ra_peer = mapa_u32(smem_u32(a_ready_peer), 0);
+  const uint32_t ra_peer = kPair ? mapa_u32(smem_u32(a_ready_peer), 0) : 0;
   auto signal_ready = [&](int g) {  // "sub-tile g of this CTA is in shared memory"
-    if (crank == 1) {
+    if (kPair && crank == 1) {
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(ra_peer + g * 8);
     } else {
@@ -158,10 +172,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
                                kTileImageBytes);
             for (int c = 0; c < kChunks; ++c) {
               mbar_wait(&w_empty[st], ph ^ 1);
-              if (crank == 0) mbar_arrive_expect_tx(&w_full[st], 2 * kWChunkBytes);
-              const int32_t row =
-                  (int32_t)(((size_t)((l - 1) * 2 + crank) * (kWImageBytes / 2) + (size_t)c * kWChunkBytes) / 256);
-              tma2_load_2d(smem + BwdSmem::kRing + st * kWChunkBytes, &p.wmap, 0, row, mapa_u32(smem_u32(&w_full[st]), 0));
+              if (kPair) {
+                if (crank == 0) mbar_arrive_expect_tx(&w_full[st], 2 * kWChunkBytes);
+                const int32_t row =
+                    (int32_t)(((size_t)((l - 1) * 2 + crank) * (kWImageBytes / 2) + (size_t)c * kWChunkBytes) / 256);
+                tma2_load_2d(smem + BwdSmem::kRing + st * kWChunkBytes, &p.wmap, 0, row,
+                             mapa_u32(smem_u32(&w_full[st]), 0));
+              } else {
+                mbar_arrive_expect_tx(&w_full[st], kWChunkBytes);
+                bulk_g2s(smem + BwdSmem::kRing + st * kWChunkBytes,
+                         reinterpret_cast<const uint8_t*>(p.wb) + (size_t)(l - 1) * kWImageBytes + (size_t)c * kWChunkBytes,
+                         kWChunkBytes, &w_full[st]);
+              }
               if (++st == kBwdStages) { st = 0; ph ^= 1; }
             }
           }
@@ -171,8 +193,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
   } else if (warp == 1) {
     // ============================================================ MMA issuer (leader CTA: issues for the pair)
     if (lane == 0 && crank == 0) {
-      constexpr uint32_t idesc_h = umma_idesc_f16(256, 256, 0, 0);
-      constexpr uint32_t idesc_r = umma_idesc_f16(256, kW6N, 1, 1);
+      constexpr uint32_t kM = kPair ? 256 : 128;
+      constexpr uint32_t idesc_h = umma_idesc_f16(kM, 256, 0, 0);
+      constexpr uint32_t idesc_r = umma_idesc_f16(kM, kW6N, 1, 1);
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+        if (kPair) umma2_f16_ss(d, da, db, idesc, acc);
+        else umma_f16_ss(d, da, db, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar, uint16_t mask) {
+        if (kPair) umma2_commit_multicast(bar, mask);
+        else umma_commit(bar);
+      };
       const uint32_t a_base = smem_u32(smem + BwdSmem::kA);
       const uint32_t ring_base = smem_u32(smem + BwdSmem::kRing);
       const uint32_t w6_base = smem_u32(smem + BwdSmem::kW6);
@@ -181,7 +212,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
       for (int it = 0; it < iters; ++it) {
         const int ubase = unit_base(it);
         const int nsub = clamp02(p.ntiles - ubase);           // live sub-tiles of the leader
-        const int nsub_peer = clamp02(p.ntiles - ubase - 2);  // ... of the peer
+        const int nsub_peer = kPair ? clamp02(p.ntiles - ubase - 2) : 0;  // ... of the peer
         for (int l = L + 1; l >= 0; --l) {  // l = L+1: output layer (K = 16); L..1: hidden layer l; 0: layer-0 reduction
           for (int g = 0; g < nsub; ++g) {
             mbar_wait(&a_ready[g], (a_ph >> g) & 1);
@@ -196,8 +227,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
             if (l == L + 1) {
               // A: g_y [128 x 16] of each CTA; B: each CTA's [2][128 k][8] half of W_out''
               const uint64_t da = umma_smem_desc(a_tile, 2048, 128);
-              const uint64_t db = umma_smem_desc(w6_base, 2048, 128);
-              umma2_f16_ss(d_tmem, da, db, idesc_h, 0);
+              const uint64_t db = umma_smem_desc(w6_base, kBRows * 16, 128);
+              mma(d_tmem, da, db, idesc_h, 0);
             } else if (l == 0) {
               // D_r[j, i] = sum_rows delta0_r[row, j] * F[row, i]: MN-major views of [k/8][128][8] images; CTA r
               // contributes columns 8r..8r+7 of B (its own [f | 1] features), so it reads back columns 8r.. of D
@@ -208,7 +239,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
                 for (int ks = 0; ks < kTileRows / 16; ++ks) {
                   const uint64_t da = umma_smem_desc(a_tile + mh * 16 * 2048 + ks * 256, 128, 2048);
                   const uint64_t db = umma_smem_desc(f_tile + ks * 256, 128, 2048);
-                  umma2_f16_ss(d_tmem + mh * kW6N, da, db, idesc_r, ks != 0);
+                  mma(d_tmem + mh * kW6N, da, db, idesc_r, ks != 0);
                 }
               }
             } else {
@@ -217,17 +248,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
                 tc_fence_after();
                 const uint32_t b_tile = ring_base + st * kWChunkBytes;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  // A: [j/8][128][8] -> 2048 B per 8-column group; B: [j/8][128 k][8] -> 2048 B per group
-                  const uint64_t da = umma_smem_desc(a_tile + (c * 4 + ks) * 4096, 2048, 128);
-                  const uint64_t db = umma_smem_desc(b_tile + ks * 4096, 2048, 128);
-                  umma2_f16_ss(d_tmem, da, db, idesc_h, (c | ks) != 0);
+                for (int ks = 0; ks < kSteps; ++ks) {
+                  // A: [j/8][128][8] -> 2048 B per 8-column group; B: [j/8][kBRows k][8] -> kBRows * 16 B per group
+                  const uint64_t da = umma_smem_desc(a_tile + (c * kSteps + ks) * 4096, 2048, 128);
+                  const uint64_t db = umma_smem_desc(b_tile + ks * (kBRows * 32), kBRows * 16, 128);
+                  mma(d_tmem, da, db, idesc_h, (c | ks) != 0);
                 }
-                umma2_commit_multicast(&w_empty[st], 0x3);
+                commit(&w_empty[st], 0x3);
                 if (++st == kBwdStages) { st = 0; ph ^= 1; }
               }
             }
-            umma2_commit_multicast(&acc_full[g], (g < nsub_peer) ? 0x3 : 0x1);
+            commit(&acc_full[g], (g < nsub_peer) ? 0x3 : 0x1);
           }
         }
       }
@@ -382,10 +413,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // the pair's MMAs, multicast commits and remote arrivals are all behind us
+  if (kPair) cluster_sync_all();  // the pair's MMAs, multicast commits and remote arrivals are all behind us
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc2<512>(tmem_base);
+    if (kPair) tmem_dealloc2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 

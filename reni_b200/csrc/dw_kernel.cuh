@@ -142,13 +142,17 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
       umma_commit(done);
     }
   } else {
-    // ---- bias-gradient column sums straight from the smem operand (lane <-> row: conflict-free 16 B reads)
+    // ---- converters; bias-gradient column sums straight from the smem operand: thread t owns the 8 columns of group
+    // jg = t >> 3 and every 8th row (rset = t & 7), so a quarter-warp reads 128 contiguous bytes (conflict-free) and
+    // the running sums take 8 registers (a per-row layout took 64 and kept this kernel at 157 registers, which left no
+    // room on the SM for the small kernels that are forked beside it)
     const uint32_t t = threadIdx.x - 64;  // 0..255
-    const uint32_t r = t & 63;            // row inside the 64-row block
-    const uint32_t kset = t >> 6;         // 8-column groups kset*8 .. kset*8+7
-    float acc[64];
+    const uint32_t r = t & 63;            // conversion: row inside the 64-row block
+    const uint32_t kset = t >> 6;         // conversion: 8-column groups kset*8 .. kset*8+7
+    const uint32_t jg = t >> 3, rset = t & 7;
+    float acc[8];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     {
       uint32_t st = 0, ph = 0;
       for (int s = s_begin; s < s_end; ++s) {
@@ -172,22 +176,17 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
         }
         // (2) bias-gradient column sums from the delta / g_y image
         const uint8_t* base = stage + img_off;
-        if (!is_out) {
+        if (!is_out || jg == 0) {  // (g_y has 16 padded columns: only group 0 carries data)
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint4 v = *reinterpret_cast<const uint4*>(base + ((kset * 8 + kk) * kHalfRows + r) * 16);
+          for (int i = 0; i < 8; ++i) {
+            const uint4 v = *reinterpret_cast<const uint4*>(base + (jg * kHalfRows + rset + 8 * i) * 16);
             const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
             const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
             const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
             const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
-            acc[kk * 8 + 0] += f0.x; acc[kk * 8 + 1] += f0.y; acc[kk * 8 + 2] += f1.x; acc[kk * 8 + 3] += f1.y;
-            acc[kk * 8 + 4] += f2.x; acc[kk * 8 + 5] += f2.y; acc[kk * 8 + 6] += f3.x; acc[kk * 8 + 7] += f3.y;
+            acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+            acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
           }
-        } else if (kset == 0) {
-          const uint4 v = *reinterpret_cast<const uint4*>(base + r * 16);
-          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-          acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x;
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -200,25 +199,21 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
     mbar_wait(done, 0);
     tc_fence_after();
     const float inv_s = __ldg(p.scalars + 1);
-    float* s_red = reinterpret_cast<float*>(smem + DwSmem::kRing);  // [64 rows][257] floats
-    named_bar_sync(1, 256);  // every reader is done with the last stages before the ring is reused
     if (nst > 0) {
-      if (!is_out) {
+      // column sums: add up the 8 row subsets (lanes that differ in their low 3 bits), one atomic per column
 #pragma unroll
-        for (int i = 0; i < 64; ++i) s_red[r * 257 + kset * 64 + i] = acc[i];
-      } else if (kset == 0) {
-        s_red[r * 257 + 0] = acc[0];
-        s_red[r * 257 + 1] = acc[1];
-        s_red[r * 257 + 2] = acc[2];
+      for (int i = 0; i < 8; ++i) {
+        float x = acc[i];
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        x += __shfl_xor_sync(0xffffffffu, x, 4);
+        acc[i] = x;
       }
-    }
-    named_bar_sync(1, 256);
-    if (nst > 0) {
-      const int ncol = is_out ? p.out_features : kH;
-      if ((int)t < ncol) {
-        float s = 0.f;
-        for (int rr = 0; rr < 64; ++rr) s += s_red[rr * 257 + t];
-        atomicAdd(p.db[layer] + t, s * inv_s);
+      if (rset == 0) {
+        const int ncol = is_out ? p.out_features : kH;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if ((int)(jg * 8 + i) < ncol && (!is_out || jg == 0)) atomicAdd(p.db[layer] + jg * 8 + i, acc[i] * inv_s);
       }
       const uint32_t q = warp & 3;
       const uint32_t mh = (warp - 2) >> 2;
