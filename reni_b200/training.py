@@ -185,15 +185,15 @@ class RENITrainer:
             s_idx.copy_(idx)
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):  # warm-up outside capture: lazy allocations, function attributes, NCCL
+            with torch.cuda.stream(side):  # warm-up outside capture: lazy allocations, function attributes
                 for _ in range(2):
                     self._ws.prepared_key = None
-                    self._eager_step((s_imgs, s_idx))
+                    self._eager_step((s_imgs, s_idx), exchange=False)
             torch.cuda.current_stream(self.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             self._ws.prepared_key = None  # the fp32 -> fp16 weight conversion is part of every replayed step
-            with torch.cuda.graph(graph):
-                log = self._eager_step((s_imgs, s_idx))
+            with torch.cuda.graph(graph):  # compute only: the NCCL exchange is launched behind each replay
+                log = self._eager_step((s_imgs, s_idx), exchange=False)
             entry = (graph, s_imgs, s_idx, log, self._latent_table().grad)
             self._graphs[key] = entry
         graph, s_imgs, s_idx, log, table_grad = entry
@@ -208,10 +208,11 @@ class RENITrainer:
         # the replay refreshed the captured gradient tensors in place; make sure the parameters still point at them
         self._latent_table().grad = table_grad
         if self.flat is not None:
+            self.flat.all_reduce_mean(self.group)  # the ONE exchange step of data-parallel training
             self.flat.attach()
         return log
 
-    def _eager_step(self, batch) -> Dict[str, torch.Tensor]:
+    def _eager_step(self, batch, exchange: bool = True) -> Dict[str, torch.Tensor]:
         slot = self._take_prefetched(batch)
         imgs, idx = batch
         if slot is not None:
@@ -260,7 +261,8 @@ class RENITrainer:
             if self.task == "FIT_LATENT":
                 log.update(mse_loss=res.mse_loss, prior_loss=res.prior_loss, cosine_loss=res.cosine_loss)
         if need_dw:
-            self.flat.all_reduce_mean(self.group)  # the ONE exchange step of data-parallel training
+            if exchange:
+                self.flat.all_reduce_mean(self.group)  # the ONE exchange step of data-parallel training
             self.flat.attach()
         self.last_output = res.out
         return log
