@@ -73,8 +73,9 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
     w.stash_h = -1;
     w.stash_d = dw ? take(ntiles * (L + 1) * (int64_t)kTileImageBytes) : -1;  // slot 0 unused (delta_0 stays on chip)
     w.stash_gy = take(ntiles * (int64_t)kGyImageBytes);
+    w.aout = c->last_layer_linear ? -1 : take(B * P * 3 * 4);  // sine output layer: its pre-activations
   } else {
-    w.stash_c = w.stash_h = w.stash_d = w.stash_gy = -1;
+    w.stash_c = w.stash_h = w.stash_d = w.stash_gy = w.aout = -1;
   }
   w.total = off;
   return w;
@@ -275,6 +276,7 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   p.sw = sw;
   p.sw_bstride = sw_bstride;
   p.loss_part = (flags & RENI_FLAG_LOSS) ? at<float>(ws, w.loss_part) : nullptr;
+  p.aout = at<float>(ws, w.aout);
   p.B = (int)B;
   p.P = (int)P;
   p.tiles_per_map = (int)tiles_per_map(P);
@@ -345,6 +347,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   BwdParams p{};
   p.out = out;
   p.grad_out = grad_out;
+  p.aout = at<float>(ws, w.aout);
   p.target = target;
   p.sw = sw;
   p.sw_bstride = sw_bstride;
@@ -429,6 +432,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
       q.db[i] = host_db[i];
     }
     q.scalars = at<float>(ws, w.scalars);
+    q.out_scale = c->last_layer_linear ? 1.f : c->hidden_omega_0;
     q.ntiles = ntiles;
     q.L = L;
     q.out_features = c->out_features;
@@ -506,7 +510,6 @@ int32_t reni_backward(const reni_config_t* c, const float* Z, const float* D, in
                       const float* grad_out, float* dZ, float* const* host_dW, float* const* host_db, void* ws,
                       int64_t ws_bytes, int32_t flags, void* stream_) {
   if (!config_ok(c)) return RENI_ERR_BAD_CONFIG;
-  if (!c->last_layer_linear) return RENI_ERR_BAD_CONFIG;  // sine output layer: forward only on this path
   if (Z == nullptr || D == nullptr || host_weights == nullptr || host_weights[0] == nullptr || out == nullptr ||
       grad_out == nullptr || ws == nullptr || B < 1 || P < 1)
     return RENI_ERR_BAD_ARGUMENT;
@@ -535,7 +538,6 @@ int32_t reni_loss_forward_backward(const reni_config_t* c, const float* Z, const
                                    float* const* host_dW, float* const* host_db, void* ws, int64_t ws_bytes,
                                    int32_t flags, void* stream_) {
   if (!config_ok(c)) return RENI_ERR_BAD_CONFIG;
-  if (!c->last_layer_linear) return RENI_ERR_BAD_CONFIG;
   if (host_weights == nullptr || host_biases == nullptr || host_weights[0] == nullptr || host_biases[0] == nullptr ||
       target == nullptr || sw == nullptr || out == nullptr || loss_out == nullptr)
     return RENI_ERR_BAD_ARGUMENT;

@@ -34,6 +34,7 @@ constexpr int kBwdStages = 4;
 struct BwdParams {
   const float* out;       // (B, P, 3) forward output (after tanh)
   const float* grad_out;  // (B, P, 3) external gradient, or null for the fused loss
+  const float* aout;      // sine output layer (RENI.py:164-171): (B, P, 3) pre-activations a_out, else null
   const float* target;    // fused loss
   const float* sw;
   int64_t sw_bstride;
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
             const float o = __ldg(p.out + e + c);
             float gg = __ldg(p.grad_out + e + c) * S;
             if (p.out_tanh) gg *= (1.f - o * o);
+            if (p.aout != nullptr) gg *= cosf(__ldg(p.aout + e + c));  // d sin(a_out) / d a_out
             gy[c] = gg;
           }
         } else {
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
             float gg = (o - t) * __ldg(wp + c);
             if (p.use_cos) gg += __ldg(ml + 16 + c) * t + __ldg(ml + 19 + c) * o;
             if (p.out_tanh) gg *= (1.f - o * o);
+            if (p.aout != nullptr) gg *= cosf(__ldg(p.aout + e + c));
             gy[c] = gg;
           }
         }

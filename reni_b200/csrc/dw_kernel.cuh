@@ -29,6 +29,7 @@ struct DwParams {
   float* dW[kMaxHiddenLayers + 2];  // [1..L] hidden (256x256), [L+1] output (out_features x 256); [0] unused
   float* db[kMaxHiddenLayers + 2];
   const float* scalars;  // [1] = 1 / S
+  float out_scale;       // omega of a sine output layer (its pre-activation is omega * (W h + b)), else 1
   int ntiles, L, out_features;
 };
 
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
     // ---- flush: all MMAs done -> ring is free for the cross-row reduction, TMEM holds dW
     mbar_wait(done, 0);
     tc_fence_after();
-    const float inv_s = __ldg(p.scalars + 1);
+    const float inv_s = __ldg(p.scalars + 1) * (is_out ? p.out_scale : 1.f);
     if (nst > 0) {
       // column sums: add up the 8 row subsets (lanes that differ in their low 3 bits), one atomic per column
 #pragma unroll

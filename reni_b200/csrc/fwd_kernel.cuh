@@ -54,6 +54,7 @@ struct FwdParams {
   const float* sw;       // (B or 1, P, 3)
   int64_t sw_bstride;
   float* loss_part;      // (ntiles, 4 warps, 10)
+  float* aout;           // kTrain with a sine output layer: (B, P, 3) pre-activations a_out (the backward needs cos a_out)
   int B, P, tiles_per_map, ntiles, L;
   int out_tanh, last_sine, so2;
   unsigned long long* trace;  // debug: per-role clock64 timeline of CTA 0 (reni_debug_set_trace), else null
@@ -425,7 +426,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               float y = __uint_as_float(v[c]) + bo[c];
-              if (p.last_sine) y = sinf(y);
+              if (p.last_sine) {
+                if (kTrain && rvalid) p.aout[((size_t)b * p.P + pix) * 3 + c] = y;
+                y = sinf(y);
+              }
               if (p.out_tanh) y = tanhf(y);
               o[c] = y;
             }
@@ -613,7 +617,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             float y = __uint_as_float(v[c]) + bo[c];
-            if (p.last_sine) y = sinf(y);
+            if (p.last_sine) {
+              if (kTrain && rvalid) p.aout[((size_t)b * p.P + pix) * 3 + c] = y;
+              y = sinf(y);
+            }
             if (p.out_tanh) y = tanhf(y);
             o[c] = y;
           }

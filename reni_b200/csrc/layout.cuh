@@ -41,6 +41,7 @@ struct WorkspaceLayout {
   // all offsets in bytes from the workspace base; 0-size regions are absent
   int64_t wf, wb, wf2, wb2, w6f, w6b, bias, mc;       // weight images + biases + per-map layer-0 (M_b, c_b)
   int64_t stash_h, stash_c, stash_d, stash_gy;   // per-tile activation / cos / delta stashes
+  int64_t aout;                                  // output pre-activations (sine output layer only)
   int64_t loss_part, map_loss, dmc, scalars;     // loss partials, per-map loss coefficients, per-map dM/dc
   int64_t xc, dxc, dip;                          // per-map constant encoding columns and their gradients
   int64_t total;

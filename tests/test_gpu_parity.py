@@ -208,6 +208,49 @@ def test_ragged_and_tiny_shapes_training(dev, B, P):
         assert O.rel_l2(r.db[i].cpu().numpy(), dbs[i]) < TOL_GRAD, f"db{i}"
 
 
+@pytest.mark.parametrize("act,eq", [("tanh", "SO2"), (None, "SO2"), ("tanh", "SO3")])
+def test_sine_output_layer_training_vs_oracle(dev, act, eq):
+    """last_layer_linear=False (a 7th SineLayer 256 -> 3, RENI.py:164-171): fused step and autograd path, all
+    gradients vs the oracle (the forward stashes the output pre-activation, the backward multiplies by its cosine)."""
+    torch.manual_seed(6)
+    from reni_b200 import RENIAutoDecoder
+    from reni_b200 import functional as F_
+
+    B, P, N = 3, 300, 6
+    m = RENIAutoDecoder(B, N, eq, 256, 3, 3, False, act, 30.0, 30.0, False).to(dev)
+    rng = np.random.default_rng(8)
+    D = rng.standard_normal((B, P, 3))
+    D = (D / np.linalg.norm(D, axis=-1, keepdims=True)).astype(np.float32)
+    tg = rng.uniform(-1, 1, (B, P, 3)).astype(np.float32)
+    sw = np.repeat(rng.uniform(0, 1, (B, P, 1)), 3, 2).astype(np.float32)
+    Z = m.Z.detach()
+    r = F_.loss_forward_backward(m.spec, F_.Workspace(), Z, t(D, dev), t(tg, dev), t(sw, dev), m.decoder_weights(),
+                                 m.decoder_biases(), alpha=1e-3, beta=0.3, use_cosine=True, need_dw=True)
+    torch.cuda.synchronize()
+    p = params_from_model(m)
+    Z64, D64, t64, s64 = (a.astype(np.float64) for a in (Z.cpu().numpy(), D, tg, sw))
+    o, tape = O.decoder_forward(Z64, D64, p, tape=True)
+    loss, mse, prior, cos = O.reni_test_loss(o, t64, s64, Z64, 1e-3, 0.3)
+    go = O.loss_grad_wrt_output(o, t64, s64, beta=0.3)
+    dWs, dbs, dZ = O.decoder_backward(Z64, D64, p, tape, go)
+    dZ = dZ + 2e-3 * Z64
+    assert abs(float(r.loss) - loss) < 2e-4 * abs(loss)
+    assert O.rel_l2(r.out.cpu().numpy(), o) < TOL_RADIANCE
+    assert O.rel_l2(r.dZ.cpu().numpy(), dZ) < TOL_GRAD
+    for i in range(len(dWs)):
+        assert O.rel_l2(r.dW[i].cpu().numpy(), dWs[i]) < TOL_GRAD, f"dW{i}"
+        assert O.rel_l2(r.db[i].cpu().numpy(), dbs[i]) < TOL_GRAD, f"db{i}"
+    # the autograd path (model(Z, D) -> external loss -> backward) goes through reni_backward with grad_out
+    m.zero_grad()
+    Zp = m.Z.detach().clone().requires_grad_(True)
+    out = m(Zp, t(D, dev))
+    (out * t(go.astype(np.float32), dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert O.rel_l2(Zp.grad.cpu().numpy(), dZ - 2e-3 * Z64) < TOL_GRAD
+    for i, w in enumerate(m.decoder_weights()):
+        assert O.rel_l2(w.grad.cpu().numpy(), dWs[i]) < TOL_GRAD, f"autograd dW{i}"
+
+
 def test_full_size_properties_config2(dev):
     """BASELINE configs[1] (N=36, 32 maps x 64x128): size-independent properties instead of the oracle.
     (1) SO(2) invariance: rotating Z and D about y leaves the radiance unchanged (SURVEY section 4);
