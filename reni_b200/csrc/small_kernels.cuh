@@ -140,19 +140,31 @@ __global__ void __launch_bounds__(256) reni_prologue_kernel(const PrologueParams
   const int j = blockIdx.x * 8 + warp;
   const float* w = p.W0 + (size_t)j * p.in_features;
   float c = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
-  for (int i = lane; i < p.in_features; i += 32) {
+  // the first N columns (inner products with the direction) also feed M_b; handled apart so the long loop is branch-free
+  for (int i = lane; i < N; i += 32) {
     const float wv = __ldg(w + i);
     c = fmaf(wv, s_x[i], c);
-    if (i < N) {
-      if (p.equivariance == 1) {
-        m0 = fmaf(wv, s_z[i * 3], m0);
-        m1 = fmaf(wv, s_z[i * 3 + 2], m1);
-      } else {
-        m0 = fmaf(wv, s_z[i * 3], m0);
-        m1 = fmaf(wv, s_z[i * 3 + 1], m1);
-        m2 = fmaf(wv, s_z[i * 3 + 2], m2);
-      }
+    if (p.equivariance == 1) {
+      m0 = fmaf(wv, s_z[i * 3], m0);
+      m1 = fmaf(wv, s_z[i * 3 + 2], m1);
+    } else {
+      m0 = fmaf(wv, s_z[i * 3], m0);
+      m1 = fmaf(wv, s_z[i * 3 + 1], m1);
+      m2 = fmaf(wv, s_z[i * 3 + 2], m2);
     }
+  }
+  {  // remaining columns: 4 independent loads in flight per lane (the row is read once, latency-bound otherwise)
+    float c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    int i = N + lane;
+    for (; i + 96 < p.in_features; i += 128) {
+      const float w0 = __ldg(w + i), w1 = __ldg(w + i + 32), w2 = __ldg(w + i + 64), w3 = __ldg(w + i + 96);
+      c = fmaf(w0, s_x[i], c);
+      c1 = fmaf(w1, s_x[i + 32], c1);
+      c2 = fmaf(w2, s_x[i + 64], c2);
+      c3 = fmaf(w3, s_x[i + 96], c3);
+    }
+    for (; i < p.in_features; i += 32) c = fmaf(__ldg(w + i), s_x[i], c);
+    c += c1 + c2 + c3;
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
