@@ -306,6 +306,88 @@ def test_full_size_properties_config2(dev):
     assert O.rel_max(outs, refs) < TOL_RADIANCE_MAX
 
 
+def test_full_size_properties_configs_3_4_5(dev):
+    """The other BASELINE shapes through size-independent properties:
+    cfg 3 (N=100, 128x256): per-map results do not depend on which other maps share the batch; the fused step's dZ equals
+        the autograd path's; SO(2) invariance;
+    cfg 4 (frozen decoder, masked RENITestLoss, 64x128): latent-only gradients equal the training-mode dZ; masked pixels
+        carry no MSE gradient (the loss is unchanged when the target is altered under the mask);
+    cfg 5 (inference, 256x512, N in {9, 49}): inference kernel == training-forward output bit for bit, map permutation
+        permutes the output, deterministic."""
+    from reni_b200 import RENIAutoDecoder, get_directions, get_sineweight, rectangle_mask
+    from reni_b200 import functional as F_
+
+    torch.manual_seed(21)
+    # ---- cfg 3 shape (8 of the 32 maps a GPU holds)
+    B, N, W = 8, 100, 256
+    P = W * W // 2
+    m = RENIAutoDecoder(B, N, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+    D, sw = get_directions(W).to(dev), get_sineweight(W).to(dev)
+    tg = torch.rand(B, P, 3, device=dev) * 2 - 1
+    Z = m.Z.detach()
+    ws = F_.Workspace()
+    full = F_.loss_forward_backward(m.spec, ws, Z, D, tg, sw, m.decoder_weights(), m.decoder_biases())
+    sub = F_.loss_forward_backward(m.spec, ws, Z[[5, 2]], D, tg[[5, 2]], sw, m.decoder_weights(), m.decoder_biases())
+    assert torch.equal(full.out[[5, 2]], sub.out)
+    assert torch.allclose(full.dZ[[5, 2]], sub.dZ, rtol=1e-4, atol=1e-9)
+    Zp = Z.clone().requires_grad_(True)
+    out = m(Zp, D)
+    loss = (((out - tg) ** 2) * sw).mean(dim=(1, 2)).sum()  # RENITrainLoss (loss_functions.py:6-13,39-45)
+    loss.backward()
+    assert float((out.detach() - full.out).abs().max()) == 0.0
+    assert abs(float(loss.detach()) - float(full.loss)) < 1e-5 * float(loss.detach())
+    assert float((Zp.grad - full.dZ).norm() / full.dZ.norm()) < 2e-3
+    th = 0.7
+    R = torch.tensor([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]], device=dev, dtype=torch.float32)
+    with torch.no_grad():
+        o_rot = m(Z[:2] @ R.T, D @ R.T)
+    assert float((o_rot - full.out[:2]).norm() / full.out[:2].norm()) < TOL_RADIANCE
+    del full, sub, out, ws
+    # ---- cfg 4: latent-only, masked
+    B, N, W = 64, 36, 128
+    P = W * W // 2
+    mf = RENIAutoDecoder(B, N, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+    D, sw = get_directions(W).to(dev), get_sineweight(W).to(dev)
+    mask = rectangle_mask(W, 10, 46, 40, 82).to(dev)
+    swm = sw * mask
+    tg = torch.rand(B, P, 3, device=dev) * 2 - 1
+    Z = mf.Z.detach()
+    ws = F_.Workspace()
+    kw = dict(alpha=1e-7, beta=1e-4, use_cosine=True)
+    lat = F_.loss_forward_backward(mf.spec, ws, Z, D, tg, swm, mf.decoder_weights(), mf.decoder_biases(), need_dw=False, **kw)
+    trn = F_.loss_forward_backward(mf.spec, F_.Workspace(), Z, D, tg, swm, mf.decoder_weights(), mf.decoder_biases(),
+                                   need_dw=True, **kw)
+    assert lat.dW is None
+    assert float((lat.dZ - trn.dZ).norm() / trn.dZ.norm()) < 1e-4
+    assert abs(float(lat.loss) - float(trn.loss)) <= 1e-6 * abs(float(trn.loss))
+    tg2 = torch.where(mask.expand_as(tg) == 0, -tg, tg)  # change the target only where the mask is zero
+    lat2 = F_.loss_forward_backward(mf.spec, ws, Z, D, tg2, swm, mf.decoder_weights(), mf.decoder_biases(), need_dw=False,
+                                    alpha=1e-7, beta=0.0, use_cosine=False)
+    lat3 = F_.loss_forward_backward(mf.spec, ws, Z, D, tg, swm, mf.decoder_weights(), mf.decoder_biases(), need_dw=False,
+                                    alpha=1e-7, beta=0.0, use_cosine=False)
+    assert abs(float(lat2.mse_loss) - float(lat3.mse_loss)) <= 1e-6 * abs(float(lat3.mse_loss))
+    assert float((lat2.dZ - lat3.dZ).norm() / lat3.dZ.norm()) < 1e-4
+    del lat, trn, lat2, lat3, ws
+    # ---- cfg 5: inference at 256x512
+    W = 512
+    P = W * W // 2
+    D = get_directions(W).to(dev)
+    for N in (9, 49):
+        mi = RENIAutoDecoder(4, N, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+        Z = mi.Z.detach()
+        with torch.no_grad():
+            o = mi(Z, D)
+            assert torch.equal(o, mi(Z, D))
+            perm = torch.tensor([2, 0, 3, 1], device=dev)
+            assert torch.equal(mi(Z[perm], D), o[perm])
+        tgt = torch.zeros(4, P, 3, device=dev)
+        swf = get_sineweight(W).to(dev)
+        r = F_.loss_forward_backward(mi.spec, F_.Workspace(), Z, D, tgt, swf, mi.decoder_weights(), mi.decoder_biases(),
+                                     need_dw=False)
+        assert torch.equal(r.out, o)
+        assert o.shape == (4, P, 3) and bool(torch.isfinite(o).all())
+
+
 def test_trainer_steps_autodecoder_and_vad(dev):
     """RENITrainer mirrors training_step + Adam: losses fall, gradients land where the reference puts them."""
     torch.manual_seed(7)
