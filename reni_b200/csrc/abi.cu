@@ -55,6 +55,7 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   w.wb = take(L * kWImageBytes);
   w.wf2 = take(L * kWImageBytes);
   w.wb2 = take(L * kWImageBytes);
+  w.wbias2 = take(L * 2 * kBiasBlockBytes);
   w.w6f = take(kW6ImageBytes);
   w.w6b = take(kW6ImageBytes);
   w.bias = take((L * kH + 16) * 4);
@@ -210,6 +211,7 @@ int32_t reni_prepare_weights(const reni_config_t* c, const float* const* host_we
   p.wb = at<__half>(ws, w.wb);
   p.wf2 = at<__half>(ws, w.wf2);
   p.wb2 = at<__half>(ws, w.wb2);
+  p.wbias2 = at<__half>(ws, w.wbias2);
   p.w6f = at<__half>(ws, w.w6f);
   p.w6b = at<__half>(ws, w.w6b);
   p.bias = at<float>(ws, w.bias);
@@ -287,6 +289,7 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   p.so2 = c->equivariance == RENI_EQ_SO2;
   p.trace = g_trace;
   memset(&p.wmap, 0, sizeof(p.wmap));
+  memset(&p.bmap, 0, sizeof(p.bmap));
   const int npairs = (p.ntiles + 1) / 2;
   const bool train = (flags & RENI_FLAG_SAVE_FOR_BACKWARD) != 0;
   // CTA pairs (cluster of 2) share the weight stream: half the L2 -> SM weight traffic per SM
@@ -294,6 +297,8 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   int grid = npairs < sms ? npairs : sms;
   if (pair_mode) {  // one cluster of two CTAs per tile quad
     if (!encode_rows256(&p.wmap, p.wf2, (uint64_t)p.L * kWImageBytes, kWChunkBytes / 256)) return RENI_ERR_CUDA;
+    if (!encode_rows256(&p.bmap, at<__half>(ws, w.wbias2), (uint64_t)p.L * 2 * kBiasBlockBytes, kBiasBlockBytes / 256))
+      return RENI_ERR_CUDA;
     const int nquads = (p.ntiles + 3) / 4;
     const int nclusters = nquads < sms / 2 ? nquads : sms / 2;
     grid = 2 * nclusters;

@@ -59,6 +59,7 @@ struct FwdParams {
   int out_tanh, last_sine, so2;
   unsigned long long* trace;  // debug: per-role clock64 timeline of CTA 0 (reni_debug_set_trace), else null
   alignas(64) CUtensorMap wmap;  // paired mode: wf2 as rows of 256 B, box = one 16 KB half chunk (TMA tile loads)
+  alignas(64) CUtensorMap bmap;  // paired mode: wbias2 as rows of 256 B, box = one 4 KB bias block
 };
 
 struct FwdSmem {
@@ -69,7 +70,8 @@ struct FwdSmem {
   static constexpr int kW6 = kRing + kRingBytes;                      // final-layer image
   static constexpr int kBias = kW6 + kW6ImageBytes;                   // (kMaxHiddenLayers*256 + 16) floats
   static constexpr int kMc = kBias + (kMaxHiddenLayers * kH + 16) * 4;  // 2 x 5 x 256 floats
-  static constexpr int kBars = kMc + 2 * 5 * kH * 4;                  // mbarriers
+  static constexpr int kOnes = kMc + 2 * 5 * kH * 4;                  // [2 k-groups][128][8] fp16: columns (1, 1, 0, ...)
+  static constexpr int kBars = kOnes + kBiasBlockBytes;               // mbarriers
   static constexpr int kNumBars = 2 * kMaxStages + 6;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemPtr + 16;
@@ -87,10 +89,10 @@ DEVINL void trace_ev(const FwdParams& p, int role, uint32_t& n, uint32_t code) {
 // sin of 8 pre-activations -> packed fp16 and, if kPhase, their packed 16-bit phases
 template <bool kPhase>
 DEVINL void sin8(const float (&a)[8], uint4& hv, uint4& uv) {
-  hv.x = pack_half2(abl_sin(a[0]), abl_sin(a[1]));
-  hv.y = pack_half2(abl_sin(a[2]), abl_sin(a[3]));
-  hv.z = pack_half2(abl_sin(a[4]), abl_sin(a[5]));
-  hv.w = pack_half2(abl_sin(a[6]), abl_sin(a[7]));
+  hv.x = pack_half2(epi_sin<0>(a[0]), epi_sin<1>(a[1]));
+  hv.y = pack_half2(epi_sin<2>(a[2]), epi_sin<3>(a[3]));
+  hv.z = pack_half2(epi_sin<4>(a[4]), epi_sin<5>(a[5]));
+  hv.w = pack_half2(epi_sin<6>(a[6]), epi_sin<7>(a[7]));
   if (kPhase) {
     uv.x = phase_encode2(a[0], a[1]);
     uv.y = phase_encode2(a[2], a[3]);
@@ -160,6 +162,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
     }
     const int nb = L * kH + 16;
     for (int i = threadIdx.x; i < nb; i += kFwdThreads) s_bias[i] = p.bias[i];
+    // A operand of the bias K-step: every row = (1, 1, 0, ..., 0)
+    uint4* ones = reinterpret_cast<uint4*>(smem + FwdSmem::kOnes);
+    for (int i = threadIdx.x; i < kBiasBlockBytes / 16; i += kFwdThreads)
+      ones[i] = (i < kTileRows) ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -189,6 +195,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
         const int nstream = clamp02(p.ntiles - ubase);  // passes the (leader's) MMA issuer makes over each layer
         for (int l = 0; l < L; ++l) {
           for (int g = 0; g < nstream; ++g) {
+            if (kPair) {  // the layer's bias block rides the ring as a small extra chunk ahead of the weights
+              mbar_wait(&w_empty[st], ph ^ 1);
+              if (crank == 0) mbar_arrive_expect_tx(&w_full[st], 2 * kBiasBlockBytes);
+              tma2_load_2d(smem + FwdSmem::kRing + st * kChunkBytes, &p.bmap, 0,
+                           (int32_t)((l * 2 + crank) * (kBiasBlockBytes / 256)), mapa_u32(smem_u32(&w_full[st]), 0));
+              if (++st == kStages) { st = 0; ph ^= 1; }
+            }
             for (int c = 0; c < kChunks; ++c) {
               mbar_wait(&w_empty[st], ph ^ 1);
               if (kPair) {
@@ -239,6 +252,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
             const uint32_t d_tmem = tmem_base + g * 256;
             const uint16_t live_mask = (g < nsub_peer) ? 0x3 : 0x1;
             if (l <= L) {
+              if (kPair) {  // acc = [1 1 0 ..] x [b_hi b_lo 0 ..]^T = bias, then the weight chunks accumulate on top
+                mbar_wait(&w_full[st], ph);
+                tc_fence_after();
+                const uint64_t da = umma_smem_desc(smem_u32(smem + FwdSmem::kOnes), 2048, 128);
+                const uint64_t db = umma_smem_desc(ring_base + st * kChunkBytes, 2048, 128);
+                umma2_f16_ss(d_tmem, da, db, idesc_h, 0);
+                umma2_commit_multicast(&w_empty[st], 0x3);
+                if (++st == kStages) { st = 0; ph ^= 1; }
+              }
               for (int c = 0; c < kChunks; ++c) {
                 mbar_wait(&w_full[st], ph);
                 tc_fence_after();
@@ -249,7 +271,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
                   // A: [k/8][128][8] -> 2048 B per 8-column group; B: [k/8][kBRows][8] -> kBRows*16 B per group
                   const uint64_t da = umma_smem_desc(a_tile + (c * kSteps + ks) * 4096, 2048, 128);
                   const uint64_t db = umma_smem_desc(b_tile + ks * (kBRows * 32), kBRows * 16, 128);
-                  if (kPair) umma2_f16_ss(d_tmem, da, db, idesc_h, (c | ks) != 0);
+                  if (kPair) umma2_f16_ss(d_tmem, da, db, idesc_h, 1);
                   else umma_f16_ss(d_tmem, da, db, idesc_h, (c | ks) != 0);
                 }
                 if (kPair) umma2_commit_multicast(&w_empty[st], 0x3);
@@ -371,17 +393,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
             for (int q8 = 0; q8 < 2; ++q8) {
               const int kl = it * 2 + q8;          // 8-column group inside this warp's quarter
               const int kg = cq * 8 + kl;          // ... inside the tile
-              const float4 b0 = *reinterpret_cast<const float4*>(bl + kl * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(bl + kl * 8 + 4);
               float a[8];
-              a[0] = __uint_as_float(v[q8 * 8 + 0]) + b0.x;
-              a[1] = __uint_as_float(v[q8 * 8 + 1]) + b0.y;
-              a[2] = __uint_as_float(v[q8 * 8 + 2]) + b0.z;
-              a[3] = __uint_as_float(v[q8 * 8 + 3]) + b0.w;
-              a[4] = __uint_as_float(v[q8 * 8 + 4]) + b1.x;
-              a[5] = __uint_as_float(v[q8 * 8 + 5]) + b1.y;
-              a[6] = __uint_as_float(v[q8 * 8 + 6]) + b1.z;
-              a[7] = __uint_as_float(v[q8 * 8 + 7]) + b1.w;
+              if (kPair) {  // the bias is already in the accumulator
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(v[q8 * 8 + i]);
+              } else {
+                const float4 b0 = *reinterpret_cast<const float4*>(bl + kl * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(bl + kl * 8 + 4);
+                a[0] = __uint_as_float(v[q8 * 8 + 0]) + b0.x;
+                a[1] = __uint_as_float(v[q8 * 8 + 1]) + b0.y;
+                a[2] = __uint_as_float(v[q8 * 8 + 2]) + b0.z;
+                a[3] = __uint_as_float(v[q8 * 8 + 3]) + b0.w;
+                a[4] = __uint_as_float(v[q8 * 8 + 4]) + b1.x;
+                a[5] = __uint_as_float(v[q8 * 8 + 5]) + b1.y;
+                a[6] = __uint_as_float(v[q8 * 8 + 6]) + b1.z;
+                a[7] = __uint_as_float(v[q8 * 8 + 7]) + b1.w;
+              }
               uint4 hv, uv;
               sin8<kTrain>(a, hv, uv);
               *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
@@ -567,17 +594,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
           for (int q8 = 0; q8 < 2; ++q8) {
             const int kl = it * 2 + q8;          // 8-column group inside this warp's half
             const int kg = chalf * 16 + kl;      // ... inside the tile
-            const float4 b0 = *reinterpret_cast<const float4*>(bl + kl * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bl + kl * 8 + 4);
             float a[8];
-            a[0] = __uint_as_float(v[q8 * 8 + 0]) + b0.x;
-            a[1] = __uint_as_float(v[q8 * 8 + 1]) + b0.y;
-            a[2] = __uint_as_float(v[q8 * 8 + 2]) + b0.z;
-            a[3] = __uint_as_float(v[q8 * 8 + 3]) + b0.w;
-            a[4] = __uint_as_float(v[q8 * 8 + 4]) + b1.x;
-            a[5] = __uint_as_float(v[q8 * 8 + 5]) + b1.y;
-            a[6] = __uint_as_float(v[q8 * 8 + 6]) + b1.z;
-            a[7] = __uint_as_float(v[q8 * 8 + 7]) + b1.w;
+            if (kPair) {  // the bias is already in the accumulator
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(v[q8 * 8 + i]);
+            } else {
+              const float4 b0 = *reinterpret_cast<const float4*>(bl + kl * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bl + kl * 8 + 4);
+              a[0] = __uint_as_float(v[q8 * 8 + 0]) + b0.x;
+              a[1] = __uint_as_float(v[q8 * 8 + 1]) + b0.y;
+              a[2] = __uint_as_float(v[q8 * 8 + 2]) + b0.z;
+              a[3] = __uint_as_float(v[q8 * 8 + 3]) + b0.w;
+              a[4] = __uint_as_float(v[q8 * 8 + 4]) + b1.x;
+              a[5] = __uint_as_float(v[q8 * 8 + 5]) + b1.y;
+              a[6] = __uint_as_float(v[q8 * 8 + 6]) + b1.z;
+              a[7] = __uint_as_float(v[q8 * 8 + 7]) + b1.w;
+            }
             uint4 hv, uv;
             sin8<kTrain>(a, hv, uv);
             *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;

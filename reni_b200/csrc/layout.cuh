@@ -27,6 +27,7 @@ constexpr int kChunksPerLayer = kH / kWChunkK;       // 8
 constexpr int kW6N = 16;                             // final layer padded to N = 16
 constexpr int kW6ImageBytes = kH * kW6N * 2;         // 8192
 constexpr int kGyImageBytes = kTileRows * kW6N * 2;  // 4096 : g_y tile, [16/8][128][8] per 64-row half
+constexpr int kBiasBlockBytes = 2 * 128 * 16;         // 4096: [2 k-groups][128 n][8] bias block of one N half
 constexpr int kLossPartials = 10;                    // se, dot[3], oo[3], tt[3]
 
 // byte offset of the 16-byte group (row r, columns 8*kg .. 8*kg+7) inside a [R x *] tile image
@@ -39,7 +40,7 @@ __host__ __device__ inline uint32_t stash_off(uint32_t r, uint32_t kg, uint32_t 
 
 struct WorkspaceLayout {
   // all offsets in bytes from the workspace base; 0-size regions are absent
-  int64_t wf, wb, wf2, wb2, w6f, w6b, bias, mc;       // weight images + biases + per-map layer-0 (M_b, c_b)
+  int64_t wf, wb, wf2, wb2, wbias2, w6f, w6b, bias, mc;       // weight images + biases + per-map layer-0 (M_b, c_b)
   int64_t stash_h, stash_c, stash_d, stash_gy;   // per-tile activation / cos / delta stashes
   int64_t aout;                                  // output pre-activations (sine output layer only)
   int64_t loss_part, map_loss, dmc, scalars;     // loss partials, per-map loss coefficients, per-map dM/dc

@@ -19,6 +19,31 @@ namespace reni {
 #define RENI_REMOTE_RELAXED 1
 #endif
 DEVINL float abl_sin(float x) { return (RENI_ABL & 2) ? x * 0.5f : __sinf(x); }
+
+// sin on the FMA pipe: range reduction to r = a/2pi - round(a/2pi) in [-0.5, 0.5] (magic-number rounding, two FFMA and
+// an FADD) and an odd degree-9 minimax polynomial of sin(2 pi r) (max error 6.3e-6, fitted in tools/fit_sin_poly.py).
+// Nine FMA-pipe instructions against FMUL + MUFU.SIN: used for a fraction of the epilogue's elements (RENI_POLY_SIN_MASK)
+// because the MUFU pipe (16 results/clk/SM) is the busiest unit of the sin epilogue while the FMA pipe has slack.
+DEVINL float poly_sin(float a) {
+  const float z = fmaf(a, 0.15915494309189535f, 12582912.f);
+  const float k = z - 12582912.f;
+  const float r = fmaf(a, 0.15915494309189535f, -k);
+  const float r2 = r * r;
+  float p = 32.7813832286966f;
+  p = fmaf(p, r2, -74.47799703355653f);
+  p = fmaf(p, r2, 81.36681431178144f);
+  p = fmaf(p, r2, -41.33121426664187f);
+  p = fmaf(p, r2, 6.283055798352278f);
+  return p * r;
+}
+#ifndef RENI_POLY_SIN_MASK
+#define RENI_POLY_SIN_MASK 0  // bit i: element i of every group of 8 columns takes the polynomial
+#endif
+template <int kI>
+DEVINL float epi_sin(float x) {
+  if (RENI_ABL & 2) return x * 0.5f;
+  return ((RENI_POLY_SIN_MASK >> kI) & 1) ? poly_sin(x) : __sinf(x);
+}
 DEVINL float abl_cos(float x) { return (RENI_ABL & 2) ? x * 0.5f : __cosf(x); }
 
 DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

@@ -16,6 +16,7 @@ namespace reni {
 //   w6f                [k/8][16][8] = s * W_out[n][k]   (n < out_features, else 0);  s = omega if sine-last
 //   w6b                [c/8][256][8]= omega_L * s * W_out[c][k]
 //   bias               L*256: omega_l * b_l ; then 16: s * b_out
+//   wbias2[l][n/128]   [2][128][8]  = (hi, lo, 0, ...) fp16 split of omega_l * b_l: B operand of the bias K-step
 // Reference: SineLayer.forward sin(omega*(xW^T+b)) (RENI.py:86-87), final Linear (RENI.py:153-162).
 // ------------------------------------------------------------------------------------------------
 struct PrepParams {
@@ -25,6 +26,7 @@ struct PrepParams {
   __half* wb;
   __half* wf2;
   __half* wb2;
+  __half* wbias2;  // [l][n/128][2 k-groups][128][8]: column k=0 = hi, k=1 = lo fp16 halves of omega_l*b_l, rest 0
   __half* w6f;
   __half* w6b;
   float* bias;
@@ -52,7 +54,20 @@ __global__ void reni_prep_weights_kernel(const PrepParams p) {
       wf2[(((n >> 7) * (kH / 8) + (k >> 3)) * 128 + (n & 127)) * 8 + (k & 7)] = __float2half_rn(om_f * w);
       wb2[(((k >> 7) * (kH / 8) + (n >> 3)) * 128 + (k & 127)) * 8 + (n & 7)] = __float2half_rn(om_b * w);
     }
-    for (int i = tid; i < kH; i += nthreads) p.bias[l * kH + i] = om_f * p.b[l + 1][i];
+    for (int i = tid; i < kH; i += nthreads) {
+      const float bv = om_f * p.b[l + 1][i];
+      p.bias[l * kH + i] = bv;
+      // the paired forward adds the bias on the tensor core: one extra K = 16 step [1 1 0 ..] x [hi lo 0 ..]^T
+      const __half hi = __float2half_rn(bv);
+      const __half lo = __float2half_rn(bv - __half2float(hi));
+      __half* blk = p.wbias2 + ((size_t)l * 2 + (i >> 7)) * (2 * 128 * 8);
+      uint4* row0 = reinterpret_cast<uint4*>(blk + (i & 127) * 8);
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      __half2 h2 = __halves2half2(hi, lo);
+      v.x = *reinterpret_cast<uint32_t*>(&h2);
+      row0[0] = v;
+      reinterpret_cast<uint4*>(blk + (128 + (i & 127)) * 8)[0] = make_uint4(0u, 0u, 0u, 0u);
+    }
   } else {
     const float* W = p.w[p.L + 1];
     const float s = p.last_sine ? p.hidden_omega : 1.0f;
