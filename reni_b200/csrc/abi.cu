@@ -18,6 +18,9 @@
 #ifndef RENI_FWD_TRAIN_ALLHANDS
 #define RENI_FWD_TRAIN_ALLHANDS 1
 #endif
+#ifndef RENI_BWD_TRAIN_PAIR
+#define RENI_BWD_TRAIN_PAIR 1  // CTA pairs also for the delta chain with weight gradients (0: one CTA per tile pair)
+#endif
 #ifndef RENI_FWD_PAIR
 #define RENI_FWD_PAIR 1
 #endif
@@ -376,9 +379,10 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   p.out_tanh = c->output_activation == 1;
   p.d_slots = need_dw ? L + 1 : 1;
   p.use_cos = use_cos;
-  // Latent-only (no weight gradients): CTA pairs, one cluster of two CTAs per tile quad (tcgen05.mma.cta_group::2).
-  // With weight gradients the delta-stash stores make the pair wait for its slower half: one CTA per tile pair.
-  const bool pair_mode = !need_dw;
+  // CTA pairs, one cluster of two CTAs per tile quad (tcgen05.mma.cta_group::2).  With weight gradients the pair only
+  // pays off because the delta stash is written by bulk copies from shared memory (measured at cfg 2: unpaired
+  // st.global 305 us, unpaired bulk 312, paired st.global 335, paired bulk 291).
+  const bool pair_mode = !need_dw || RENI_BWD_TRAIN_PAIR;
   memset(&p.wmap, 0, sizeof(p.wmap));
   {
     cudaLaunchConfig_t cfg{};
@@ -402,10 +406,11 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (need_dw) {
-      if (note(cudaFuncSetAttribute(reni_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      constexpr bool kTrainPair = RENI_BWD_TRAIN_PAIR != 0;
+      if (note(cudaFuncSetAttribute(reni_bwd_kernel<true, kTrainPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     BwdSmem::kTotal)) != cudaSuccess)
         return RENI_ERR_CUDA;
-      if (note(cudaLaunchKernelEx(&cfg, reni_bwd_kernel<true, false>, p)) != cudaSuccess) return RENI_ERR_CUDA;
+      if (note(cudaLaunchKernelEx(&cfg, reni_bwd_kernel<true, kTrainPair>, p)) != cudaSuccess) return RENI_ERR_CUDA;
     } else {
       if (note(cudaFuncSetAttribute(reni_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     BwdSmem::kTotal)) != cudaSuccess)

@@ -71,6 +71,20 @@ DEVINL void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
 
+// bulk async copy shared -> global (delta-stash store), tracked by the issuing thread's bulk async-group
+DEVINL void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+#ifndef RENI_BWD_BULK_STASH
+#define RENI_BWD_BULK_STASH 1  // 1: delta stash written by per-warp bulk copies of the finished smem pieces; 0: st.global
+#endif
+
 // delta = acc * cos(a) for two columns; w holds the two 16-bit phases of a
 DEVINL uint32_t delta2(float acc0, float acc1, uint32_t w) {
   return pack_half2(acc0 * abl_cos(phase_angle_lo(w)), acc1 * abl_cos(phase_angle_hi(w)));
@@ -92,9 +106,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
 
   const int L = p.L;
   // Work units are taken in DESCENDING tile order (the forward kernel's last tiles are the freshest in L2).
-  // kPair (cluster of 2, used without weight gradients): cluster k owns tile quads; leader: tiles {4q, 4q+1}, peer:
-  // {4q+2, 4q+3}.  Unpaired (with weight gradients: the stash traffic makes the coupled pair wait for its slower half,
-  // measured 327 vs 307 us at cfg 2): CTA c owns tile pairs.
+  // kPair (cluster of 2): cluster k owns tile quads; leader: tiles {4q, 4q+1}, peer: {4q+2, 4q+3}.
+  // Unpaired (compile-time fallback): CTA c owns tile pairs.
   const uint32_t crank = kPair ? cluster_ctarank() : 0;
   constexpr int kUnitTiles = kPair ? 4 : 2;
   const int nunits = (p.ntiles + kUnitTiles - 1) / kUnitTiles;
@@ -361,6 +374,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
         mbar_wait(&acc_full[g], acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
+        if (RENI_BWD_BULK_STASH && kNeedDW) {  // this warp's previous pieces have been read out of the tile image
+          if (lane < 16) bulk_wait_read0();
+          __syncwarp();
+        }
         auto process16 = [&](const uint32_t (&v)[16], int it) {
 #pragma unroll
           for (int q8 = 0; q8 < 2; ++q8) {
@@ -373,7 +390,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
             dv.z = delta2(__uint_as_float(v[q8 * 8 + 4]), __uint_as_float(v[q8 * 8 + 5]), hw.z);
             dv.w = delta2(__uint_as_float(v[q8 * 8 + 6]), __uint_as_float(v[q8 * 8 + 7]), hw.w);
             *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = dv;
-            if (dl != nullptr && !(RENI_ABL & 1)) *reinterpret_cast<uint4*>(dl + stash_off(row, kg, kH)) = dv;
+            if (!RENI_BWD_BULK_STASH && dl != nullptr && !(RENI_ABL & 1))
+              *reinterpret_cast<uint4*>(dl + stash_off(row, kg, kH)) = dv;
           }
         };
         {
@@ -391,9 +409,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
         }
         tc_fence_before();
         fence_proxy_async_smem();
+        if (RENI_BWD_BULK_STASH && dl != nullptr && !(RENI_ABL & 1)) {
+          // this warp's block of the finished tile image (32 rows x 16 column groups) goes to the stash as 16 bulk
+          // copies of 512 B, one per lane: no st.global in the epilogue, the copy engine reads while the tensor core does
+          __syncwarp();
+          if (lane < 16) {
+            const uint32_t kg = chalf * 16 + lane;
+            bulk_s2g(dl + (q >> 1) * kHalfImageBytes + kg * (kHalfRows * 16) + (q & 1) * 512,
+                     a_tile + kg * (kTileRows * 16) + q * 512, 512);
+            bulk_commit();
+          }
+        }
         signal_ready(g);
       }
-
       // ---- layer-0 reduction result: D[j, 0..4] for j = row (columns 0..15) and j = 128 + row (columns 16..31)
       mbar_wait(&acc_full[g], acc_ph);
       acc_ph ^= 1;
@@ -414,6 +442,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
     }
   }
 
+  if (RENI_BWD_BULK_STASH && kNeedDW && warp >= 2 && lane < 16) bulk_wait0();  // stash writes have landed
   tc_fence_before();
   __syncthreads();
   if (kPair) cluster_sync_all();  // the pair's MMAs, multicast commits and remote arrivals are all behind us
