@@ -16,13 +16,13 @@
 #define RENI_NO_FORK 0  // 1: keep every kernel of the step on the caller's stream (A/B switch for the fork/join)
 #endif
 #ifndef RENI_FWD_TRAIN_ALLHANDS
-#define RENI_FWD_TRAIN_ALLHANDS 1
+#define RENI_FWD_TRAIN_ALLHANDS 1  // paired training forward: all-hands epilogue (0: grouped)
 #endif
 #ifndef RENI_BWD_TRAIN_PAIR
 #define RENI_BWD_TRAIN_PAIR 1  // CTA pairs also for the delta chain with weight gradients (0: one CTA per tile pair)
 #endif
 #ifndef RENI_FWD_PAIR
-#define RENI_FWD_PAIR 1
+#define RENI_FWD_PAIR 1  // forward on CTA pairs (0: one CTA per tile pair, grouped training / all-hands inference epilogue)
 #endif
 
 using namespace reni;

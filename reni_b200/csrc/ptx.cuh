@@ -117,15 +117,6 @@ DEVINL void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// one L2 read, delivered to the same smem offset (and the same mbarrier offset) of every CTA in cta_mask
-DEVINL void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
-
 // shared::cluster address of the same smem offset in CTA `rank` of the cluster
 DEVINL uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;
@@ -205,16 +196,6 @@ DEVINL void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint3
 DEVINL void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-
-// ... and on the mbarrier at the same offset in every CTA of cta_mask (a ring slot shared by a CTA pair is free
-// once BOTH consumers have read it)
-DEVINL void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
 }
 
 // ---- cta_group::2: one tcgen05.mma spans a CTA pair (M = 256: 128 rows from each CTA's A image and TMEM; each CTA
