@@ -67,20 +67,50 @@ struct BwdSmem {
 };
 static_assert(BwdSmem::kTotal <= 232448, "backward kernel shared memory over budget");
 
+#ifndef RENI_BWD_L2_HINTS
+#define RENI_BWD_L2_HINTS 0  // bit 0: evict_first on the delta-stash stores, bit 1: evict_last on the phase prefetch
+#endif
+// L2 cache policies: the delta stash is a pure stream for this kernel (read back only by the next kernel), the phase
+// tiles pulled in by the prefetch must survive until the epilogue reads them
+DEVINL uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+DEVINL uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 DEVINL void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
+#if RENI_BWD_L2_HINTS & 2
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(gmem), "r"(bytes),
+               "l"(l2_policy_evict_last())
+               : "memory");
+#else
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+#endif
 }
 
 // bulk async copy shared -> global (delta-stash store), tracked by the issuing thread's bulk async-group
 DEVINL void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+#if RENI_BWD_L2_HINTS & 1
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes), "l"(l2_policy_evict_first())
+               : "memory");
+#else
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
                "r"(bytes)
                : "memory");
+#endif
 }
 DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+#ifndef RENI_BWD_PF_DIST
+#define RENI_BWD_PF_DIST 1
+#endif
 #ifndef RENI_BWD_BULK_STASH
 #define RENI_BWD_BULK_STASH 1  // 1: delta stash written by per-warp bulk copies of the finished smem pieces; 0: st.global
 #endif
@@ -173,16 +203,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
         const int tbase = ubase + 2 * (int)crank;
         const int nsub = clamp02(p.ntiles - tbase);          // this CTA's live sub-tiles
         const int nstream = clamp02(p.ntiles - ubase);       // passes the leader makes over each layer
+        // phase-stash tiles are pulled towards L2 kPfDist layers before the epilogue that multiplies by their cosine
+        constexpr int kPfDist = RENI_BWD_PF_DIST;
         for (int g = 0; g < nsub; ++g)
-          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
-                               ((size_t)(tbase + g) * (L + 1) + L) * kTileImageBytes,
-                           kTileImageBytes);
+          for (int d = 0; d < kPfDist && L - d >= 0; ++d)
+            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
+                                 ((size_t)(tbase + g) * (L + 1) + (L - d)) * kTileImageBytes,
+                             kTileImageBytes);
         for (int l = L; l >= 1; --l) {
           for (int g = 0; g < nstream; ++g) {
-            // the epilogue of this GEMM multiplies by cos(a_{l-1}): pull that stash tile towards L2 now
-            if (g < nsub)
+            if (kPfDist > 0 && g < nsub && l - kPfDist >= 0)
               bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
-                                   ((size_t)(tbase + g) * (L + 1) + (l - 1)) * kTileImageBytes,
+                                   ((size_t)(tbase + g) * (L + 1) + (l - kPfDist)) * kTileImageBytes,
                                kTileImageBytes);
             for (int c = 0; c < kChunks; ++c) {
               mbar_wait(&w_empty[st], ph ^ 1);
