@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RENI_ABI_VERSION 1
+#define RENI_ABI_VERSION 2
 
 typedef enum {
   RENI_OK = 0,
@@ -59,6 +59,7 @@ typedef struct {
 #define RENI_FLAG_SAVE_FOR_BACKWARD 1 /* forward stashes cos(a_l) (and h_l if NEED_DW) for reni_backward */
 #define RENI_FLAG_NEED_DW 2           /* weight gradients wanted (otherwise latent gradients only)     */
 #define RENI_FLAG_LOSS 4              /* forward also produces per-map loss sums (target / sw given)   */
+#define RENI_FLAG_FILM 8              /* workspace query for the FiLM core (reni_film_forward/backward) */
 
 int32_t reni_abi_version(void);
 const char* reni_strerror(int32_t code);
@@ -116,6 +117,34 @@ int32_t reni_loss_forward_backward(const reni_config_t* cfg, const float* Z, con
                                    int32_t use_cosine, float* out, float* loss_out, float* dZ,
                                    float* const* host_dW, float* const* host_db, void* workspace,
                                    int64_t workspace_bytes, int32_t flags, void* stream);
+
+/* FiLM-conditioned decoder core (RENIAutoDecoderFiLM, src/models/RENI.py:515-524,527-678):
+ *     h_0 = sin([f | 1] . mc[b]),   h_l = sin(freq_l[b] * (W_l h_{l-1} + b_l) + phase_l[b]),  l = 1..L,
+ *     out = act(W_out h_L + b_out)
+ * replaces FiLMLayer.forward x L + final_layer (forward_with_frequencies_phase_shifts, RENI.py:666-678).  Everything
+ * that is constant per map stays with the caller, which can differentiate it with autograd on (B, .) tensors:
+ *   mc   (B, 5, 256) : rows 0..3 = freq_0 * M_b (first FiLM layer hoisted onto the direction features
+ *                      f = [dx, dz, |d_xz|, dy] for SO2 (RENI.py:418-436) or f = [dx, dy, dz, 0] for SO3 (:405-415)),
+ *                      row 4 = freq_0 * b_0 + phase_0
+ *   film (B, L, 2, 256) : freq_l = 15 * raw + 30 and phase_l of the mapping network (RENI.py:481-512,667), l = 1..L
+ * cfg: hidden_layers = L = siren_hidden_layers - 1, hidden_omega_0 = first_omega_0 = 1, last_layer_linear = 1,
+ * equivariance SO2 / SO3, output_activation none / tanh ("exp" is applied by the caller).  reni_prepare_weights must
+ * have been called with that cfg (weights[0] / biases[0] are ignored by it); workspace size = reni_workspace_bytes
+ * with RENI_FLAG_FILM [| RENI_FLAG_SAVE_FOR_BACKWARD]. */
+int32_t reni_film_forward(const reni_config_t* cfg, const float* mc, const float* film, const float* D,
+                          int64_t d_batch_stride, int64_t B, int64_t P, float* out, void* workspace,
+                          int64_t workspace_bytes, int32_t flags, void* stream);
+
+/* Backward of reni_film_forward (made with RENI_FLAG_SAVE_FOR_BACKWARD on the same workspace):
+ *   d_mc (B, 5, 256), d_film (B, L, 2, 256) : written -- gradients w.r.t. mc and film
+ *   host_weights / host_biases : fp32 parameters as in reni_prepare_weights ([1..L] are read)
+ *   host_dW / host_db          : with RENI_FLAG_NEED_DW, entries [1..L+1] are ACCUMULATED into ([0] is unused: the
+ *                                first layer is differentiated by the caller through d_mc); NULL otherwise. */
+int32_t reni_film_backward(const reni_config_t* cfg, const float* film, const float* D, int64_t d_batch_stride,
+                           const float* const* host_weights, const float* const* host_biases, int64_t B, int64_t P,
+                           const float* out, const float* grad_out, float* d_mc, float* d_film,
+                           float* const* host_dW, float* const* host_db, void* workspace, int64_t workspace_bytes,
+                           int32_t flags, void* stream);
 
 /* Debug / measurement hook: register up to 16 CUDA events (cudaEvent_t handles, HOST array) that the
  * calling thread's subsequent reni_forward / reni_backward / reni_loss_forward_backward calls record on

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("RENI_B200_LIB") or os.path.join(_HERE, "lib", "libren
 FLAG_SAVE_FOR_BACKWARD = 1
 FLAG_NEED_DW = 2
 FLAG_LOSS = 4
+FLAG_FILM = 8
 
 EQUIVARIANCE = {"None": 0, "SO2": 1, "SO3": 2}
 
@@ -57,6 +58,9 @@ SIGNATURES = {
     "reni_loss_forward_backward": (_i32, [_cfgp, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _vp,
                                           _i64, C.c_float, C.c_float, _i32, _vp, _vp, _vp, C.POINTER(_vp),
                                           C.POINTER(_vp), _vp, _i64, _i32, _vp]),
+    "reni_film_forward": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp]),
+    "reni_film_backward": (_i32, [_cfgp, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _vp, _vp, _vp,
+                                  C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _i32, _vp]),
     "reni_debug_set_phase_events": (_i32, [C.POINTER(_vp), _i32]),
     "reni_debug_last_cuda_error": (C.c_char_p, []),
     "reni_debug_set_trace": (_i32, [_vp]),

@@ -72,7 +72,7 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   w.dxc = take(B * 5 * nin * 4);  // E: gradient w.r.t. xfull
   w.dip = -1;
   if (flags & RENI_FLAG_SAVE_FOR_BACKWARD) {
-    const bool dw = (flags & RENI_FLAG_NEED_DW) != 0;
+    const bool dw = (flags & (RENI_FLAG_NEED_DW | RENI_FLAG_FILM)) != 0;  // (FiLM: dfreq / dphase need the delta stash)
     w.stash_c = take(ntiles * (L + 1) * (int64_t)kTileImageBytes);  // 16-bit phase stash (rebuilds both h and cos)
     w.stash_h = -1;
     w.stash_d = dw ? take(ntiles * (L + 1) * (int64_t)kTileImageBytes) : -1;  // slot 0 unused (delta_0 stays on chip)
@@ -80,6 +80,11 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
     w.aout = c->last_layer_linear ? -1 : take(B * P * 3 * 4);  // sine output layer: its pre-activations
   } else {
     w.stash_c = w.stash_h = w.stash_d = w.stash_gy = w.aout = -1;
+  }
+  w.film_S = w.film_cs = -1;
+  if ((flags & RENI_FLAG_FILM) && (flags & RENI_FLAG_SAVE_FOR_BACKWARD)) {
+    w.film_S = take(B * L * (int64_t)kH * kH * 4);  // per-map delta_l^T h_{l-1}
+    w.film_cs = take(B * L * (int64_t)kH * 4);      // per-map column sums of delta_l
   }
   w.total = off;
   return w;
@@ -165,6 +170,10 @@ int num_sms() {
 }  // namespace
 
 extern "C" {
+
+static int32_t launch_forward(const reni_config_t* c, const WorkspaceLayout& w, const float* mc, const float* film,
+                              const float* D, int64_t d_bstride, int64_t B, int64_t P, float* out, const float* target,
+                              const float* sw, int64_t sw_bstride, void* ws, int32_t flags, cudaStream_t stream, int sms);
 
 int32_t reni_abi_version(void) { return RENI_ABI_VERSION; }
 
@@ -265,12 +274,20 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
     if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   }
   mark_phase(1, stream);
+  return launch_forward(c, w, at<float>(ws, w.mc), nullptr, D, d_bstride, B, P, out, target, sw, sw_bstride, ws, flags,
+                        stream, sms);
+}
 
-  // ---- fused decoder forward
+// Fused decoder forward over hoisted per-map layer-0 operands mc (B, 5, 256); film != null selects the FiLM epilogue.
+static int32_t launch_forward(const reni_config_t* c, const WorkspaceLayout& w, const float* mc, const float* film,
+                              const float* D, int64_t d_bstride, int64_t B, int64_t P, float* out, const float* target,
+                              const float* sw, int64_t sw_bstride, void* ws, int32_t flags, cudaStream_t stream,
+                              int sms) {
   FwdParams p{};
   p.D = D;
   p.d_bstride = d_bstride;
-  p.mc = at<float>(ws, w.mc);
+  p.mc = mc;
+  p.film = film;
   p.wf = at<__half>(ws, w.wf);
   p.wf2 = at<__half>(ws, w.wf2);
   p.w6f = at<__half>(ws, w.w6f);
@@ -324,7 +341,11 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
     cfg.numAttrs = 1;
     e = note(cudaLaunchKernelEx(&cfg, kernel, p));
   };
-  if (pair_mode) {
+  if (film != nullptr) {
+    if (!pair_mode) return RENI_ERR_BAD_CONFIG;  // (the unpaired build is an A/B fallback without the FiLM epilogue)
+    if (train) launch(reni_fwd_kernel<true, true, true, true>);
+    else launch(reni_fwd_kernel<false, true, true, true>);
+  } else if (pair_mode) {
     if (train && RENI_FWD_TRAIN_ALLHANDS) launch(reni_fwd_kernel<true, true, true>);
     else if (train) launch(reni_fwd_kernel<true, false, true>);
     else launch(reni_fwd_kernel<false, true, true>);
@@ -337,19 +358,31 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
+// FiLM extras of the shared backward tail (null: Cond-by-Concat decoder)
+struct FilmBackwardArgs {
+  const float* film;                     // (B, L, 2, 256)
+  float* d_mc;                           // (B, 5, 256), written
+  float* d_film;                         // (B, L, 2, 256), written
+  const float* const* host_weights;      // fp32 parameters [1..L] are read (dfreq needs W_l and b_l)
+  const float* const* host_biases;
+};
+
 // Shared tail of reni_backward / reni_loss_forward_backward: delta chain, weight-gradient GEMMs, layer-0 and
 // map-level reductions.  scalars[0..1] (gradient scale) must already be on the stream.
 static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w, const float* Z, const float* D,
                                int64_t d_bstride, const float* weight0, int64_t B, int64_t P, const float* out,
                                const float* grad_out, const float* target, const float* sw, int64_t sw_bstride,
                                float alpha, float* dZ, float* const* host_dW, float* const* host_db, void* ws,
-                               int32_t flags, cudaStream_t stream, int use_cos = 1, SideStream* side = nullptr) {
+                               int32_t flags, cudaStream_t stream, int use_cos = 1, SideStream* side = nullptr,
+                               const FilmBackwardArgs* film = nullptr) {
   const int sms = num_sms();
   if (sms <= 0) return RENI_ERR_NO_DEVICE;
-  const bool need_dw = (flags & RENI_FLAG_NEED_DW) != 0;
+  const bool want_dw = (flags & RENI_FLAG_NEED_DW) != 0;   // the caller wants weight gradients
+  const bool need_dw = want_dw || film != nullptr;         // the delta stash + weight-gradient GEMM run
   const int L = c->hidden_layers;
   const int ntiles = (int)(B * tiles_per_map(P));
-  if (cudaMemsetAsync(at<float>(ws, w.dmc), 0, (size_t)B * 5 * kH * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
+  float* dmc = film != nullptr ? film->d_mc : at<float>(ws, w.dmc);
+  if (cudaMemsetAsync(dmc, 0, (size_t)B * 5 * kH * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
   mark_phase(3, stream);
 
   BwdParams p{};
@@ -369,7 +402,8 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   p.stash_gy = at<__half>(ws, w.stash_gy);
   p.D = D;
   p.d_bstride = d_bstride;
-  p.dmc = at<float>(ws, w.dmc);
+  p.dmc = dmc;
+  p.film = film != nullptr ? film->film : nullptr;
   p.so2 = c->equivariance == RENI_EQ_SO2;
   p.B = (int)B;
   p.P = (int)P;
@@ -382,7 +416,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   // CTA pairs, one cluster of two CTAs per tile quad (tcgen05.mma.cta_group::2).  With weight gradients the pair only
   // pays off because the delta stash is written by bulk copies from shared memory (measured at cfg 2: unpaired
   // st.global 305 us, unpaired bulk 312, paired st.global 335, paired bulk 291).
-  const bool pair_mode = !need_dw || RENI_BWD_TRAIN_PAIR;
+  const bool pair_mode = !need_dw || RENI_BWD_TRAIN_PAIR || film != nullptr;
   memset(&p.wmap, 0, sizeof(p.wmap));
   {
     cudaLaunchConfig_t cfg{};
@@ -405,7 +439,12 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (need_dw) {
+    if (film != nullptr) {
+      if (note(cudaFuncSetAttribute(reni_bwd_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    BwdSmem::kTotal)) != cudaSuccess)
+        return RENI_ERR_CUDA;
+      if (note(cudaLaunchKernelEx(&cfg, reni_bwd_kernel<true, true, true>, p)) != cudaSuccess) return RENI_ERR_CUDA;
+    } else if (need_dw) {
       constexpr bool kTrainPair = RENI_BWD_TRAIN_PAIR != 0;
       if (note(cudaFuncSetAttribute(reni_bwd_kernel<true, kTrainPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     BwdSmem::kTotal)) != cudaSuccess)
@@ -424,7 +463,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   // fork: the map-level backward below only needs dmc from the delta chain; with the per-kernel timing hook active
   // everything stays on the caller's stream so the phase events keep their meaning
   cudaStream_t mstream = stream;
-  if (need_dw && g_num_phase_events == 0 && !RENI_NO_FORK) {
+  if (need_dw && film == nullptr && g_num_phase_events == 0 && !RENI_NO_FORK) {
     if (side == nullptr && !side_stream(&side)) return RENI_ERR_CUDA;
     if (note(cudaEventRecord(side->fork, stream)) != cudaSuccess) return RENI_ERR_CUDA;
     if (note(cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return RENI_ERR_CUDA;
@@ -437,10 +476,14 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     q.stash_d = at<__half>(ws, w.stash_d);
     q.stash_gy = at<__half>(ws, w.stash_gy);
     for (int i = 1; i <= L + 1; ++i) {
-      if (host_dW[i] == nullptr || host_db[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
-      q.dW[i] = host_dW[i];
-      q.db[i] = host_db[i];
+      if (want_dw && (host_dW[i] == nullptr || host_db[i] == nullptr)) return RENI_ERR_BAD_ARGUMENT;
+      q.dW[i] = want_dw ? host_dW[i] : nullptr;
+      q.db[i] = want_dw ? host_db[i] : nullptr;
     }
+    q.njobs = want_dw ? L + 1 : L;  // (frozen FiLM decoder: the output-layer job has no consumer)
+    q.tiles_per_map = (int)tiles_per_map(P);
+    q.film_S = film != nullptr ? at<float>(ws, w.film_S) : nullptr;
+    q.film_cs = film != nullptr ? at<float>(ws, w.film_cs) : nullptr;
     q.scalars = at<float>(ws, w.scalars);
     q.out_scale = c->last_layer_linear ? 1.f : c->hidden_omega_0;
     q.ntiles = ntiles;
@@ -449,6 +492,36 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     if (note(cudaFuncSetAttribute(reni_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem::kTotal)) !=
         cudaSuccess)
       return RENI_ERR_CUDA;
+    if (film != nullptr) {
+      // one grid row per map: S[b][l] and cs[b][l] accumulate with atomics, then the map-level FiLM reduction
+      if (cudaMemsetAsync(q.film_S, 0, (size_t)B * L * kH * kH * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
+      if (cudaMemsetAsync(q.film_cs, 0, (size_t)B * L * kH * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
+      int slices = (2 * sms) / (q.njobs * (int)B);  // about two waves of CTAs over all maps
+      if (slices < 1) slices = 1;
+      if (slices > 2 * q.tiles_per_map) slices = 2 * q.tiles_per_map;
+      reni_dw_kernel<<<dim3((unsigned)(q.njobs * slices), (unsigned)B), kDwThreads, DwSmem::kTotal, stream>>>(q);
+      if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
+      FilmReduceParams r{};
+      r.S = q.film_S;
+      r.cs = q.film_cs;
+      r.film = film->film;
+      r.dfilm = film->d_film;
+      r.B = (int)B;
+      r.L = L;
+      for (int i = 1; i <= L; ++i) {
+        if (film->host_weights[i] == nullptr || film->host_biases[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+        r.W[i] = film->host_weights[i];
+        r.b[i] = film->host_biases[i];
+        r.dW[i] = want_dw ? host_dW[i] : nullptr;
+        r.db[i] = want_dw ? host_db[i] : nullptr;
+      }
+      reni_film_dfilm_kernel<<<dim3(kH / 8, (unsigned)L, (unsigned)B), 256, 0, stream>>>(r);
+      if (want_dw) reni_film_dw_kernel<<<dim3(kH, (unsigned)L), 256, 0, stream>>>(r);
+      if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
+      mark_phase(5, stream);
+      mark_phase(6, stream);
+      return RENI_OK;  // (layer 0 and the mapping network are differentiated by the caller from d_mc / d_film)
+    }
     int g = sms;
     const int max_useful = ntiles * 2 * (L + 1);
     if (g > max_useful) g = max_useful;
@@ -589,6 +662,51 @@ int32_t reni_loss_forward_backward(const reni_config_t* c, const float* Z, const
   rc = launch_backward(c, w, Z, D, d_bstride, host_weights[0], B, P, out, nullptr, target, sw, sw_bstride, alpha, dZ,
                        host_dW, host_db, ws, flags, stream, use_cosine, side);
   return rc;  // (launch_backward joins the side stream before it returns)
+}
+
+int32_t reni_film_forward(const reni_config_t* c, const float* mc, const float* film, const float* D,
+                          int64_t d_bstride, int64_t B, int64_t P, float* out, void* ws, int64_t ws_bytes,
+                          int32_t flags, void* stream_) {
+  if (!config_ok(c) || !c->last_layer_linear) return RENI_ERR_BAD_CONFIG;
+  if (mc == nullptr || film == nullptr || D == nullptr || out == nullptr || ws == nullptr || B < 1 || P < 1)
+    return RENI_ERR_BAD_ARGUMENT;
+  flags = (flags & RENI_FLAG_SAVE_FOR_BACKWARD) | RENI_FLAG_FILM;
+  const WorkspaceLayout w = make_layout(c, B, P, flags);
+  if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
+  const int sms = num_sms();
+  if (sms <= 0) return RENI_ERR_NO_DEVICE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  mark_phase(0, stream);
+  mark_phase(1, stream);
+  return launch_forward(c, w, mc, film, D, d_bstride, B, P, out, nullptr, nullptr, 0, ws, flags, stream, sms);
+}
+
+int32_t reni_film_backward(const reni_config_t* c, const float* film, const float* D, int64_t d_bstride,
+                           const float* const* host_weights, const float* const* host_biases, int64_t B, int64_t P,
+                           const float* out, const float* grad_out, float* d_mc, float* d_film,
+                           float* const* host_dW, float* const* host_db, void* ws, int64_t ws_bytes, int32_t flags,
+                           void* stream_) {
+  if (!config_ok(c) || !c->last_layer_linear) return RENI_ERR_BAD_CONFIG;
+  if (film == nullptr || D == nullptr || host_weights == nullptr || host_biases == nullptr || out == nullptr ||
+      grad_out == nullptr || d_mc == nullptr || d_film == nullptr || ws == nullptr || B < 1 || P < 1)
+    return RENI_ERR_BAD_ARGUMENT;
+  if ((flags & RENI_FLAG_NEED_DW) && (host_dW == nullptr || host_db == nullptr)) return RENI_ERR_BAD_ARGUMENT;
+  flags = (flags & RENI_FLAG_NEED_DW) | RENI_FLAG_SAVE_FOR_BACKWARD | RENI_FLAG_FILM;
+  const WorkspaceLayout w = make_layout(c, B, P, flags);
+  if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* scalars = at<float>(ws, w.scalars);
+  unsigned int* slot = reinterpret_cast<unsigned int*>(scalars + 2);
+  if (cudaMemsetAsync(slot, 0, 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
+  const int64_t n = B * P * 3;
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 1184) blocks = 1184;
+  reni_absmax_kernel<<<blocks, 256, 0, stream>>>(grad_out, n, slot);
+  reni_scale_from_absmax_kernel<<<1, 1, 0, stream>>>(slot, scalars);
+  if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
+  FilmBackwardArgs fa{film, d_mc, d_film, host_weights, host_biases};
+  return launch_backward(c, w, nullptr, D, d_bstride, nullptr, B, P, out, grad_out, nullptr, nullptr, 0, 0.f, nullptr,
+                         host_dW, host_db, ws, flags, stream, 1, nullptr, &fa);
 }
 
 int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, uint32_t a_lbo,

@@ -49,6 +49,7 @@ struct BwdParams {
   const float* D;         // directions (for the layer-0 feature columns f)
   int64_t d_bstride;
   float* dmc;             // (B, 5, 256): dM_b rows 0..3, dc_b row 4; accumulated with atomics (caller zeroes)
+  const float* film;      // kFilm: (B, L, 2, 256) per-map (freq_l, phase_l) of the hidden layers
   int B, P, tiles_per_map, ntiles, L;
   int out_tanh, d_slots, so2;
   int use_cos;            // fused loss: 0 = no cosine term (map_loss is not read, it may still be in flight)
@@ -120,8 +121,15 @@ DEVINL uint32_t delta2(float acc0, float acc1, uint32_t w) {
   return pack_half2(acc0 * abl_cos(phase_angle_lo(w)), acc1 * abl_cos(phase_angle_hi(w)));
 }
 
-template <bool kNeedDW, bool kPair>
+// kFilm (FiLM conditioning, RENI.py:515-524): a_l = freq_l[b] * u_l + phase_l[b] with u_l = W_l h_{l-1} + b_l, so
+// dL/du_l = delta_l * freq_l[b].  The epilogue of hidden layer l keeps TWO values per element: the unscaled
+// delta_l = dL/da_l goes to the stash (the weight-gradient kernel turns it into dW_l, dfreq_l, dphase_l per map) and
+// delta_l * freq_l[b] goes to the shared-memory tile that feeds the next GEMM.  The stash is therefore written with
+// st.global (the bulk copies of the non-FiLM kernel move the shared-memory tile as it is).
+template <bool kNeedDW, bool kPair, bool kFilm = false>
 __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_constant__ BwdParams p) {
+  static_assert(!kFilm || kNeedDW, "the FiLM backward always stashes delta (dfreq / dphase come from the dW kernel)");
+  constexpr bool kBulk = RENI_BWD_BULK_STASH && !kFilm;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -406,7 +414,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
         mbar_wait(&acc_full[g], acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
-        if (RENI_BWD_BULK_STASH && kNeedDW) {  // this warp's previous pieces have been read out of the tile image
+        const float* fl = nullptr;  // this map's freq_l (hidden layers only; layer 0 is modulated by the caller)
+        if (kFilm && l > 0) fl = p.film + ((size_t)b * L + (l - 1)) * 2 * kH;
+        if (kBulk && kNeedDW) {  // this warp's previous pieces have been read out of the tile image
           if (lane < 16) bulk_wait_read0();
           __syncwarp();
         }
@@ -416,13 +426,34 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
             const int kl = it * 2 + q8;
             const int kg = chalf * 16 + kl;
             const uint4 hw = hh[kl];
+            float d[8];  // delta = acc * cos(a), cos rebuilt from the 16-bit phases
+            d[0] = __uint_as_float(v[q8 * 8 + 0]) * abl_cos(phase_angle_lo(hw.x));
+            d[1] = __uint_as_float(v[q8 * 8 + 1]) * abl_cos(phase_angle_hi(hw.x));
+            d[2] = __uint_as_float(v[q8 * 8 + 2]) * abl_cos(phase_angle_lo(hw.y));
+            d[3] = __uint_as_float(v[q8 * 8 + 3]) * abl_cos(phase_angle_hi(hw.y));
+            d[4] = __uint_as_float(v[q8 * 8 + 4]) * abl_cos(phase_angle_lo(hw.z));
+            d[5] = __uint_as_float(v[q8 * 8 + 5]) * abl_cos(phase_angle_hi(hw.z));
+            d[6] = __uint_as_float(v[q8 * 8 + 6]) * abl_cos(phase_angle_lo(hw.w));
+            d[7] = __uint_as_float(v[q8 * 8 + 7]) * abl_cos(phase_angle_hi(hw.w));
             uint4 dv;
-            dv.x = delta2(__uint_as_float(v[q8 * 8 + 0]), __uint_as_float(v[q8 * 8 + 1]), hw.x);
-            dv.y = delta2(__uint_as_float(v[q8 * 8 + 2]), __uint_as_float(v[q8 * 8 + 3]), hw.y);
-            dv.z = delta2(__uint_as_float(v[q8 * 8 + 4]), __uint_as_float(v[q8 * 8 + 5]), hw.z);
-            dv.w = delta2(__uint_as_float(v[q8 * 8 + 6]), __uint_as_float(v[q8 * 8 + 7]), hw.w);
+            dv.x = pack_half2(d[0], d[1]);
+            dv.y = pack_half2(d[2], d[3]);
+            dv.z = pack_half2(d[4], d[5]);
+            dv.w = pack_half2(d[6], d[7]);
+            if (kFilm && fl != nullptr) {
+              // stash the unscaled delta, hand delta * freq to the next GEMM
+              *reinterpret_cast<uint4*>(dl + stash_off(row, kg, kH)) = dv;
+              const float4 f0 = __ldg(reinterpret_cast<const float4*>(fl + kg * 8));
+              const float4 f1 = __ldg(reinterpret_cast<const float4*>(fl + kg * 8 + 4));
+              dv.x = pack_half2(d[0] * f0.x, d[1] * f0.y);
+              dv.y = pack_half2(d[2] * f0.z, d[3] * f0.w);
+              dv.z = pack_half2(d[4] * f1.x, d[5] * f1.y);
+              dv.w = pack_half2(d[6] * f1.z, d[7] * f1.w);
+              *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = dv;
+              continue;
+            }
             *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = dv;
-            if (!RENI_BWD_BULK_STASH && dl != nullptr && !(RENI_ABL & 1))
+            if (!kBulk && dl != nullptr && !(RENI_ABL & 1))
               *reinterpret_cast<uint4*>(dl + stash_off(row, kg, kH)) = dv;
           }
         };
@@ -441,7 +472,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
         }
         tc_fence_before();
         fence_proxy_async_smem();
-        if (RENI_BWD_BULK_STASH && dl != nullptr && !(RENI_ABL & 1)) {
+        if (kBulk && dl != nullptr && !(RENI_ABL & 1)) {
           // this warp's block of the finished tile image (32 rows x 16 column groups) goes to the stash as 16 bulk
           // copies of 512 B, one per lane: no st.global in the epilogue, the copy engine reads while the tensor core does
           __syncwarp();
@@ -474,7 +505,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
     }
   }
 
-  if (RENI_BWD_BULK_STASH && kNeedDW && warp >= 2 && lane < 16) bulk_wait0();  // stash writes have landed
+  if (kBulk && kNeedDW && warp >= 2 && lane < 16) bulk_wait0();  // stash writes have landed
   tc_fence_before();
   __syncthreads();
   if (kPair) cluster_sync_all();  // the pair's MMAs, multicast commits and remote arrivals are all behind us

@@ -31,6 +31,13 @@ struct DwParams {
   const float* scalars;  // [1] = 1 / S
   float out_scale;       // omega of a sine output layer (its pre-activation is omega * (W h + b)), else 1
   int ntiles, L, out_features;
+  // FiLM mode (film_S != null): grid.y = maps; the CTAs of row b reduce over the tiles of map b only and the hidden
+  // jobs accumulate into per-map buffers -- S[b][l-1] = delta_l^T h_{l-1} (256 x 256) and cs[b][l-1] = column sums of
+  // delta_l -- from which reni_film_reduce_kernel forms dW_l, db_l, dfreq_l[b], dphase_l[b].  The output-layer job
+  // (not modulated) still accumulates straight into dW[L+1] / db[L+1]; njobs = L drops it (frozen decoder).
+  float* film_S;
+  float* film_cs;
+  int tiles_per_map, njobs;
 };
 
 struct DwSmem {
@@ -58,13 +65,15 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + DwSmem::kTmemPtr);
 
   const int L = p.L;
-  const int njobs = L + 1;
+  const int njobs = p.njobs;
   const int job = blockIdx.x % njobs;   // 0..L-1 -> hidden layer job+1 ; L -> output layer
   const int slice = blockIdx.x / njobs;
   const int nslices = ((int)gridDim.x - 1 - job) / njobs + 1;
-  const int total = p.ntiles * 2;       // 64-row stash blocks
-  const int s_begin = (int)((int64_t)slice * total / nslices);
-  const int s_end = (int)((int64_t)(slice + 1) * total / nslices);
+  const bool film = p.film_S != nullptr;
+  const int total = (film ? p.tiles_per_map : p.ntiles) * 2;  // 64-row stash blocks this grid row reduces over
+  const int s_base = film ? (int)blockIdx.y * p.tiles_per_map * 2 : 0;
+  const int s_begin = s_base + (int)((int64_t)slice * total / nslices);
+  const int s_end = s_base + (int)((int64_t)(slice + 1) * total / nslices);
   const int nst = s_end - s_begin;
   const bool is_out = (job == L);
   const int layer = job + 1;
@@ -200,6 +209,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
     mbar_wait(done, 0);
     tc_fence_after();
     const float inv_s = __ldg(p.scalars + 1) * (is_out ? p.out_scale : 1.f);
+    float* dW_dst = p.dW[layer];
+    float* db_dst = p.db[layer];
+    if (film && !is_out) {
+      dW_dst = p.film_S + ((size_t)blockIdx.y * L + job) * kH * kH;
+      db_dst = p.film_cs + ((size_t)blockIdx.y * L + job) * kH;
+    }
     if (nst > 0) {
       // column sums: add up the 8 row subsets (lanes that differ in their low 3 bits), one atomic per column
 #pragma unroll
@@ -214,14 +229,14 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
         const int ncol = is_out ? p.out_features : kH;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if ((int)(jg * 8 + i) < ncol && (!is_out || jg == 0)) atomicAdd(p.db[layer] + jg * 8 + i, acc[i] * inv_s);
+          if ((int)(jg * 8 + i) < ncol && (!is_out || jg == 0)) atomicAdd(db_dst + jg * 8 + i, acc[i] * inv_s);
       }
       const uint32_t q = warp & 3;
       const uint32_t mh = (warp - 2) >> 2;
       const uint32_t j = mh * 128 + q * 32 + lane;  // accumulator row
       const uint32_t t_acc = tmem_base + ((q * 32) << 16) + mh * 256;
       if (!is_out) {
-        float* dst = p.dW[layer] + (size_t)j * kH;
+        float* dst = dW_dst + (size_t)j * kH;
 #pragma unroll 1
         for (int ch = 0; ch < kH / 32; ++ch) {
           uint32_t v[32];
@@ -238,7 +253,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          if (c < p.out_features) atomicAdd(p.dW[layer] + (size_t)c * kH + j, __uint_as_float(v[c]) * inv_s);
+          if (c < p.out_features) atomicAdd(dW_dst + (size_t)c * kH + j, __uint_as_float(v[c]) * inv_s);
       }
     }
   }

@@ -55,6 +55,7 @@ struct FwdParams {
   int64_t sw_bstride;
   float* loss_part;      // (ntiles, 4 warps, 10)
   float* aout;           // kTrain with a sine output layer: (B, P, 3) pre-activations a_out (the backward needs cos a_out)
+  const float* film;     // kFilm: (B, L, 2, 256) per-map FiLM modulation of the hidden layers: a_l = freq_l * acc + phase_l
   int B, P, tiles_per_map, ntiles, L;
   int out_tanh, last_sine, so2;
   unsigned long long* trace;  // debug: per-role clock64 timeline of CTA 0 (reni_debug_set_trace), else null
@@ -101,8 +102,13 @@ DEVINL void sin8(const float (&a)[8], uint4& hv, uint4& uv) {
   }
 }
 
-template <bool kTrain, bool kAllHands, bool kPair>
+// kFilm (FiLM conditioning, RENI.py:515-524,666-678): the hidden layers compute sin(freq_l[b] * (W_l h + b_l) + phase_l[b])
+// with per-map vectors freq_l, phase_l; W_l and b_l enter unscaled (omega = 1), the bias rides in the accumulator, and
+// the epilogue applies one FFMA per element with the map's (freq, phase) read through L1 (the same 2 KB for a whole
+// sub-tile).  Layer 0 arrives hoisted and already modulated in p.mc.
+template <bool kTrain, bool kAllHands, bool kPair, bool kFilm = false>
 __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_constant__ FwdParams p) {
+  static_assert(!kFilm || (kAllHands && kPair), "FiLM epilogue exists for the paired all-hands kernel only");
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -383,6 +389,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
           if (kTrain)
             su = reinterpret_cast<uint8_t*>(p.stash_u) + ((size_t)(tbase + g) * (L + 1) + l) * kTileImageBytes;
           const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256 + cq * 64;
+          const float* fl = nullptr;  // this map's (freq_l, phase_l)
+          if (kFilm) fl = p.film + ((size_t)(g ? bmap1 : bmap0) * L + (l - 1)) * 2 * kH;
           mbar_wait(&acc_full[g], (acc_ph >> g) & 1);
           acc_ph ^= 1u << g;
           tc_fence_after();
@@ -394,7 +402,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
               const int kl = it * 2 + q8;          // 8-column group inside this warp's quarter
               const int kg = cq * 8 + kl;          // ... inside the tile
               float a[8];
-              if (kPair) {  // the bias is already in the accumulator
+              if (kFilm) {  // a = freq * (acc incl. bias) + phase, per-map vectors (uniform over the warp's rows)
+                const float4 f0 = __ldg(reinterpret_cast<const float4*>(fl + kg * 8));
+                const float4 f1 = __ldg(reinterpret_cast<const float4*>(fl + kg * 8 + 4));
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(fl + kH + kg * 8));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(fl + kH + kg * 8 + 4));
+                a[0] = fmaf(__uint_as_float(v[q8 * 8 + 0]), f0.x, s0.x);
+                a[1] = fmaf(__uint_as_float(v[q8 * 8 + 1]), f0.y, s0.y);
+                a[2] = fmaf(__uint_as_float(v[q8 * 8 + 2]), f0.z, s0.z);
+                a[3] = fmaf(__uint_as_float(v[q8 * 8 + 3]), f0.w, s0.w);
+                a[4] = fmaf(__uint_as_float(v[q8 * 8 + 4]), f1.x, s1.x);
+                a[5] = fmaf(__uint_as_float(v[q8 * 8 + 5]), f1.y, s1.y);
+                a[6] = fmaf(__uint_as_float(v[q8 * 8 + 6]), f1.z, s1.z);
+                a[7] = fmaf(__uint_as_float(v[q8 * 8 + 7]), f1.w, s1.w);
+              } else if (kPair) {  // the bias is already in the accumulator
 #pragma unroll
                 for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(v[q8 * 8 + i]);
               } else {

@@ -45,6 +45,7 @@ struct WorkspaceLayout {
   int64_t aout;                                  // output pre-activations (sine output layer only)
   int64_t loss_part, map_loss, dmc, scalars;     // loss partials, per-map loss coefficients, per-map dM/dc
   int64_t xc, dxc, dip;                          // per-map constant encoding columns and their gradients
+  int64_t film_S, film_cs;                       // FiLM backward: per-map delta_l^T h_{l-1} and column sums of delta_l
   int64_t total;
 };
 

@@ -603,4 +603,61 @@ __global__ void __launch_bounds__(128) reni_dz_kernel(const MapBwdParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FiLM backward, map level (RENI.py:515-524: a_l = freq_l[b] * (W_l h_{l-1} + b_l) + phase_l[b]).
+// The weight-gradient kernel leaves, per map b and hidden layer l,
+//     S[b][l]  = sum_{p in b} delta_l[p]^T h_{l-1}[p]   (256 x 256)      cs[b][l] = sum_{p in b} delta_l[p]   (256)
+// with delta_l = dL/da_l.  From these
+//     dphase_l[b][j] = cs[b][l][j]
+//     dfreq_l[b][j]  = sum_p delta_l[p,j] (W_l h_{l-1}[p] + b_l)[j] = sum_k S[b][l][j,k] W_l[j,k] + b_l[j] cs[b][l][j]
+//     dW_l[j,k]     += sum_b freq_l[b][j] S[b][l][j,k]         db_l[j] += sum_b freq_l[b][j] cs[b][l][j]
+// ------------------------------------------------------------------------------------------------
+struct FilmReduceParams {
+  const float* S;     // (B, L, 256, 256)
+  const float* cs;    // (B, L, 256)
+  const float* film;  // (B, L, 2, 256)
+  const float* W[kMaxHiddenLayers + 2];  // [1..L]: fp32 hidden weights (256, 256)
+  const float* b[kMaxHiddenLayers + 2];
+  float* dfilm;       // (B, L, 2, 256), written
+  float* dW[kMaxHiddenLayers + 2];  // [1..L]: accumulated (+=); null entries are skipped
+  float* db[kMaxHiddenLayers + 2];
+  int B, L;
+};
+
+// grid (256 / 8, L, B), 256 threads: one warp per (map, layer, output feature j)
+__global__ void __launch_bounds__(256) reni_film_dfilm_kernel(const FilmReduceParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp, l = blockIdx.y, b = blockIdx.z;
+  const float4* srow = reinterpret_cast<const float4*>(p.S + (((size_t)b * p.L + l) * kH + j) * kH);
+  const float4* wrow = reinterpret_cast<const float4*>(p.W[l + 1] + (size_t)j * kH);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < kH / 128; ++i) {
+    const float4 sv = __ldg(srow + i * 32 + lane), wv = __ldg(wrow + i * 32 + lane);
+    acc = fmaf(sv.x, wv.x, fmaf(sv.y, wv.y, fmaf(sv.z, wv.z, fmaf(sv.w, wv.w, acc))));
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    const float c = p.cs[((size_t)b * p.L + l) * kH + j];
+    float* o = p.dfilm + ((size_t)b * p.L + l) * 2 * kH;
+    o[j] = fmaf(p.b[l + 1][j], c, acc);
+    o[kH + j] = c;
+  }
+}
+
+// grid (256, L), 256 threads: block = (output feature j, layer), thread = input feature k; sums over the maps
+__global__ void __launch_bounds__(256) reni_film_dw_kernel(const FilmReduceParams p) {
+  const int j = blockIdx.x, l = blockIdx.y, k = threadIdx.x;
+  if (p.dW[l + 1] == nullptr) return;
+  float acc = 0.f, accb = 0.f;
+  for (int b = 0; b < p.B; ++b) {
+    const float f = __ldg(p.film + ((size_t)b * p.L + l) * 2 * kH + j);
+    acc = fmaf(f, __ldg(p.S + (((size_t)b * p.L + l) * kH + j) * kH + k), acc);
+    if (k == 0) accb = fmaf(f, __ldg(p.cs + ((size_t)b * p.L + l) * kH + j), accb);
+  }
+  p.dW[l + 1][(size_t)j * kH + k] += acc;
+  if (k == 0 && p.db[l + 1] != nullptr) p.db[l + 1][j] += accb;
+}
+
 }  // namespace reni

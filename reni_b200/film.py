@@ -1,0 +1,254 @@
+"""Drop-in FiLM-conditioned RENI decoders backed by the sm_100a kernels.
+
+Same class names, constructor arguments, attributes, parameter names (``net.{i}.layer.*``, ``final_layer.*``,
+``mapping_network.network.{2i}.*``, ``Z`` / ``mu`` / ``log_var``), ``forward`` dispatch and ``load_state_dict``
+semantics as the reference's ``RENIAutoDecoderFiLM`` / ``RENIVariationalAutoDecoderFiLM``
+(src/models/RENI.py:527-858), which is the reference's default conditioning (configs/default.py:9).
+
+Split of the work (reference ``forward``: RENI.py:653-678):
+
+* per MAP, in PyTorch with autograd (a few (B, .) tensors): the invariant mapping-network input
+  (``G = Z_xz Z_xz^T`` and ``Z_y``, RENI.py:418-436), the mapping network (RENI.py:481-512; the reference evaluates
+  it on an input replicated over all P pixels -- it is constant per map), ``freq = 15 raw + 30`` (RENI.py:667), and the
+  hoisted first FiLM layer: its input ``[|d_xz|, d_y, D_xz Z_xz^T]`` is linear in the direction features, so
+  ``freq_0 (W_0 x + b_0) + phase_0 = [f | 1] . mc`` with a per-map (5, 256) matrix ``mc``;
+* per DIRECTION, in libreni_b200.so (``reni_film_forward`` / ``reni_film_backward``): the direction features, layer 0,
+  the modulated 256x256 layers on the tensor cores, the output layer, and in the backward the gradients w.r.t. ``mc``,
+  ``film`` and the decoder weights.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import List
+
+import torch
+from torch import nn
+
+from . import functional as F_
+from .functional import FilmSpec, Workspace
+
+
+def kaiming_leaky_init(m):
+    """RENI.py:455-460."""
+    if m.__class__.__name__.find("Linear") != -1:
+        torch.nn.init.kaiming_normal_(m.weight, a=0.2, mode="fan_in", nonlinearity="leaky_relu")
+
+
+class CustomMappingNetwork(nn.Module):
+    """RENI.py:481-512: ``map_hidden_layers`` x (Linear, LeakyReLU(0.2)) + Linear; the last weight is scaled by 0.25.
+    Evaluated in PyTorch once per map."""
+
+    def __init__(self, in_features, map_hidden_layers, map_hidden_dim, map_output_dim):
+        super().__init__()
+        network: List[nn.Module] = []
+        for _ in range(map_hidden_layers):
+            network.append(nn.Linear(in_features, map_hidden_dim))
+            network.append(nn.LeakyReLU(0.2, inplace=True))
+            in_features = map_hidden_dim
+        network.append(nn.Linear(map_hidden_dim, map_output_dim))
+        self.network = nn.Sequential(*network)
+        self.network.apply(kaiming_leaky_init)
+        with torch.no_grad():
+            self.network[-1].weight *= 0.25
+
+    def forward(self, z):
+        frequencies_offsets = self.network(z)
+        half = frequencies_offsets.shape[-1] // 2
+        return frequencies_offsets[..., :half], frequencies_offsets[..., half:]
+
+
+class FiLMLayer(nn.Module):
+    """Parameter holder (RENI.py:515-524).  ``forward`` exists for API compatibility; the decoder evaluates
+    sin(freq * layer(x) + phase_shift) inside the fused kernel."""
+
+    def __init__(self, input_dim, hidden_dim):
+        super().__init__()
+        self.layer = nn.Linear(input_dim, hidden_dim)
+
+    def forward(self, x, freq, phase_shift):  # pragma: no cover - not on the product path
+        raise RuntimeError("FiLMLayer is evaluated inside the fused reni_b200 decoder kernel; call the decoder module")
+
+
+def _frequency_init(layer: nn.Linear, freq: float) -> None:
+    """RENI.py:463-471."""
+    with torch.no_grad():
+        n = layer.weight.size(-1)
+        b = math.sqrt(6 / n) / freq
+        layer.weight.uniform_(-b, b)
+
+
+class _FilmDecoderBase(nn.Module):
+    def __init__(self, dataset_size, ndims, equivariance, siren_hidden_features, siren_hidden_layers,
+                 mapping_network_features, mapping_network_layers, out_features, output_activation, fixed_decoder):
+        super().__init__()
+        self.dataset_size = dataset_size
+        self.ndims = ndims
+        self.equivariance = equivariance
+        self.siren_hidden_features = siren_hidden_features
+        self.siren_hidden_layers = siren_hidden_layers
+        self.mapping_network_features = mapping_network_features
+        self.mapping_network_layers = mapping_network_layers
+        self.out_features = out_features
+        self.output_activation = output_activation
+        self.fixed_decoder = fixed_decoder
+
+        if equivariance == "None":     # RENI.py:556-567
+            self.in_features = ndims * 3
+            self.mn_in_features = ndims
+        elif equivariance == "SO2":
+            self.in_features = 2 + ndims
+            self.mn_in_features = ndims * ndims + ndims
+        elif equivariance == "SO3":
+            self.in_features = ndims
+            self.mn_in_features = ndims * ndims
+        else:
+            raise ValueError(f"unknown equivariance {equivariance!r}")
+
+        self.init_latent_codes(dataset_size, ndims, fixed_decoder)
+
+        self.net = nn.ModuleList()
+        self.net.append(FiLMLayer(self.in_features, siren_hidden_features))
+        for _ in range(siren_hidden_layers - 1):
+            self.net.append(FiLMLayer(siren_hidden_features, siren_hidden_features))
+        self.final_layer = nn.Linear(siren_hidden_features, out_features)
+        self.mapping_network = CustomMappingNetwork(self.mn_in_features, mapping_network_layers,
+                                                    mapping_network_features,
+                                                    len(self.net) * siren_hidden_features * 2)
+        for layer in self.net:         # RENI.py:584-586
+            _frequency_init(layer.layer, 25)
+        _frequency_init(self.final_layer, 25)
+        with torch.no_grad():
+            n = self.net[0].layer.weight.size(-1)
+            self.net[0].layer.weight.uniform_(-1 / n, 1 / n)
+
+        if fixed_decoder:              # RENI.py:595-601
+            for group in (self.net, self.final_layer, self.mapping_network):
+                for param in group.parameters():
+                    param.requires_grad = False
+        self._ws = Workspace()
+
+    # ---- plumbing -------------------------------------------------------------------------
+    @property
+    def spec(self) -> FilmSpec:
+        return FilmSpec(self.ndims, self.equivariance, self.siren_hidden_features, self.siren_hidden_layers,
+                        self.out_features, self.output_activation)
+
+    def core_parameters(self) -> List[torch.Tensor]:
+        """[W_1, b_1, ..., W_L, b_L, W_out, b_out]: what the fused kernel streams (net.0 is hoisted per map)."""
+        ps: List[torch.Tensor] = []
+        for layer in list(self.net)[1:]:
+            ps += [layer.layer.weight, layer.layer.bias]
+        return ps + [self.final_layer.weight, self.final_layer.bias]
+
+    def map_level(self, Z: torch.Tensor):
+        """Per-map operands of the core: mc (B, 5, H) and film (B, L, 2, H).  Plain differentiable torch ops."""
+        B, N, _ = Z.shape
+        H, Lf = self.siren_hidden_features, self.siren_hidden_layers
+        W0, b0 = self.net[0].layer.weight, self.net[0].layer.bias
+        if self.equivariance == "SO2":
+            Z_xz = torch.stack((Z[:, :, 0], Z[:, :, 2]), -1)
+            G = torch.bmm(Z_xz, Z_xz.transpose(1, 2))
+            mapping_input = torch.cat((G.flatten(start_dim=1), Z[:, :, 1]), 1)        # RENI.py:424-435
+            W_ip = W0[:, 2:]
+            M = torch.stack((Z_xz[:, :, 0] @ W_ip.T, Z_xz[:, :, 1] @ W_ip.T,          # d_x, d_z
+                             W0[:, 0].expand(B, H), W0[:, 1].expand(B, H)), 1)        # |d_xz|, d_y (RENI.py:434)
+        else:  # SO3 (RENI.py:405-415)
+            G = Z @ Z.transpose(1, 2)
+            mapping_input = G.flatten(start_dim=1)
+            M = torch.cat((Z.transpose(1, 2) @ W0.T, torch.zeros(B, 1, H, device=Z.device, dtype=Z.dtype)), 1)
+        frequencies, phase_shifts = self.mapping_network(mapping_input)
+        frequencies = frequencies * 15 + 30                                             # RENI.py:667
+        freq = frequencies.view(B, Lf, H)
+        phase = phase_shifts.view(B, Lf, H)
+        mc = torch.cat((M * freq[:, :1], (freq[:, 0] * b0 + phase[:, 0]).unsqueeze(1)), 1)
+        film = torch.stack((freq[:, 1:], phase[:, 1:]), 2)
+        return mc, film
+
+    def decode(self, Z: torch.Tensor, directions: torch.Tensor) -> torch.Tensor:
+        spec = self.spec
+        spec.validate()
+        if Z.dim() != 3 or Z.shape[1] != self.ndims or Z.shape[2] != 3:
+            raise ValueError(f"latent codes must have shape (B, {self.ndims}, 3), got {tuple(Z.shape)}")
+        if Z.device.type != "cuda":
+            raise RuntimeError("reni_b200 runs on CUDA (sm_100a) only and has no CPU fallback; got latent codes on "
+                               f"{Z.device}.  Move the module and its inputs to a B200.")
+        mc, film = self.map_level(Z.float())
+        out = F_.film_decode_core(spec, self._ws, mc, film, directions, self.core_parameters())
+        if self.output_activation == "exp":
+            out = torch.exp(out)
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        """Reference semantics (RENI.py:608-627): keep keys prefixed ``model.``; a fixed decoder loads net,
+        mapping_network and final_layer only and keeps its fresh latents."""
+        new_state_dict = {k[6:]: v for k, v in state_dict.items() if k.startswith("model.")}
+        if self.fixed_decoder:
+            net_sd = {k[4:]: v for k, v in new_state_dict.items() if k.startswith("net.")}
+            map_sd = {k[16:]: v for k, v in new_state_dict.items() if k.startswith("mapping_network.")}
+            self.net.load_state_dict(net_sd, strict=strict)
+            self.mapping_network.load_state_dict(map_sd, strict=strict)
+            dev = self.final_layer.weight.device
+            self.final_layer.weight = nn.Parameter(new_state_dict["final_layer.weight"].to(dev), requires_grad=False)
+            self.final_layer.bias = nn.Parameter(new_state_dict["final_layer.bias"].to(dev), requires_grad=False)
+            return None
+        return super().load_state_dict(new_state_dict, strict=strict)
+
+    # ---- forward dispatch (RENI.py:629-664 / :806-858) ----------------------------------------
+    def _latents_for(self, idx):
+        raise NotImplementedError
+
+    def forward(self, x, directions):
+        if not isinstance(x, (int, list, torch.Tensor)):
+            raise NotImplementedError(
+                "x must be either an int (idx), torch.Tensor (idxs or latent codes) or a list of ints (idxs)")
+        if isinstance(x, int):
+            assert len([x]) == directions.shape[0]
+            Z = self._latents_for([x])
+        elif isinstance(x, list):
+            assert len(x) == directions.shape[0]
+            Z = self._latents_for(x)
+        elif len(x.shape) == 1:
+            Z = self._latents_for(x)
+        else:
+            Z = x
+        return self.decode(Z, directions)
+
+
+class RENIAutoDecoderFiLM(_FilmDecoderBase):
+    """Reference: src/models/RENI.py:527-678."""
+
+    def init_latent_codes(self, dataset_size, ndims, fixed_decoder=False):
+        if fixed_decoder:
+            self.Z = nn.Parameter(torch.zeros(dataset_size, ndims, 3))
+        else:
+            self.Z = nn.Parameter(torch.randn((dataset_size, ndims, 3)))
+
+    def _latents_for(self, idx):
+        return self.Z[idx, :, :]
+
+
+class RENIVariationalAutoDecoderFiLM(_FilmDecoderBase):
+    """Reference: src/models/RENI.py:681-858.  Sampling stays in PyTorch; the decoder differentiates through the
+    sampled (non-leaf) latent tensor."""
+
+    def init_latent_codes(self, dataset_size, ndims, fixed_decoder=True):
+        self.log_var = nn.Parameter(torch.normal(-5, 1, size=(dataset_size, ndims, 3)))
+        if fixed_decoder:
+            self.mu = nn.Parameter(torch.zeros(dataset_size, ndims, 3))
+            self.log_var.requires_grad = False
+        else:
+            self.mu = nn.Parameter(torch.randn((dataset_size, ndims, 3)))
+
+    def sample_latent(self, idx):
+        mu = self.mu[idx, :, :]
+        log_var = self.log_var[idx, :, :]
+        std = torch.exp(0.5 * log_var)
+        eps = torch.randn_like(std)
+        sample = mu + (eps * std)
+        return sample, mu, log_var
+
+    def _latents_for(self, idx):
+        if self.fixed_decoder:
+            return self.mu[idx, :, :]
+        Z, _, _ = self.sample_latent(idx)
+        return Z

@@ -294,3 +294,128 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
         _stream(dev))
     _lib.check(rc, "reni_loss_forward_backward")
     return StepResult(loss[0], loss[1], loss[2], loss[3], out, dZ, dW, db)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# FiLM-conditioned decoder core (reference: RENIAutoDecoderFiLM.forward_with_frequencies_phase_shifts,
+# src/models/RENI.py:666-678 with FiLMLayer :515-524)
+# ----------------------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class FilmSpec:
+    """Hyper-parameters of one FiLM decoder as the reference constructor takes them (RENI.py:528-540)."""
+
+    ndims: int
+    equivariance: str
+    siren_hidden_features: int
+    siren_hidden_layers: int
+    out_features: int
+    output_activation: Optional[str]
+
+    def validate(self) -> None:
+        if self.equivariance not in ("SO2", "SO3"):
+            # the reference builds net[0] = Linear(3N, H) for "None" but feeds it the (B, P, N) inner products and
+            # gives the mapping network N instead of 3N inputs (RENI.py:556-559,438-441): its forward raises
+            raise RuntimeError("equivariance 'None' with FiLM conditioning is broken in the reference (shape mismatch "
+                               "in net[0] and the mapping network, RENI.py:438-441,556-559)")
+        if self.output_activation not in (None, "tanh", "exp"):
+            raise ValueError(f"unsupported output_activation {self.output_activation!r}")
+        if self.siren_hidden_features != HIDDEN_FEATURES:
+            raise NotImplementedError(
+                f"reni_b200 kernels are built for hidden_features={HIDDEN_FEATURES}, got {self.siren_hidden_features}")
+        if not 2 <= self.siren_hidden_layers <= 7:
+            raise NotImplementedError("reni_b200 FiLM kernels support 2..7 FiLM layers")
+        if not 1 <= self.out_features <= 3:
+            raise NotImplementedError("reni_b200 kernels support out_features <= 3")
+
+    def c_config(self) -> RENIConfig:
+        """The core sees L = siren_hidden_layers - 1 modulated 256x256 layers with omega = 1 (the per-map frequencies
+        take the place of omega_0) and a linear output layer; exp is applied by the caller."""
+        self.validate()
+        return RENIConfig(self.ndims, _lib.EQUIVARIANCE[self.equivariance], self.siren_hidden_features,
+                          self.siren_hidden_layers - 1, self.out_features, 1,
+                          1 if self.output_activation == "tanh" else 0, 1.0, 1.0)
+
+
+class _FilmCoreFunction(torch.autograd.Function):
+    """out = core(mc, film, D; W_1..W_L, b_1..b_L, W_out, b_out) with gradients for mc, film and the parameters."""
+
+    @staticmethod
+    def forward(ctx, spec: FilmSpec, inference_ws: Workspace, mc, film, D, *params):
+        lib = _lib.load()
+        cfg = spec.c_config()
+        L = spec.siren_hidden_layers - 1
+        weights = [_f32c(p) for p in params[0::2]]   # W_1 .. W_L, W_out
+        biases = [_f32c(p) for p in params[1::2]]
+        assert len(weights) == L + 1 and len(biases) == L + 1
+        dev = _require_cuda(mc, film, D, *weights, *biases)
+        mcc, filmc = _f32c(mc), _f32c(film)
+        B = mcc.shape[0]
+        if tuple(mcc.shape) != (B, 5, HIDDEN_FEATURES) or tuple(filmc.shape) != (B, L, 2, HIDDEN_FEATURES):
+            raise ValueError(f"mc must be (B,5,256) and film (B,{L},2,256); got {tuple(mcc.shape)}, {tuple(filmc.shape)}")
+        Dc, d_bs = _batch_stride(D, B, "directions")
+        P = Dc.shape[1]
+        need_in = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        need_dw = any(ctx.needs_input_grad[5:])
+        flags = _lib.FLAG_FILM
+        if need_in or need_dw:
+            flags |= FLAG_SAVE_FOR_BACKWARD | (FLAG_NEED_DW if need_dw else 0)
+        ws = Workspace() if (flags & FLAG_SAVE_FOR_BACKWARD) else inference_ws
+        ws.ensure(workspace_bytes(cfg, B, P, flags), dev)
+        # weight images: slot 0 of the parameter arrays (the first layer) is not used by the core
+        prepare_weights(cfg, [weights[0]] + weights, [biases[0]] + biases, ws, dev)
+        out = torch.empty(B, P, 3, device=dev, dtype=torch.float32)
+        rc = lib.reni_film_forward(C.byref(cfg), _vp(mcc), _vp(filmc), _vp(Dc), d_bs, B, P, _vp(out), _vp(ws.view),
+                                   ws.nbytes, flags, _stream(dev))
+        _lib.check(rc, "reni_film_forward")
+        if flags & FLAG_SAVE_FOR_BACKWARD:
+            ctx.spec, ctx.ws, ctx.flags, ctx.d_bs = spec, ws, flags, d_bs
+            ctx.save_for_backward(filmc, Dc, out, *weights, *biases)
+        if spec.out_features != 3:
+            return out[:, :, : spec.out_features]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        spec: FilmSpec = ctx.spec
+        cfg = spec.c_config()
+        L = spec.siren_hidden_layers - 1
+        saved = ctx.saved_tensors
+        filmc, Dc, out = saved[0], saved[1], saved[2]
+        weights, biases = list(saved[3:3 + L + 1]), list(saved[3 + L + 1:3 + 2 * (L + 1)])
+        dev = filmc.device
+        B, P = filmc.shape[0], Dc.shape[1]
+        g = _f32c(grad_out)
+        if g.shape[2] != 3:
+            gp = torch.zeros(B, P, 3, device=dev)
+            gp[:, :, : g.shape[2]] = g
+            g = gp
+        need_dw = bool(ctx.flags & FLAG_NEED_DW)
+        d_mc = torch.empty(B, 5, HIDDEN_FEATURES, device=dev, dtype=torch.float32)
+        d_film = torch.empty_like(filmc)
+        dW = [torch.zeros_like(w) for w in weights] if need_dw else None
+        db = [torch.zeros_like(b) for b in biases] if need_dw else None
+        rc = lib.reni_film_backward(
+            C.byref(cfg), _vp(filmc), _vp(Dc), ctx.d_bs, _ptr_array([weights[0]] + weights),
+            _ptr_array([biases[0]] + biases), B, P, _vp(out), _vp(g), _vp(d_mc), _vp(d_film),
+            _ptr_array([None] + dW) if need_dw else None, _ptr_array([None] + db) if need_dw else None,
+            _vp(ctx.ws.view), ctx.ws.nbytes, ctx.flags, _stream(dev))
+        _lib.check(rc, "reni_film_backward")
+        ctx.ws = None  # release the stash
+        grads: List[Optional[torch.Tensor]] = []
+        for i in range(L + 1):
+            grads.append(dW[i] if need_dw and ctx.needs_input_grad[5 + 2 * i] else None)
+            grads.append(db[i] if need_dw and ctx.needs_input_grad[6 + 2 * i] else None)
+        return (None, None, d_mc if ctx.needs_input_grad[2] else None, d_film if ctx.needs_input_grad[3] else None,
+                None, *grads)
+
+
+def film_decode_core(spec: FilmSpec, inference_ws: Workspace, mc: torch.Tensor, film: torch.Tensor, D: torch.Tensor,
+                     params: Sequence[torch.Tensor]) -> torch.Tensor:
+    """``params`` = [W_1, b_1, ..., W_L, b_L, W_out, b_out] (net.1.. and final_layer of the reference's FiLM module).
+    Differentiable w.r.t. mc, film and the parameters; the output activation (tanh in-kernel) excludes ``exp``."""
+    spec.validate()
+    if torch.is_grad_enabled() and (mc.requires_grad or film.requires_grad or any(p.requires_grad for p in params)):
+        return _FilmCoreFunction.apply(spec, inference_ws, mc, film, D, *params)
+    with torch.no_grad():
+        return _FilmCoreFunction.forward(_NoGradCtx(len(params) + 1), spec, inference_ws, mc, film, D, *params)

@@ -200,15 +200,20 @@ class RENIVariationalAutoDecoder(_DecoderBase):
 
 
 def get_model(config, dataset_size, task):
-    """Reference factory (RENI.py:861-933) for the Cond-by-Concat family this path implements.
+    """Reference factory (RENI.py:861-933).
 
     ``config`` is the reference's yacs node (``config.RENI.*``) or any object with the same attributes."""
+    from .film import RENIAutoDecoderFiLM, RENIVariationalAutoDecoderFiLM
+
     r = config.RENI
     fixed_decoder = task in ["FIT_LATENT", "FIT_INVERSE"]
-    if r.CONDITIONING != "Cond-by-Concat":
-        raise NotImplementedError(
-            "reni_b200 implements the Cond-by-Concat decoder (the BASELINE north-star path); FiLM conditioning "
-            "(RENI.py:407-858) is listed as the next row in DESIGN.md")
-    cls = {"AutoDecoder": RENIAutoDecoder, "VariationalAutoDecoder": RENIVariationalAutoDecoder}[r.MODEL_TYPE]
-    return cls(dataset_size, r.LATENT_DIMENSION, r.EQUIVARIANCE, r.HIDDEN_FEATURES, r.HIDDEN_LAYERS, r.OUT_FEATURES,
-               r.LAST_LAYER_LINEAR, r.OUTPUT_ACTIVATION, r.FIRST_OMEGA_0, r.HIDDEN_OMEGA_0, fixed_decoder)
+    if r.CONDITIONING == "Cond-by-Concat":
+        cls = {"AutoDecoder": RENIAutoDecoder, "VariationalAutoDecoder": RENIVariationalAutoDecoder}[r.MODEL_TYPE]
+        return cls(dataset_size, r.LATENT_DIMENSION, r.EQUIVARIANCE, r.HIDDEN_FEATURES, r.HIDDEN_LAYERS,
+                   r.OUT_FEATURES, r.LAST_LAYER_LINEAR, r.OUTPUT_ACTIVATION, r.FIRST_OMEGA_0, r.HIDDEN_OMEGA_0,
+                   fixed_decoder)
+    if r.CONDITIONING == "FiLM":
+        cls = {"AutoDecoder": RENIAutoDecoderFiLM, "VariationalAutoDecoder": RENIVariationalAutoDecoderFiLM}[r.MODEL_TYPE]
+        return cls(dataset_size, r.LATENT_DIMENSION, r.EQUIVARIANCE, r.HIDDEN_FEATURES, r.HIDDEN_LAYERS,
+                   r.MAPPING_FEATURES, r.MAPPING_LAYERS, r.OUT_FEATURES, r.OUTPUT_ACTIVATION, fixed_decoder)
+    return None  # (the reference falls through and returns None for an unknown conditioning)

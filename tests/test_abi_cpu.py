@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_strerror(lib):
-    assert lib.reni_abi_version() == 1
+    assert lib.reni_abi_version() == 2
     assert lib.reni_strerror(0) == b"ok"
     for code in (-1, -2, -3, -4, -5):
         assert len(lib.reni_strerror(code)) > 4

@@ -1,0 +1,164 @@
+"""FiLM-conditioned decoder on the GPU (run with -m gpu on a B200): the CUDA core behind RENIAutoDecoderFiLM, called
+through the drop-in module (autograd -> reni_film_forward / reni_film_backward), against (a) golden fixtures produced by
+the reference's RENIAutoDecoderFiLM and (b) the numpy FiLM oracle on seeded inputs.  Tolerances as for the
+Cond-by-Concat path: radiance 1e-3 relative, gradients 1e-2 relative (rel-L2)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, TOL_GRAD, TOL_RADIANCE, TOL_RADIANCE_MAX
+
+import reni_film_oracle as FO  # noqa: E402
+from make_golden_film import sub  # noqa: E402
+from test_film_models_cpu import film_model_from_params
+from test_film_oracle_golden import load_film_case
+
+pytestmark = pytest.mark.gpu
+
+FILM_H256 = ["film_so2_n9_h256", "film_so2_n36_h256", "film_so3_n9_h256_tanh"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    import __graft_entry__ as entry
+
+    entry.build()
+    return torch.device("cuda:0")
+
+
+def t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.mark.parametrize("name", FILM_H256)
+def test_film_forward_matches_reference_golden(dev, name):
+    c = load_film_case(name)
+    m = film_model_from_params(c["p"], c["N"], dev)
+    with torch.no_grad():
+        out = m(t(c["Z"], dev), t(c["D"], dev)).cpu().numpy()
+    ref = c["g"]["out_f32"]
+    assert out.shape == ref.shape
+    assert O.rel_l2(out, ref) < TOL_RADIANCE
+    assert O.rel_max(out, ref) < TOL_RADIANCE_MAX
+
+
+@pytest.mark.parametrize("name", FILM_H256)
+def test_film_training_and_latent_gradients_match_reference_golden(dev, name):
+    """The reference's calling pattern: out = model(Z, D); loss = criterion(out, ...); loss.backward()."""
+    from reni_b200 import RENITestLoss, RENITrainLoss
+
+    c = load_film_case(name)
+    g = c["g"]
+    m = film_model_from_params(c["p"], c["N"], dev)
+    Z = t(c["Z"], dev).requires_grad_(True)
+    D, tg, sw = (t(c[k], dev) for k in ("D", "target", "sw"))
+    out = m(Z, D)
+    loss = RENITrainLoss()(out, tg, sw)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(g["train_loss_f32"])) < 1e-3 * abs(float(g["train_loss_f32"]))
+    assert O.rel_l2(out.detach().cpu().numpy(), g["out_f32"]) < TOL_RADIANCE
+    assert O.rel_l2(Z.grad.cpu().numpy(), g["train_dZ_f32"]) < TOL_GRAD
+    for i in range(c["Lf"]):
+        dw = m.net[i].layer.weight.grad.cpu().numpy()
+        assert O.rel_l2(sub(dw), g[f"net_dW{i}_f32"]) < TOL_GRAD, f"net_dW{i}"
+        assert abs(np.linalg.norm(dw) / float(g[f"net_dW{i}_norm_f32"]) - 1) < TOL_GRAD
+        assert O.rel_l2(m.net[i].layer.bias.grad.cpu().numpy(), g[f"net_db{i}_f32"]) < TOL_GRAD, f"net_db{i}"
+    assert O.rel_l2(m.final_layer.weight.grad.cpu().numpy(), g["final_dW_f32"]) < TOL_GRAD
+    assert O.rel_l2(m.final_layer.bias.grad.cpu().numpy(), g["final_db_f32"]) < TOL_GRAD
+    for i in range(len(c["p"].map_w)):
+        lin = m.mapping_network.network[2 * i]
+        assert O.rel_l2(sub(lin.weight.grad.cpu().numpy()), g[f"map_dW{i}_f32"]) < TOL_GRAD, f"map_dW{i}"
+        assert O.rel_l2(lin.bias.grad.cpu().numpy(), g[f"map_db{i}_f32"]) < TOL_GRAD, f"map_db{i}"
+
+    # FIT_LATENT: frozen decoder, RENITestLoss (prior + cosine), latent gradients only
+    mf = film_model_from_params(c["p"], c["N"], dev, fixed=True)
+    Z2 = t(c["Z"], dev).requires_grad_(True)
+    out2 = mf(Z2, D)
+    l, mse, prior, cos = RENITestLoss(alpha=c["alpha"], beta=c["beta"])(out2, tg, sw, Z2)
+    l.backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose([float(l), float(mse), float(prior), float(cos)], g["test_loss_f32"], rtol=1e-3, atol=1e-8)
+    assert O.rel_l2(Z2.grad.cpu().numpy(), g["test_dZ_f32"]) < TOL_GRAD
+    assert all(p.grad is None for p in mf.core_parameters())
+
+
+@pytest.mark.parametrize("eq,act,P,B,Lf", [("SO2", "exp", 200, 5, 5), ("SO3", None, 1024, 3, 2), ("SO2", "tanh", 8192, 2, 7)])
+def test_film_vs_oracle_ragged_tiles_exp_and_depth(dev, eq, act, P, B, Lf):
+    """Shapes the fixtures do not cover: a ragged last tile (P = 200), several maps per CTA pair, the exp output
+    activation, 2 and 7 FiLM layers, 64 tiles per map."""
+    rng = np.random.default_rng(101)
+    N = 7
+    p = FO.film_init(rng, N, eq, 256, Lf, 64, 2, 3, act)
+    p.map_w[-1] = (2.0 * p.map_w[-1]).astype(np.float32)
+    Z = (0.5 * rng.standard_normal((B, N, 3))).astype(np.float32)
+    Dn = rng.standard_normal((B, P, 3))
+    D = (Dn / np.linalg.norm(Dn, axis=-1, keepdims=True)).astype(np.float32)
+    tg = rng.uniform(-1, 1, (B, P, 3)).astype(np.float32)
+    sw = np.repeat(rng.uniform(0, 1, (B, P, 1)), 3, 2).astype(np.float32)
+    p64 = p.astype(np.float64)
+    out_o, tape = FO.film_forward(Z.astype(np.float64), D.astype(np.float64), p64, tape=True)
+    go = O.loss_grad_wrt_output(out_o, tg.astype(np.float64), sw.astype(np.float64))
+    ref = FO.film_backward(Z.astype(np.float64), D.astype(np.float64), p64, tape, go)
+
+    from reni_b200 import RENITrainLoss
+
+    m = film_model_from_params(p, N, dev)
+    Zt = t(Z, dev).requires_grad_(True)
+    out = m(Zt, t(D, dev))
+    RENITrainLoss()(out, t(tg, dev), t(sw, dev)).backward()
+    torch.cuda.synchronize()
+    assert O.rel_l2(out.detach().cpu().numpy(), out_o) < TOL_RADIANCE
+    assert O.rel_l2(Zt.grad.cpu().numpy(), ref["dZ"]) < TOL_GRAD
+    for i in range(Lf):
+        assert O.rel_l2(m.net[i].layer.weight.grad.cpu().numpy(), ref["net_dW"][i]) < TOL_GRAD, i
+        assert O.rel_l2(m.net[i].layer.bias.grad.cpu().numpy(), ref["net_db"][i]) < TOL_GRAD, i
+    assert O.rel_l2(m.final_layer.weight.grad.cpu().numpy(), ref["final_dW"]) < TOL_GRAD
+    for i in range(len(p.map_w)):
+        assert O.rel_l2(m.mapping_network.network[2 * i].weight.grad.cpu().numpy(), ref["map_dW"][i]) < TOL_GRAD, i
+
+
+def test_film_core_gradients_wrt_film_and_mc(dev):
+    """The C-ABI core in isolation: d_mc and d_film against the oracle's dfreq / dphase."""
+    from reni_b200 import functional as F_
+
+    c = load_film_case("film_so2_n9_h256")
+    p64 = c["p"].astype(np.float64)
+    Z, D, tg, sw = (c[k].astype(np.float64) for k in ("Z", "D", "target", "sw"))
+    out_o, tape = FO.film_forward(Z, D, p64, tape=True)
+    go = O.loss_grad_wrt_output(out_o, tg, sw)
+    ref = FO.film_backward(Z, D, p64, tape, go)
+    B, Lf, H = c["B"], c["Lf"], 256
+    mc_o, film_o = FO.film_core_inputs(Z, p64)
+    m = film_model_from_params(c["p"], c["N"], dev)
+    mc = t(mc_o.astype(np.float32), dev).requires_grad_(True)
+    film = t(film_o.astype(np.float32), dev).requires_grad_(True)
+    out = F_.film_decode_core(m.spec, F_.Workspace(), mc, film, t(c["D"], dev), m.core_parameters())
+    out.backward(t(go.astype(np.float32), dev))
+    torch.cuda.synchronize()
+    dfreq = ref["dfreq"].reshape(B, Lf, H)
+    dphase = ref["dphase"].reshape(B, Lf, H)
+    got = film.grad.cpu().numpy()
+    assert O.rel_l2(got[:, :, 0], dfreq[:, 1:]) < TOL_GRAD
+    assert O.rel_l2(got[:, :, 1], dphase[:, 1:]) < TOL_GRAD
+    # row 4 of d_mc is dL/d(c_b) = sum_p delta_0 = dphase_0
+    assert O.rel_l2(mc.grad.cpu().numpy()[:, 4], dphase[:, 0]) < TOL_GRAD
+
+
+def test_film_dispatch_and_batch_independence(dev):
+    torch.manual_seed(0)
+    from reni_b200 import RENIAutoDecoderFiLM, get_directions
+
+    m = RENIAutoDecoderFiLM(6, 9, "SO2", 256, 5, 256, 3, 3, None, False).to(dev)
+    D = get_directions(32).to(dev)
+    with torch.no_grad():
+        a = m(3, D)
+        b = m([1, 3, 4], D.expand(3, -1, -1))
+        cc = m(torch.tensor([3, 0], device=dev), D.expand(2, -1, -1))
+        d = m(m.Z[[3]], D)
+    # (the per-map stage is a handful of torch matmuls whose reduction order depends on the batch size, so the
+    # same map decoded in different batches agrees to rounding, not bitwise)
+    for x, y in ((a[0], b[1]), (a[0], cc[0])):
+        assert torch.allclose(x, y, rtol=1e-3, atol=2e-5)
+    assert torch.equal(a, d)

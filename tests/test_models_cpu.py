@@ -103,8 +103,12 @@ def test_get_model_factory():
     assert isinstance(m, RENIAutoDecoder) and not m.fixed_decoder and m.Z.shape == (11, 9, 3)
     m = get_model(cfg("VariationalAutoDecoder"), 11, "FIT_LATENT")
     assert isinstance(m, RENIVariationalAutoDecoder) and m.fixed_decoder   # RENI.py:874
-    with pytest.raises(NotImplementedError):
-        get_model(cfg("AutoDecoder", "FiLM"), 11, "FIT_DECODER")
+    from reni_b200 import RENIAutoDecoderFiLM, RENIVariationalAutoDecoderFiLM
+    m = get_model(cfg("AutoDecoder", "FiLM"), 11, "FIT_DECODER")       # RENI.py:905-917
+    assert isinstance(m, RENIAutoDecoderFiLM) and not m.fixed_decoder and m.Z.shape == (11, 9, 3)
+    assert m.siren_hidden_layers == 5 and m.mapping_network_layers == 3 and m.output_activation == "tanh"
+    m = get_model(cfg("VariationalAutoDecoder", "FiLM"), 11, "FIT_INVERSE")
+    assert isinstance(m, RENIVariationalAutoDecoderFiLM) and m.fixed_decoder and float(m.mu.abs().max()) == 0.0
 
 
 def test_geometry_matches_reference_fixtures():
