@@ -150,7 +150,8 @@ int32_t reni_film_backward(const reni_config_t* cfg, const float* film, const fl
  * calling thread's subsequent reni_forward / reni_backward / reni_loss_forward_backward calls record on
  * their stream between kernels: [0] start, [1] after the per-map prologue, [2] after the forward kernel,
  * [3] after the loss reduction, [4] after the delta-chain kernel, [5] after the weight-gradient GEMM,
- * [6] end of the step.  n = 0 clears.  Thread-local; this is the only state the library keeps. */
+ * [6] end of the step.  n = 0 clears.  Process-wide (autograd calls the backward on its own thread): set and
+ * clear it while no library call is in flight; besides per-thread side streams this is the only state kept. */
 int32_t reni_debug_set_phase_events(void* const* host_events, int32_t n);
 
 /* Debug hook: device buffer of 3 x 4096 uint64 into which CTA 0 of the calling thread's next forward kernels

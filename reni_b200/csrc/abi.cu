@@ -96,9 +96,10 @@ T* at(void* ws, int64_t off) {
 }
 
 // Optional phase timing (debug hook, reni_debug_set_phase_events): CUDA events recorded between the kernels of a
-// step so a caller can time each kernel on the launching stream.  Thread-local; empty by default.
-thread_local cudaEvent_t g_phase_events[16];
-thread_local int g_num_phase_events = 0;
+// step so a caller can time each kernel on the launching stream.  Process-wide (autograd runs reni_backward /
+// reni_film_backward on its own thread); empty by default; set and cleared by the measuring thread while no call runs.
+cudaEvent_t g_phase_events[16];
+volatile int g_num_phase_events = 0;
 thread_local unsigned long long* g_trace = nullptr;  // reni_debug_set_trace
 inline void mark_phase(int i, cudaStream_t s) {
   if (i < g_num_phase_events && g_phase_events[i] != nullptr) cudaEventRecord(g_phase_events[i], s);

@@ -23,7 +23,8 @@ import torch.distributed as dist
 from . import functional as F_
 from .functional import Workspace
 from .geometry import get_directions, get_sineweight
-from .losses import KLD
+from .film import RENIVariationalAutoDecoderFiLM, _FilmDecoderBase
+from .losses import KLD, RENITestLoss, RENITrainLoss, RENIVADTrainLoss
 from .models import RENIAutoDecoder, RENIVariationalAutoDecoder, _DecoderBase
 
 
@@ -94,7 +95,10 @@ class RENITrainer:
         self.alpha = prior_loss_weight
         self.beta = cosine_similarity_weight
         self.kld_weighting = kld_weighting
-        self.is_vad = isinstance(model, RENIVariationalAutoDecoder)
+        self.is_vad = isinstance(model, (RENIVariationalAutoDecoder, RENIVariationalAutoDecoderFiLM))
+        # FiLM decoders (the reference's default conditioning) step through autograd: the per-map stage (mapping
+        # network, hoisted first layer) is torch, the per-direction stage is reni_film_forward / reni_film_backward
+        self.is_film = isinstance(model, _FilmDecoderBase)
         self.fixed = task == "FIT_LATENT"
         self._ws = Workspace()
         # cuda_graph=True: the whole step (weight images, prologue, fwd, loss, bwd, grad exchange) is captured once per
@@ -113,7 +117,9 @@ class RENITrainer:
             self.flat = None
         else:
             opt_params = list(model.parameters())
-            self.flat = FlatGradBuffer(model.decoder_parameters())
+            latents = {id(p) for p in (getattr(model, n, None) for n in ("Z", "mu", "log_var")) if p is not None}
+            self.flat = FlatGradBuffer([p for p in model.parameters() if id(p) not in latents] if self.is_film
+                                       else model.decoder_parameters())
         self.optimizer = torch.optim.Adam(opt_params, lr=lr)
 
     # -- multi-resolution curriculum hook (callbacks.py:11-29 doubles the resolution at curriculum epochs)
@@ -132,9 +138,94 @@ class RENITrainer:
 
     def training_step(self, batch, batch_idx: int = 0) -> Dict[str, torch.Tensor]:
         """Same inputs and returned keys as RENI_module.training_step; gradients are left in ``.grad``."""
+        if self.is_film:
+            return self._film_step(batch)
         if self.cuda_graph and not (self.is_vad and not self.fixed):  # (the VAD sampler draws from torch's RNG: eager)
             return self._graphed_step(batch)
         return self._eager_step(batch)
+
+    def _film_step(self, batch) -> Dict[str, torch.Tensor]:
+        """RENI_module.training_step (:80-146) for a FiLM decoder, op for op: model(Z, D) -> criterion -> backward.
+        Decoder-side gradients accumulate straight into the flat all-reduce buffer (its views are the ``.grad``s).
+        With ``cuda_graph=True`` the whole autograd step (mapping network, fused core, loss, backward: ~150 launches
+        for ~1 ms of GPU work) is captured once per batch shape and replayed from static inputs."""
+        slot = self._take_prefetched(batch)
+        imgs, idx = batch
+        idx = torch.as_tensor(idx, dtype=torch.long)
+        graphed = self.cuda_graph and not (self.is_vad and not self.fixed)  # (the VAD sampler draws from torch's RNG)
+        if not graphed:
+            if slot is not None:
+                imgs, idx = slot["imgs"].clone(), slot["idx"].clone()
+                slot["free"].record(torch.cuda.current_stream(self.device))
+            log = self._film_body(imgs.to(self.device, non_blocking=True), idx.to(self.device, non_blocking=True))
+        else:
+            key = ("film", tuple(imgs.shape), imgs.dtype, int(idx.numel()))
+            entry = self._graphs.get(key)
+            if entry is None:
+                s_imgs = torch.empty(imgs.shape, dtype=imgs.dtype, device=self.device)
+                s_idx = torch.empty(idx.shape, dtype=torch.long, device=self.device)
+                s_imgs.copy_(imgs)
+                s_idx.copy_(idx)
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):  # warm-up outside capture (lazy initialisation, cuBLAS workspaces)
+                    for _ in range(3):
+                        self._film_body(s_imgs, s_idx)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    log = self._film_body(s_imgs, s_idx)
+                grads = [(p, p.grad) for p in self.model.parameters()]
+                entry = (graph, s_imgs, s_idx, log, grads, self.last_output)
+                self._graphs[key] = entry
+            graph, s_imgs, s_idx, log, grads, last_out = entry
+            src_imgs, src_idx = (slot["imgs"], slot["idx"]) if slot is not None else (imgs, idx)
+            s_imgs.copy_(src_imgs, non_blocking=True)
+            s_idx.copy_(src_idx, non_blocking=True)
+            if slot is not None:
+                slot["free"].record(torch.cuda.current_stream(self.device))
+            graph.replay()
+            for p, g in grads:  # the replay refreshed the captured gradient tensors in place
+                p.grad = g
+            self.last_output = last_out
+        if self.world_size > 1 and self.ddp_latent_scaling:
+            for p in (getattr(self.model, n, None) for n in ("Z", "mu", "log_var")):
+                if p is not None and p.grad is not None:
+                    p.grad.div_(self.world_size)
+        if self.flat is not None:
+            self.flat.all_reduce_mean(self.group)
+        return log
+
+    def _film_body(self, imgs: torch.Tensor, idx: torch.Tensor) -> Dict[str, torch.Tensor]:
+        B = imgs.shape[0]
+        imgs = imgs.permute(0, 2, 3, 1).reshape(B, -1, 3)
+        sw = self.sineweight if self.mask is None else self.sineweight * self.mask
+        sw = sw.expand(B, -1, -1)
+        D = self.directions.expand(B, -1, -1)
+        model = self.model
+        for p in model.parameters():
+            p.grad = None
+        if self.flat is not None:
+            self.flat.zero_()
+            self.flat.attach()
+        if self.is_vad and not self.fixed:
+            Z, mu, log_var = model.sample_latent(idx)
+        else:
+            Z = self._latent_table()[idx]
+        out = model(Z, D)
+        if self.task == "FIT_LATENT":
+            loss, mse, prior, cos = RENITestLoss(alpha=self.alpha, beta=self.beta)(out, imgs, sw, Z)
+            log = {"loss": loss.detach(), "mse_loss": mse.detach(), "prior_loss": prior.detach(),
+                   "cosine_loss": cos.detach()}
+        elif self.is_vad:
+            loss, mse, kld = RENIVADTrainLoss(beta=self.kld_weighting, Z_dims=model.ndims * 3)(out, imgs, sw, mu, log_var)
+            log = {"loss": loss.detach(), "mse_loss": mse.detach(), "kld_loss": kld.detach()}
+        else:
+            loss = RENITrainLoss()(out, imgs, sw)
+            log = {"loss": loss.detach()}
+        loss.backward()
+        self.last_output = out.detach()
+        return log
 
     def prefetch(self, batch) -> None:
         """Start copying ``batch`` (pinned host tensors) to the device on a side stream.  The next
