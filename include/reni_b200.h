@@ -146,6 +146,21 @@ int32_t reni_film_backward(const reni_config_t* cfg, const float* film, const fl
                            float* const* host_dW, float* const* host_db, void* workspace, int64_t workspace_bytes,
                            int32_t flags, void* stream);
 
+/* Fused Adam step over a list of fp32 segments: replaces torch.optim.Adam(params, lr).step() as the reference's
+ * configure_optimizers builds it (src/lightning/RENI_module.py:185-192: default betas (0.9, 0.999), eps 1e-8, no
+ * weight decay, dense over every parameter including the whole latent table).  One launch per 24 segments.
+ *   host_segments : HOST array of nseg descriptors of DEVICE buffers (param and both moments are updated in place)
+ *   step          : DEVICE int32, number of completed steps; read as t = *step + 1 and incremented on the stream */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} reni_adam_segment_t;
+int32_t reni_adam_step(const reni_adam_segment_t* host_segments, int32_t nseg, int32_t* step, double lr, double beta1,
+                       double beta2, double eps, void* stream);
+
 /* Debug / measurement hook: register up to 16 CUDA events (cudaEvent_t handles, HOST array) that the
  * calling thread's subsequent reni_forward / reni_backward / reni_loss_forward_backward calls record on
  * their stream between kernels: [0] start, [1] after the per-map prologue, [2] after the forward kernel,

@@ -37,6 +37,13 @@ class RENIConfig(C.Structure):
     ]
 
 
+class AdamSegment(C.Structure):
+    """reni_adam_segment_t."""
+
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64)]
+
+
 class RENILibraryError(RuntimeError):
     pass
 
@@ -61,6 +68,7 @@ SIGNATURES = {
     "reni_film_forward": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp]),
     "reni_film_backward": (_i32, [_cfgp, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _vp, _vp, _vp,
                                   C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _i32, _vp]),
+    "reni_adam_step": (_i32, [C.POINTER(AdamSegment), _i32, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp]),
     "reni_debug_set_phase_events": (_i32, [C.POINTER(_vp), _i32]),
     "reni_debug_last_cuda_error": (C.c_char_p, []),
     "reni_debug_set_trace": (_i32, [_vp]),

@@ -710,6 +710,40 @@ int32_t reni_film_backward(const reni_config_t* c, const float* film, const floa
                          host_dW, host_db, ws, flags, stream, 1, nullptr, &fa);
 }
 
+int32_t reni_adam_step(const reni_adam_segment_t* host_segments, int32_t nseg, int32_t* step, double lr, double beta1,
+                       double beta2, double eps, void* stream_) {
+  if (host_segments == nullptr || nseg < 1 || step == nullptr) return RENI_ERR_BAD_ARGUMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int sms = num_sms();
+  if (sms <= 0) return RENI_ERR_NO_DEVICE;
+  for (int base = 0; base < nseg; base += kAdamMaxSegments) {
+    AdamParams a{};
+    const int n = nseg - base < kAdamMaxSegments ? nseg - base : kAdamMaxSegments;
+    int64_t total = 0;
+    for (int i = 0; i < n; ++i) {
+      const reni_adam_segment_t& sgm = host_segments[base + i];
+      if (sgm.param == nullptr || sgm.grad == nullptr || sgm.exp_avg == nullptr || sgm.exp_avg_sq == nullptr ||
+          sgm.numel < 0)
+        return RENI_ERR_BAD_ARGUMENT;
+      a.p[i] = sgm.param;
+      a.g[i] = sgm.grad;
+      a.m[i] = sgm.exp_avg;
+      a.v[i] = sgm.exp_avg_sq;
+      total += sgm.numel;
+      a.end[i] = total;
+    }
+    if (total == 0) continue;
+    a.nseg = n;
+    a.step = step;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+    int64_t blocks = (total + 1023) / 1024;  // ~4 elements per thread
+    if (blocks > 8LL * sms) blocks = 8LL * sms;
+    reni_adam_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+  }
+  reni_adam_advance_kernel<<<1, 1, 0, stream>>>(step);
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
 int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, uint32_t a_lbo,
                            uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t a_kstep, uint32_t b_kstep,
                            uint32_t a_mn, uint32_t b_mn, uint32_t n, uint32_t ksteps, float* d_out, void* stream) {

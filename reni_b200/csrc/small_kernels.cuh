@@ -660,4 +660,50 @@ __global__ void __launch_bounds__(256) reni_film_dw_kernel(const FilmReduceParam
   if (k == 0 && p.db[l + 1] != nullptr) p.db[l + 1][j] += accb;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused Adam over a list of fp32 segments (the flat decoder-weight buffer, the latent table, ...): ONE launch
+// replaces the ~12 foreach kernels x tensors of torch.optim.Adam.  Same arithmetic as torch's default
+// (non-amsgrad, no weight decay) single-tensor Adam, the optimiser the reference constructs
+// (src/lightning/RENI_module.py:191-192: Adam(params, lr) -- the configured betas are never passed):
+//     m = m + (g - m)(1 - b1);  v = b2 v + (1 - b2) g^2;
+//     p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// The step count t lives in device memory (the kernel uses *step + 1, reni_adam_advance_kernel increments it), so a
+// captured CUDA graph replays correctly.  Dense semantics: rows of the latent table whose gradient is zero still move
+// by their momentum, exactly as with the reference's dense Adam.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAdamMaxSegments = 24;
+struct AdamParams {
+  float* p[kAdamMaxSegments];
+  const float* g[kAdamMaxSegments];
+  float* m[kAdamMaxSegments];
+  float* v[kAdamMaxSegments];
+  int64_t end[kAdamMaxSegments];  // exclusive prefix sums of the segment lengths
+  int nseg;
+  const int* step;                // device: completed steps
+  double lr, beta1, beta2, eps;   // (doubles: torch forms 1 - beta^t and lr / (1 - beta1^t) in double before it casts)
+};
+
+__global__ void __launch_bounds__(256) reni_adam_kernel(const AdamParams a) {
+  const int t = *a.step + 1;
+  const float step_size = (float)(a.lr / (1.0 - pow(a.beta1, (double)t)));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow(a.beta2, (double)t));
+  const float w1 = (float)(1.0 - a.beta1), w2 = (float)(1.0 - a.beta2), b2 = (float)a.beta2, eps = (float)a.eps;
+  const int64_t total = a.end[a.nseg - 1];
+  int seg = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    while (i >= a.end[seg]) ++seg;  // (monotone in i: grid-stride loop)
+    const int64_t j = i - (seg ? a.end[seg - 1] : 0);
+    const float g = a.g[seg][j];
+    float m = a.m[seg][j], v = a.v[seg][j];
+    m = m + (g - m) * w1;                              // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * b2 + w2 * g * g;                           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    a.m[seg][j] = m;
+    a.v[seg][j] = v;
+    a.p[seg][j] -= step_size * (m / denom);            // param.addcdiv_(exp_avg, denom, value=-step_size)
+  }
+}
+
+__global__ void reni_adam_advance_kernel(int* step) { *step += 1; }
+
 }  // namespace reni

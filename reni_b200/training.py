@@ -26,6 +26,7 @@ from .geometry import get_directions, get_sineweight
 from .film import RENIVariationalAutoDecoderFiLM, _FilmDecoderBase
 from .losses import KLD, RENITestLoss, RENITrainLoss, RENIVADTrainLoss
 from .models import RENIAutoDecoder, RENIVariationalAutoDecoder, _DecoderBase
+from .optim import FusedAdam
 
 
 def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -120,7 +121,7 @@ class RENITrainer:
             latents = {id(p) for p in (getattr(model, n, None) for n in ("Z", "mu", "log_var")) if p is not None}
             self.flat = FlatGradBuffer([p for p in model.parameters() if id(p) not in latents] if self.is_film
                                        else model.decoder_parameters())
-        self.optimizer = torch.optim.Adam(opt_params, lr=lr)
+        self.optimizer = FusedAdam(opt_params, lr=lr)  # one launch; same arithmetic as torch.optim.Adam(params, lr)
 
     # -- multi-resolution curriculum hook (callbacks.py:11-29 doubles the resolution at curriculum epochs)
     def set_resolution(self, sidelen: int) -> None:
