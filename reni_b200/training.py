@@ -129,6 +129,21 @@ class RENITrainer:
         self.directions = get_directions(sidelen).to(self.device)   # (1, P, 3), shared by every map
         self.sineweight = get_sineweight(sidelen).to(self.device)   # (1, P, 3)
 
+    def on_train_epoch_end(self, current_epoch: int, curriculum: Sequence[int], mask_fn=None) -> bool:
+        """MultiResTrainingCallback.on_train_epoch_end (callbacks.py:11-25): when ``current_epoch + 1`` is a curriculum
+        epoch, double the resolution of the directions, the sine weights and (through ``mask_fn(sidelen)``, the
+        reference re-reads the PNG with get_mask) the mask.  Returns True when the resolution changed, i.e. when the
+        caller must also switch its dataset to the doubled resolution (``dataset.double_resolution()``).  Captured
+        CUDA graphs are keyed by batch shape, so the new resolution simply captures its own graph."""
+        if current_epoch + 1 not in curriculum:
+            return False
+        self.set_resolution(2 * self.sidelen)
+        if self.mask is not None:
+            if mask_fn is None:
+                raise ValueError("a masked task needs mask_fn(sidelen) to rebuild the mask at the new resolution")
+            self.mask = mask_fn(self.sidelen).to(self.device)
+        return True
+
     def exponential_lr(self, lr_start: float, lr_end: float, epochs: int):
         """Per-epoch ExponentialLR with gamma = exp(ln(lr_end/lr_start)/epochs) (RENI_module.py:212-214)."""
         gamma = math.exp(math.log(lr_end / lr_start) / epochs)

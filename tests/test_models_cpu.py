@@ -152,3 +152,19 @@ def test_shard_range_partitions_maps():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_multires_curriculum_hook_doubles_resolution_like_the_callback():
+    """callbacks.py:11-25 with the default schedule (configs/default.py: 16x32 -> 64x128 at epochs 25, 80[, 150])."""
+    from reni_b200 import RENITrainer
+
+    m = make(N=4, ds=3, fixed=True)
+    mask_fn = lambda w: rectangle_mask(w, w // 8, w // 4, w // 4, w // 2)  # noqa: E731
+    tr = RENITrainer(m, "FIT_LATENT", 32, mask=mask_fn(32))
+    curriculum = [25, 80]
+    changed = [e for e in range(100) if tr.on_train_epoch_end(e, curriculum, mask_fn)]
+    assert changed == [24, 79]                       # current_epoch + 1 in curriculum
+    assert tr.sidelen == 128 and tr.directions.shape == (1, 8192, 3) and tr.sineweight.shape == (1, 8192, 3)
+    assert tr.mask.shape == (1, 8192, 3)
+    with pytest.raises(ValueError):
+        tr.on_train_epoch_end(24, curriculum)        # masked task without a way to rebuild the mask
