@@ -21,6 +21,11 @@
 #ifndef RENI_BWD_TRAIN_PAIR
 #define RENI_BWD_TRAIN_PAIR 1  // CTA pairs also for the delta chain with weight gradients (0: one CTA per tile pair)
 #endif
+#ifndef RENI_DW_BALANCE
+#define RENI_DW_BALANCE 0  // weight-gradient GEMM: 1 = CTAs per job in proportion to the job's stash bytes.  Measured
+                           // slower (dW 328 vs 256 us at cfg 2): a CTA's throughput is set by its three stages in
+                           // flight, not by its bytes, so the output-layer job needs as many CTAs as a hidden job
+#endif
 #ifndef RENI_FWD_PAIR
 #define RENI_FWD_PAIR 1  // forward on CTA pairs (0: one CTA per tile pair, grouped training / all-hands inference epilogue)
 #endif
@@ -527,6 +532,13 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     const int max_useful = ntiles * 2 * (L + 1);
     if (g > max_useful) g = max_useful;
     if (g < L + 1) g = L + 1;
+#if RENI_DW_BALANCE
+    // bytes per stash block: hidden job 64 KB (delta + phase), output job 34 KB (g_y + phase) -> its share of the CTAs
+    if (g >= 4 * (L + 1)) {
+      q.out_ctas = (int)((double)g * 34.0 / (64.0 * L + 34.0) + 0.5);
+      if (q.out_ctas < 1) q.out_ctas = 1;
+    }
+#endif
     reni_dw_kernel<<<g, kDwThreads, DwSmem::kTotal, stream>>>(q);
     if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   }

@@ -38,6 +38,7 @@ struct DwParams {
   float* film_S;
   float* film_cs;
   int tiles_per_map, njobs;
+  int out_ctas;  // > 0: CTAs given to the output-layer job (non-FiLM grid), 0: plain round robin
 };
 
 struct DwSmem {
@@ -66,10 +67,23 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
 
   const int L = p.L;
   const int njobs = p.njobs;
-  const int job = blockIdx.x % njobs;   // 0..L-1 -> hidden layer job+1 ; L -> output layer
-  const int slice = blockIdx.x / njobs;
-  const int nslices = ((int)gridDim.x - 1 - job) / njobs + 1;
   const bool film = p.film_S != nullptr;
+  // CTA -> (job, slice).  Round robin over the jobs, except that the output-layer job (whose stash blocks are half
+  // the bytes and whose MMAs are N = 16) only gets p.out_ctas CTAs when that is set: the hidden jobs, which carry the
+  // HBM traffic, then share the remaining CTAs evenly.
+  int job, slice, nslices;
+  if (p.out_ctas > 0 && njobs == L + 1) {
+    if ((int)blockIdx.x < p.out_ctas) {
+      job = L; slice = blockIdx.x; nslices = p.out_ctas;
+    } else {
+      const int i = (int)blockIdx.x - p.out_ctas, nh = (int)gridDim.x - p.out_ctas;
+      job = i % L; slice = i / L; nslices = (nh - 1 - job) / L + 1;
+    }
+  } else {
+    job = blockIdx.x % njobs;   // 0..L-1 -> hidden layer job+1 ; L -> output layer
+    slice = blockIdx.x / njobs;
+    nslices = ((int)gridDim.x - 1 - job) / njobs + 1;
+  }
   const int total = (film ? p.tiles_per_map : p.ntiles) * 2;  // 64-row stash blocks this grid row reduces over
   const int s_base = film ? (int)blockIdx.y * p.tiles_per_map * 2 : 0;
   const int s_begin = s_base + (int)((int64_t)slice * total / nslices);
