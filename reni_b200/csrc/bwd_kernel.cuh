@@ -109,6 +109,18 @@ DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memo
 DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+#ifndef RENI_BWD_PHASE_HINT
+#define RENI_BWD_PHASE_HINT 1  // phase-stash loads: 0 ld.global.nc, 1 ld.global.cs (streaming), 2 ld.global.lu (293 -> 289..291 us)
+#endif
+DEVINL uint4 phase_load(const uint4* p) {
+#if RENI_BWD_PHASE_HINT == 1
+  return __ldcs(p);
+#elif RENI_BWD_PHASE_HINT == 2
+  return __ldlu(p);
+#else
+  return __ldg(p);
+#endif
+}
 #ifndef RENI_BWD_PF_DIST
 #define RENI_BWD_PF_DIST 1
 #endif
@@ -410,7 +422,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
 #pragma unroll
         for (int k = 0; k < 16; ++k)
           hh[k] = (RENI_ABL & 8) ? make_uint4(k, row, l, g)
-                                 : __ldg(reinterpret_cast<const uint4*>(hl + stash_off(row, chalf * 16 + k, kH)));
+                                 : phase_load(reinterpret_cast<const uint4*>(hl + stash_off(row, chalf * 16 + k, kH)));
         mbar_wait(&acc_full[g], acc_ph);
         acc_ph ^= 1;
         tc_fence_after();

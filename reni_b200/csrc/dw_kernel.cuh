@@ -22,6 +22,10 @@ constexpr int kDwStages = 3;
 constexpr int kDwStageBytes = 2 * kHalfImageBytes;  // 64 KB: A operand + B operand; the phase block lands in the
                                                     // operand slot of h and is converted in place
 
+#ifndef RENI_DW_LOAD_HINT
+#define RENI_DW_LOAD_HINT 1  // stash blocks loaded with an L2 evict-first policy (258 -> 252 us at cfg 2)
+#endif
+
 struct DwParams {
   const uint16_t* stash_u;
   const __half* stash_d;
@@ -135,8 +139,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
         mbar_wait(&empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&full[st], img_bytes + kHalfImageBytes);
         uint8_t* dst = smem + DwSmem::kRing + st * kDwStageBytes;
+#if RENI_DW_LOAD_HINT  // both stash blocks are read exactly once in this kernel: do not keep them in L2
+        bulk_g2s_stream(dst + img_off, img_src(s), img_bytes, &full[st]);
+        bulk_g2s_stream(dst + cvt_off, phase_src(s), kHalfImageBytes, &full[st]);
+#else
         bulk_g2s(dst + img_off, img_src(s), img_bytes, &full[st]);
         bulk_g2s(dst + cvt_off, phase_src(s), kHalfImageBytes, &full[st]);
+#endif
         if (++st == kDwStages) { st = 0; ph ^= 1; }
       }
     }

@@ -106,6 +106,17 @@ DEVINL void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint6
       : "memory");
 }
 
+// the same with an L2 evict-first policy: for streams that are read exactly once (the weight-gradient GEMM's stash blocks)
+DEVINL void bulk_g2s_stream(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ CTA pairs (thread-block cluster of 2)
 DEVINL uint32_t cluster_ctarank() {
   uint32_t r;
