@@ -240,3 +240,64 @@ def test_film_trainer_cuda_graph_matches_eager(dev, task):
             assert len(got) == len(dps)
             for a_, b_ in zip(got, dps):
                 assert O.rel_l2(a_.cpu().numpy(), b_.cpu().numpy()) < 1e-4
+
+
+def test_film_full_size_properties(dev):
+    """The default FiLM decoder (N=36, 5 FiLM layers, 3x256 mapping network) at the BASELINE configs[1] size
+    (32 maps x 64x128) through size-independent properties:
+    (1) SO(2) invariance of the radiance; (2) additivity of every decoder gradient over the two halves of the batch and
+    per-map independence of dZ; (3) the inference kernel equals the differentiated forward bit for bit;
+    (4) spot check of 2 maps (forward and dZ) against the oracle."""
+    torch.manual_seed(7)
+    from reni_b200 import RENIAutoDecoderFiLM, RENITrainLoss, get_directions, get_sineweight
+
+    B, N, W = 32, 36, 128
+    P = W * W // 2
+    m = RENIAutoDecoderFiLM(B, N, "SO2", 256, 5, 256, 3, 3, None, False).to(dev)
+    with torch.no_grad():
+        m.mapping_network.network[-1].weight.mul_(2.0)  # move freq / phase away from their init
+    D = get_directions(W).to(dev)
+    sw = get_sineweight(W).to(dev).expand(B, -1, -1)
+    tg = torch.rand(B, P, 3, device=dev) * 2 - 1
+    Z = (0.5 * m.Z.detach()).clone()
+    with torch.no_grad():
+        o1 = m(Z, D.expand(B, -1, -1))
+        th = 0.7
+        R = torch.tensor([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]], device=dev,
+                         dtype=torch.float32)
+        o2 = m(Z @ R.T, (D @ R.T).expand(B, -1, -1))
+    assert float((o1 - o2).norm() / o1.norm()) < TOL_RADIANCE
+
+    def grads(sel):
+        for p in m.parameters():
+            p.grad = None
+        Zs = Z[sel].clone().requires_grad_(True)
+        out = m(Zs, D.expand(Zs.shape[0], -1, -1))
+        RENITrainLoss()(out, tg[sel], sw[sel]).backward()
+        return out.detach(), Zs.grad.clone(), [p.grad.clone() for n, p in m.named_parameters() if n != "Z"]
+
+    o_full, dZ_full, g_full = grads(slice(0, B))
+    _, dZ_a, g_a = grads(slice(0, 16))
+    _, dZ_b, g_b = grads(slice(16, B))
+    assert torch.equal(o_full, o1)
+    for a, b1, b2 in zip(g_full, g_a, g_b):
+        assert float((a - b1 - b2).norm() / a.norm()) < 2e-3
+    assert float((dZ_full[:16] - dZ_a).norm() / dZ_a.norm()) < 1e-3
+    assert float((dZ_full[16:] - dZ_b).norm() / dZ_b.norm()) < 1e-3
+
+    f64 = lambda x: x.detach().cpu().numpy().astype(np.float64)  # noqa: E731
+    nm = len(m.mapping_network.network) // 2 + 1
+    p = FO.FilmParams([f64(l.layer.weight) for l in m.net], [f64(l.layer.bias) for l in m.net], f64(m.final_layer.weight),
+                      f64(m.final_layer.bias), [f64(m.mapping_network.network[2 * i].weight) for i in range(nm)],
+                      [f64(m.mapping_network.network[2 * i].bias) for i in range(nm)], "SO2", None)
+    D64, outs, refs = f64(D), [], []
+    for b in (3, 20):
+        Zb = f64(Z[[b]])
+        out_o, tape = FO.film_forward(Zb, D64, p, tape=True)
+        ref = FO.film_backward(Zb, D64, p, tape, O.loss_grad_wrt_output(out_o, f64(tg[[b]]), f64(sw[[b]])))
+        outs.append(o_full[[b]].cpu().numpy())
+        refs.append(out_o)
+        assert O.rel_l2(dZ_full[[b]].cpu().numpy(), ref["dZ"]) < TOL_GRAD
+    outs, refs = np.concatenate(outs), np.concatenate(refs)
+    print("FiLM config-2 radiance over 2 maps: rel-L2", O.rel_l2(outs, refs), "max abs err", np.abs(outs - refs).max())
+    assert O.rel_l2(outs, refs) < 1.5 * TOL_RADIANCE and np.abs(outs - refs).max() < 5e-4
