@@ -502,9 +502,18 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
       // one grid row per map: S[b][l] and cs[b][l] accumulate with atomics, then the map-level FiLM reduction
       if (cudaMemsetAsync(q.film_S, 0, (size_t)B * L * kH * kH * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
       if (cudaMemsetAsync(q.film_cs, 0, (size_t)B * L * kH * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
-      int slices = (2 * sms) / (q.njobs * (int)B);  // about two waves of CTAs over all maps
-      if (slices < 1) slices = 1;
-      if (slices > 2 * q.tiles_per_map) slices = 2 * q.tiles_per_map;
+      // slices per (map, job): a CTA costs one pass over its share of the map's 2 * tiles_per_map stash blocks plus
+      // a 256 KB flush of atomics (~ 4 blocks' worth of time); the grid runs in ceil(CTAs / SMs) rounds.  Pick the
+      // split that minimises rounds * (blocks per CTA + flush).
+      const int blocks_per_job = 2 * q.tiles_per_map;
+      int slices = 1;
+      double best = 1e30;
+      for (int s_ = 1; s_ <= 16 && s_ <= blocks_per_job; ++s_) {
+        const int64_t ctas = (int64_t)q.njobs * s_ * B;
+        const double rounds = (double)((ctas + sms - 1) / sms);
+        const double cost = rounds * ((double)blocks_per_job / s_ + 4.0);
+        if (cost < best * 0.98) { best = cost; slices = s_; }
+      }
       reni_dw_kernel<<<dim3((unsigned)(q.njobs * slices), (unsigned)B), kDwThreads, DwSmem::kTotal, stream>>>(q);
       if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
       FilmReduceParams r{};
