@@ -651,10 +651,26 @@ __global__ void __launch_bounds__(256) reni_film_dw_kernel(const FilmReduceParam
   const int j = blockIdx.x, l = blockIdx.y, k = threadIdx.x;
   if (p.dW[l + 1] == nullptr) return;
   float acc = 0.f, accb = 0.f;
-  for (int b = 0; b < p.B; ++b) {
-    const float f = __ldg(p.film + ((size_t)b * p.L + l) * 2 * kH + j);
-    acc = fmaf(f, __ldg(p.S + (((size_t)b * p.L + l) * kH + j) * kH + k), acc);
-    if (k == 0) accb = fmaf(f, __ldg(p.cs + ((size_t)b * p.L + l) * kH + j), accb);
+  const size_t sstride = (size_t)p.L * kH * kH, fstride = (size_t)p.L * 2 * kH, cstride = (size_t)p.L * kH;
+  const float* sp = p.S + ((size_t)l * kH + j) * kH + k;
+  const float* fp = p.film + (size_t)l * 2 * kH + j;
+  const float* cp = p.cs + (size_t)l * kH + j;
+  int b = 0;
+  for (; b + 4 <= p.B; b += 4) {  // four maps in flight per thread: the loop is latency-bound otherwise
+    const float f0 = __ldg(fp + (b + 0) * fstride), f1 = __ldg(fp + (b + 1) * fstride);
+    const float f2 = __ldg(fp + (b + 2) * fstride), f3 = __ldg(fp + (b + 3) * fstride);
+    const float s0 = __ldg(sp + (b + 0) * sstride), s1 = __ldg(sp + (b + 1) * sstride);
+    const float s2 = __ldg(sp + (b + 2) * sstride), s3 = __ldg(sp + (b + 3) * sstride);
+    acc = fmaf(f0, s0, acc); acc = fmaf(f1, s1, acc); acc = fmaf(f2, s2, acc); acc = fmaf(f3, s3, acc);
+    if (k == 0) {
+      accb = fmaf(f0, __ldg(cp + (b + 0) * cstride), accb); accb = fmaf(f1, __ldg(cp + (b + 1) * cstride), accb);
+      accb = fmaf(f2, __ldg(cp + (b + 2) * cstride), accb); accb = fmaf(f3, __ldg(cp + (b + 3) * cstride), accb);
+    }
+  }
+  for (; b < p.B; ++b) {
+    const float f = __ldg(fp + b * fstride);
+    acc = fmaf(f, __ldg(sp + b * sstride), acc);
+    if (k == 0) accb = fmaf(f, __ldg(cp + b * cstride), accb);
   }
   p.dW[l + 1][(size_t)j * kH + k] += acc;
   if (k == 0 && p.db[l + 1] != nullptr) p.db[l + 1][j] += accb;

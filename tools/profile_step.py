@@ -16,6 +16,16 @@ D, sw = get_directions(W).to(dev), get_sineweight(W).to(dev)
 tg = torch.rand(B, P, 3, device=dev) * 2 - 1
 Z = torch.randn(B, N, 3, device=dev)
 ws = F_.Workspace()
+if mode == "film":  # the default FiLM decoder (5 FiLM layers, 3 x 256 mapping network): autograd training steps
+    from reni_b200 import RENIAutoDecoderFiLM, RENITrainer
+    mf = RENIAutoDecoderFiLM(B, N, "SO2", 256, 5, 256, 3, 3, None, False).to(dev)
+    tr = RENITrainer(mf, "FIT_DECODER", W)
+    imgs = torch.rand(B, 3, W // 2, W, device=dev) * 2 - 1
+    for _ in range(steps):
+        tr.training_step((imgs, torch.arange(B, device=dev)))
+    torch.cuda.synchronize()
+    print("done", mode, steps)
+    sys.exit(0)
 for _ in range(steps):
     if mode == "infer":
         with torch.no_grad():
