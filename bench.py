@@ -287,6 +287,36 @@ def run_gpu_arm(args):
     barrier()
     e2e_ms = s0.elapsed_time(s1)
 
+    # ---- informational: the same step with the reference's DEFAULT conditioning (FiLM, configs/default.py:9): default
+    # FiLM decoder (5 FiLM layers, 3 x 256 mapping network) through RENITrainer with the autograd step captured in a
+    # CUDA graph; not part of `value` (BASELINE's metric is quoted on the Cond-by-Concat decoder)
+    film_info = None
+    if world == 1:
+        from reni_b200 import RENIAutoDecoderFiLM
+        fm = RENIAutoDecoderFiLM(B, N_LATENT, "SO2", 256, 5, 256, 3, 3, None, False).to(dev)
+        ftr = RENITrainer(fm, "FIT_DECODER", SIDELEN, lr=1e-5, cuda_graph=True)
+        fbatch = (host_batches[0][0].to(dev), torch.arange(B, device=dev))
+        for _ in range(4):
+            ftr.training_step(fbatch)
+        torch.cuda.synchronize()
+        fms = []
+        for _ in range(min(args.steps, 50)):
+            flush.zero_()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            ftr.training_step(fbatch)
+            f1.record()
+            torch.cuda.synchronize()
+            fms.append(f0.elapsed_time(f1))
+        fmed = statistics.median(fms)
+        film_flops = 3 * 2 * (4 * 256 + 4 * 256 * 256 + 256 * 3)
+        film_info = {"workload": "RENIAutoDecoderFiLM N=36 (5 FiLM layers, 3x256 mapping network) training step, "
+                                 "32 maps x 64x128, RENITrainer(cuda_graph=True)",
+                     "ms_per_step": fmed, "value": B * P / (fmed * 1e-3), "unit": UNIT,
+                     "flops_per_direction": film_flops,
+                     "step_frac": film_flops * B * P / (fmed * 1e-3) / 1e12 / peaks()["tflops"]}
+        del ftr, fm
+
     times = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -335,6 +365,8 @@ def run_gpu_arm(args):
             "gpu_launches": 10 * args.steps * 2,  # 10 kernels per step, K device-resident + K end-to-end steps
             "clocks": clocks,
         }
+        if film_info is not None:
+            line["film"] = film_info
         if world == 1 and not args.no_cpu_baseline:
             base, _, _ = cpu_reference_run(steps=1000, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = base
