@@ -146,6 +146,20 @@ int32_t reni_film_backward(const reni_config_t* cfg, const float* film, const fl
                            float* const* host_dW, float* const* host_db, void* workspace, int64_t workspace_bytes,
                            int32_t flags, void* stream);
 
+/* One fused FiLM training / latent-fit step around the core: reni_film_forward with the loss sums, the loss reduction
+ * and reni_film_backward with the loss gradient formed in the kernel (replaces the criterion + loss.backward() of
+ * training_step, src/lightning/RENI_module.py:105-134, for a FiLM decoder).
+ *   loss = sum_b mean_{p,c}((o-t)^2 sw) + beta * WeightedCosineSimilarity(o,t,sw)   (loss_functions.py:6-32)
+ *   loss_out : 4 floats {loss, mse, 0, cosine}; the prior alpha * sum Z^2 and the KLD are per-map terms of the caller
+ *   d_mc, d_film, host_dW/db as in reni_film_backward.  output_activation none / tanh only. */
+int32_t reni_film_loss_forward_backward(const reni_config_t* cfg, const float* mc, const float* film, const float* D,
+                                        int64_t d_batch_stride, const float* const* host_weights,
+                                        const float* const* host_biases, int64_t B, int64_t P, const float* target,
+                                        const float* sw, int64_t sw_batch_stride, float beta, int32_t use_cosine,
+                                        float* out, float* loss_out, float* d_mc, float* d_film,
+                                        float* const* host_dW, float* const* host_db, void* workspace,
+                                        int64_t workspace_bytes, int32_t flags, void* stream);
+
 /* Fused Adam step over a list of fp32 segments: replaces torch.optim.Adam(params, lr).step() as the reference's
  * configure_optimizers builds it (src/lightning/RENI_module.py:185-192: default betas (0.9, 0.999), eps 1e-8, no
  * weight decay, dense over every parameter including the whole latent table).  One launch per 24 segments.

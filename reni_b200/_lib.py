@@ -68,6 +68,9 @@ SIGNATURES = {
     "reni_film_forward": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp]),
     "reni_film_backward": (_i32, [_cfgp, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _vp, _vp, _vp,
                                   C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _i32, _vp]),
+    "reni_film_loss_forward_backward": (_i32, [_cfgp, _vp, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp,
+                                               _vp, _i64, C.c_float, _i32, _vp, _vp, _vp, _vp, C.POINTER(_vp),
+                                               C.POINTER(_vp), _vp, _i64, _i32, _vp]),
     "reni_adam_step": (_i32, [C.POINTER(AdamSegment), _i32, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp]),
     "reni_debug_set_phase_events": (_i32, [C.POINTER(_vp), _i32]),
     "reni_debug_last_cuda_error": (C.c_char_p, []),

@@ -765,6 +765,53 @@ int32_t reni_adam_step(const reni_adam_segment_t* host_segments, int32_t nseg, i
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
+int32_t reni_film_loss_forward_backward(const reni_config_t* c, const float* mc, const float* film, const float* D,
+                                        int64_t d_bstride, const float* const* host_weights,
+                                        const float* const* host_biases, int64_t B, int64_t P, const float* target,
+                                        const float* sw, int64_t sw_bstride, float beta, int32_t use_cosine, float* out,
+                                        float* loss_out, float* d_mc, float* d_film, float* const* host_dW,
+                                        float* const* host_db, void* ws, int64_t ws_bytes, int32_t flags,
+                                        void* stream_) {
+  if (!config_ok(c) || !c->last_layer_linear) return RENI_ERR_BAD_CONFIG;
+  if (mc == nullptr || film == nullptr || D == nullptr || host_weights == nullptr || host_biases == nullptr ||
+      target == nullptr || sw == nullptr || out == nullptr || loss_out == nullptr || d_mc == nullptr ||
+      d_film == nullptr || ws == nullptr || B < 1 || P < 1)
+    return RENI_ERR_BAD_ARGUMENT;
+  if ((flags & RENI_FLAG_NEED_DW) && (host_dW == nullptr || host_db == nullptr)) return RENI_ERR_BAD_ARGUMENT;
+  flags = (flags & RENI_FLAG_NEED_DW) | RENI_FLAG_SAVE_FOR_BACKWARD | RENI_FLAG_FILM | RENI_FLAG_LOSS;
+  const WorkspaceLayout w = make_layout(c, B, P, flags);
+  if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
+  const int sms = num_sms();
+  if (sms <= 0) return RENI_ERR_NO_DEVICE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  mark_phase(0, stream);
+  reni_set_scale_kernel<<<1, 1, 0, stream>>>(at<float>(ws, w.scalars), 1.5f * (float)P);  // S = 3P/2, see loss finish
+  mark_phase(1, stream);
+  int32_t rc = launch_forward(c, w, mc, film, D, d_bstride, B, P, out, target, sw, sw_bstride, ws, flags, stream, sms);
+  if (rc != RENI_OK) return rc;
+  if (cudaMemsetAsync(loss_out, 0, 16, stream) != cudaSuccess) return RENI_ERR_CUDA;
+  LossFinishParams f{};
+  f.loss_part = at<float>(ws, w.loss_part);
+  f.sw = sw;
+  f.sw_bstride = sw_bstride;
+  f.Z = nullptr;  // the prior term alpha * sum Z^2 belongs to the caller's per-map stage
+  f.map_loss = at<float>(ws, w.map_loss);
+  f.loss_out = loss_out;
+  f.scalars = at<float>(ws, w.scalars);
+  f.B = (int)B;
+  f.P = (int)P;
+  f.tiles_per_map = (int)tiles_per_map(P);
+  f.nz = 0;
+  f.alpha = 0.f;
+  f.beta = beta;
+  f.use_cos = use_cosine;
+  reni_loss_finish_kernel<<<(unsigned)B, 128, 0, stream>>>(f);
+  if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
+  FilmBackwardArgs fa{film, d_mc, d_film, host_weights, host_biases};
+  return launch_backward(c, w, nullptr, D, d_bstride, nullptr, B, P, out, nullptr, target, sw, sw_bstride, 0.f, nullptr,
+                         host_dW, host_db, ws, flags, stream, use_cosine, nullptr, &fa);
+}
+
 int32_t reni_selftest_umma(const void* a_img, uint32_t a_bytes, const void* b_img, uint32_t b_bytes, uint32_t a_lbo,
                            uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t a_kstep, uint32_t b_kstep,
                            uint32_t a_mn, uint32_t b_mn, uint32_t n, uint32_t ksteps, float* d_out, void* stream) {

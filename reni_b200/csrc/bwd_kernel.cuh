@@ -453,8 +453,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
             dv.z = pack_half2(d[4], d[5]);
             dv.w = pack_half2(d[6], d[7]);
             if (kFilm && fl != nullptr) {
-              // stash the unscaled delta, hand delta * freq to the next GEMM
-              *reinterpret_cast<uint4*>(dl + stash_off(row, kg, kH)) = dv;
+              // stash the unscaled delta (streaming store: read back only by the weight-gradient kernel), hand
+              // delta * freq to the next GEMM
+              __stcs(reinterpret_cast<uint4*>(dl + stash_off(row, kg, kH)), dv);
               const float4 f0 = __ldg(reinterpret_cast<const float4*>(fl + kg * 8));
               const float4 f1 = __ldg(reinterpret_cast<const float4*>(fl + kg * 8 + 4));
               dv.x = pack_half2(d[0] * f0.x, d[1] * f0.y);

@@ -470,6 +470,11 @@ __global__ void reni_absmax_kernel(const float* g, int64_t n, unsigned int* slot
   for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
   if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
 }
+// fused-loss gradient scale written without the Cond-by-Concat prologue (FiLM core): scalars = [S, 1/S]
+__global__ void reni_set_scale_kernel(float* scalars, float S) {
+  scalars[0] = S;
+  scalars[1] = 1.f / S;
+}
 __global__ void reni_scale_from_absmax_kernel(const unsigned int* slot, float* scalars) {
   const float m = __uint_as_float(*slot);
   const float S = (m > 0.f && isfinite(m)) ? 1.f / m : 1.f;

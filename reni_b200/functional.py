@@ -419,3 +419,64 @@ def film_decode_core(spec: FilmSpec, inference_ws: Workspace, mc: torch.Tensor, 
         return _FilmCoreFunction.apply(spec, inference_ws, mc, film, D, *params)
     with torch.no_grad():
         return _FilmCoreFunction.forward(_NoGradCtx(len(params) + 1), spec, inference_ws, mc, film, D, *params)
+
+
+@dataclass
+class FilmStepResult:
+    """Fused FiLM step around the core: loss parts, radiance, and the gradients the per-map stage continues from."""
+
+    loss: torch.Tensor        # mse + beta * cosine  (the prior / KLD terms are per-map terms of the caller)
+    mse_loss: torch.Tensor
+    cosine_loss: torch.Tensor
+    out: torch.Tensor         # (B, P, 3)
+    d_mc: torch.Tensor        # (B, 5, 256)
+    d_film: torch.Tensor      # (B, L, 2, 256)
+    dW: Optional[List[torch.Tensor]]   # [W_1 .. W_L, W_out]
+    db: Optional[List[torch.Tensor]]
+
+
+def film_loss_forward_backward(spec: FilmSpec, ws: Workspace, mc: torch.Tensor, film: torch.Tensor, D: torch.Tensor,
+                               target: torch.Tensor, sineweight: torch.Tensor, params: Sequence[torch.Tensor],
+                               beta: float = 0.0, use_cosine: bool = False, need_dw: bool = True,
+                               grad_weights: Optional[Sequence[torch.Tensor]] = None,
+                               grad_biases: Optional[Sequence[torch.Tensor]] = None) -> FilmStepResult:
+    """Forward + WeightedMSE (+ beta * WeightedCosineSimilarity) + backward of the FiLM core in one library call
+    (loss_functions.py:6-32; RENI_module.py:105-134 without the per-map terms).  ``params`` as in
+    ``film_decode_core``; ``grad_weights`` / ``grad_biases`` (one per core parameter pair) are ACCUMULATED into."""
+    spec.validate()
+    if spec.output_activation == "exp":
+        raise NotImplementedError("the fused FiLM step covers output_activation None / 'tanh'; use the autograd path")
+    lib = _lib.load()
+    cfg = spec.c_config()
+    L = spec.siren_hidden_layers - 1
+    weights = [_f32c(p) for p in params[0::2]]
+    biases = [_f32c(p) for p in params[1::2]]
+    dev = _require_cuda(mc, film, D, target, sineweight, *weights, *biases)
+    mcc, filmc = _f32c(mc), _f32c(film)
+    B = mcc.shape[0]
+    if tuple(mcc.shape) != (B, 5, HIDDEN_FEATURES) or tuple(filmc.shape) != (B, L, 2, HIDDEN_FEATURES):
+        raise ValueError(f"mc must be (B,5,256) and film (B,{L},2,256); got {tuple(mcc.shape)}, {tuple(filmc.shape)}")
+    Dc, d_bs = _batch_stride(D, B, "directions")
+    swc, sw_bs = _batch_stride(sineweight, B, "sineweight")
+    P = Dc.shape[1]
+    tc = _f32c(target)
+    if tuple(tc.shape) != (B, P, 3):
+        raise ValueError(f"target must have shape {(B, P, 3)}, got {tuple(tc.shape)}")
+    flags = _lib.FLAG_FILM | FLAG_SAVE_FOR_BACKWARD | FLAG_LOSS | (FLAG_NEED_DW if need_dw else 0)
+    ws.ensure(workspace_bytes(cfg, B, P, flags), dev)
+    prepare_weights(cfg, [weights[0]] + weights, [biases[0]] + biases, ws, dev)
+    out = torch.empty(B, P, 3, device=dev, dtype=torch.float32)
+    loss = torch.empty(4, device=dev, dtype=torch.float32)
+    d_mc = torch.empty(B, 5, HIDDEN_FEATURES, device=dev, dtype=torch.float32)
+    d_film = torch.empty_like(filmc)
+    dW = db = None
+    if need_dw:
+        dW = list(grad_weights) if grad_weights is not None else [torch.zeros_like(w) for w in weights]
+        db = list(grad_biases) if grad_biases is not None else [torch.zeros_like(b) for b in biases]
+    rc = lib.reni_film_loss_forward_backward(
+        C.byref(cfg), _vp(mcc), _vp(filmc), _vp(Dc), d_bs, _ptr_array([weights[0]] + weights),
+        _ptr_array([biases[0]] + biases), B, P, _vp(tc), _vp(swc), sw_bs, float(beta), 1 if use_cosine else 0, _vp(out),
+        _vp(loss), _vp(d_mc), _vp(d_film), _ptr_array([None] + dW) if need_dw else None,
+        _ptr_array([None] + db) if need_dw else None, _vp(ws.view), ws.nbytes, flags, _stream(dev))
+    _lib.check(rc, "reni_film_loss_forward_backward")
+    return FilmStepResult(loss[0], loss[1], loss[3], out, d_mc, d_film, dW, db)

@@ -228,6 +228,39 @@ class RENITrainer:
             Z, mu, log_var = model.sample_latent(idx)
         else:
             Z = self._latent_table()[idx]
+        if model.output_activation != "exp":
+            # fused core step: forward + WeightedMSE (+ cosine) + backward in one library call; the per-map stage
+            # (mapping network, hoisted first layer, prior / KLD) is differentiated by autograd from d_mc / d_film
+            mc, film = model.map_level(Z.float())
+            need_dw = not self.fixed
+            core = model.core_parameters()
+            views = None
+            if need_dw:
+                by_id = {id(p): v for p, v in zip(self.flat.params, self.flat.views)}
+                views = [by_id[id(p)] for p in core]
+            fit_latent = self.task == "FIT_LATENT"
+            res = F_.film_loss_forward_backward(
+                model.spec, self._ws, mc.detach(), film.detach(), self.directions, imgs,
+                self.sineweight if self.mask is None else self.sineweight * self.mask, core,
+                beta=self.beta if fit_latent else 0.0, use_cosine=fit_latent, need_dw=need_dw,
+                grad_weights=views[0::2] if need_dw else None, grad_biases=views[1::2] if need_dw else None)
+            roots, grads = [mc, film], [res.d_mc, res.d_film]
+            if fit_latent:
+                prior = self.alpha * torch.sum(Z ** 2)                      # RENITestLoss (loss_functions.py:68)
+                roots.append(prior)
+                grads.append(torch.ones_like(prior))
+                log = {"loss": res.loss + prior.detach(), "mse_loss": res.mse_loss, "prior_loss": prior.detach(),
+                       "cosine_loss": res.cosine_loss}
+            elif self.is_vad:
+                kld = self.kld_weighting * KLD(mu, log_var, Z_dims=model.ndims * 3)   # RENI_module.py:312-315
+                roots.append(kld)
+                grads.append(torch.ones_like(kld))
+                log = {"loss": res.loss + kld.detach(), "mse_loss": res.mse_loss, "kld_loss": kld.detach()}
+            else:
+                log = {"loss": res.loss}
+            torch.autograd.backward(roots, grads)
+            self.last_output = res.out
+            return log
         out = model(Z, D)
         if self.task == "FIT_LATENT":
             loss, mse, prior, cos = RENITestLoss(alpha=self.alpha, beta=self.beta)(out, imgs, sw, Z)
