@@ -301,3 +301,44 @@ def test_film_full_size_properties(dev):
     outs, refs = np.concatenate(outs), np.concatenate(refs)
     print("FiLM config-2 radiance over 2 maps: rel-L2", O.rel_l2(outs, refs), "max abs err", np.abs(outs - refs).max())
     assert O.rel_l2(outs, refs) < 1.5 * TOL_RADIANCE and np.abs(outs - refs).max() < 5e-4
+
+
+@pytest.mark.parametrize("name", FILM_H256)
+def test_film_fused_step_matches_reference_golden(dev, name):
+    """reni_film_loss_forward_backward (loss and its gradient formed in the kernels) + autograd of the per-map stage
+    against the reference: RENITrainLoss with every gradient, RENITestLoss (cosine term) with the latent gradient."""
+    from reni_b200 import functional as F_
+
+    c = load_film_case(name)
+    g = c["g"]
+    m = film_model_from_params(c["p"], c["N"], dev)
+    D, tg, sw = (t(c[k], dev) for k in ("D", "target", "sw"))
+    Z = t(c["Z"], dev).requires_grad_(True)
+    mc, film = m.map_level(Z)
+    res = F_.film_loss_forward_backward(m.spec, F_.Workspace(), mc.detach(), film.detach(), D, tg, sw,
+                                        m.core_parameters(), need_dw=True)
+    torch.autograd.backward([mc, film], [res.d_mc, res.d_film])
+    torch.cuda.synchronize()
+    assert abs(float(res.loss) - float(g["train_loss_f32"])) < 1e-3 * abs(float(g["train_loss_f32"]))
+    assert O.rel_l2(res.out.cpu().numpy(), g["out_f32"]) < TOL_RADIANCE
+    assert O.rel_l2(Z.grad.cpu().numpy(), g["train_dZ_f32"]) < TOL_GRAD
+    Lf = c["Lf"]
+    assert O.rel_l2(sub(m.net[0].layer.weight.grad.cpu().numpy()), g["net_dW0_f32"]) < TOL_GRAD
+    for i in range(1, Lf):
+        assert O.rel_l2(sub(res.dW[i - 1].cpu().numpy()), g[f"net_dW{i}_f32"]) < TOL_GRAD, i
+        assert O.rel_l2(res.db[i - 1].cpu().numpy(), g[f"net_db{i}_f32"]) < TOL_GRAD, i
+    assert O.rel_l2(res.dW[Lf - 1].cpu().numpy(), g["final_dW_f32"]) < TOL_GRAD
+    assert O.rel_l2(res.db[Lf - 1].cpu().numpy(), g["final_db_f32"]) < TOL_GRAD
+    assert O.rel_l2(sub(m.mapping_network.network[0].weight.grad.cpu().numpy()), g["map_dW0_f32"]) < TOL_GRAD
+
+    Z2 = t(c["Z"], dev).requires_grad_(True)
+    mc2, film2 = m.map_level(Z2)
+    r2 = F_.film_loss_forward_backward(m.spec, F_.Workspace(), mc2.detach(), film2.detach(), D, tg, sw,
+                                       m.core_parameters(), beta=c["beta"], use_cosine=True, need_dw=False)
+    prior = c["alpha"] * torch.sum(Z2 ** 2)
+    torch.autograd.backward([mc2, film2, prior], [r2.d_mc, r2.d_film, torch.ones_like(prior)])
+    torch.cuda.synchronize()
+    got = [float(r2.loss) + float(prior), float(r2.mse_loss), float(prior), float(r2.cosine_loss)]
+    np.testing.assert_allclose(got, g["test_loss_f32"], rtol=1e-3, atol=1e-8)
+    assert O.rel_l2(Z2.grad.cpu().numpy(), g["test_dZ_f32"]) < TOL_GRAD
+    assert r2.dW is None
