@@ -128,11 +128,6 @@ DEVINL uint4 phase_load(const uint4* p) {
 #define RENI_BWD_BULK_STASH 1  // 1: delta stash written by per-warp bulk copies of the finished smem pieces; 0: st.global
 #endif
 
-// delta = acc * cos(a) for two columns; w holds the two 16-bit phases of a
-DEVINL uint32_t delta2(float acc0, float acc1, uint32_t w) {
-  return pack_half2(acc0 * abl_cos(phase_angle_lo(w)), acc1 * abl_cos(phase_angle_hi(w)));
-}
-
 // kFilm (FiLM conditioning, RENI.py:515-524): a_l = freq_l[b] * u_l + phase_l[b] with u_l = W_l h_{l-1} + b_l, so
 // dL/du_l = delta_l * freq_l[b].  The epilogue of hidden layer l keeps TWO values per element: the unscaled
 // delta_l = dL/da_l goes to the stash (the weight-gradient kernel turns it into dW_l, dfreq_l, dphase_l per map) and
