@@ -168,3 +168,37 @@ def test_multires_curriculum_hook_doubles_resolution_like_the_callback():
     assert tr.mask.shape == (1, 8192, 3)
     with pytest.raises(ValueError):
         tr.on_train_epoch_end(24, curriculum)        # masked task without a way to rebuild the mask
+
+
+def test_get_mask_nearest_resize(tmp_path):
+    """get_mask (utils.py:81-91): PNG -> ToTensor -> NEAREST resize -> (1, P, 3).  Checked against direct index sampling
+    of a synthetic 512x256 mask (the geometry of data/Masks/*.png) and, where the reference is mounted, against the
+    reference's own get_mask on the same file."""
+    import sys
+    import types
+
+    from PIL import Image
+
+    from reni_b200 import get_mask
+
+    rng = np.random.default_rng(0)
+    src = np.zeros((256, 512), dtype=np.uint8)
+    src[40:186, 162:329] = 255                       # Mask-3-like rectangle
+    src[rng.integers(0, 256, 300), rng.integers(0, 512, 300)] = 255   # plus isolated pixels
+    for mode, name in (("L", "m1.png"), ("RGB", "m3.png")):
+        arr = src if mode == "L" else np.repeat(src[:, :, None], 3, 2)
+        path = str(tmp_path / name)
+        Image.fromarray(arr, mode=mode).save(path)
+        for W in (32, 128):
+            got = get_mask(W, path)
+            assert got.shape == (1, W * W // 2, 3)
+            rows = (np.arange(W // 2) * (256 / (W // 2))).astype(np.int64)
+            cols = (np.arange(W) * (512 / W)).astype(np.int64)
+            want = (src[np.ix_(rows, cols)] / 255.0).astype(np.float32).reshape(-1, 1).repeat(3, 1)[None]
+            np.testing.assert_array_equal(got.numpy(), want)
+            if os.path.isdir("/root/reference/src"):
+                sys.modules.setdefault("gdown", types.ModuleType("gdown"))
+                if "/root/reference" not in sys.path:
+                    sys.path.insert(0, "/root/reference")
+                from src.utils import utils as ref_utils
+                np.testing.assert_array_equal(got.numpy(), ref_utils.get_mask(W, path).numpy())
