@@ -765,6 +765,47 @@ int32_t reni_adam_step(const reni_adam_segment_t* host_segments, int32_t nseg, i
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
+int32_t reni_film_map_forward(const reni_config_t* c, const float* Z, const float* weight0, const float* bias0,
+                              const float* const* host_map_weights, const float* const* host_map_biases,
+                              const int32_t* host_map_dims, int32_t n_linears, int64_t B, float* mc, float* film,
+                              void* stream_) {
+  if (!config_ok(c) || c->equivariance == RENI_EQ_NONE) return RENI_ERR_BAD_CONFIG;
+  if (Z == nullptr || weight0 == nullptr || bias0 == nullptr || host_map_weights == nullptr ||
+      host_map_biases == nullptr || host_map_dims == nullptr || mc == nullptr || film == nullptr || B < 1 ||
+      n_linears < 1 || n_linears > kFilmMapMaxLinears)
+    return RENI_ERR_BAD_ARGUMENT;
+  const int N = c->ndims, Lf = c->hidden_layers + 1;
+  const int mn_in = c->equivariance == RENI_EQ_SO2 ? N * N + N : N * N;
+  if (host_map_dims[0] != mn_in || host_map_dims[n_linears] != 2 * Lf * kH) return RENI_ERR_BAD_ARGUMENT;
+  FilmMapParams p{};
+  p.Z = Z;
+  p.W0 = weight0;
+  p.b0 = bias0;
+  p.maxdim = 0;
+  for (int i = 0; i < n_linears; ++i) {
+    if (host_map_weights[i] == nullptr || host_map_biases[i] == nullptr || host_map_dims[i] < 1) return RENI_ERR_BAD_ARGUMENT;
+    p.mw[i] = host_map_weights[i];
+    p.mb[i] = host_map_biases[i];
+    p.mdim[i] = host_map_dims[i];
+    if (host_map_dims[i] > p.maxdim) p.maxdim = host_map_dims[i];
+  }
+  p.mdim[n_linears] = host_map_dims[n_linears];
+  p.nlin = n_linears;
+  p.N = N;
+  p.so2 = c->equivariance == RENI_EQ_SO2;
+  p.Lf = Lf;
+  p.mc = mc;
+  p.film = film;
+  const size_t smem = (size_t)(3 * N + 2 * p.maxdim + 2 * kH) * sizeof(float);
+  if (smem > 200 * 1024) return RENI_ERR_BAD_CONFIG;
+  if (smem > 48 * 1024 &&
+      note(cudaFuncSetAttribute(reni_film_map_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=
+          cudaSuccess)
+    return RENI_ERR_CUDA;
+  reni_film_map_forward_kernel<<<(unsigned)B, 256, smem, static_cast<cudaStream_t>(stream_)>>>(p);
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
 int32_t reni_film_loss_forward_backward(const reni_config_t* c, const float* mc, const float* film, const float* D,
                                         int64_t d_bstride, const float* const* host_weights,
                                         const float* const* host_biases, int64_t B, int64_t P, const float* target,

@@ -727,4 +727,118 @@ __global__ void __launch_bounds__(256) reni_adam_kernel(const AdamParams a) {
 
 __global__ void reni_adam_advance_kernel(int* step) { *step += 1; }
 
+// ------------------------------------------------------------------------------------------------
+// FiLM per-map stage, forward only (inference / no-grad decoding): everything RENIAutoDecoderFiLM.forward computes
+// that is constant per map (RENI.py:405-452 mapping input, :481-512 mapping network, :667 freq = 15 raw + 30) plus the
+// hoisted first FiLM layer, in ONE launch -- a decode of a single latent otherwise spends its time in ~25 tiny launches.
+// One CTA per map, 256 threads; every dense layer is warp-per-output-feature with lanes striding the input (coalesced
+// reads of the weight row, shuffle reduction).  Meant for small batches (the weights are re-read from L2 by every CTA);
+// large batches and differentiated calls use the caller's batched GEMMs.
+//   mc   (B, 5, 256): rows 0..3 = freq_0 * M_b, row 4 = freq_0 * b_0 + phase_0      film (B, L, 2, 256), L = Lf - 1
+// ------------------------------------------------------------------------------------------------
+constexpr int kFilmMapMaxLinears = 8;
+struct FilmMapParams {
+  const float* Z;    // (B, N, 3)
+  const float* W0;   // (256, in0): in0 = 2 + N (SO2: [|d_xz|, d_y, innerprod]) or N (SO3)
+  const float* b0;   // (256)
+  const float* mw[kFilmMapMaxLinears];  // mapping-network linears (out_i, in_i), row-major like nn.Linear
+  const float* mb[kFilmMapMaxLinears];
+  int mdim[kFilmMapMaxLinears + 1];     // mdim[0] = mapping input size, mdim[i + 1] = out features of linear i
+  int nlin, N, so2, Lf, maxdim;         // maxdim = max over mdim[0 .. nlin - 1] (smem ping-pong buffer size)
+  float* mc;
+  float* film;
+};
+
+__global__ void __launch_bounds__(256) reni_film_map_forward_kernel(const FilmMapParams p) {
+  extern __shared__ float s_fm[];
+  const int b = blockIdx.x, N = p.N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_z = s_fm;                       // 3N
+  float* s_a = s_z + 3 * N;                // maxdim
+  float* s_b = s_a + p.maxdim;             // maxdim
+  float* s_fp = s_b + p.maxdim;            // 2 * 256: freq_0, phase_0
+  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_z[i] = p.Z[(size_t)b * 3 * N + i];
+  __syncthreads();
+  // mapping input (RENI.py:424-435 / :407-415)
+  for (int i = threadIdx.x; i < p.mdim[0]; i += blockDim.x) {
+    float v;
+    if (i < N * N) {
+      const int n = i / N, m = i % N;
+      v = s_z[n * 3] * s_z[m * 3] + s_z[n * 3 + 2] * s_z[m * 3 + 2];
+      if (!p.so2) v = fmaf(s_z[n * 3 + 1], s_z[m * 3 + 1], v);
+    } else {
+      v = s_z[(i - N * N) * 3 + 1];  // Z_y (SO2 only)
+    }
+    s_a[i] = v;
+  }
+  __syncthreads();
+  float* x = s_a;
+  float* y = s_b;
+  const int half = p.Lf * kH;  // raw output = [frequencies | phase_shifts]
+  for (int li = 0; li < p.nlin; ++li) {
+    const int in = p.mdim[li], out = p.mdim[li + 1];
+    const bool last = li == p.nlin - 1;
+    for (int o = warp; o < out; o += 8) {
+      const float* w = p.mw[li] + (size_t)o * in;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int k = lane;
+      for (; k + 96 < in; k += 128) {
+        a0 = fmaf(__ldg(w + k), x[k], a0);
+        a1 = fmaf(__ldg(w + k + 32), x[k + 32], a1);
+        a2 = fmaf(__ldg(w + k + 64), x[k + 64], a2);
+        a3 = fmaf(__ldg(w + k + 96), x[k + 96], a3);
+      }
+      for (; k < in; k += 32) a0 = fmaf(__ldg(w + k), x[k], a0);
+      float acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (lane == 0) {
+        acc += p.mb[li][o];
+        if (!last) {
+          y[o] = acc > 0.f ? acc : 0.2f * acc;  // LeakyReLU(0.2)
+        } else {
+          const bool is_freq = o < half;
+          const int j = is_freq ? o : o - half;           // layer * 256 + feature
+          const int layer = j / kH, f = j % kH;
+          const float v = is_freq ? fmaf(acc, 15.f, 30.f) : acc;  // RENI.py:667
+          if (layer == 0) s_fp[(is_freq ? 0 : kH) + f] = v;
+          else p.film[(((size_t)b * (p.Lf - 1) + (layer - 1)) * 2 + (is_freq ? 0 : 1)) * kH + f] = v;
+        }
+      }
+    }
+    __syncthreads();
+    float* t = x; x = y; y = t;
+  }
+  // hoisted first FiLM layer: thread j = output feature
+  {
+    const int j = threadIdx.x;
+    const int in0 = p.so2 ? N + 2 : N;
+    const float* w = p.W0 + (size_t)j * in0;
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    if (p.so2) {
+      for (int n = 0; n < N; ++n) {
+        const float wv = __ldg(w + 2 + n);
+        m0 = fmaf(wv, s_z[n * 3], m0);      // d_x
+        m1 = fmaf(wv, s_z[n * 3 + 2], m1);  // d_z
+      }
+      m2 = __ldg(w);      // |d_xz|
+      m3 = __ldg(w + 1);  // d_y
+    } else {
+      for (int n = 0; n < N; ++n) {
+        const float wv = __ldg(w + n);
+        m0 = fmaf(wv, s_z[n * 3], m0);
+        m1 = fmaf(wv, s_z[n * 3 + 1], m1);
+        m2 = fmaf(wv, s_z[n * 3 + 2], m2);
+      }
+    }
+    const float f0 = s_fp[j], ph0 = s_fp[kH + j];
+    float* o = p.mc + (size_t)b * 5 * kH + j;
+    o[0] = f0 * m0;
+    o[kH] = f0 * m1;
+    o[2 * kH] = f0 * m2;
+    o[3 * kH] = f0 * m3;
+    o[4 * kH] = fmaf(f0, p.b0[j], ph0);
+  }
+}
+
 }  // namespace reni

@@ -140,6 +140,40 @@ class _FilmDecoderBase(nn.Module):
             ps += [layer.layer.weight, layer.layer.bias]
         return ps + [self.final_layer.weight, self.final_layer.bias]
 
+    # Batches up to this size take the one-launch native per-map stage under no_grad.  0 = always the torch stage:
+    # measured on B200 the two are equally fast from Python (a single-latent decode is host-bound at ~0.47 ms either
+    # way), and keeping one per-map stage makes the no-grad forward bit-identical to the differentiated one.  The
+    # native entry point (reni_film_map_forward) is there for callers without PyTorch and for graph-captured decoding.
+    NATIVE_MAP_LEVEL_MAX_BATCH = 0
+
+    def _map_level_native(self, Z: torch.Tensor):
+        """The same per-map operands from ONE kernel (reni_film_map_forward): no-grad decoding of a few latents
+        otherwise spends its time in ~25 tiny launches.  One CTA per map re-reads the weights from L2, hence the cap
+        on the batch."""
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        B = Z.shape[0]
+        H, L = self.siren_hidden_features, self.siren_hidden_layers - 1
+        Zc = Z.detach().float().contiguous()
+        lins = [m for m in self.mapping_network.network if isinstance(m, nn.Linear)]
+        ws = [m.weight.detach().float().contiguous() for m in lins]
+        bs = [m.bias.detach().float().contiguous() for m in lins]
+        dims = (C.c_int32 * (len(lins) + 1))(lins[0].in_features, *[m.out_features for m in lins])
+        W0 = self.net[0].layer.weight.detach().float().contiguous()
+        b0 = self.net[0].layer.bias.detach().float().contiguous()
+        mc = torch.empty(B, 5, H, device=Z.device, dtype=torch.float32)
+        film = torch.empty(B, L, 2, H, device=Z.device, dtype=torch.float32)
+        ptrs = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
+        rc = lib.reni_film_map_forward(
+            C.byref(self.spec.c_config()), C.c_void_p(Zc.data_ptr()), C.c_void_p(W0.data_ptr()),
+            C.c_void_p(b0.data_ptr()), ptrs(ws), ptrs(bs), dims, len(lins), B, C.c_void_p(mc.data_ptr()),
+            C.c_void_p(film.data_ptr()), C.c_void_p(torch.cuda.current_stream(Z.device).cuda_stream))
+        _lib.check(rc, "reni_film_map_forward")
+        return mc, film
+
     def map_level(self, Z: torch.Tensor):
         """Per-map operands of the core: mc (B, 5, H) and film (B, L, 2, H).  Plain differentiable torch ops."""
         B, N, _ = Z.shape
@@ -172,7 +206,12 @@ class _FilmDecoderBase(nn.Module):
         if Z.device.type != "cuda":
             raise RuntimeError("reni_b200 runs on CUDA (sm_100a) only and has no CPU fallback; got latent codes on "
                                f"{Z.device}.  Move the module and its inputs to a B200.")
-        mc, film = self.map_level(Z.float())
+        differentiated = torch.is_grad_enabled() and (Z.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if not differentiated and Z.shape[0] <= self.NATIVE_MAP_LEVEL_MAX_BATCH and len(
+                [m for m in self.mapping_network.network if isinstance(m, nn.Linear)]) <= 8:
+            mc, film = self._map_level_native(Z)
+        else:
+            mc, film = self.map_level(Z.float())
         out = F_.film_decode_core(spec, self._ws, mc, film, directions, self.core_parameters())
         if self.output_activation == "exp":
             out = torch.exp(out)

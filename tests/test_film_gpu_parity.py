@@ -342,3 +342,20 @@ def test_film_fused_step_matches_reference_golden(dev, name):
     np.testing.assert_allclose(got, g["test_loss_f32"], rtol=1e-3, atol=1e-8)
     assert O.rel_l2(Z2.grad.cpu().numpy(), g["test_dZ_f32"]) < TOL_GRAD
     assert r2.dW is None
+
+
+@pytest.mark.parametrize("name", ["film_so2_n9_h256", "film_so2_n36_h256", "film_so3_n9_h256_tanh"])
+def test_film_native_map_level_matches_torch_and_oracle(dev, name):
+    """reni_film_map_forward (one launch: mapping input, mapping network, freq/phase, hoisted first layer) against the
+    differentiable torch stage and the fp64 oracle."""
+    c = load_film_case(name)
+    m = film_model_from_params(c["p"], c["N"], dev)
+    Z = t(c["Z"], dev)
+    with torch.no_grad():
+        mc_t, film_t = m.map_level(Z)
+        mc_n, film_n = m._map_level_native(Z)
+    torch.cuda.synchronize()
+    mc_o, film_o = FO.film_core_inputs(c["Z"].astype(np.float64), c["p"].astype(np.float64))
+    assert O.rel_l2(mc_n.cpu().numpy(), mc_o) < 2e-6 and O.rel_l2(film_n.cpu().numpy(), film_o) < 2e-6
+    assert O.rel_l2(mc_n.cpu().numpy(), mc_t.cpu().numpy()) < 2e-6
+    assert O.rel_l2(film_n.cpu().numpy(), film_t.cpu().numpy()) < 2e-6
