@@ -148,15 +148,17 @@ int32_t reni_film_backward(const reni_config_t* cfg, const float* film, const fl
 
 /* FiLM per-map stage, forward only (no-grad decoding of a few latents): mapping-network input (RENI.py:405-452),
  * mapping network (Linear / LeakyReLU(0.2) stack, RENI.py:481-512), freq = 15 raw + 30 (:667) and the hoisted first FiLM
- * layer, one launch, one CTA per map -> mc (B, 5, 256) and film (B, L, 2, 256) for reni_film_forward.
+ * layer -> mc (B, 5, 256) and film (B, L, 2, 256) for reni_film_forward, in 2 + n_linears launches.
  *   weight0 / bias0            : net[0].layer parameters (256, 2 + N) for SO2, (256, N) for SO3
  *   host_map_weights / biases  : HOST arrays of n_linears (<= 8) DEVICE pointers, mapping_network.network[2 i]
  *   host_map_dims              : HOST array of n_linears + 1 sizes: mapping input, then each linear's out features
- * Differentiated calls and large batches keep this stage with the caller (batched GEMMs + autograd). */
+ *   scratch                    : caller-owned device buffer of reni_film_map_scratch_bytes(...) bytes
+ * Differentiated calls keep this stage with the caller (batched GEMMs + autograd). */
+int64_t reni_film_map_scratch_bytes(const int32_t* host_map_dims, int32_t n_linears, int64_t B);
 int32_t reni_film_map_forward(const reni_config_t* cfg, const float* Z, const float* weight0, const float* bias0,
                               const float* const* host_map_weights, const float* const* host_map_biases,
                               const int32_t* host_map_dims, int32_t n_linears, int64_t B, float* mc, float* film,
-                              void* stream);
+                              void* scratch, int64_t scratch_bytes, void* stream);
 
 /* One fused FiLM training / latent-fit step around the core: reni_film_forward with the loss sums, the loss reduction
  * and reni_film_backward with the loss gradient formed in the kernel (replaces the criterion + loss.backward() of

@@ -16,6 +16,7 @@ from .losses import (KLD, CosineSimilarity, RENITestLoss, RENITrainLoss, RENIVAD
 from .film import CustomMappingNetwork, FiLMLayer, RENIAutoDecoderFiLM, RENIVariationalAutoDecoderFiLM
 from .models import RENIAutoDecoder, RENIVariationalAutoDecoder, SineLayer, get_model
 from .optim import FusedAdam
+from .serving import GraphedDecoder
 from .training import FlatGradBuffer, RENITrainer, shard_range
 
 __all__ = [
@@ -24,5 +25,5 @@ __all__ = [
     "WeightedMSE", "KLD", "WeightedCosineSimilarity", "CosineSimilarity",
     "RENITrainLoss", "RENIVADTrainLoss", "RENITestLoss",
     "get_directions", "get_sineweight", "get_mask", "rectangle_mask",
-    "RENITrainer", "FlatGradBuffer", "shard_range", "FusedAdam",
+    "RENITrainer", "FlatGradBuffer", "shard_range", "FusedAdam", "GraphedDecoder",
 ]

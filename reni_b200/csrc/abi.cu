@@ -765,44 +765,60 @@ int32_t reni_adam_step(const reni_adam_segment_t* host_segments, int32_t nseg, i
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
+int64_t reni_film_map_scratch_bytes(const int32_t* host_map_dims, int32_t n_linears, int64_t B) {
+  if (host_map_dims == nullptr || n_linears < 1 || n_linears > kFilmMapMaxLinears || B < 1) return RENI_ERR_BAD_ARGUMENT;
+  int64_t widest = 0;
+  for (int i = 0; i <= n_linears; ++i) {
+    if (host_map_dims[i] < 1) return RENI_ERR_BAD_ARGUMENT;
+    if (host_map_dims[i] > widest) widest = host_map_dims[i];
+  }
+  return 2 * B * widest * (int64_t)sizeof(float);  // two ping-pong activation buffers
+}
+
 int32_t reni_film_map_forward(const reni_config_t* c, const float* Z, const float* weight0, const float* bias0,
                               const float* const* host_map_weights, const float* const* host_map_biases,
                               const int32_t* host_map_dims, int32_t n_linears, int64_t B, float* mc, float* film,
-                              void* stream_) {
+                              void* scratch, int64_t scratch_bytes, void* stream_) {
   if (!config_ok(c) || c->equivariance == RENI_EQ_NONE) return RENI_ERR_BAD_CONFIG;
   if (Z == nullptr || weight0 == nullptr || bias0 == nullptr || host_map_weights == nullptr ||
-      host_map_biases == nullptr || host_map_dims == nullptr || mc == nullptr || film == nullptr || B < 1 ||
-      n_linears < 1 || n_linears > kFilmMapMaxLinears)
+      host_map_biases == nullptr || host_map_dims == nullptr || mc == nullptr || film == nullptr || scratch == nullptr ||
+      B < 1 || B > 65535 || n_linears < 1 || n_linears > kFilmMapMaxLinears)
     return RENI_ERR_BAD_ARGUMENT;
   const int N = c->ndims, Lf = c->hidden_layers + 1;
   const int mn_in = c->equivariance == RENI_EQ_SO2 ? N * N + N : N * N;
   if (host_map_dims[0] != mn_in || host_map_dims[n_linears] != 2 * Lf * kH) return RENI_ERR_BAD_ARGUMENT;
-  FilmMapParams p{};
-  p.Z = Z;
-  p.W0 = weight0;
-  p.b0 = bias0;
-  p.maxdim = 0;
+  const int64_t need = reni_film_map_scratch_bytes(host_map_dims, n_linears, B);
+  if (need < 0) return (int32_t)need;
+  if (scratch_bytes < need) return RENI_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* buf[2] = {static_cast<float*>(scratch), static_cast<float*>(scratch) + need / (2 * sizeof(float))};
+  const int so2 = c->equivariance == RENI_EQ_SO2;
+  reni_film_map_input_kernel<<<(unsigned)B, 256, 3 * N * sizeof(float), stream>>>(Z, buf[0], N, so2, mn_in);
+  int cur = 0;
   for (int i = 0; i < n_linears; ++i) {
-    if (host_map_weights[i] == nullptr || host_map_biases[i] == nullptr || host_map_dims[i] < 1) return RENI_ERR_BAD_ARGUMENT;
-    p.mw[i] = host_map_weights[i];
-    p.mb[i] = host_map_biases[i];
-    p.mdim[i] = host_map_dims[i];
-    if (host_map_dims[i] > p.maxdim) p.maxdim = host_map_dims[i];
+    if (host_map_weights[i] == nullptr || host_map_biases[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+    const int in = host_map_dims[i], out = host_map_dims[i + 1];
+    const size_t smem = (size_t)in * sizeof(float);
+    if (smem > 200 * 1024) return RENI_ERR_BAD_CONFIG;
+    if (smem > 48 * 1024 &&
+        note(cudaFuncSetAttribute(reni_film_map_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=
+            cudaSuccess)
+      return RENI_ERR_CUDA;
+    reni_film_map_linear_kernel<<<dim3((unsigned)((out + 31) / 32), (unsigned)B), 256, smem, stream>>>(
+        buf[cur], host_map_weights[i], host_map_biases[i], buf[cur ^ 1], in, out, i + 1 < n_linears ? 1 : 0);
+    cur ^= 1;
   }
-  p.mdim[n_linears] = host_map_dims[n_linears];
-  p.nlin = n_linears;
-  p.N = N;
-  p.so2 = c->equivariance == RENI_EQ_SO2;
-  p.Lf = Lf;
-  p.mc = mc;
-  p.film = film;
-  const size_t smem = (size_t)(3 * N + 2 * p.maxdim + 2 * kH) * sizeof(float);
-  if (smem > 200 * 1024) return RENI_ERR_BAD_CONFIG;
-  if (smem > 48 * 1024 &&
-      note(cudaFuncSetAttribute(reni_film_map_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=
-          cudaSuccess)
-    return RENI_ERR_CUDA;
-  reni_film_map_forward_kernel<<<(unsigned)B, 256, smem, static_cast<cudaStream_t>(stream_)>>>(p);
+  FilmMapFinishParams f{};
+  f.Z = Z;
+  f.W0 = weight0;
+  f.b0 = bias0;
+  f.raw = buf[cur];
+  f.mc = mc;
+  f.film = film;
+  f.N = N;
+  f.so2 = so2;
+  f.Lf = Lf;
+  reni_film_map_finish_kernel<<<(unsigned)B, 256, 3 * N * sizeof(float), stream>>>(f);
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 

@@ -730,115 +730,122 @@ __global__ void reni_adam_advance_kernel(int* step) { *step += 1; }
 // ------------------------------------------------------------------------------------------------
 // FiLM per-map stage, forward only (inference / no-grad decoding): everything RENIAutoDecoderFiLM.forward computes
 // that is constant per map (RENI.py:405-452 mapping input, :481-512 mapping network, :667 freq = 15 raw + 30) plus the
-// hoisted first FiLM layer, in ONE launch -- a decode of a single latent otherwise spends its time in ~25 tiny launches.
-// One CTA per map, 256 threads; every dense layer is warp-per-output-feature with lanes striding the input (coalesced
-// reads of the weight row, shuffle reduction).  Meant for small batches (the weights are re-read from L2 by every CTA);
-// large batches and differentiated calls use the caller's batched GEMMs.
+// hoisted first FiLM layer.  A decode of a single latent otherwise spends its time in ~25 tiny torch launches; here it
+// is 2 + n_linears launches that spread every dense layer over (out / 32) x B CTAs (a single CTA per map is bound by
+// the bytes one SM can keep in flight: measured 390 us for one map).
 //   mc   (B, 5, 256): rows 0..3 = freq_0 * M_b, row 4 = freq_0 * b_0 + phase_0      film (B, L, 2, 256), L = Lf - 1
 // ------------------------------------------------------------------------------------------------
 constexpr int kFilmMapMaxLinears = 8;
-struct FilmMapParams {
-  const float* Z;    // (B, N, 3)
-  const float* W0;   // (256, in0): in0 = 2 + N (SO2: [|d_xz|, d_y, innerprod]) or N (SO3)
-  const float* b0;   // (256)
-  const float* mw[kFilmMapMaxLinears];  // mapping-network linears (out_i, in_i), row-major like nn.Linear
-  const float* mb[kFilmMapMaxLinears];
-  int mdim[kFilmMapMaxLinears + 1];     // mdim[0] = mapping input size, mdim[i + 1] = out features of linear i
-  int nlin, N, so2, Lf, maxdim;         // maxdim = max over mdim[0 .. nlin - 1] (smem ping-pong buffer size)
-  float* mc;
-  float* film;
-};
 
-__global__ void __launch_bounds__(256) reni_film_map_forward_kernel(const FilmMapParams p) {
-  extern __shared__ float s_fm[];
-  const int b = blockIdx.x, N = p.N;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* s_z = s_fm;                       // 3N
-  float* s_a = s_z + 3 * N;                // maxdim
-  float* s_b = s_a + p.maxdim;             // maxdim
-  float* s_fp = s_b + p.maxdim;            // 2 * 256: freq_0, phase_0
-  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_z[i] = p.Z[(size_t)b * 3 * N + i];
+// mapping input per map (RENI.py:424-435 SO2: [vec(Z_xz Z_xz^T), Z_y]; :407-415 SO3: vec(Z Z^T)); grid (B)
+__global__ void __launch_bounds__(256) reni_film_map_input_kernel(const float* Z, float* x, int N, int so2, int mn_in) {
+  extern __shared__ float s_fz[];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_fz[i] = Z[(size_t)b * 3 * N + i];
   __syncthreads();
-  // mapping input (RENI.py:424-435 / :407-415)
-  for (int i = threadIdx.x; i < p.mdim[0]; i += blockDim.x) {
+  for (int i = threadIdx.x; i < mn_in; i += blockDim.x) {
     float v;
     if (i < N * N) {
       const int n = i / N, m = i % N;
-      v = s_z[n * 3] * s_z[m * 3] + s_z[n * 3 + 2] * s_z[m * 3 + 2];
-      if (!p.so2) v = fmaf(s_z[n * 3 + 1], s_z[m * 3 + 1], v);
+      v = s_fz[n * 3] * s_fz[m * 3] + s_fz[n * 3 + 2] * s_fz[m * 3 + 2];
+      if (!so2) v = fmaf(s_fz[n * 3 + 1], s_fz[m * 3 + 1], v);
     } else {
-      v = s_z[(i - N * N) * 3 + 1];  // Z_y (SO2 only)
+      v = s_fz[(i - N * N) * 3 + 1];
     }
-    s_a[i] = v;
+    x[(size_t)b * mn_in + i] = v;
   }
+}
+
+// y[b, o] = act(b[o] + sum_k W[o, k] x[b, k]); grid (ceil(out / 32), B), 256 threads = 8 warps x 4 output rows each,
+// lanes stride the input (coalesced weight reads, 4 rows x 2 loads in flight per lane), x[b] staged in shared memory
+__global__ void __launch_bounds__(256) reni_film_map_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                                   const float* __restrict__ bias, float* __restrict__ y,
+                                                                   int in, int out, int leaky) {
+  extern __shared__ float s_fx[];
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < in; i += blockDim.x) s_fx[i] = x[(size_t)b * in + i];
   __syncthreads();
-  float* x = s_a;
-  float* y = s_b;
-  const int half = p.Lf * kH;  // raw output = [frequencies | phase_shifts]
-  for (int li = 0; li < p.nlin; ++li) {
-    const int in = p.mdim[li], out = p.mdim[li + 1];
-    const bool last = li == p.nlin - 1;
-    for (int o = warp; o < out; o += 8) {
-      const float* w = p.mw[li] + (size_t)o * in;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int k = lane;
-      for (; k + 96 < in; k += 128) {
-        a0 = fmaf(__ldg(w + k), x[k], a0);
-        a1 = fmaf(__ldg(w + k + 32), x[k + 32], a1);
-        a2 = fmaf(__ldg(w + k + 64), x[k + 64], a2);
-        a3 = fmaf(__ldg(w + k + 96), x[k + 96], a3);
-      }
-      for (; k < in; k += 32) a0 = fmaf(__ldg(w + k), x[k], a0);
-      float acc = (a0 + a1) + (a2 + a3);
+  const int o0 = blockIdx.x * 32 + warp * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* w[4];
 #pragma unroll
-      for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-      if (lane == 0) {
-        acc += p.mb[li][o];
-        if (!last) {
-          y[o] = acc > 0.f ? acc : 0.2f * acc;  // LeakyReLU(0.2)
-        } else {
-          const bool is_freq = o < half;
-          const int j = is_freq ? o : o - half;           // layer * 256 + feature
-          const int layer = j / kH, f = j % kH;
-          const float v = is_freq ? fmaf(acc, 15.f, 30.f) : acc;  // RENI.py:667
-          if (layer == 0) s_fp[(is_freq ? 0 : kH) + f] = v;
-          else p.film[(((size_t)b * (p.Lf - 1) + (layer - 1)) * 2 + (is_freq ? 0 : 1)) * kH + f] = v;
-        }
-      }
-    }
-    __syncthreads();
-    float* t = x; x = y; y = t;
+  for (int r = 0; r < 4; ++r) w[r] = W + (size_t)min(o0 + r, out - 1) * in;
+  int k = lane;
+  for (; k + 32 < in; k += 64) {
+    float a[4], c[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { a[r] = __ldg(w[r] + k); c[r] = __ldg(w[r] + k + 32); }
+    const float x0 = s_fx[k], x1 = s_fx[k + 32];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = fmaf(c[r], x1, fmaf(a[r], x0, acc[r]));
   }
-  // hoisted first FiLM layer: thread j = output feature
-  {
-    const int j = threadIdx.x;
-    const int in0 = p.so2 ? N + 2 : N;
-    const float* w = p.W0 + (size_t)j * in0;
-    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
-    if (p.so2) {
-      for (int n = 0; n < N; ++n) {
-        const float wv = __ldg(w + 2 + n);
-        m0 = fmaf(wv, s_z[n * 3], m0);      // d_x
-        m1 = fmaf(wv, s_z[n * 3 + 2], m1);  // d_z
-      }
-      m2 = __ldg(w);      // |d_xz|
-      m3 = __ldg(w + 1);  // d_y
-    } else {
-      for (int n = 0; n < N; ++n) {
-        const float wv = __ldg(w + n);
-        m0 = fmaf(wv, s_z[n * 3], m0);
-        m1 = fmaf(wv, s_z[n * 3 + 1], m1);
-        m2 = fmaf(wv, s_z[n * 3 + 2], m2);
-      }
-    }
-    const float f0 = s_fp[j], ph0 = s_fp[kH + j];
-    float* o = p.mc + (size_t)b * 5 * kH + j;
-    o[0] = f0 * m0;
-    o[kH] = f0 * m1;
-    o[2 * kH] = f0 * m2;
-    o[3 * kH] = f0 * m3;
-    o[4 * kH] = fmaf(f0, p.b0[j], ph0);
+  for (; k < in; k += 32) {
+    const float x0 = s_fx[k];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = fmaf(__ldg(w[r] + k), x0, acc[r]);
   }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float v = acc[r];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0 && o0 + r < out) {
+      v += bias[o0 + r];
+      y[(size_t)b * out + o0 + r] = (leaky && v < 0.f) ? 0.2f * v : v;
+    }
+  }
+}
+
+struct FilmMapFinishParams {
+  const float* Z;    // (B, N, 3)
+  const float* W0;   // (256, in0): in0 = 2 + N (SO2: [|d_xz|, d_y, innerprod]) or N (SO3)
+  const float* b0;   // (256)
+  const float* raw;  // (B, 2 * Lf * 256): mapping-network output [frequencies | phase_shifts]
+  float* mc;
+  float* film;
+  int N, so2, Lf;
+};
+
+// freq = 15 raw + 30 (RENI.py:667), film for the hidden layers, hoisted + modulated first layer; grid (B), thread = feature
+__global__ void __launch_bounds__(256) reni_film_map_finish_kernel(const FilmMapFinishParams p) {
+  extern __shared__ float s_fz[];
+  const int b = blockIdx.x, N = p.N, j = threadIdx.x;
+  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_fz[i] = p.Z[(size_t)b * 3 * N + i];
+  __syncthreads();
+  const int half = p.Lf * kH;
+  const float* raw = p.raw + (size_t)b * 2 * half;
+  for (int l = 1; l < p.Lf; ++l) {
+    float* o = p.film + ((size_t)b * (p.Lf - 1) + (l - 1)) * 2 * kH;
+    o[j] = fmaf(raw[l * kH + j], 15.f, 30.f);
+    o[kH + j] = raw[half + l * kH + j];
+  }
+  const float f0 = fmaf(raw[j], 15.f, 30.f), ph0 = raw[half + j];
+  const int in0 = p.so2 ? N + 2 : N;
+  const float* w = p.W0 + (size_t)j * in0;
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+  if (p.so2) {
+    for (int n = 0; n < N; ++n) {
+      const float wv = __ldg(w + 2 + n);
+      m0 = fmaf(wv, s_fz[n * 3], m0);      // d_x
+      m1 = fmaf(wv, s_fz[n * 3 + 2], m1);  // d_z
+    }
+    m2 = __ldg(w);      // |d_xz|
+    m3 = __ldg(w + 1);  // d_y
+  } else {
+    for (int n = 0; n < N; ++n) {
+      const float wv = __ldg(w + n);
+      m0 = fmaf(wv, s_fz[n * 3], m0);
+      m1 = fmaf(wv, s_fz[n * 3 + 1], m1);
+      m2 = fmaf(wv, s_fz[n * 3 + 2], m2);
+    }
+  }
+  float* o = p.mc + (size_t)b * 5 * kH + j;
+  o[0] = f0 * m0;
+  o[kH] = f0 * m1;
+  o[2 * kH] = f0 * m2;
+  o[3 * kH] = f0 * m3;
+  o[4 * kH] = fmaf(f0, p.b0[j], ph0);
 }
 
 }  // namespace reni

@@ -140,16 +140,15 @@ class _FilmDecoderBase(nn.Module):
             ps += [layer.layer.weight, layer.layer.bias]
         return ps + [self.final_layer.weight, self.final_layer.bias]
 
-    # Batches up to this size take the one-launch native per-map stage under no_grad.  0 = always the torch stage:
-    # measured on B200 the two are equally fast from Python (a single-latent decode is host-bound at ~0.47 ms either
-    # way), and keeping one per-map stage makes the no-grad forward bit-identical to the differentiated one.  The
-    # native entry point (reni_film_map_forward) is there for callers without PyTorch and for graph-captured decoding.
-    NATIVE_MAP_LEVEL_MAX_BATCH = 0
+    # No-grad decodes of up to this many latents take the native per-map stage (reni_film_map_forward: 6 launches
+    # instead of ~25 torch ops; it re-reads the mapping-network weights from L2 for every map, so large batches keep
+    # the batched torch GEMMs).  The two stages agree to fp32 rounding (2e-6), not bit for bit.
+    NATIVE_MAP_LEVEL_MAX_BATCH = 128
 
     def _map_level_native(self, Z: torch.Tensor):
-        """The same per-map operands from ONE kernel (reni_film_map_forward): no-grad decoding of a few latents
-        otherwise spends its time in ~25 tiny launches.  One CTA per map re-reads the weights from L2, hence the cap
-        on the batch."""
+        """The same per-map operands from reni_film_map_forward (2 + n_linears launches of GEMV-style kernels instead
+        of ~25 torch launches): for no-grad decoding of a few latents; every map re-reads the weights from L2, hence
+        the cap on the batch."""
         import ctypes as C
 
         from . import _lib
@@ -167,10 +166,15 @@ class _FilmDecoderBase(nn.Module):
         mc = torch.empty(B, 5, H, device=Z.device, dtype=torch.float32)
         film = torch.empty(B, L, 2, H, device=Z.device, dtype=torch.float32)
         ptrs = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
+        nbytes = int(lib.reni_film_map_scratch_bytes(dims, len(lins), B))
+        if nbytes < 0:
+            _lib.check(nbytes, "reni_film_map_scratch_bytes")
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=Z.device)
         rc = lib.reni_film_map_forward(
             C.byref(self.spec.c_config()), C.c_void_p(Zc.data_ptr()), C.c_void_p(W0.data_ptr()),
             C.c_void_p(b0.data_ptr()), ptrs(ws), ptrs(bs), dims, len(lins), B, C.c_void_p(mc.data_ptr()),
-            C.c_void_p(film.data_ptr()), C.c_void_p(torch.cuda.current_stream(Z.device).cuda_stream))
+            C.c_void_p(film.data_ptr()), C.c_void_p(scratch.data_ptr()), nbytes,
+            C.c_void_p(torch.cuda.current_stream(Z.device).cuda_stream))
         _lib.check(rc, "reni_film_map_forward")
         return mc, film
 

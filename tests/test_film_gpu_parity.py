@@ -246,7 +246,7 @@ def test_film_full_size_properties(dev):
     """The default FiLM decoder (N=36, 5 FiLM layers, 3x256 mapping network) at the BASELINE configs[1] size
     (32 maps x 64x128) through size-independent properties:
     (1) SO(2) invariance of the radiance; (2) additivity of every decoder gradient over the two halves of the batch and
-    per-map independence of dZ; (3) the inference kernel equals the differentiated forward bit for bit;
+    per-map independence of dZ; (3) the no-grad decode equals the differentiated forward (to the rounding of the two per-map stages);
     (4) spot check of 2 maps (forward and dZ) against the oracle."""
     torch.manual_seed(7)
     from reni_b200 import RENIAutoDecoderFiLM, RENITrainLoss, get_directions, get_sineweight
@@ -279,7 +279,8 @@ def test_film_full_size_properties(dev):
     o_full, dZ_full, g_full = grads(slice(0, B))
     _, dZ_a, g_a = grads(slice(0, 16))
     _, dZ_b, g_b = grads(slice(16, B))
-    assert torch.equal(o_full, o1)
+    # (no-grad decodes of <= 128 latents use the native per-map stage, the differentiated forward the torch one)
+    assert float((o_full - o1).norm() / o1.norm()) < 2e-4
     for a, b1, b2 in zip(g_full, g_a, g_b):
         assert float((a - b1 - b2).norm() / a.norm()) < 2e-3
     assert float((dZ_full[:16] - dZ_a).norm() / dZ_a.norm()) < 1e-3
@@ -359,3 +360,27 @@ def test_film_native_map_level_matches_torch_and_oracle(dev, name):
     assert O.rel_l2(mc_n.cpu().numpy(), mc_o) < 2e-6 and O.rel_l2(film_n.cpu().numpy(), film_o) < 2e-6
     assert O.rel_l2(mc_n.cpu().numpy(), mc_t.cpu().numpy()) < 2e-6
     assert O.rel_l2(film_n.cpu().numpy(), film_t.cpu().numpy()) < 2e-6
+
+
+def test_graphed_decoder_replays_and_follows_weight_updates(dev):
+    """GraphedDecoder: one CUDA-graph replay per decode, for both decoder families; weights are read at replay time."""
+    from reni_b200 import GraphedDecoder, RENIAutoDecoder, RENIAutoDecoderFiLM, get_directions
+
+    torch.manual_seed(3)
+    D = get_directions(32).to(dev)
+    for m, exact in ((RENIAutoDecoder(4, 9, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, True).to(dev), True),
+                     (RENIAutoDecoderFiLM(4, 9, "SO2", 256, 5, 256, 3, 3, None, True).to(dev), False)):
+        gd = GraphedDecoder(m, 2, D)
+        for trial in range(3):
+            Z = torch.randn(2, 9, 3, device=dev)
+            got = gd(Z).clone()
+            with torch.no_grad():
+                want = m(Z, D.expand(2, -1, -1))
+            if exact:
+                assert torch.equal(got, want)
+            else:  # (native per-map stage in the graph, torch stage eagerly: equal to rounding)
+                assert O.rel_l2(got.cpu().numpy(), want.cpu().numpy()) < 5e-4
+            with torch.no_grad():  # an "optimiser step": the next replay must see the new weights
+                for p in m.parameters():
+                    if p.dim() == 2:
+                        p.mul_(1.01)
