@@ -60,6 +60,7 @@ typedef struct {
 #define RENI_FLAG_NEED_DW 2           /* weight gradients wanted (otherwise latent gradients only)     */
 #define RENI_FLAG_LOSS 4              /* forward also produces per-map loss sums (target / sw given)   */
 #define RENI_FLAG_FILM 8              /* workspace query for the FiLM core (reni_film_forward/backward) */
+#define RENI_FLAG_FILM_PERMAP 16      /* FiLM core on per-map weight images (reni_film_prepare_maps), see below */
 
 int32_t reni_abi_version(void);
 const char* reni_strerror(int32_t code);
@@ -146,6 +147,19 @@ int32_t reni_film_backward(const reni_config_t* cfg, const float* film, const fl
                            float* const* host_dW, float* const* host_db, void* workspace, int64_t workspace_bytes,
                            int32_t flags, void* stream);
 
+/* FiLM core on PER-MAP weight images (RENI_FLAG_FILM_PERMAP in the flags of the workspace query and of every
+ * reni_film_* compute call of the step).  sin(freq_l[b] (W_l h + b_l) + phase_l[b]) = sin((diag(freq_l[b]) W_l) h +
+ * (freq_l[b] b_l + phase_l[b])): with the modulation folded into fp16 weight / bias images of each map, built here from
+ * the fp32 parameters (one rounding, as for the shared images), the FiLM layers run on the kernels of the
+ * Cond-by-Concat decoder -- plain sin epilogue with the bias on the tensor core, delta stash written by bulk copies --
+ * and the backward's delta_l * freq_l becomes part of the backward image.  Costs B * L * 264 KB of workspace and one
+ * launch; requires (P / 128) % 4 == 0 with P % 128 == 0 (the four tiles of a CTA pair's unit share one map), else
+ * RENI_ERR_BAD_ARGUMENT.  Call after reni_prepare_weights and before reni_film_forward /
+ * reni_film_loss_forward_backward, on the same stream. */
+int32_t reni_film_prepare_maps(const reni_config_t* cfg, const float* film, const float* const* host_weights,
+                               const float* const* host_biases, int64_t B, int64_t P, void* workspace,
+                               int64_t workspace_bytes, int32_t flags, void* stream);
+
 /* FiLM per-map stage, forward only (no-grad decoding of a few latents): mapping-network input (RENI.py:405-452),
  * mapping network (Linear / LeakyReLU(0.2) stack, RENI.py:481-512), freq = 15 raw + 30 (:667) and the hoisted first FiLM
  * layer -> mc (B, 5, 256) and film (B, L, 2, 256) for reni_film_forward, in 2 + n_linears launches.
@@ -201,6 +215,15 @@ int32_t reni_debug_set_phase_events(void* const* host_events, int32_t n);
  * writes a clock64 timeline (event code << 48 | clock) per role: [0] MMA issuer, [1], [2] epilogue groups.
  * NULL clears.  Used by tools/trace_fwd.py to read the pipeline's critical path. */
 int32_t reni_debug_set_trace(void* device_buffer);
+
+/* Measurement / tuning hook for the training backward's OVERLAP mode, in which the weight-gradient kernel runs beside
+ * the delta-chain kernel on `dw_ctas` of the SMs (side stream) and takes each tile's stash blocks out of L2 as the
+ * chain finishes them (per-tile ready counters in the workspace) instead of re-reading them from HBM afterwards.
+ * dw_ctas = 0 (the default): overlap off, kernels back to back; -1: a 36 % share of the SMs; else the SM count
+ * (rounded down to even); out_ctas = how many of them take the output-layer job (0: round robin over jobs).
+ * Process-wide; results are identical up to the order of the fp32 gradient reductions.  Measured slower than the
+ * back-to-back kernels at cfg 2, hence off by default. */
+int32_t reni_debug_set_overlap(int32_t dw_ctas, int32_t out_ctas);
 
 /* Debug hook: cudaGetErrorString of the last CUDA runtime error this thread saw inside the library
  * ("no error" if none); lets a caller turn RENI_ERR_CUDA into a readable message. */

@@ -17,6 +17,7 @@ FLAG_SAVE_FOR_BACKWARD = 1
 FLAG_NEED_DW = 2
 FLAG_LOSS = 4
 FLAG_FILM = 8
+FLAG_FILM_PERMAP = 16
 
 EQUIVARIANCE = {"None": 0, "SO2": 1, "SO3": 2}
 
@@ -68,6 +69,7 @@ SIGNATURES = {
     "reni_film_forward": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp]),
     "reni_film_backward": (_i32, [_cfgp, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _vp, _vp, _vp,
                                   C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _i32, _vp]),
+    "reni_film_prepare_maps": (_i32, [_cfgp, _vp, C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp, _i64, _i32, _vp]),
     "reni_film_map_scratch_bytes": (_i64, [C.POINTER(C.c_int32), _i32, _i64]),
     "reni_film_map_forward": (_i32, [_cfgp, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int32), _i32, _i64,
                                      _vp, _vp, _vp, _i64, _vp]),
@@ -78,6 +80,7 @@ SIGNATURES = {
     "reni_debug_set_phase_events": (_i32, [C.POINTER(_vp), _i32]),
     "reni_debug_last_cuda_error": (C.c_char_p, []),
     "reni_debug_set_trace": (_i32, [_vp]),
+    "reni_debug_set_overlap": (_i32, [_i32, _i32]),
     "reni_probe_remote_tx": (_i32, [_vp, _u32, _vp, _i32, _vp]),
     "reni_selftest_umma": (_i32, [_vp, _u32, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]),
     "reni_selftest_umma2": (_i32, [_vp, _u32, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]),

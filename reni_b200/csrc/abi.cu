@@ -76,6 +76,12 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   w.xc = take(B * 5 * nin * 4);   // xfull: input columns paired with [dM0..dM3, dc]
   w.dxc = take(B * 5 * nin * 4);  // E: gradient w.r.t. xfull
   w.dip = -1;
+  w.wf2m = w.wb2m = w.wbias2m = -1;
+  if ((flags & RENI_FLAG_FILM) && (flags & RENI_FLAG_FILM_PERMAP)) {  // (placed ahead of everything the other flags size)
+    w.wf2m = take(B * L * (int64_t)kWImageBytes);
+    w.wb2m = take(B * L * (int64_t)kWImageBytes);
+    w.wbias2m = take(B * L * 2 * (int64_t)kBiasBlockBytes);
+  }
   if (flags & RENI_FLAG_SAVE_FOR_BACKWARD) {
     const bool dw = (flags & (RENI_FLAG_NEED_DW | RENI_FLAG_FILM)) != 0;  // (FiLM: dfreq / dphase need the delta stash)
     w.stash_c = take(ntiles * (L + 1) * (int64_t)kTileImageBytes);  // 16-bit phase stash (rebuilds both h and cos)
@@ -83,8 +89,9 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
     w.stash_d = dw ? take(ntiles * (L + 1) * (int64_t)kTileImageBytes) : -1;  // slot 0 unused (delta_0 stays on chip)
     w.stash_gy = take(ntiles * (int64_t)kGyImageBytes);
     w.aout = c->last_layer_linear ? -1 : take(B * P * 3 * 4);  // sine output layer: its pre-activations
+    w.ready = dw ? take((ntiles + 16) * 4) : -1;
   } else {
-    w.stash_c = w.stash_h = w.stash_d = w.stash_gy = w.aout = -1;
+    w.stash_c = w.stash_h = w.stash_d = w.stash_gy = w.aout = w.ready = -1;
   }
   w.film_S = w.film_cs = -1;
   if ((flags & RENI_FLAG_FILM) && (flags & RENI_FLAG_SAVE_FOR_BACKWARD)) {
@@ -94,6 +101,9 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   w.total = off;
   return w;
 }
+
+// RENI_FLAG_FILM_PERMAP needs every unit of four tiles inside one map
+bool permap_ok(int64_t P) { return P % kTileRows == 0 && (P / kTileRows) % 4 == 0; }
 
 template <class T>
 T* at(void* ws, int64_t off) {
@@ -106,6 +116,10 @@ T* at(void* ws, int64_t off) {
 cudaEvent_t g_phase_events[16];
 volatile int g_num_phase_events = 0;
 thread_local unsigned long long* g_trace = nullptr;  // reni_debug_set_trace
+// reni_debug_set_overlap: SMs given to the co-resident weight-gradient kernel (-1: 36 % share, 0: overlap off) and
+// how many of them take the output-layer job (0: round robin over the jobs)
+volatile int g_overlap_dw_ctas = 0;  // (measured slower than back-to-back kernels at cfg 2: off unless asked for)
+volatile int g_overlap_out_ctas = 0;
 inline void mark_phase(int i, cudaStream_t s) {
   if (i < g_num_phase_events && g_phase_events[i] != nullptr) cudaEventRecord(g_phase_events[i], s);
 }
@@ -321,7 +335,22 @@ static int32_t launch_forward(const reni_config_t* c, const WorkspaceLayout& w, 
   // CTA pairs (cluster of 2) share the weight stream: half the L2 -> SM weight traffic per SM
   const bool pair_mode = RENI_FWD_PAIR != 0;
   int grid = npairs < sms ? npairs : sms;
-  if (pair_mode) {  // one cluster of two CTAs per tile quad
+  // FiLM on per-map images: the modulation lives in each map's weight / bias images, the kernel is the plain one
+  const bool permap = film != nullptr && (flags & RENI_FLAG_FILM_PERMAP) != 0;
+  if (permap) {
+    if (!pair_mode || w.wf2m < 0) return RENI_ERR_BAD_CONFIG;
+    p.film = nullptr;
+    p.w_map_rows = p.L * (kWImageBytes / 256);
+    p.b_map_rows = p.L * 2 * (kBiasBlockBytes / 256);
+    if (!encode_rows256(&p.wmap, at<__half>(ws, w.wf2m), (uint64_t)B * p.L * kWImageBytes, kWChunkBytes / 256))
+      return RENI_ERR_CUDA;
+    if (!encode_rows256(&p.bmap, at<__half>(ws, w.wbias2m), (uint64_t)B * p.L * 2 * kBiasBlockBytes,
+                        kBiasBlockBytes / 256))
+      return RENI_ERR_CUDA;
+    const int nquads = (p.ntiles + 3) / 4;
+    const int nclusters = nquads < sms / 2 ? nquads : sms / 2;
+    grid = 2 * nclusters;
+  } else if (pair_mode) {  // one cluster of two CTAs per tile quad
     if (!encode_rows256(&p.wmap, p.wf2, (uint64_t)p.L * kWImageBytes, kWChunkBytes / 256)) return RENI_ERR_CUDA;
     if (!encode_rows256(&p.bmap, at<__half>(ws, w.wbias2), (uint64_t)p.L * 2 * kBiasBlockBytes, kBiasBlockBytes / 256))
       return RENI_ERR_CUDA;
@@ -347,7 +376,10 @@ static int32_t launch_forward(const reni_config_t* c, const WorkspaceLayout& w, 
     cfg.numAttrs = 1;
     e = note(cudaLaunchKernelEx(&cfg, kernel, p));
   };
-  if (film != nullptr) {
+  if (permap) {
+    if (train) launch(reni_fwd_kernel<true, true, true>);
+    else launch(reni_fwd_kernel<false, true, true>);
+  } else if (film != nullptr) {
     if (!pair_mode) return RENI_ERR_BAD_CONFIG;  // (the unpaired build is an A/B fallback without the FiLM epilogue)
     if (train) launch(reni_fwd_kernel<true, true, true, true>);
     else launch(reni_fwd_kernel<false, true, true, true>);
@@ -409,7 +441,8 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   p.D = D;
   p.d_bstride = d_bstride;
   p.dmc = dmc;
-  p.film = film != nullptr ? film->film : nullptr;
+  const bool permap = film != nullptr && (flags & RENI_FLAG_FILM_PERMAP) != 0;  // modulation folded into per-map images
+  p.film = (film != nullptr && !permap) ? film->film : nullptr;
   p.so2 = c->equivariance == RENI_EQ_SO2;
   p.B = (int)B;
   p.P = (int)P;
@@ -423,14 +456,39 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   // pays off because the delta stash is written by bulk copies from shared memory (measured at cfg 2: unpaired
   // st.global 305 us, unpaired bulk 312, paired st.global 335, paired bulk 291).
   const bool pair_mode = !need_dw || RENI_BWD_TRAIN_PAIR || film != nullptr;
+  // Overlap mode: the weight-gradient kernel runs BESIDE the delta chain on dw_ctas of the SMs (side stream, forked
+  // before the chain) and consumes each tile's stash blocks from L2 as the chain finishes them (per-tile counters),
+  // instead of re-reading 1.5 GB from HBM in a kernel of its own afterwards.  Only when there are several waves of
+  // tile quads per cluster to pipeline over; off under the per-kernel timing hook (which wants kernels back to back).
+  int dw_ctas = 0;
+  if (want_dw && film == nullptr && pair_mode && RENI_BWD_BULK_STASH && g_num_phase_events == 0 && !RENI_NO_FORK &&
+      w.ready >= 0 && (ntiles + 3) / 4 >= 3 * (sms / 2)) {
+    dw_ctas = g_overlap_dw_ctas < 0 ? ((int)(sms * 0.36) & ~1) : (g_overlap_dw_ctas & ~1);
+    if (dw_ctas < 2 * (L + 1) || dw_ctas > sms - 4) dw_ctas = 0;
+  }
+  if (dw_ctas > 0) {
+    p.ready = at<uint32_t>(ws, w.ready);
+    if (cudaMemsetAsync(p.ready, 0, ((size_t)ntiles + 16) * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
+    if (side == nullptr && !side_stream(&side)) return RENI_ERR_CUDA;
+    if (note(cudaEventRecord(side->fork, stream)) != cudaSuccess) return RENI_ERR_CUDA;
+    if (note(cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return RENI_ERR_CUDA;
+  }
   memset(&p.wmap, 0, sizeof(p.wmap));
   {
     cudaLaunchConfig_t cfg{};
     if (pair_mode) {
       const int nquads = (ntiles + 3) / 4;
-      const int nclusters = nquads < sms / 2 ? nquads : sms / 2;
+      const int avail = (sms - dw_ctas) / 2;
+      const int nclusters = nquads < avail ? nquads : avail;
       cfg.gridDim = dim3((unsigned)(2 * nclusters));
-      if (!encode_rows256(&p.wmap, p.wb2, (uint64_t)L * kWImageBytes, kWChunkBytes / 256)) return RENI_ERR_CUDA;
+      if (permap) {
+        if (w.wb2m < 0) return RENI_ERR_BAD_CONFIG;
+        p.w_map_rows = L * (kWImageBytes / 256);
+        if (!encode_rows256(&p.wmap, at<__half>(ws, w.wb2m), (uint64_t)B * L * kWImageBytes, kWChunkBytes / 256))
+          return RENI_ERR_CUDA;
+      } else if (!encode_rows256(&p.wmap, p.wb2, (uint64_t)L * kWImageBytes, kWChunkBytes / 256)) {
+        return RENI_ERR_CUDA;
+      }
     } else {
       const int npairs = (ntiles + 1) / 2;
       cfg.gridDim = dim3((unsigned)(npairs < sms ? npairs : sms));
@@ -445,7 +503,12 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (film != nullptr) {
+    if (permap) {
+      if (note(cudaFuncSetAttribute(reni_bwd_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    BwdSmem::kTotal)) != cudaSuccess)
+        return RENI_ERR_CUDA;
+      if (note(cudaLaunchKernelEx(&cfg, reni_bwd_kernel<true, true, false>, p)) != cudaSuccess) return RENI_ERR_CUDA;
+    } else if (film != nullptr) {
       if (note(cudaFuncSetAttribute(reni_bwd_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     BwdSmem::kTotal)) != cudaSuccess)
         return RENI_ERR_CUDA;
@@ -468,8 +531,13 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
 
   // fork: the map-level backward below only needs dmc from the delta chain; with the per-kernel timing hook active
   // everything stays on the caller's stream so the phase events keep their meaning
-  cudaStream_t mstream = stream;
-  if (need_dw && film == nullptr && g_num_phase_events == 0 && !RENI_NO_FORK) {
+  // (overlap mode: the fork happened before the chain, the weight-gradient kernel takes the side stream -- launched
+  // AFTER the chain so that a tool that serialises kernels in launch order still terminates -- and the map-level
+  // kernels follow the chain on the caller's stream while the weight-gradient CTAs drain)
+  cudaStream_t mstream = stream, dwstream = stream;
+  if (dw_ctas > 0) {
+    dwstream = side->stream;
+  } else if (need_dw && film == nullptr && g_num_phase_events == 0 && !RENI_NO_FORK) {
     if (side == nullptr && !side_stream(&side)) return RENI_ERR_CUDA;
     if (note(cudaEventRecord(side->fork, stream)) != cudaSuccess) return RENI_ERR_CUDA;
     if (note(cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return RENI_ERR_CUDA;
@@ -531,12 +599,30 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
         r.db[i] = want_dw ? host_db[i] : nullptr;
       }
       reni_film_dfilm_kernel<<<dim3(kH / 8, (unsigned)L, (unsigned)B), 256, 0, stream>>>(r);
-      if (want_dw) reni_film_dw_kernel<<<dim3(kH, (unsigned)L), 256, 0, stream>>>(r);
+      if (want_dw) reni_film_dw_kernel<<<dim3(kH / 4, (unsigned)L), 256, 0, stream>>>(r);
       if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
       mark_phase(5, stream);
       mark_phase(6, stream);
       return RENI_OK;  // (layer 0 and the mapping network are differentiated by the caller from d_mc / d_film)
     }
+    if (dw_ctas > 0) {
+      q.ready = at<uint32_t>(ws, w.ready);
+      q.stuck = at<uint32_t>(ws, w.ready) + ntiles;
+      q.out_ctas = g_overlap_out_ctas;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)dw_ctas);
+      cfg.blockDim = dim3(kDwThreads);
+      cfg.dynamicSmemBytes = DwSmem::kTotal;
+      cfg.stream = dwstream;
+      cudaLaunchAttribute attr[1];  // allocated in SM pairs like the chain's clusters, so neither fragments the other
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (note(cudaLaunchKernelEx(&cfg, reni_dw_kernel, q)) != cudaSuccess) return RENI_ERR_CUDA;
+    } else {
     int g = sms;
     const int max_useful = ntiles * 2 * (L + 1);
     if (g > max_useful) g = max_useful;
@@ -549,6 +635,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     }
 #endif
     reni_dw_kernel<<<g, kDwThreads, DwSmem::kTotal, stream>>>(q);
+    }
     if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   }
   mark_phase(5, stream);
@@ -602,6 +689,13 @@ int32_t reni_debug_set_trace(void* device_buffer) {
 }
 
 const char* reni_debug_last_cuda_error(void) { return cudaGetErrorString(g_last_cuda); }
+
+int32_t reni_debug_set_overlap(int32_t dw_ctas, int32_t out_ctas) {
+  if (dw_ctas < -1 || out_ctas < 0) return RENI_ERR_BAD_ARGUMENT;
+  g_overlap_dw_ctas = dw_ctas;
+  g_overlap_out_ctas = out_ctas;
+  return RENI_OK;
+}
 
 int32_t reni_debug_set_phase_events(void* const* events, int32_t n) {
   if (n < 0 || n > 16 || (n > 0 && events == nullptr)) return RENI_ERR_BAD_ARGUMENT;
@@ -692,7 +786,8 @@ int32_t reni_film_forward(const reni_config_t* c, const float* mc, const float* 
   if (!config_ok(c) || !c->last_layer_linear) return RENI_ERR_BAD_CONFIG;
   if (mc == nullptr || film == nullptr || D == nullptr || out == nullptr || ws == nullptr || B < 1 || P < 1)
     return RENI_ERR_BAD_ARGUMENT;
-  flags = (flags & RENI_FLAG_SAVE_FOR_BACKWARD) | RENI_FLAG_FILM;
+  flags = (flags & (RENI_FLAG_SAVE_FOR_BACKWARD | RENI_FLAG_FILM_PERMAP)) | RENI_FLAG_FILM;
+  if ((flags & RENI_FLAG_FILM_PERMAP) && !permap_ok(P)) return RENI_ERR_BAD_ARGUMENT;
   const WorkspaceLayout w = make_layout(c, B, P, flags);
   if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
   const int sms = num_sms();
@@ -713,7 +808,8 @@ int32_t reni_film_backward(const reni_config_t* c, const float* film, const floa
       grad_out == nullptr || d_mc == nullptr || d_film == nullptr || ws == nullptr || B < 1 || P < 1)
     return RENI_ERR_BAD_ARGUMENT;
   if ((flags & RENI_FLAG_NEED_DW) && (host_dW == nullptr || host_db == nullptr)) return RENI_ERR_BAD_ARGUMENT;
-  flags = (flags & RENI_FLAG_NEED_DW) | RENI_FLAG_SAVE_FOR_BACKWARD | RENI_FLAG_FILM;
+  flags = (flags & (RENI_FLAG_NEED_DW | RENI_FLAG_FILM_PERMAP)) | RENI_FLAG_SAVE_FOR_BACKWARD | RENI_FLAG_FILM;
+  if ((flags & RENI_FLAG_FILM_PERMAP) && !permap_ok(P)) return RENI_ERR_BAD_ARGUMENT;
   const WorkspaceLayout w = make_layout(c, B, P, flags);
   if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -822,6 +918,32 @@ int32_t reni_film_map_forward(const reni_config_t* c, const float* Z, const floa
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
+int32_t reni_film_prepare_maps(const reni_config_t* c, const float* film, const float* const* host_weights,
+                               const float* const* host_biases, int64_t B, int64_t P, void* ws, int64_t ws_bytes,
+                               int32_t flags, void* stream_) {
+  if (!config_ok(c) || !c->last_layer_linear) return RENI_ERR_BAD_CONFIG;
+  if (film == nullptr || host_weights == nullptr || host_biases == nullptr || ws == nullptr || B < 1 || B > 65535 ||
+      !permap_ok(P))
+    return RENI_ERR_BAD_ARGUMENT;
+  flags |= RENI_FLAG_FILM | RENI_FLAG_FILM_PERMAP;
+  const WorkspaceLayout w = make_layout(c, B, P, flags);
+  if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
+  FilmPrepParams q{};
+  const int L = c->hidden_layers;
+  for (int i = 1; i <= L; ++i) {
+    if (host_weights[i] == nullptr || host_biases[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+    q.w[i] = host_weights[i];
+    q.b[i] = host_biases[i];
+  }
+  q.film = film;
+  q.wf2m = at<__half>(ws, w.wf2m);
+  q.wb2m = at<__half>(ws, w.wb2m);
+  q.wbias2m = at<__half>(ws, w.wbias2m);
+  q.L = L;
+  reni_film_prep_maps_kernel<<<dim3(8, (unsigned)L, (unsigned)B), 256, 0, static_cast<cudaStream_t>(stream_)>>>(q);
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
 int32_t reni_film_loss_forward_backward(const reni_config_t* c, const float* mc, const float* film, const float* D,
                                         int64_t d_bstride, const float* const* host_weights,
                                         const float* const* host_biases, int64_t B, int64_t P, const float* target,
@@ -835,7 +957,8 @@ int32_t reni_film_loss_forward_backward(const reni_config_t* c, const float* mc,
       d_film == nullptr || ws == nullptr || B < 1 || P < 1)
     return RENI_ERR_BAD_ARGUMENT;
   if ((flags & RENI_FLAG_NEED_DW) && (host_dW == nullptr || host_db == nullptr)) return RENI_ERR_BAD_ARGUMENT;
-  flags = (flags & RENI_FLAG_NEED_DW) | RENI_FLAG_SAVE_FOR_BACKWARD | RENI_FLAG_FILM | RENI_FLAG_LOSS;
+  flags = (flags & (RENI_FLAG_NEED_DW | RENI_FLAG_FILM_PERMAP)) | RENI_FLAG_SAVE_FOR_BACKWARD | RENI_FLAG_FILM | RENI_FLAG_LOSS;
+  if ((flags & RENI_FLAG_FILM_PERMAP) && !permap_ok(P)) return RENI_ERR_BAD_ARGUMENT;
   const WorkspaceLayout w = make_layout(c, B, P, flags);
   if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
   const int sms = num_sms();

@@ -30,6 +30,10 @@ namespace reni {
 
 constexpr int kBwdThreads = 576;
 constexpr int kBwdStages = 4;
+#ifndef RENI_LAYER_RESIDENT
+#define RENI_LAYER_RESIDENT 0  // see fwd_kernel.cuh: measured slower, kept as a build switch
+#endif
+constexpr bool kBwdLayerResident = RENI_LAYER_RESIDENT != 0;
 
 struct BwdParams {
   const float* out;       // (B, P, 3) forward output (after tanh)
@@ -53,6 +57,9 @@ struct BwdParams {
   int B, P, tiles_per_map, ntiles, L;
   int out_tanh, d_slots, so2;
   int use_cos;            // fused loss: 0 = no cosine term (map_loss is not read, it may still be in flight)
+  int w_map_rows;         // per-map backward images (FiLM on per-map images): rows of 256 B per map in wmap, 0 = shared
+  uint32_t* ready;        // overlap mode (weight-gradient kernel co-resident on the other SMs): per-tile counter, +1 per
+                          // epilogue warp each time a stashed delta_l of the tile is complete in global memory
   alignas(64) CUtensorMap wmap;  // wb2 as rows of 256 B, box = one 16 KB half chunk
 };
 
@@ -108,6 +115,12 @@ DEVINL void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
 DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+DEVINL void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// gpu-scope release of everything this warp has written (call after __syncwarp, one lane): the co-resident
+// weight-gradient CTAs acquire the counter before they pull the tile's stash blocks
+DEVINL void ready_signal(uint32_t* ctr) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+}
 
 #ifndef RENI_BWD_PHASE_HINT
 #define RENI_BWD_PHASE_HINT 1  // phase-stash loads: 0 ld.global.nc, 1 ld.global.cs (streaming), 2 ld.global.lu (293 -> 289..291 us)
@@ -218,6 +231,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
         const int tbase = ubase + 2 * (int)crank;
         const int nsub = clamp02(p.ntiles - tbase);          // this CTA's live sub-tiles
         const int nstream = clamp02(p.ntiles - ubase);       // passes the leader makes over each layer
+        const int32_t wrow0 = (ubase / p.tiles_per_map) * p.w_map_rows;  // (per-map images: one map per unit)
         // phase-stash tiles are pulled towards L2 kPfDist layers before the epilogue that multiplies by their cosine
         constexpr int kPfDist = RENI_BWD_PF_DIST;
         for (int g = 0; g < nsub; ++g)
@@ -225,6 +239,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
             bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
                                  ((size_t)(tbase + g) * (L + 1) + (L - d)) * kTileImageBytes,
                              kTileImageBytes);
+        if (kPair && kBwdLayerResident) {
+          // layer-resident weights (see the forward kernel): slot c = chunk c of the current layer for both passes
+          for (int l = L; l >= 1; --l) {
+            for (int g = 0; g < nsub; ++g)
+              if (kPfDist > 0 && l - kPfDist >= 0)
+                bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
+                                     ((size_t)(tbase + g) * (L + 1) + (l - kPfDist)) * kTileImageBytes,
+                                 kTileImageBytes);
+            for (int c = 0; c < kChunks; ++c) {
+              mbar_wait(&w_empty[c], ph ^ 1);
+              if (crank == 0) mbar_arrive_expect_tx(&w_full[c], 2 * kWChunkBytes);
+              const int32_t row =
+                  (int32_t)(((size_t)((l - 1) * 2 + crank) * (kWImageBytes / 2) + (size_t)c * kWChunkBytes) / 256);
+              tma2_load_2d(smem + BwdSmem::kRing + c * kWChunkBytes, &p.wmap, 0, wrow0 + row, mapa_u32(smem_u32(&w_full[c]), 0));
+            }
+            ph ^= 1;
+          }
+        } else {
         for (int l = L; l >= 1; --l) {
           for (int g = 0; g < nstream; ++g) {
             if (kPfDist > 0 && g < nsub && l - kPfDist >= 0)
@@ -237,7 +269,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
                 if (crank == 0) mbar_arrive_expect_tx(&w_full[st], 2 * kWChunkBytes);
                 const int32_t row =
                     (int32_t)(((size_t)((l - 1) * 2 + crank) * (kWImageBytes / 2) + (size_t)c * kWChunkBytes) / 256);
-                tma2_load_2d(smem + BwdSmem::kRing + st * kWChunkBytes, &p.wmap, 0, row,
+                tma2_load_2d(smem + BwdSmem::kRing + st * kWChunkBytes, &p.wmap, 0, wrow0 + row,
                              mapa_u32(smem_u32(&w_full[st]), 0));
               } else {
                 mbar_arrive_expect_tx(&w_full[st], kWChunkBytes);
@@ -248,6 +280,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
               if (++st == kBwdStages) { st = 0; ph ^= 1; }
             }
           }
+        }
         }
       }
     }
@@ -303,6 +336,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
                   mma(d_tmem + mh * kW6N, da, db, idesc_r, ks != 0);
                 }
               }
+            } else if (kPair && kBwdLayerResident) {
+              const bool first = (g == 0), last = (g == nsub - 1);
+              for (int c = 0; c < kChunks; ++c) {
+                if (first) {
+                  mbar_wait(&w_full[c], ph);
+                  tc_fence_after();
+                }
+                const uint32_t b_tile = ring_base + c * kWChunkBytes;
+#pragma unroll
+                for (int ks = 0; ks < kSteps; ++ks) {
+                  const uint64_t da = umma_smem_desc(a_tile + (c * kSteps + ks) * 4096, 2048, 128);
+                  const uint64_t db = umma_smem_desc(b_tile + ks * (kBRows * 32), kBRows * 16, 128);
+                  mma(d_tmem, da, db, idesc_h, (c | ks) != 0);
+                }
+                if (last) commit(&w_empty[c], 0x3);
+              }
+              if (last) ph ^= 1;
             } else {
               for (int c = 0; c < kChunks; ++c) {
                 mbar_wait(&w_full[st], ph);
@@ -423,7 +473,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
         tc_fence_after();
         const float* fl = nullptr;  // this map's freq_l (hidden layers only; layer 0 is modulated by the caller)
         if (kFilm && l > 0) fl = p.film + ((size_t)b * L + (l - 1)) * 2 * kH;
-        if (kBulk && kNeedDW) {  // this warp's previous pieces have been read out of the tile image
+        if (kNeedDW && p.ready != nullptr && l < L) {
+          // overlap mode: delta_{l+1} (and, behind the first signal, g_y) of this warp's block must be complete in global
+          // memory -- not just read out of the tile image -- before the tile's counter moves
+          if (kBulk && lane < 16) {
+            bulk_wait0();
+            fence_proxy_async_all();
+          }
+          __syncwarp();
+          if (lane == 0) ready_signal(p.ready + tile);
+        } else if (kBulk && kNeedDW) {  // this warp's previous pieces have been read out of the tile image
           if (lane < 16) bulk_wait_read0();
           __syncwarp();
         }

@@ -43,6 +43,13 @@ struct DwParams {
   float* film_cs;
   int tiles_per_map, njobs;
   int out_ctas;  // > 0: CTAs given to the output-layer job (non-FiLM grid), 0: plain round robin
+  // Overlap mode (ready != null): this grid runs BESIDE the delta-chain kernel on the SMs that kernel leaves free.  The
+  // chain bumps ready[tile] by one per epilogue warp (8 per tile) each time a delta_l of the tile is complete in global
+  // memory (l = L..1; g_y is behind the first bump), so hidden job l may pull the tile's blocks once
+  // ready[tile] >= 8 * (L - l + 1) and the output job once it is >= 8.  Blocks are then taken in DESCENDING order,
+  // interleaved over the job's slices -- the order the chain finishes them -- and arrive from L2 instead of HBM.
+  const uint32_t* ready;
+  uint32_t* stuck;  // set to 1 if a wait ran into its poll limit (the result is then wrong; the host checks in tests)
 };
 
 struct DwSmem {
@@ -90,9 +97,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
   }
   const int total = (film ? p.tiles_per_map : p.ntiles) * 2;  // 64-row stash blocks this grid row reduces over
   const int s_base = film ? (int)blockIdx.y * p.tiles_per_map * 2 : 0;
+  const bool overlap = p.ready != nullptr;
   const int s_begin = s_base + (int)((int64_t)slice * total / nslices);
   const int s_end = s_base + (int)((int64_t)(slice + 1) * total / nslices);
-  const int nst = s_end - s_begin;
+  const int nst = overlap ? (total > slice ? (total - slice + nslices - 1) / nslices : 0) : s_end - s_begin;
+  // i-th stash block of this CTA
+  auto blk = [&](int i) { return overlap ? total - 1 - (slice + i * nslices) : s_begin + i; };
   const bool is_out = (job == L);
   const int layer = job + 1;
 
@@ -135,7 +145,25 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
   if (warp == 0) {
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
-      for (int s = s_begin; s < s_end; ++s) {
+      const uint32_t need = is_out ? 8u : 8u * (uint32_t)(L - layer + 1);
+      int tile_ok = -1;
+      for (int i = 0; i < nst; ++i) {
+        const int s = blk(i);
+        if (overlap && (s >> 1) != tile_ok) {
+          const uint32_t* ctr = p.ready + (s >> 1);
+          uint32_t v, spins = 0;
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            if (v >= need) break;
+            if (++spins > (1u << 22)) {  // ~ seconds: never hang the device on a scheduling surprise
+              *p.stuck = 1u;
+              break;
+            }
+            __nanosleep(200);
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what was just acquired
+          tile_ok = s >> 1;
+        }
         mbar_wait(&empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&full[st], img_bytes + kHalfImageBytes);
         uint8_t* dst = smem + DwSmem::kRing + st * kDwStageBytes;
@@ -154,7 +182,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
       const uint32_t idesc = is_out ? umma_idesc_f16(128, kW6N, 1, 1) : umma_idesc_f16(128, 256, 1, 1);
       const uint32_t ring_base = smem_u32(smem + DwSmem::kRing);
       uint32_t st = 0, ph = 0;
-      for (int s = s_begin; s < s_end; ++s) {
+      for (int i = 0; i < nst; ++i) {
         mbar_wait(&conv[st], ph);
         tc_fence_after();
         const uint32_t sa = ring_base + st * kDwStageBytes;
@@ -166,7 +194,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
             // MN-major operands: 8-column groups are 64 rows x 16 B = 1024 B apart (SBO), 8-row groups 128 B (LBO)
             const uint64_t da = umma_smem_desc(sa + mh * 16 * 1024 + ks * 256, 128, 1024);
             const uint64_t db = umma_smem_desc(sb + ks * 256, 128, 1024);
-            umma_f16_ss(tmem_base + mh * 256, da, db, idesc, (s != s_begin) || (ks != 0));
+            umma_f16_ss(tmem_base + mh * 256, da, db, idesc, (i != 0) || (ks != 0));
           }
         }
         umma_commit(&empty[st]);
@@ -188,7 +216,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     {
       uint32_t st = 0, ph = 0;
-      for (int s = s_begin; s < s_end; ++s) {
+      for (int i = 0; i < nst; ++i) {
         mbar_wait(&full[st], ph);
         uint8_t* stage = smem + DwSmem::kRing + st * kDwStageBytes;
         // (1) phase block -> h = sin(angle) operand image, in place (same [k/8][64][8] geometry, 16 B per thread/group)

@@ -37,6 +37,12 @@ constexpr int kFwdThreads = 576;
 #define RENI_FWD_STAGES 4
 #endif
 constexpr int kFwdStages = RENI_FWD_STAGES;
+#ifndef RENI_LAYER_RESIDENT
+#define RENI_LAYER_RESIDENT 0  // paired kernels: each layer's weight half enters the SM once for both sub-tile passes
+                               // (measured: inference unchanged at 67 %, training step 795 -> 856 us -- the refill can only
+                               // start behind the last pass, so the ring no longer runs ahead of the tensor pipe)
+#endif
+constexpr bool kLayerResident = RENI_LAYER_RESIDENT != 0 && RENI_FWD_STAGES == 4;
 constexpr int kGroupThreads = 256;  // epilogue threads per sub-tile (grouped mode)
 constexpr int kEpiThreads = 512;    // all epilogue threads (all-hands mode)
 
@@ -58,6 +64,8 @@ struct FwdParams {
   const float* film;     // kFilm: (B, L, 2, 256) per-map FiLM modulation of the hidden layers: a_l = freq_l * acc + phase_l
   int B, P, tiles_per_map, ntiles, L;
   int out_tanh, last_sine, so2;
+  int w_map_rows, b_map_rows;  // per-map weight / bias images (FiLM on per-map images): rows of 256 B per map in wmap / bmap,
+                               // 0 = one image shared by all maps
   unsigned long long* trace;  // debug: per-role clock64 timeline of CTA 0 (reni_debug_set_trace), else null
   alignas(64) CUtensorMap wmap;  // paired mode: wf2 as rows of 256 B, box = one 16 KB half chunk (TMA tile loads)
   alignas(64) CUtensorMap bmap;  // paired mode: wbias2 as rows of 256 B, box = one 4 KB bias block
@@ -72,8 +80,9 @@ struct FwdSmem {
   static constexpr int kBias = kW6 + kW6ImageBytes;                   // (kMaxHiddenLayers*256 + 16) floats
   static constexpr int kMc = kBias + (kMaxHiddenLayers * kH + 16) * 4;  // 2 x 5 x 256 floats
   static constexpr int kOnes = kMc + 2 * 5 * kH * 4;                  // [2 k-groups][128][8] fp16: columns (1, 1, 0, ...)
-  static constexpr int kBars = kOnes + kBiasBlockBytes;               // mbarriers
-  static constexpr int kNumBars = 2 * kMaxStages + 6;
+  static constexpr int kBiasSlot = (kOnes + kBiasBlockBytes + 127) / 128 * 128;  // paired: the current layer's bias block (TMA dst)
+  static constexpr int kBars = kBiasSlot + kBiasBlockBytes;           // mbarriers
+  static constexpr int kNumBars = 2 * (kMaxStages + 1) + 6;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemPtr + 16;
 };
@@ -129,9 +138,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBars);
   constexpr int kStages = kFwdStages;
-  uint64_t* w_full = bars;                                 // [kStages]
-  uint64_t* w_empty = bars + FwdSmem::kMaxStages;          // [kStages]
-  uint64_t* a_ready = bars + 2 * FwdSmem::kMaxStages;      // [2]  epilogue -> MMA (one arrival per thread)
+  uint64_t* w_full = bars;                                 // [kStages + 1]
+  uint64_t* w_empty = bars + FwdSmem::kMaxStages + 1;      // [kStages + 1]
+  uint64_t* a_ready = bars + 2 * (FwdSmem::kMaxStages + 1);  // [2]  epilogue -> MMA (one arrival per thread)
   uint64_t* acc_full = a_ready + 2;             // [2]  MMA -> epilogue group (tcgen05.commit)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + FwdSmem::kTmemPtr);
   float* s_bias = reinterpret_cast<float*>(smem + FwdSmem::kBias);
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
 
   // ---------------------------------------------------------------- one-time setup
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kStages + 1; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
@@ -213,13 +222,34 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
       for (int it = 0; it < iters; ++it) {
         const int ubase = (worker + it * nworkers) * unit_tiles;
         const int nstream = clamp02(p.ntiles - ubase);  // passes the (leader's) MMA issuer makes over each layer
+        const int umap = ubase / p.tiles_per_map;       // (per-map images: the unit's four tiles lie in one map)
+        const int32_t wrow0 = umap * p.w_map_rows, brow0 = umap * p.b_map_rows;
+        if (kPair && kLayerResident) {
+          // Layer-resident weights: ring slot c holds chunk c of the current layer for BOTH sub-tile passes of the pair
+          // (the ring is exactly one layer's 128-column half), so the half enters the SM once per tile quad and layer
+          // instead of once per pass; slot kStages holds the layer's bias block.  A slot is released by the commit
+          // behind the LAST pass's MMAs on it, and refilled with the next layer's chunk while the epilogues run.
+          for (int l = 0; l < L; ++l) {
+            mbar_wait(&w_empty[kStages], ph ^ 1);
+            if (crank == 0) mbar_arrive_expect_tx(&w_full[kStages], 2 * kBiasBlockBytes);
+            tma2_load_2d(smem + FwdSmem::kBiasSlot, &p.bmap, 0,
+                         brow0 + (int32_t)((l * 2 + crank) * (kBiasBlockBytes / 256)), mapa_u32(smem_u32(&w_full[kStages]), 0));
+            for (int c = 0; c < kChunks; ++c) {
+              mbar_wait(&w_empty[c], ph ^ 1);
+              if (crank == 0) mbar_arrive_expect_tx(&w_full[c], 2 * kChunkBytes);
+              const int32_t row = (int32_t)(((size_t)(l * 2 + crank) * (kWImageBytes / 2) + (size_t)c * kChunkBytes) / 256);
+              tma2_load_2d(smem + FwdSmem::kRing + c * kChunkBytes, &p.wmap, 0, wrow0 + row, mapa_u32(smem_u32(&w_full[c]), 0));
+            }
+            ph ^= 1;
+          }
+        } else {
         for (int l = 0; l < L; ++l) {
           for (int g = 0; g < nstream; ++g) {
             if (kPair) {  // the layer's bias block rides the ring as a small extra chunk ahead of the weights
               mbar_wait(&w_empty[st], ph ^ 1);
               if (crank == 0) mbar_arrive_expect_tx(&w_full[st], 2 * kBiasBlockBytes);
               tma2_load_2d(smem + FwdSmem::kRing + st * kChunkBytes, &p.bmap, 0,
-                           (int32_t)((l * 2 + crank) * (kBiasBlockBytes / 256)), mapa_u32(smem_u32(&w_full[st]), 0));
+                           brow0 + (int32_t)((l * 2 + crank) * (kBiasBlockBytes / 256)), mapa_u32(smem_u32(&w_full[st]), 0));
               if (++st == kStages) { st = 0; ph ^= 1; }
             }
             for (int c = 0; c < kChunks; ++c) {
@@ -228,7 +258,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
                 // both halves complete on the LEADER's barrier (TMA tile load with .cta_group::2): no relay, one wait
                 if (crank == 0) mbar_arrive_expect_tx(&w_full[st], 2 * kChunkBytes);
                 const int32_t row = (int32_t)(((size_t)(l * 2 + crank) * (kWImageBytes / 2) + (size_t)c * kChunkBytes) / 256);
-                tma2_load_2d(smem + FwdSmem::kRing + st * kChunkBytes, &p.wmap, 0, row,
+                tma2_load_2d(smem + FwdSmem::kRing + st * kChunkBytes, &p.wmap, 0, wrow0 + row,
                              mapa_u32(smem_u32(&w_full[st]), 0));
               } else {
                 mbar_arrive_expect_tx(&w_full[st], kChunkBytes);
@@ -238,6 +268,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
               if (++st == kStages) { st = 0; ph ^= 1; }
             }
           }
+        }
         }
       }
     }
@@ -271,7 +302,34 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
             const uint32_t a_tile = a_base + g * kTileImageBytes;
             const uint32_t d_tmem = tmem_base + g * 256;
             const uint16_t live_mask = (g < nsub_peer) ? 0x3 : 0x1;
-            if (l <= L) {
+            if (kPair && kLayerResident && l <= L) {
+              // layer-resident weights: wait for each slot's fill in the first pass only, release it in the last
+              const bool first = (g == 0), last = (g == nsub - 1);
+              if (first) mbar_wait(&w_full[kStages], ph);
+              tc_fence_after();
+              {
+                const uint64_t da = umma_smem_desc(smem_u32(smem + FwdSmem::kOnes), 2048, 128);
+                const uint64_t db = umma_smem_desc(smem_u32(smem + FwdSmem::kBiasSlot), 2048, 128);
+                umma2_f16_ss(d_tmem, da, db, idesc_h, 0);
+                if (last) umma2_commit_multicast(&w_empty[kStages], 0x3);
+              }
+              for (int c = 0; c < kChunks; ++c) {
+                if (first) {
+                  mbar_wait(&w_full[c], ph);
+                  tc_fence_after();
+                }
+                const uint32_t b_tile = ring_base + c * kChunkBytes;
+                constexpr int kSteps = kChunkBytes / (kBRows * 32);  // K = 16 steps per chunk
+#pragma unroll
+                for (int ks = 0; ks < kSteps; ++ks) {
+                  const uint64_t da = umma_smem_desc(a_tile + (c * kSteps + ks) * 4096, 2048, 128);
+                  const uint64_t db = umma_smem_desc(b_tile + ks * (kBRows * 32), kBRows * 16, 128);
+                  umma2_f16_ss(d_tmem, da, db, idesc_h, 1);
+                }
+                if (last) umma2_commit_multicast(&w_empty[c], 0x3);
+              }
+              if (last) ph ^= 1;
+            } else if (l <= L) {
               if (kPair) {  // acc = [1 1 0 ..] x [b_hi b_lo 0 ..]^T = bias, then the weight chunks accumulate on top
                 mbar_wait(&w_full[st], ph);
                 tc_fence_after();

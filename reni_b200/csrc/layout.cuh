@@ -46,6 +46,8 @@ struct WorkspaceLayout {
   int64_t loss_part, map_loss, dmc, scalars;     // loss partials, per-map loss coefficients, per-map dM/dc
   int64_t xc, dxc, dip;                          // per-map constant encoding columns and their gradients
   int64_t film_S, film_cs;                       // FiLM backward: per-map delta_l^T h_{l-1} and column sums of delta_l
+  int64_t wf2m, wb2m, wbias2m;                   // FiLM per-map weight / bias images (RENI_FLAG_FILM_PERMAP)
+  int64_t ready;                                 // overlap mode: per-tile "delta_l is out" counters (+ 1 word: stuck flag)
   int64_t total;
 };
 

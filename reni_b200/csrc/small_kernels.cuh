@@ -84,6 +84,75 @@ __global__ void reni_prep_weights_kernel(const PrepParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// FiLM per-map operand images (RENI_FLAG_FILM_PERMAP).  FiLMLayer (RENI.py:515-524):
+//     sin(freq_l[b] * (W_l h + b_l) + phase_l[b]) = sin((diag(freq_l[b]) W_l) h + (freq_l[b] * b_l + phase_l[b]))
+// so with V[n][k] = freq_l[b][n] * W_l[n][k] (one fp16 rounding of the fp32 product) as map b's forward image, the same
+// values in the backward layout (delta_{l-1} = cos(a_{l-1}) * sum_j delta_l[j] freq_l[b][j] W_l[j][k]) and
+// freq * b + phase as its bias block, the FiLM layers run on the kernels of the Cond-by-Concat decoder.
+//   wf2m[b][l][n/128][k/8][n%128][k%8]   wb2m[b][l][k/128][n/8][k%128][n%8]   wbias2m[b][l][n/128] [2][128][8]
+// Grid (8, L, B) x 256 threads; every thread writes whole 16-byte groups, a warp 512 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+struct FilmPrepParams {
+  const float* w[kMaxHiddenLayers + 2];  // [1..L] are read
+  const float* b[kMaxHiddenLayers + 2];
+  const float* film;                     // (B, L, 2, 256)
+  __half* wf2m;
+  __half* wb2m;
+  __half* wbias2m;
+  int L;
+};
+
+__global__ void __launch_bounds__(256) reni_film_prep_maps_kernel(const FilmPrepParams p) {
+  const int l = blockIdx.y, b = blockIdx.z;
+  const float* W = p.w[l + 1];
+  const float* freq = p.film + ((size_t)b * p.L + l) * 2 * kH;
+  const float* phase = freq + kH;
+  __shared__ float s_freq[kH];
+  s_freq[threadIdx.x] = freq[threadIdx.x];
+  __syncthreads();
+  uint4* wf = reinterpret_cast<uint4*>(p.wf2m + ((size_t)b * p.L + l) * kH * kH);
+  uint4* wb = reinterpret_cast<uint4*>(p.wb2m + ((size_t)b * p.L + l) * kH * kH);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthreads = gridDim.x * blockDim.x;
+  for (int i = tid; i < kH * (kH / 8); i += nthreads) {
+    {  // forward image: thread = (n, 8 consecutive k)
+      const int n = i & (kH - 1), kg = i >> 8;
+      const float f = s_freq[n];
+      const float4 a = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * kH + kg * 8));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * kH + kg * 8 + 4));
+      uint4 v;
+      v.x = pack_half2(f * a.x, f * a.y);
+      v.y = pack_half2(f * a.z, f * a.w);
+      v.z = pack_half2(f * c.x, f * c.y);
+      v.w = pack_half2(f * c.z, f * c.w);
+      wf[((n >> 7) * (kH / 8) + kg) * 128 + (n & 127)] = v;
+    }
+    {  // backward image: thread = (8 consecutive n, k)
+      const int k = i & (kH - 1), ng = i >> 8;
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = s_freq[ng * 8 + j] * __ldg(W + (size_t)(ng * 8 + j) * kH + k);
+      uint4 v;
+      v.x = pack_half2(x[0], x[1]);
+      v.y = pack_half2(x[2], x[3]);
+      v.z = pack_half2(x[4], x[5]);
+      v.w = pack_half2(x[6], x[7]);
+      wb[((k >> 7) * (kH / 8) + ng) * 128 + (k & 127)] = v;
+    }
+  }
+  if (blockIdx.x == 0) {  // bias block: (hi, lo) fp16 split of freq * b + phase in k-group 0, zeros in k-group 1
+    const int i = threadIdx.x;
+    const float bv = s_freq[i] * __ldg(p.b[l + 1] + i) + __ldg(phase + i);
+    const __half hi = __float2half_rn(bv);
+    const __half lo = __float2half_rn(bv - __half2float(hi));
+    __half2 h2 = __halves2half2(hi, lo);
+    uint4* blk = reinterpret_cast<uint4*>(p.wbias2m + (((size_t)b * p.L + l) * 2 + (i >> 7)) * (2 * 128 * 8));
+    blk[i & 127] = make_uint4(*reinterpret_cast<uint32_t*>(&h2), 0u, 0u, 0u);
+    blk[128 + (i & 127)] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Prologue: per-map hoisting of layer 0.  With the invariant encodings (RENI.py:23-60) every column of
 // the first-layer input is either constant per map or linear in <= 4 direction features f, so
 //     omega0 * (x W0^T + b0) = f . M_b' + c_b'        (M_b' 4x256, c_b' 256, omega0 folded)
@@ -651,34 +720,47 @@ __global__ void __launch_bounds__(256) reni_film_dfilm_kernel(const FilmReducePa
   }
 }
 
-// grid (256, L), 256 threads: block = (output feature j, layer), thread = input feature k; sums over the maps
+// grid (256 / 4, L), 256 threads: block = (4 output features j, layer), thread = (j, 4 input features k); sums over the
+// maps with eight 16-byte loads in flight per thread (32 MB of S at 32 maps: the loop is latency-bound otherwise)
 __global__ void __launch_bounds__(256) reni_film_dw_kernel(const FilmReduceParams p) {
-  const int j = blockIdx.x, l = blockIdx.y, k = threadIdx.x;
+  const int j = blockIdx.x * 4 + (threadIdx.x >> 6), l = blockIdx.y, k4 = threadIdx.x & 63;
   if (p.dW[l + 1] == nullptr) return;
-  float acc = 0.f, accb = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float accb = 0.f;
   const size_t sstride = (size_t)p.L * kH * kH, fstride = (size_t)p.L * 2 * kH, cstride = (size_t)p.L * kH;
-  const float* sp = p.S + ((size_t)l * kH + j) * kH + k;
+  const float* sp = p.S + ((size_t)l * kH + j) * kH + k4 * 4;
   const float* fp = p.film + (size_t)l * 2 * kH + j;
   const float* cp = p.cs + (size_t)l * kH + j;
   int b = 0;
-  for (; b + 4 <= p.B; b += 4) {  // four maps in flight per thread: the loop is latency-bound otherwise
-    const float f0 = __ldg(fp + (b + 0) * fstride), f1 = __ldg(fp + (b + 1) * fstride);
-    const float f2 = __ldg(fp + (b + 2) * fstride), f3 = __ldg(fp + (b + 3) * fstride);
-    const float s0 = __ldg(sp + (b + 0) * sstride), s1 = __ldg(sp + (b + 1) * sstride);
-    const float s2 = __ldg(sp + (b + 2) * sstride), s3 = __ldg(sp + (b + 3) * sstride);
-    acc = fmaf(f0, s0, acc); acc = fmaf(f1, s1, acc); acc = fmaf(f2, s2, acc); acc = fmaf(f3, s3, acc);
-    if (k == 0) {
-      accb = fmaf(f0, __ldg(cp + (b + 0) * cstride), accb); accb = fmaf(f1, __ldg(cp + (b + 1) * cstride), accb);
-      accb = fmaf(f2, __ldg(cp + (b + 2) * cstride), accb); accb = fmaf(f3, __ldg(cp + (b + 3) * cstride), accb);
+  for (; b + 8 <= p.B; b += 8) {
+    float f[8];
+    float4 sv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      f[u] = __ldg(fp + (b + u) * fstride);
+      sv[u] = __ldcs(reinterpret_cast<const float4*>(sp + (b + u) * sstride));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x = fmaf(f[u], sv[u].x, acc.x); acc.y = fmaf(f[u], sv[u].y, acc.y);
+      acc.z = fmaf(f[u], sv[u].z, acc.z); acc.w = fmaf(f[u], sv[u].w, acc.w);
+    }
+    if (k4 == 0) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) accb = fmaf(f[u], __ldg(cp + (b + u) * cstride), accb);
     }
   }
   for (; b < p.B; ++b) {
     const float f = __ldg(fp + b * fstride);
-    acc = fmaf(f, __ldg(sp + b * sstride), acc);
-    if (k == 0) accb = fmaf(f, __ldg(cp + b * cstride), accb);
+    const float4 sv = __ldcs(reinterpret_cast<const float4*>(sp + b * sstride));
+    acc.x = fmaf(f, sv.x, acc.x); acc.y = fmaf(f, sv.y, acc.y); acc.z = fmaf(f, sv.z, acc.z); acc.w = fmaf(f, sv.w, acc.w);
+    if (k4 == 0) accb = fmaf(f, __ldg(cp + b * cstride), accb);
   }
-  p.dW[l + 1][(size_t)j * kH + k] += acc;
-  if (k == 0 && p.db[l + 1] != nullptr) p.db[l + 1][j] += accb;
+  float4* dst = reinterpret_cast<float4*>(p.dW[l + 1] + (size_t)j * kH + k4 * 4);
+  float4 d = *dst;
+  d.x += acc.x; d.y += acc.y; d.z += acc.z; d.w += acc.w;
+  *dst = d;
+  if (k4 == 0 && p.db[l + 1] != nullptr) p.db[l + 1][j] += accb;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@ arithmetic happens in libreni_b200.so.  There is no CPU path: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -336,6 +337,23 @@ class FilmSpec:
                           1 if self.output_activation == "tanh" else 0, 1.0, 1.0)
 
 
+def _film_permap_flag(P: int) -> int:
+    """FLAG_FILM_PERMAP when the FiLM core can run on per-map weight images (include/reni_b200.h,
+    reni_film_prepare_maps): every unit of four 128-direction tiles must lie inside one map.  RENI_FILM_PERMAP=0 keeps
+    the in-epilogue modulation (A/B switch)."""
+    if os.environ.get("RENI_FILM_PERMAP", "1") == "0":
+        return 0
+    return _lib.FLAG_FILM_PERMAP if P % 512 == 0 else 0
+
+
+def _film_prepare_maps(lib, cfg, filmc, weights, biases, B: int, P: int, ws: "Workspace", flags: int, dev) -> None:
+    if flags & _lib.FLAG_FILM_PERMAP:
+        rc = lib.reni_film_prepare_maps(C.byref(cfg), _vp(filmc), _ptr_array([weights[0]] + weights),
+                                        _ptr_array([biases[0]] + biases), B, P, _vp(ws.view), ws.nbytes, flags,
+                                        _stream(dev))
+        _lib.check(rc, "reni_film_prepare_maps")
+
+
 class _FilmCoreFunction(torch.autograd.Function):
     """out = core(mc, film, D; W_1..W_L, b_1..b_L, W_out, b_out) with gradients for mc, film and the parameters."""
 
@@ -356,13 +374,14 @@ class _FilmCoreFunction(torch.autograd.Function):
         P = Dc.shape[1]
         need_in = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         need_dw = any(ctx.needs_input_grad[5:])
-        flags = _lib.FLAG_FILM
+        flags = _lib.FLAG_FILM | _film_permap_flag(P)
         if need_in or need_dw:
             flags |= FLAG_SAVE_FOR_BACKWARD | (FLAG_NEED_DW if need_dw else 0)
         ws = Workspace() if (flags & FLAG_SAVE_FOR_BACKWARD) else inference_ws
         ws.ensure(workspace_bytes(cfg, B, P, flags), dev)
         # weight images: slot 0 of the parameter arrays (the first layer) is not used by the core
         prepare_weights(cfg, [weights[0]] + weights, [biases[0]] + biases, ws, dev)
+        _film_prepare_maps(lib, cfg, filmc, weights, biases, B, P, ws, flags, dev)
         out = torch.empty(B, P, 3, device=dev, dtype=torch.float32)
         rc = lib.reni_film_forward(C.byref(cfg), _vp(mcc), _vp(filmc), _vp(Dc), d_bs, B, P, _vp(out), _vp(ws.view),
                                    ws.nbytes, flags, _stream(dev))
@@ -462,9 +481,10 @@ def film_loss_forward_backward(spec: FilmSpec, ws: Workspace, mc: torch.Tensor, 
     tc = _f32c(target)
     if tuple(tc.shape) != (B, P, 3):
         raise ValueError(f"target must have shape {(B, P, 3)}, got {tuple(tc.shape)}")
-    flags = _lib.FLAG_FILM | FLAG_SAVE_FOR_BACKWARD | FLAG_LOSS | (FLAG_NEED_DW if need_dw else 0)
+    flags = _lib.FLAG_FILM | FLAG_SAVE_FOR_BACKWARD | FLAG_LOSS | (FLAG_NEED_DW if need_dw else 0) | _film_permap_flag(P)
     ws.ensure(workspace_bytes(cfg, B, P, flags), dev)
     prepare_weights(cfg, [weights[0]] + weights, [biases[0]] + biases, ws, dev)
+    _film_prepare_maps(lib, cfg, filmc, weights, biases, B, P, ws, flags, dev)
     out = torch.empty(B, P, 3, device=dev, dtype=torch.float32)
     loss = torch.empty(4, device=dev, dtype=torch.float32)
     d_mc = torch.empty(B, 5, HIDDEN_FEATURES, device=dev, dtype=torch.float32)

@@ -384,3 +384,46 @@ def test_graphed_decoder_replays_and_follows_weight_updates(dev):
                 for p in m.parameters():
                     if p.dim() == 2:
                         p.mul_(1.01)
+
+
+def test_film_per_map_images_match_in_epilogue_modulation(dev, monkeypatch):
+    """The two FiLM cores -- modulation folded into per-map fp16 weight / bias images (reni_film_prepare_maps, the
+    default when P % 512 == 0) and modulation applied in the kernel epilogues (RENI_FILM_PERMAP=0, the only path for
+    other P) -- on the same inputs: radiance and every gradient agree to well inside the parity tolerances, and a P
+    that is not a multiple of 512 is refused by the per-map entry point."""
+    import ctypes as C
+
+    from reni_b200 import RENIAutoDecoderFiLM, RENITrainLoss, _lib
+
+    torch.manual_seed(21)
+    B, N, P = 5, 9, 1024
+    m = RENIAutoDecoderFiLM(B, N, "SO2", 256, 5, 256, 3, 3, "tanh", False).to(dev)
+    with torch.no_grad():
+        m.mapping_network.network[-1].weight.mul_(2.0)
+    D = torch.nn.functional.normalize(torch.randn(B, P, 3, device=dev), dim=-1)
+    tg = torch.rand(B, P, 3, device=dev) * 2 - 1
+    sw = torch.rand(B, P, 1, device=dev).expand(B, P, 3).contiguous()
+
+    def run():
+        for p in m.parameters():
+            p.grad = None
+        Z = m.Z.detach().clone().requires_grad_(True)
+        out = m(Z, D)
+        RENITrainLoss()(out, tg, sw).backward()
+        return out.detach(), Z.grad.clone(), [p.grad.clone() for n, p in m.named_parameters() if n != "Z"]
+
+    o_map, dz_map, g_map = run()
+    monkeypatch.setenv("RENI_FILM_PERMAP", "0")
+    o_epi, dz_epi, g_epi = run()
+    monkeypatch.delenv("RENI_FILM_PERMAP")
+    assert float((o_map - o_epi).norm() / o_epi.norm()) < TOL_RADIANCE
+    assert float((dz_map - dz_epi).norm() / dz_epi.norm()) < 0.3 * TOL_GRAD
+    for a, b in zip(g_map, g_epi):
+        assert float((a - b).norm() / b.norm()) < 0.3 * TOL_GRAD
+    lib = _lib.load()
+    cfg = _lib.RENIConfig(N, 1, 256, 4, 3, 1, 1, 1.0, 1.0)
+    dummy = torch.zeros(1 << 20, device=dev)
+    ptrs = (C.c_void_p * 6)(*[dummy.data_ptr()] * 6)
+    rc = lib.reni_film_prepare_maps(C.byref(cfg), dummy.data_ptr(), ptrs, ptrs, 2, 640, dummy.data_ptr(), 1 << 22,
+                                    _lib.FLAG_FILM, None)
+    assert rc != 0

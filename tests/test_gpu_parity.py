@@ -453,3 +453,37 @@ def test_trainer_cuda_graph_and_prefetch_match_eager(dev):
         assert float((g_z - m.Z.grad).abs().max()) <= 1e-5 * float(m.Z.grad.abs().max()) + 1e-12
         for a, p in zip(g_w, m.net.parameters()):
             assert float((a - p.grad).abs().max()) <= 2e-4 * float(p.grad.abs().max()) + 1e-12
+
+
+@pytest.mark.gpu
+def test_overlap_mode_matches_back_to_back_kernels(dev):
+    """reni_debug_set_overlap: the weight-gradient kernel co-resident with the delta chain (per-tile ready counters,
+    stash blocks taken in the chain's completion order) must give the gradients of the back-to-back kernels up to the
+    order of the fp32 reductions; also under CUDA-graph replay (fork/join captured)."""
+    torch.manual_seed(11)
+    from reni_b200 import RENIAutoDecoder, get_directions, get_sineweight, _lib
+    from reni_b200 import functional as F_
+
+    B, N, W = 32, 9, 128  # 2048 tiles: enough quads per cluster for the mode to engage
+    P = W * W // 2
+    m = RENIAutoDecoder(B, N, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+    D, sw = get_directions(W).to(dev), get_sineweight(W).to(dev)
+    tg = torch.rand(B, P, 3, device=dev) * 2 - 1
+    Z = m.Z.detach()
+    ws = F_.Workspace()
+    lib = _lib.load()
+
+    def run():
+        r = F_.loss_forward_backward(m.spec, ws, Z, D, tg, sw, m.decoder_weights(), m.decoder_biases())
+        return [t.clone() for t in r.dW + r.db] + [r.dZ.clone()]
+
+    ref = run()
+    try:
+        for dw_ctas in (-1, 60):
+            assert lib.reni_debug_set_overlap(dw_ctas, 0) == 0
+            got = run()
+            for a, b in zip(got, ref):
+                assert float((a - b).norm() / b.norm()) < 2e-4
+        assert lib.reni_debug_set_overlap(0, -1) != 0  # bad argument
+    finally:
+        lib.reni_debug_set_overlap(0, 0)
