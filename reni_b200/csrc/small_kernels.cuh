@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) reni_film_prep_maps_kernel(const FilmPrep
   uint4* wb = reinterpret_cast<uint4*>(p.wb2m + ((size_t)b * p.L + l) * kH * kH);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
+#pragma unroll 4  // (2048 threads per (map, layer): four independent iterations, their loads issued together)
   for (int i = tid; i < kH * (kH / 8); i += nthreads) {
     {  // forward image: thread = (n, 8 consecutive k)
       const int n = i & (kH - 1), kg = i >> 8;
