@@ -174,6 +174,25 @@ int32_t reni_film_map_forward(const reni_config_t* cfg, const float* Z, const fl
                               const int32_t* host_map_dims, int32_t n_linears, int64_t B, float* mc, float* film,
                               void* scratch, int64_t scratch_bytes, void* stream);
 
+/* FiLM per-map stage for TRAINING / latent fitting: the same forward keeping every activation of the mapping network
+ * (`acts`, reni_film_map_acts_bytes bytes, caller-owned, must stay untouched until the backward), and its hand-derived
+ * backward from the core's d_mc / d_film (replaces ~120 autograd launches of (B, .) torch ops by 6 + 3 + 2 n_linears):
+ *   dZ (B, N, 3)                 : written
+ *   dW0, db0, host_map_dW/db[i]  : ACCUMULATED (+=) gradients of net[0].layer and mapping_network.network[2 i];
+ *                                  all NULL for a frozen decoder (latent fitting: only dZ is produced)
+ *   scratch                      : reni_film_map_acts_bytes(...) + B * 4 * 256 * 4 bytes
+ * Reference: RENI.py:405-452 (mapping input), :481-512 (mapping network), :515-524 + :666-678 (first FiLM layer). */
+int64_t reni_film_map_acts_bytes(const int32_t* host_map_dims, int32_t n_linears, int64_t B);
+int32_t reni_film_map_forward_train(const reni_config_t* cfg, const float* Z, const float* weight0, const float* bias0,
+                                    const float* const* host_map_weights, const float* const* host_map_biases,
+                                    const int32_t* host_map_dims, int32_t n_linears, int64_t B, float* mc, float* film,
+                                    void* acts, int64_t acts_bytes, void* stream);
+int32_t reni_film_map_backward(const reni_config_t* cfg, const float* Z, const float* weight0, const float* bias0,
+                               const float* const* host_map_weights, const int32_t* host_map_dims, int32_t n_linears,
+                               int64_t B, const void* acts, const float* d_mc, const float* d_film, float* dZ,
+                               float* dW0, float* db0, float* const* host_map_dW, float* const* host_map_db,
+                               void* scratch, int64_t scratch_bytes, void* stream);
+
 /* One fused FiLM training / latent-fit step around the core: reni_film_forward with the loss sums, the loss reduction
  * and reni_film_backward with the loss gradient formed in the kernel (replaces the criterion + loss.backward() of
  * training_step, src/lightning/RENI_module.py:105-134, for a FiLM decoder).

@@ -73,6 +73,11 @@ SIGNATURES = {
     "reni_film_map_scratch_bytes": (_i64, [C.POINTER(C.c_int32), _i32, _i64]),
     "reni_film_map_forward": (_i32, [_cfgp, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int32), _i32, _i64,
                                      _vp, _vp, _vp, _i64, _vp]),
+    "reni_film_map_acts_bytes": (_i64, [C.POINTER(C.c_int32), _i32, _i64]),
+    "reni_film_map_forward_train": (_i32, [_cfgp, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int32),
+                                           _i32, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "reni_film_map_backward": (_i32, [_cfgp, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(C.c_int32), _i32, _i64, _vp, _vp,
+                                      _vp, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _vp]),
     "reni_film_loss_forward_backward": (_i32, [_cfgp, _vp, _vp, _vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _i64, _i64, _vp,
                                                _vp, _i64, C.c_float, _i32, _vp, _vp, _vp, _vp, C.POINTER(_vp),
                                                C.POINTER(_vp), _vp, _i64, _i32, _vp]),

@@ -871,26 +871,15 @@ int64_t reni_film_map_scratch_bytes(const int32_t* host_map_dims, int32_t n_line
   return 2 * B * widest * (int64_t)sizeof(float);  // two ping-pong activation buffers
 }
 
-int32_t reni_film_map_forward(const reni_config_t* c, const float* Z, const float* weight0, const float* bias0,
-                              const float* const* host_map_weights, const float* const* host_map_biases,
-                              const int32_t* host_map_dims, int32_t n_linears, int64_t B, float* mc, float* film,
-                              void* scratch, int64_t scratch_bytes, void* stream_) {
-  if (!config_ok(c) || c->equivariance == RENI_EQ_NONE) return RENI_ERR_BAD_CONFIG;
-  if (Z == nullptr || weight0 == nullptr || bias0 == nullptr || host_map_weights == nullptr ||
-      host_map_biases == nullptr || host_map_dims == nullptr || mc == nullptr || film == nullptr || scratch == nullptr ||
-      B < 1 || B > 65535 || n_linears < 1 || n_linears > kFilmMapMaxLinears)
-    return RENI_ERR_BAD_ARGUMENT;
+// Shared body of the two per-map forwards: act[i] = input of linear i (act[0] = mapping input), act[n] = raw output
+static int32_t film_map_forward_impl(const reni_config_t* c, const float* Z, const float* weight0, const float* bias0,
+                                     const float* const* host_map_weights, const float* const* host_map_biases,
+                                     const int32_t* host_map_dims, int32_t n_linears, int64_t B, float* mc, float* film,
+                                     float* const* act, cudaStream_t stream) {
   const int N = c->ndims, Lf = c->hidden_layers + 1;
   const int mn_in = c->equivariance == RENI_EQ_SO2 ? N * N + N : N * N;
-  if (host_map_dims[0] != mn_in || host_map_dims[n_linears] != 2 * Lf * kH) return RENI_ERR_BAD_ARGUMENT;
-  const int64_t need = reni_film_map_scratch_bytes(host_map_dims, n_linears, B);
-  if (need < 0) return (int32_t)need;
-  if (scratch_bytes < need) return RENI_ERR_WORKSPACE;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  float* buf[2] = {static_cast<float*>(scratch), static_cast<float*>(scratch) + need / (2 * sizeof(float))};
   const int so2 = c->equivariance == RENI_EQ_SO2;
-  reni_film_map_input_kernel<<<(unsigned)B, 256, 3 * N * sizeof(float), stream>>>(Z, buf[0], N, so2, mn_in);
-  int cur = 0;
+  reni_film_map_input_kernel<<<(unsigned)B, 256, 3 * N * sizeof(float), stream>>>(Z, act[0], N, so2, mn_in);
   for (int i = 0; i < n_linears; ++i) {
     if (host_map_weights[i] == nullptr || host_map_biases[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
     const int in = host_map_dims[i], out = host_map_dims[i + 1];
@@ -901,20 +890,143 @@ int32_t reni_film_map_forward(const reni_config_t* c, const float* Z, const floa
             cudaSuccess)
       return RENI_ERR_CUDA;
     reni_film_map_linear_kernel<<<dim3((unsigned)((out + 31) / 32), (unsigned)B), 256, smem, stream>>>(
-        buf[cur], host_map_weights[i], host_map_biases[i], buf[cur ^ 1], in, out, i + 1 < n_linears ? 1 : 0);
-    cur ^= 1;
+        act[i], host_map_weights[i], host_map_biases[i], act[i + 1], in, out, i + 1 < n_linears ? 1 : 0);
   }
   FilmMapFinishParams f{};
   f.Z = Z;
   f.W0 = weight0;
   f.b0 = bias0;
-  f.raw = buf[cur];
+  f.raw = act[n_linears];
   f.mc = mc;
   f.film = film;
   f.N = N;
   f.so2 = so2;
   f.Lf = Lf;
   reni_film_map_finish_kernel<<<(unsigned)B, 256, 3 * N * sizeof(float), stream>>>(f);
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+static bool film_map_args_ok(const reni_config_t* c, const int32_t* host_map_dims, int32_t n_linears, int64_t B) {
+  if (host_map_dims == nullptr || B < 1 || B > 65535 || n_linears < 1 || n_linears > kFilmMapMaxLinears) return false;
+  const int N = c->ndims, Lf = c->hidden_layers + 1;
+  const int mn_in = c->equivariance == RENI_EQ_SO2 ? N * N + N : N * N;
+  return host_map_dims[0] == mn_in && host_map_dims[n_linears] == 2 * Lf * kH;
+}
+
+int32_t reni_film_map_forward(const reni_config_t* c, const float* Z, const float* weight0, const float* bias0,
+                              const float* const* host_map_weights, const float* const* host_map_biases,
+                              const int32_t* host_map_dims, int32_t n_linears, int64_t B, float* mc, float* film,
+                              void* scratch, int64_t scratch_bytes, void* stream_) {
+  if (!config_ok(c) || c->equivariance == RENI_EQ_NONE) return RENI_ERR_BAD_CONFIG;
+  if (Z == nullptr || weight0 == nullptr || bias0 == nullptr || host_map_weights == nullptr ||
+      host_map_biases == nullptr || mc == nullptr || film == nullptr || scratch == nullptr ||
+      !film_map_args_ok(c, host_map_dims, n_linears, B))
+    return RENI_ERR_BAD_ARGUMENT;
+  const int64_t need = reni_film_map_scratch_bytes(host_map_dims, n_linears, B);
+  if (need < 0) return (int32_t)need;
+  if (scratch_bytes < need) return RENI_ERR_WORKSPACE;
+  float* act[kFilmMapMaxLinears + 1];  // two ping-pong buffers
+  for (int i = 0; i <= n_linears; ++i)
+    act[i] = static_cast<float*>(scratch) + (i & 1) * (need / (2 * sizeof(float)));
+  return film_map_forward_impl(c, Z, weight0, bias0, host_map_weights, host_map_biases, host_map_dims, n_linears, B, mc,
+                               film, act, static_cast<cudaStream_t>(stream_));
+}
+
+int64_t reni_film_map_acts_bytes(const int32_t* host_map_dims, int32_t n_linears, int64_t B) {
+  if (host_map_dims == nullptr || n_linears < 1 || n_linears > kFilmMapMaxLinears || B < 1) return RENI_ERR_BAD_ARGUMENT;
+  int64_t total = 0;
+  for (int i = 0; i <= n_linears; ++i) {
+    if (host_map_dims[i] < 1) return RENI_ERR_BAD_ARGUMENT;
+    total += align_up(B * host_map_dims[i] * (int64_t)sizeof(float), 256);
+  }
+  return total;
+}
+
+static void film_map_act_ptrs(float* base, const int32_t* dims, int32_t n_linears, int64_t B, float** act) {
+  int64_t off = 0;
+  for (int i = 0; i <= n_linears; ++i) {
+    act[i] = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(base) + off);
+    off += align_up(B * dims[i] * (int64_t)sizeof(float), 256);
+  }
+}
+
+int32_t reni_film_map_forward_train(const reni_config_t* c, const float* Z, const float* weight0, const float* bias0,
+                                    const float* const* host_map_weights, const float* const* host_map_biases,
+                                    const int32_t* host_map_dims, int32_t n_linears, int64_t B, float* mc, float* film,
+                                    void* acts, int64_t acts_bytes, void* stream_) {
+  if (!config_ok(c) || c->equivariance == RENI_EQ_NONE) return RENI_ERR_BAD_CONFIG;
+  if (Z == nullptr || weight0 == nullptr || bias0 == nullptr || host_map_weights == nullptr ||
+      host_map_biases == nullptr || mc == nullptr || film == nullptr || acts == nullptr ||
+      !film_map_args_ok(c, host_map_dims, n_linears, B))
+    return RENI_ERR_BAD_ARGUMENT;
+  const int64_t need = reni_film_map_acts_bytes(host_map_dims, n_linears, B);
+  if (need < 0) return (int32_t)need;
+  if (acts_bytes < need) return RENI_ERR_WORKSPACE;
+  float* act[kFilmMapMaxLinears + 1];
+  film_map_act_ptrs(static_cast<float*>(acts), host_map_dims, n_linears, B, act);
+  return film_map_forward_impl(c, Z, weight0, bias0, host_map_weights, host_map_biases, host_map_dims, n_linears, B, mc,
+                               film, act, static_cast<cudaStream_t>(stream_));
+}
+
+int32_t reni_film_map_backward(const reni_config_t* c, const float* Z, const float* weight0, const float* bias0,
+                               const float* const* host_map_weights, const int32_t* host_map_dims, int32_t n_linears,
+                               int64_t B, const void* acts, const float* d_mc, const float* d_film, float* dZ,
+                               float* dW0, float* db0, float* const* host_map_dW, float* const* host_map_db,
+                               void* scratch, int64_t scratch_bytes, void* stream_) {
+  if (!config_ok(c) || c->equivariance == RENI_EQ_NONE) return RENI_ERR_BAD_CONFIG;
+  if (Z == nullptr || weight0 == nullptr || bias0 == nullptr || host_map_weights == nullptr || acts == nullptr ||
+      d_mc == nullptr || d_film == nullptr || dZ == nullptr || scratch == nullptr ||
+      !film_map_args_ok(c, host_map_dims, n_linears, B))
+    return RENI_ERR_BAD_ARGUMENT;
+  const bool want_dw = dW0 != nullptr;  // (a frozen decoder only wants dZ)
+  if (want_dw && (db0 == nullptr || host_map_dW == nullptr || host_map_db == nullptr)) return RENI_ERR_BAD_ARGUMENT;
+  const int64_t acts_bytes = reni_film_map_acts_bytes(host_map_dims, n_linears, B);
+  if (acts_bytes < 0) return (int32_t)acts_bytes;
+  const int64_t dm_bytes = B * 4 * kH * (int64_t)sizeof(float);
+  if (scratch_bytes < acts_bytes + dm_bytes) return RENI_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int N = c->ndims, Lf = c->hidden_layers + 1;
+  const int so2 = c->equivariance == RENI_EQ_SO2;
+  float* act[kFilmMapMaxLinears + 1];
+  float* dact[kFilmMapMaxLinears + 1];  // gradient w.r.t. act[i]
+  film_map_act_ptrs(const_cast<float*>(static_cast<const float*>(acts)), host_map_dims, n_linears, B, act);
+  film_map_act_ptrs(static_cast<float*>(scratch), host_map_dims, n_linears, B, dact);
+  float* dM = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + acts_bytes);
+  // the dX kernels add their output-row slices with atomics
+  if (cudaMemsetAsync(scratch, 0, (size_t)(acts_bytes - align_up(B * host_map_dims[n_linears] * 4, 256)), stream) !=
+      cudaSuccess)
+    return RENI_ERR_CUDA;
+  {
+    FilmMapBwdHeadParams h{};
+    h.Z = Z; h.W0 = weight0; h.b0 = bias0; h.raw = act[n_linears]; h.d_mc = d_mc; h.d_film = d_film;
+    h.d_raw = dact[n_linears]; h.dM = dM; h.N = N; h.so2 = so2; h.Lf = Lf;
+    reni_film_map_bwd_head_kernel<<<(unsigned)B, 256, 3 * N * sizeof(float), stream>>>(h);
+  }
+  if (want_dw) {
+    FilmMapBwdW0Params q{};
+    q.Z = Z; q.raw = act[n_linears]; q.d_mc = d_mc; q.dM = dM; q.dW0 = dW0; q.db0 = db0;
+    q.B = (int)B; q.N = N; q.so2 = so2; q.Lf = Lf;
+    reni_film_map_bwd_w0_kernel<<<kH / 8, 256, 0, stream>>>(q);
+  }
+  for (int i = n_linears - 1; i >= 0; --i) {
+    if (host_map_weights[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+    const int in = host_map_dims[i], out = host_map_dims[i + 1];
+    const int leaky = i + 1 < n_linears ? 1 : 0;
+    if (want_dw) {
+      if (host_map_dW[i] == nullptr || host_map_db[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+      reni_film_map_bwd_dw_kernel<<<dim3((unsigned)((in + 255) / 256), (unsigned)((out + kMapBwdRows - 1) / kMapBwdRows)),
+                                    256, 0, stream>>>(dact[i + 1], act[i + 1], act[i], host_map_dW[i], host_map_db[i],
+                                                      (int)B, in, out, leaky);
+    }
+    reni_film_map_bwd_dx_kernel<<<dim3((unsigned)((in + 127) / 128), (unsigned)((out + 31) / 32), (unsigned)((B + 31) / 32)),
+                                  128, 0, stream>>>(dact[i + 1], act[i + 1], host_map_weights[i], dact[i], (int)B, in, out,
+                                                    leaky);
+  }
+  {
+    FilmMapBwdDzParams z{};
+    z.Z = Z; z.W0 = weight0; z.dM = dM; z.dx0 = dact[0]; z.dZ = dZ; z.N = N; z.so2 = so2;
+    reni_film_map_bwd_dz_kernel<<<dim3((unsigned)B, (unsigned)((3 * N + 7) / 8)), 256, 3 * N * sizeof(float), stream>>>(z);
+  }
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 

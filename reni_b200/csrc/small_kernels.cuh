@@ -931,4 +931,261 @@ __global__ void __launch_bounds__(256) reni_film_map_finish_kernel(const FilmMap
   o[4 * kH] = fmaf(f0, p.b0[j], ph0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// FiLM per-map stage, BACKWARD (training / latent fitting): gradients of everything reni_film_map_forward computes,
+// from d_mc (B, 5, 256) and d_film (B, L, 2, 256) as the core returns them, hand-derived (checked against autograd of
+// reni_b200.film.map_level in fp64) and run as 3 + 2 n_linears small launches instead of ~80 autograd kernels:
+//   head   : d_raw = [15 d_freq | d_phase] (freq_0 collects the hoisted first layer: sum_r d_mc[r] M[r] + d_mc[4] b_0),
+//            dM[r] = d_mc[r] freq_0
+//   w0     : dW_0, db_0 += sums over the maps of dM (x) Z and d_mc[4] freq_0
+//   per linear i = n-1..0 (y_i = act(W_i x_i + b_i), LeakyReLU(0.2) except the last, RENI.py:481-512):
+//            dpre = dY * act'(y);  dW_i += dpre^T x_i;  db_i += sum_b dpre;  dX = dpre W_i
+//   dz     : dZ = hoisted-layer part (dM W_ip) + mapping-input part ((dG + dG^T) Z_xz, d Z_y)
+// Parameter gradients are ACCUMULATED into caller buffers (views of the flat all-reduce buffer), dZ is written.
+// ------------------------------------------------------------------------------------------------
+struct FilmMapBwdHeadParams {
+  const float* Z;
+  const float* W0;
+  const float* b0;
+  const float* raw;     // (B, 2 Lf 256) mapping-network output saved by the forward
+  const float* d_mc;    // (B, 5, 256)
+  const float* d_film;  // (B, Lf - 1, 2, 256)
+  float* d_raw;         // (B, 2 Lf 256), written
+  float* dM;            // (B, 4, 256), written
+  int N, so2, Lf;
+};
+
+// grid (B), thread = feature j
+__global__ void __launch_bounds__(256) reni_film_map_bwd_head_kernel(const FilmMapBwdHeadParams p) {
+  extern __shared__ float s_fz[];
+  const int b = blockIdx.x, N = p.N, j = threadIdx.x;
+  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_fz[i] = p.Z[(size_t)b * 3 * N + i];
+  __syncthreads();
+  const int half = p.Lf * kH;
+  const float* raw = p.raw + (size_t)b * 2 * half;
+  float* d_raw = p.d_raw + (size_t)b * 2 * half;
+  for (int l = 1; l < p.Lf; ++l) {
+    const float* g = p.d_film + ((size_t)b * (p.Lf - 1) + (l - 1)) * 2 * kH;
+    d_raw[l * kH + j] = 15.f * g[j];
+    d_raw[half + l * kH + j] = g[kH + j];
+  }
+  const float f0 = fmaf(raw[j], 15.f, 30.f);
+  const int in0 = p.so2 ? N + 2 : N;
+  const float* w = p.W0 + (size_t)j * in0;
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+  if (p.so2) {
+    for (int n = 0; n < N; ++n) {
+      const float wv = __ldg(w + 2 + n);
+      m0 = fmaf(wv, s_fz[n * 3], m0);
+      m1 = fmaf(wv, s_fz[n * 3 + 2], m1);
+    }
+    m2 = __ldg(w);
+    m3 = __ldg(w + 1);
+  } else {
+    for (int n = 0; n < N; ++n) {
+      const float wv = __ldg(w + n);
+      m0 = fmaf(wv, s_fz[n * 3], m0);
+      m1 = fmaf(wv, s_fz[n * 3 + 1], m1);
+      m2 = fmaf(wv, s_fz[n * 3 + 2], m2);
+    }
+  }
+  const float* g = p.d_mc + (size_t)b * 5 * kH + j;
+  const float g0 = g[0], g1 = g[kH], g2 = g[2 * kH], g3 = g[3 * kH], g4 = g[4 * kH];
+  d_raw[j] = 15.f * fmaf(g0, m0, fmaf(g1, m1, fmaf(g2, m2, fmaf(g3, m3, g4 * p.b0[j]))));
+  d_raw[half + j] = g4;
+  float* dM = p.dM + (size_t)b * 4 * kH + j;
+  dM[0] = g0 * f0;
+  dM[kH] = g1 * f0;
+  dM[2 * kH] = g2 * f0;
+  dM[3 * kH] = g3 * f0;
+}
+
+struct FilmMapBwdW0Params {
+  const float* Z;
+  const float* raw;
+  const float* d_mc;
+  const float* dM;
+  float* dW0;  // (256, in0), accumulated
+  float* db0;  // (256), accumulated
+  int B, N, so2, Lf;
+};
+
+// grid (256 / 8), 256 threads: warp = feature j, lanes stride the input columns of W_0; sums over the maps with the
+// loads of eight maps in flight
+__global__ void __launch_bounds__(256) reni_film_map_bwd_w0_kernel(const FilmMapBwdW0Params p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp, N = p.N;
+  const int in0 = p.so2 ? N + 2 : N;
+  for (int col = lane; col < in0; col += 32) {
+    float acc = 0.f;
+    for (int b0 = 0; b0 < p.B; b0 += 8) {
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int b = b0 + u;
+        t[u] = 0.f;
+        if (b < p.B) {
+          const float* dM = p.dM + (size_t)b * 4 * kH + j;
+          const float* z = p.Z + (size_t)b * 3 * N;
+          if (p.so2) {
+            if (col == 0) t[u] = __ldg(dM + 2 * kH);
+            else if (col == 1) t[u] = __ldg(dM + 3 * kH);
+            else t[u] = fmaf(__ldg(dM), __ldg(z + (col - 2) * 3), __ldg(dM + kH) * __ldg(z + (col - 2) * 3 + 2));
+          } else {
+            t[u] = fmaf(__ldg(dM), __ldg(z + col * 3),
+                        fmaf(__ldg(dM + kH), __ldg(z + col * 3 + 1), __ldg(dM + 2 * kH) * __ldg(z + col * 3 + 2)));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += t[u];
+    }
+    p.dW0[(size_t)j * in0 + col] += acc;
+  }
+  {  // db_0[j] += sum_b d_mc[b][4][j] * freq_0[b][j]: lanes stride the maps
+    float acc = 0.f;
+    const int half = p.Lf * kH;
+    for (int b = lane; b < p.B; b += 32)
+      acc = fmaf(__ldg(p.d_mc + (size_t)b * 5 * kH + 4 * kH + j), fmaf(__ldg(p.raw + (size_t)b * 2 * half + j), 15.f, 30.f),
+                 acc);
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+    if (lane == 0) p.db0[j] += acc;
+  }
+}
+
+// dW[o, k] += sum_b dpre[b, o] x[b, k],  db[o] += sum_b dpre[b, o],  dpre = dY * act'(y)
+// grid (ceil(in / 256), ceil(out / 8)), 256 threads: thread = input column k with x[b, k] of 32 maps in registers (all
+// 32 loads in flight at once), block = 8 output rows whose dpre is staged in shared memory
+constexpr int kMapBwdRows = 8;
+__global__ void __launch_bounds__(256) reni_film_map_bwd_dw_kernel(const float* __restrict__ dY, const float* __restrict__ y,
+                                                                   const float* __restrict__ x, float* __restrict__ dW,
+                                                                   float* __restrict__ db, int B, int in, int out,
+                                                                   int leaky) {
+  __shared__ float s_g[32][kMapBwdRows];
+  const int o0 = blockIdx.y * kMapBwdRows, k = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[kMapBwdRows], accb = 0.f;
+#pragma unroll
+  for (int r = 0; r < kMapBwdRows; ++r) acc[r] = 0.f;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    __syncthreads();
+    {
+      const int bb = threadIdx.x / kMapBwdRows, r = threadIdx.x % kMapBwdRows;  // 32 x 8 = 256 entries
+      float g = 0.f;
+      if (b0 + bb < B && o0 + r < out) {
+        g = __ldg(dY + (size_t)(b0 + bb) * out + o0 + r);
+        if (leaky && __ldg(y + (size_t)(b0 + bb) * out + o0 + r) < 0.f) g *= 0.2f;
+      }
+      s_g[bb][r] = g;
+    }
+    float xr[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) xr[u] = (k < in && b0 + u < B) ? __ldg(x + (size_t)(b0 + u) * in + k) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+#pragma unroll
+      for (int r = 0; r < kMapBwdRows; ++r) acc[r] = fmaf(s_g[u][r], xr[u], acc[r]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < kMapBwdRows) {
+      for (int u = 0; u < 32; ++u) accb += s_g[u][threadIdx.x];
+    }
+  }
+  if (k < in) {
+#pragma unroll
+    for (int r = 0; r < kMapBwdRows; ++r)
+      if (o0 + r < out) dW[(size_t)(o0 + r) * in + k] += acc[r];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < kMapBwdRows && o0 + (int)threadIdx.x < out) db[o0 + threadIdx.x] += accb;
+}
+
+// dX[b, k] += sum_{o in this block's slice of 32} dpre[b, o] W[o, k] for 32 maps at once: grid (ceil(in / 128),
+// ceil(out / 32), ceil(B / 32)), 128 threads; thread = input column k (coalesced weight rows, each weight read once for
+// all 32 maps), 32 accumulators in registers, dpre of the slice in shared memory; the slices add up with atomics
+// (dX zeroed by the caller)
+__global__ void __launch_bounds__(128) reni_film_map_bwd_dx_kernel(const float* __restrict__ dY, const float* __restrict__ y,
+                                                                   const float* __restrict__ W, float* __restrict__ dX,
+                                                                   int B, int in, int out, int leaky) {
+  __shared__ __align__(16) float s_g[32][32];  // [o][b]
+  const int o0 = blockIdx.y * 32, b0 = blockIdx.z * 32, k = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+    const int bb = i >> 5, o = i & 31;  // consecutive threads read consecutive o of one map
+    float g = 0.f;
+    if (b0 + bb < B && o0 + o < out) {
+      g = __ldg(dY + (size_t)(b0 + bb) * out + o0 + o);
+      if (leaky && __ldg(y + (size_t)(b0 + bb) * out + o0 + o) < 0.f) g *= 0.2f;
+    }
+    s_g[o][bb] = g;
+  }
+  __syncthreads();
+  if (k >= in) return;
+  float acc[32];
+#pragma unroll
+  for (int u = 0; u < 32; ++u) acc[u] = 0.f;
+  const int no = min(32, out - o0);
+  for (int oc = 0; oc < no; oc += 8) {
+    float w[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) w[t] = (oc + t < no) ? __ldg(W + (size_t)(o0 + oc + t) * in + k) : 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float4* g4 = reinterpret_cast<const float4*>(s_g[oc + t]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 g = g4[q];
+        acc[q * 4 + 0] = fmaf(g.x, w[t], acc[q * 4 + 0]);
+        acc[q * 4 + 1] = fmaf(g.y, w[t], acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(g.z, w[t], acc[q * 4 + 2]);
+        acc[q * 4 + 3] = fmaf(g.w, w[t], acc[q * 4 + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 32; ++u)
+    if (b0 + u < B) atomicAdd(dX + (size_t)(b0 + u) * in + k, acc[u]);
+}
+
+struct FilmMapBwdDzParams {
+  const float* Z;
+  const float* W0;
+  const float* dM;   // (B, 4, 256)
+  const float* dx0;  // (B, mn_in): gradient w.r.t. the mapping input
+  float* dZ;         // (B, N, 3), written
+  int N, so2;
+};
+
+// grid (B, ceil(3 N / 8)), 256 threads: warp = (latent row n, component c), lanes split the two reductions
+__global__ void __launch_bounds__(256) reni_film_map_bwd_dz_kernel(const FilmMapBwdDzParams p) {
+  extern __shared__ float s_fz[];
+  const int b = blockIdx.x, N = p.N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_fz[i] = p.Z[(size_t)b * 3 * N + i];
+  __syncthreads();
+  const int i = blockIdx.y * 8 + warp;
+  if (i >= 3 * N) return;
+  const int in0 = p.so2 ? N + 2 : N;
+  const int mn_in = p.so2 ? N * N + N : N * N;
+  const float* dx0 = p.dx0 + (size_t)b * mn_in;
+  const float* dM = p.dM + (size_t)b * 4 * kH;
+  const int n = i / 3, c = i % 3;
+  float acc = 0.f;
+  if (p.so2 && c == 1) {
+    if (lane == 0) acc = dx0[N * N + n];  // Z_y enters the mapping input as it is
+  } else {
+    // hoisted first layer: dZ[n, c] = sum_j dM[r(c)][j] W_ip[j, n]
+    const float* dm = dM + (p.so2 ? (c == 0 ? 0 : 1) : c) * kH;
+    const float* w = p.W0 + (p.so2 ? 2 : 0) + n;
+#pragma unroll
+    for (int jj = 0; jj < kH / 32; ++jj) {
+      const int j = jj * 32 + lane;
+      acc = fmaf(__ldg(dm + j), __ldg(w + (size_t)j * in0), acc);
+    }
+    // mapping input G = sum over its components of Z_c Z_c^T: dZ[n, c] += sum_m (dG[n, m] + dG[m, n]) Z[m, c]
+    for (int m = lane; m < N; m += 32) acc = fmaf(__ldg(dx0 + n * N + m) + __ldg(dx0 + m * N + n), s_fz[m * 3 + c], acc);
+  }
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+  if (lane == 0) p.dZ[(size_t)b * 3 * N + i] = acc;
+}
+
 }  // namespace reni

@@ -77,6 +77,85 @@ def _frequency_init(layer: nn.Linear, freq: float) -> None:
         layer.weight.uniform_(-b, b)
 
 
+class _FilmMapStage(torch.autograd.Function):
+    """(mc, film) = per-map stage(Z; net[0].layer, mapping network) through libreni_b200.so in BOTH directions
+    (reni_film_map_forward_train / reni_film_map_backward): what ``_FilmDecoderBase.map_level`` computes with ~40 torch
+    ops and differentiates with ~80 more, in 6 + 11 launches.  ``sinks`` (optional) = tensors the parameter gradients
+    are accumulated into directly ([dW0, db0, dW_map0, db_map0, ...], e.g. views of the trainer's flat all-reduce
+    buffer); the backward then returns None for the parameters.  Reference: RENI.py:405-452, :481-512, :666-678."""
+
+    @staticmethod
+    def forward(ctx, cfg, sinks, Z, W0, b0, *map_params):
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        B = Z.shape[0]
+        H = 256
+        L = cfg.hidden_layers
+        ws = [p.detach().float().contiguous() for p in map_params[0::2]]
+        bs = [p.detach().float().contiguous() for p in map_params[1::2]]
+        n = len(ws)
+        dims = (C.c_int32 * (n + 1))(ws[0].shape[1], *[w.shape[0] for w in ws])
+        Zc = Z.detach().float().contiguous()
+        W0c, b0c = W0.detach().float().contiguous(), b0.detach().float().contiguous()
+        mc = torch.empty(B, 5, H, device=Z.device, dtype=torch.float32)
+        film = torch.empty(B, L, 2, H, device=Z.device, dtype=torch.float32)
+        nbytes = int(lib.reni_film_map_acts_bytes(dims, n, B))
+        if nbytes < 0:
+            _lib.check(nbytes, "reni_film_map_acts_bytes")
+        acts = torch.empty(nbytes, dtype=torch.uint8, device=Z.device)
+        ptrs = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
+        stream = C.c_void_p(torch.cuda.current_stream(Z.device).cuda_stream)
+        rc = lib.reni_film_map_forward_train(C.byref(cfg), C.c_void_p(Zc.data_ptr()), C.c_void_p(W0c.data_ptr()),
+                                             C.c_void_p(b0c.data_ptr()), ptrs(ws), ptrs(bs), dims, n, B,
+                                             C.c_void_p(mc.data_ptr()), C.c_void_p(film.data_ptr()),
+                                             C.c_void_p(acts.data_ptr()), nbytes, stream)
+        _lib.check(rc, "reni_film_map_forward_train")
+        ctx.cfg, ctx.sinks, ctx.dims, ctx.n, ctx.nbytes = cfg, sinks, dims, n, nbytes
+        ctx.save_for_backward(Zc, W0c, b0c, acts, *ws)
+        return mc, film
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_mc, d_film):
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        Zc, W0c, b0c, acts = ctx.saved_tensors[:4]
+        ws = list(ctx.saved_tensors[4:])
+        n, B, dev = ctx.n, Zc.shape[0], Zc.device
+        L = ctx.cfg.hidden_layers
+        d_mc = torch.zeros(B, 5, 256, device=dev) if d_mc is None else d_mc.float().contiguous()
+        d_film = torch.zeros(B, L, 2, 256, device=dev) if d_film is None else d_film.float().contiguous()
+        want_dw = any(ctx.needs_input_grad[3:])
+        sinks = ctx.sinks
+        own = None
+        if want_dw and sinks is None:
+            own = [torch.zeros_like(W0c), torch.zeros_like(b0c)]
+            for w in ws:
+                own += [torch.zeros_like(w), torch.zeros(w.shape[0], device=dev, dtype=torch.float32)]
+            sinks = own
+        dZ = torch.empty_like(Zc)
+        scratch_bytes = ctx.nbytes + B * 4 * 256 * 4
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+        ptrs = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
+        vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        rc = lib.reni_film_map_backward(
+            C.byref(ctx.cfg), vp(Zc), vp(W0c), vp(b0c), ptrs(ws), ctx.dims, n, B, vp(acts), vp(d_mc), vp(d_film), vp(dZ),
+            vp(sinks[0]) if want_dw else None, vp(sinks[1]) if want_dw else None,
+            ptrs(sinks[2::2]) if want_dw else None, ptrs(sinks[3::2]) if want_dw else None, vp(scratch), scratch_bytes,
+            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "reni_film_map_backward")
+        grads = [None] * (2 + 2 * n)
+        if own is not None:
+            grads = [g if need else None for g, need in zip(own, ctx.needs_input_grad[3:])]
+        return (None, None, dZ if ctx.needs_input_grad[2] else None, *grads)
+
+
 class _FilmDecoderBase(nn.Module):
     def __init__(self, dataset_size, ndims, equivariance, siren_hidden_features, siren_hidden_layers,
                  mapping_network_features, mapping_network_layers, out_features, output_activation, fixed_decoder):
@@ -178,8 +257,26 @@ class _FilmDecoderBase(nn.Module):
         _lib.check(rc, "reni_film_map_forward")
         return mc, film
 
-    def map_level(self, Z: torch.Tensor):
-        """Per-map operands of the core: mc (B, 5, H) and film (B, L, 2, H).  Plain differentiable torch ops."""
+    def _map_params(self) -> List[torch.Tensor]:
+        """[W0, b0, W_map0, b_map0, ...]: the parameters of the per-map stage, in the order of its gradient sinks."""
+        ps: List[torch.Tensor] = [self.net[0].layer.weight, self.net[0].layer.bias]
+        for m in self.mapping_network.network:
+            if isinstance(m, nn.Linear):
+                ps += [m.weight, m.bias]
+        return ps
+
+    def map_level(self, Z: torch.Tensor, grad_sinks=None):
+        """Per-map operands of the core: mc (B, 5, H) and film (B, L, 2, H), differentiable w.r.t. Z, net[0] and the
+        mapping network.  On the GPU, for up to NATIVE_MAP_LEVEL_MAX_BATCH maps, the stage runs natively in both
+        directions (``_FilmMapStage``; RENI_FILM_NATIVE_MAP=0 keeps the torch ops below, which are also what larger
+        batches use).  ``grad_sinks``: see ``_FilmMapStage``."""
+        import os
+
+        n_lin = len([m for m in self.mapping_network.network if isinstance(m, nn.Linear)])
+        if (Z.is_cuda and Z.dtype == torch.float32 and Z.shape[0] <= self.NATIVE_MAP_LEVEL_MAX_BATCH and n_lin <= 8
+                and self.equivariance in ("SO2", "SO3") and os.environ.get("RENI_FILM_NATIVE_MAP", "1") != "0"
+                and self.net[0].layer.weight.dtype == torch.float32):
+            return _FilmMapStage.apply(self.spec.c_config(), grad_sinks, Z, *self._map_params())
         B, N, _ = Z.shape
         H, Lf = self.siren_hidden_features, self.siren_hidden_layers
         W0, b0 = self.net[0].layer.weight, self.net[0].layer.bias

@@ -231,8 +231,12 @@ class RENITrainer:
         if model.output_activation != "exp":
             # fused core step: forward + WeightedMSE (+ cosine) + backward in one library call; the per-map stage
             # (mapping network, hoisted first layer, prior / KLD) is differentiated by autograd from d_mc / d_film
-            mc, film = model.map_level(Z.float())
             need_dw = not self.fixed
+            sinks = None
+            if need_dw:  # the native per-map stage adds its parameter gradients straight into the flat buffer's views
+                by_id0 = {id(p): v for p, v in zip(self.flat.params, self.flat.views)}
+                sinks = [by_id0[id(p)] for p in model._map_params()]
+            mc, film = model.map_level(Z.float(), grad_sinks=sinks)
             core = model.core_parameters()
             views = None
             if need_dw:

@@ -416,10 +416,12 @@ def test_film_per_map_images_match_in_epilogue_modulation(dev, monkeypatch):
     monkeypatch.setenv("RENI_FILM_PERMAP", "0")
     o_epi, dz_epi, g_epi = run()
     monkeypatch.delenv("RENI_FILM_PERMAP")
-    assert float((o_map - o_epi).norm() / o_epi.norm()) < TOL_RADIANCE
-    assert float((dz_map - dz_epi).norm() / dz_epi.norm()) < 0.3 * TOL_GRAD
+    # (two fp16 roundings of the same weights, each within TOL_RADIANCE of the reference: their mutual distance is
+    # up to sqrt(2) of it)
+    assert float((o_map - o_epi).norm() / o_epi.norm()) < 2 * TOL_RADIANCE
+    assert float((dz_map - dz_epi).norm() / dz_epi.norm()) < 0.5 * TOL_GRAD
     for a, b in zip(g_map, g_epi):
-        assert float((a - b).norm() / b.norm()) < 0.3 * TOL_GRAD
+        assert float((a - b).norm() / b.norm()) < 0.5 * TOL_GRAD
     lib = _lib.load()
     cfg = _lib.RENIConfig(N, 1, 256, 4, 3, 1, 1, 1.0, 1.0)
     dummy = torch.zeros(1 << 20, device=dev)
@@ -427,3 +429,49 @@ def test_film_per_map_images_match_in_epilogue_modulation(dev, monkeypatch):
     rc = lib.reni_film_prepare_maps(C.byref(cfg), dummy.data_ptr(), ptrs, ptrs, 2, 640, dummy.data_ptr(), 1 << 22,
                                     _lib.FLAG_FILM, None)
     assert rc != 0
+
+
+@pytest.mark.parametrize("eq", ["SO2", "SO3"])
+def test_native_per_map_stage_matches_torch_stage(dev, eq, monkeypatch):
+    """reni_film_map_forward_train / reni_film_map_backward (the per-map stage of a differentiated FiLM decode: mapping
+    input, mapping network, freq / phase, hoisted first layer) against the plain torch ops + autograd of
+    ``map_level`` on the same inputs: outputs, dZ and every parameter gradient; then with gradient sinks (accumulated
+    in place, None returned) as the trainer uses it."""
+    from reni_b200 import RENIAutoDecoderFiLM
+
+    torch.manual_seed(31)
+    B, N = 7, 9
+    m = RENIAutoDecoderFiLM(B, N, eq, 256, 5, 256, 3, 3, None, False).to(dev)
+    with torch.no_grad():
+        m.mapping_network.network[-1].weight.mul_(3.0)
+    params = m._map_params()
+    d_mc = torch.randn(B, 5, 256, device=dev)
+    d_film = torch.randn(B, 4, 2, 256, device=dev)
+
+    def run(sinks=None):
+        Z = m.Z.detach().clone().requires_grad_(True)
+        mc, film = m.map_level(Z, grad_sinks=sinks)
+        gs = torch.autograd.grad([mc, film], [Z] + params, [d_mc, d_film], allow_unused=True)
+        return mc.detach(), film.detach(), gs
+
+    mc_n, film_n, g_n = run()
+    monkeypatch.setenv("RENI_FILM_NATIVE_MAP", "0")
+    mc_t, film_t, g_t = run()
+    monkeypatch.delenv("RENI_FILM_NATIVE_MAP")
+    assert float((mc_n - mc_t).norm() / mc_t.norm()) < 1e-5
+    assert float((film_n - film_t).norm() / film_t.norm()) < 1e-5
+    for a, b in zip(g_n, g_t):
+        assert a is not None and float((a - b).norm() / b.norm()) < 1e-4
+    sinks = [torch.ones_like(p) for p in params]
+    _, _, g_s = run(sinks)
+    assert all(g is None for g in g_s[1:])
+    assert float((g_s[0] - g_t[0]).norm() / g_t[0].norm()) < 1e-4
+    for s_, b in zip(sinks, g_t[1:]):
+        assert float((s_ - 1.0 - b).norm() / b.norm()) < 1e-4
+    # frozen decoder: only dZ
+    for p in m.parameters():
+        p.requires_grad_(False)
+    Z = m.Z.detach().clone().requires_grad_(True)
+    mc, film = m.map_level(Z)
+    (dz,) = torch.autograd.grad([mc, film], [Z], [d_mc, d_film])
+    assert float((dz - g_t[0]).norm() / g_t[0].norm()) < 1e-4
