@@ -227,7 +227,8 @@ class RENITrainer:
         if self.is_vad and not self.fixed:
             Z, mu, log_var = model.sample_latent(idx)
         else:
-            Z = self._latent_table()[idx]
+            # (== table[idx]; index_select's backward is one index_add_ instead of advanced indexing's sort + scatter)
+            Z = self._latent_table().index_select(0, idx)
         if model.output_activation != "exp":
             # fused core step: forward + WeightedMSE (+ cosine) + backward in one library call; the per-map stage
             # (mapping network, hoisted first layer, prior / KLD) is differentiated by autograd from d_mc / d_film
