@@ -139,6 +139,7 @@ struct SideStream {
   int dev = -1;
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t step[kFilmMapMaxLinears + 1] = {};  // per-layer forks of reni_film_map_backward, created on first use
 };
 thread_local SideStream g_side;
 bool side_stream(SideStream** out) {
@@ -1002,11 +1003,28 @@ int32_t reni_film_map_backward(const reni_config_t* c, const float* Z, const flo
     h.d_raw = dact[n_linears]; h.dM = dM; h.N = N; h.so2 = so2; h.Lf = Lf;
     reni_film_map_bwd_head_kernel<<<(unsigned)B, 256, 3 * N * sizeof(float), stream>>>(h);
   }
+  // The weight-gradient kernels have no consumer inside this call: they run on the side stream, each behind the event
+  // that marks its dY ready, while the dX chain (the critical path to dZ) continues on the caller's stream.
+  SideStream* side = nullptr;
+  cudaStream_t wstream = stream;
+  if (want_dw && !RENI_NO_FORK) {
+    if (!side_stream(&side)) return RENI_ERR_CUDA;
+    wstream = side->stream;
+  }
+  auto fork_to_side = [&](int slot) -> bool {
+    if (side == nullptr) return true;
+    if (side->step[slot] == nullptr &&
+        note(cudaEventCreateWithFlags(&side->step[slot], cudaEventDisableTiming)) != cudaSuccess)
+      return false;
+    return note(cudaEventRecord(side->step[slot], stream)) == cudaSuccess &&
+           note(cudaStreamWaitEvent(side->stream, side->step[slot], 0)) == cudaSuccess;
+  };
   if (want_dw) {
+    if (!fork_to_side(n_linears)) return RENI_ERR_CUDA;
     FilmMapBwdW0Params q{};
     q.Z = Z; q.raw = act[n_linears]; q.d_mc = d_mc; q.dM = dM; q.dW0 = dW0; q.db0 = db0;
     q.B = (int)B; q.N = N; q.so2 = so2; q.Lf = Lf;
-    reni_film_map_bwd_w0_kernel<<<kH / 8, 256, 0, stream>>>(q);
+    reni_film_map_bwd_w0_kernel<<<kH / 8, 256, 0, wstream>>>(q);
   }
   for (int i = n_linears - 1; i >= 0; --i) {
     if (host_map_weights[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
@@ -1014,9 +1032,10 @@ int32_t reni_film_map_backward(const reni_config_t* c, const float* Z, const flo
     const int leaky = i + 1 < n_linears ? 1 : 0;
     if (want_dw) {
       if (host_map_dW[i] == nullptr || host_map_db[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+      if (i + 1 < n_linears && !fork_to_side(i + 1)) return RENI_ERR_CUDA;  // dact[i + 1] has just been produced
       reni_film_map_bwd_dw_kernel<<<dim3((unsigned)((in + 255) / 256), (unsigned)((out + kMapBwdRows - 1) / kMapBwdRows)),
-                                    256, 0, stream>>>(dact[i + 1], act[i + 1], act[i], host_map_dW[i], host_map_db[i],
-                                                      (int)B, in, out, leaky);
+                                    256, 0, wstream>>>(dact[i + 1], act[i + 1], act[i], host_map_dW[i], host_map_db[i],
+                                                       (int)B, in, out, leaky);
     }
     reni_film_map_bwd_dx_kernel<<<dim3((unsigned)((in + 127) / 128), (unsigned)((out + 31) / 32), (unsigned)((B + 31) / 32)),
                                   128, 0, stream>>>(dact[i + 1], act[i + 1], host_map_weights[i], dact[i], (int)B, in, out,
@@ -1026,6 +1045,10 @@ int32_t reni_film_map_backward(const reni_config_t* c, const float* Z, const flo
     FilmMapBwdDzParams z{};
     z.Z = Z; z.W0 = weight0; z.dM = dM; z.dx0 = dact[0]; z.dZ = dZ; z.N = N; z.so2 = so2;
     reni_film_map_bwd_dz_kernel<<<dim3((unsigned)B, (unsigned)((3 * N + 7) / 8)), 256, 3 * N * sizeof(float), stream>>>(z);
+  }
+  if (side != nullptr) {  // join
+    if (note(cudaEventRecord(side->join, side->stream)) != cudaSuccess) return RENI_ERR_CUDA;
+    if (note(cudaStreamWaitEvent(stream, side->join, 0)) != cudaSuccess) return RENI_ERR_CUDA;
   }
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }

@@ -880,6 +880,10 @@ __global__ void __launch_bounds__(256) reni_film_map_linear_kernel(const float* 
   }
 }
 
+// (A batched variant -- warp = output row, 32 per-map partial sums per lane against the maps' inputs staged in shared
+// memory, so that every weight is read once for 32 maps -- measured SLOWER than this per-map kernel for 8 and 32 maps
+// (decode of 32 latents 211 -> 254 us): the first layer's 1332-column rows leave it only out / 8 = 32 blocks that each
+// walk six staged chunks in sequence.  Removed again.)
 struct FilmMapFinishParams {
   const float* Z;    // (B, N, 3)
   const float* W0;   // (256, in0): in0 = 2 + N (SO2: [|d_xz|, d_y, innerprod]) or N (SO3)
