@@ -137,6 +137,15 @@ DEVINL uint4 phase_load(const uint4* p) {
 #ifndef RENI_BWD_PF_DIST
 #define RENI_BWD_PF_DIST 1
 #endif
+#ifndef RENI_BWD_PF_DIST_LATENT
+#define RENI_BWD_PF_DIST_LATENT 1  // the same for the latent-only chain (no delta-stash writes competing for bandwidth)
+#endif
+#ifndef RENI_BWD_PF_NEXT_UNIT
+#define RENI_BWD_PF_NEXT_UNIT 1  // L2-prefetch the next unit's top-layer phase tiles during the current unit's last pass:
+                                 // 0 off, 1 latent-only chain (225 -> 213 us at cfg 2), 2 also with weight gradients
+                                 // (293 -> 307 us: that kernel is short of bandwidth, early requests hurt it); also
+                                 // prefetching the unit's out / target rows changed nothing
+#endif
 #ifndef RENI_BWD_BULK_STASH
 #define RENI_BWD_BULK_STASH 1  // 1: delta stash written by per-warp bulk copies of the finished smem pieces; 0: st.global
 #endif
@@ -233,12 +242,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
         const int nstream = clamp02(p.ntiles - ubase);       // passes the leader makes over each layer
         const int32_t wrow0 = (ubase / p.tiles_per_map) * p.w_map_rows;  // (per-map images: one map per unit)
         // phase-stash tiles are pulled towards L2 kPfDist layers before the epilogue that multiplies by their cosine
-        constexpr int kPfDist = RENI_BWD_PF_DIST;
-        for (int g = 0; g < nsub; ++g)
-          for (int d = 0; d < kPfDist && L - d >= 0; ++d)
-            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
-                                 ((size_t)(tbase + g) * (L + 1) + (L - d)) * kTileImageBytes,
-                             kTileImageBytes);
+        constexpr int kPfDist = kNeedDW ? RENI_BWD_PF_DIST : RENI_BWD_PF_DIST_LATENT;
+        // (the first unit's top layer here; with kPfNext every later unit's top layer is requested during the previous
+        // unit's last layer pass, so that its first epilogue does not start with an HBM miss)
+        constexpr bool kPfNext = RENI_BWD_PF_NEXT_UNIT == 2 || (RENI_BWD_PF_NEXT_UNIT == 1 && !kNeedDW);
+        if (it == 0 || !kPfNext)
+          for (int g = 0; g < nsub; ++g)
+            for (int d = 0; d < kPfDist && L - d >= 0; ++d)
+              bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
+                                   ((size_t)(tbase + g) * (L + 1) + (L - d)) * kTileImageBytes,
+                               kTileImageBytes);
+        auto prefetch_next_unit = [&]() {
+          if (!kPfNext || it + 1 >= iters) return;
+          const int tnext = unit_base(it + 1) + 2 * (int)crank;
+          const int nnext = clamp02(p.ntiles - tnext);
+          for (int g = 0; g < nnext; ++g) {
+            for (int d = 0; d < kPfDist && L - d >= 0; ++d)
+              bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
+                                   ((size_t)(tnext + g) * (L + 1) + (L - d)) * kTileImageBytes,
+                               kTileImageBytes);
+          }
+        };
         if (kPair && kBwdLayerResident) {
           // layer-resident weights (see the forward kernel): slot c = chunk c of the current layer for both passes
           for (int l = L; l >= 1; --l) {
@@ -247,6 +271,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
                 bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
                                      ((size_t)(tbase + g) * (L + 1) + (l - kPfDist)) * kTileImageBytes,
                                  kTileImageBytes);
+            if (l == 1) prefetch_next_unit();
             for (int c = 0; c < kChunks; ++c) {
               mbar_wait(&w_empty[c], ph ^ 1);
               if (crank == 0) mbar_arrive_expect_tx(&w_full[c], 2 * kWChunkBytes);
@@ -263,6 +288,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
               bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
                                    ((size_t)(tbase + g) * (L + 1) + (l - kPfDist)) * kTileImageBytes,
                                kTileImageBytes);
+            if (l == 1 && g == 0) prefetch_next_unit();
             for (int c = 0; c < kChunks; ++c) {
               mbar_wait(&w_empty[st], ph ^ 1);
               if (kPair) {
