@@ -884,14 +884,17 @@ static int32_t film_map_forward_impl(const reni_config_t* c, const float* Z, con
   for (int i = 0; i < n_linears; ++i) {
     if (host_map_weights[i] == nullptr || host_map_biases[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
     const int in = host_map_dims[i], out = host_map_dims[i + 1];
-    const size_t smem = (size_t)in * sizeof(float);
+    const int leaky = i + 1 < n_linears ? 1 : 0;
+    // four maps per block (each weight read once for the four) when there are enough maps and their inputs fit
+    const bool quad = B >= 16 && (size_t)4 * in * sizeof(float) <= 200 * 1024;  // (fewer maps: the wider grid wins)
+    const size_t smem = (size_t)(quad ? 4 : 1) * in * sizeof(float);
     if (smem > 200 * 1024) return RENI_ERR_BAD_CONFIG;
+    auto kernel = quad ? reni_film_map_linear_kernel<4> : reni_film_map_linear_kernel<1>;
     if (smem > 48 * 1024 &&
-        note(cudaFuncSetAttribute(reni_film_map_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) !=
-            cudaSuccess)
+        note(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
       return RENI_ERR_CUDA;
-    reni_film_map_linear_kernel<<<dim3((unsigned)((out + 31) / 32), (unsigned)B), 256, smem, stream>>>(
-        act[i], host_map_weights[i], host_map_biases[i], act[i + 1], in, out, i + 1 < n_linears ? 1 : 0);
+    kernel<<<dim3((unsigned)((out + 31) / 32), (unsigned)((B + (quad ? 3 : 0)) / (quad ? 4 : 1))), 256, smem, stream>>>(
+        act[i], host_map_weights[i], host_map_biases[i], act[i + 1], (int)B, in, out, leaky);
   }
   FilmMapFinishParams f{};
   f.Z = Z;

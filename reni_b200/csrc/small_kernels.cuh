@@ -839,18 +839,28 @@ __global__ void __launch_bounds__(256) reni_film_map_input_kernel(const float* Z
   }
 }
 
-// y[b, o] = act(b[o] + sum_k W[o, k] x[b, k]); grid (ceil(out / 32), B), 256 threads = 8 warps x 4 output rows each,
-// lanes stride the input (coalesced weight reads, 4 rows x 2 loads in flight per lane), x[b] staged in shared memory
+// y[b, o] = act(b[o] + sum_k W[o, k] x[b, k]); grid (ceil(out / 32), ceil(B / kMaps)), 256 threads = 8 warps x 4 output
+// rows each, lanes stride the input (coalesced weight reads, 4 rows x 2 loads in flight per lane), x of the block's kMaps
+// maps staged in shared memory.  kMaps = 4 reads every weight once for four maps: the weight matrices are re-read from L2
+// by every block row, 84 MB for the 2560 x 256 output layer at 32 maps with kMaps = 1.
+template <int kMaps>
 __global__ void __launch_bounds__(256) reni_film_map_linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                                    const float* __restrict__ bias, float* __restrict__ y,
-                                                                   int in, int out, int leaky) {
-  extern __shared__ float s_fx[];
-  const int b = blockIdx.y;
+                                                                   int B, int in, int out, int leaky) {
+  extern __shared__ float s_fx[];  // [kMaps][in]
+  const int b0 = blockIdx.y * kMaps;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < in; i += blockDim.x) s_fx[i] = x[(size_t)b * in + i];
+  for (int i = threadIdx.x; i < kMaps * in; i += blockDim.x) {
+    const int m = i / in, k = i - m * in;
+    s_fx[i] = (b0 + m < B) ? x[(size_t)(b0 + m) * in + k] : 0.f;
+  }
   __syncthreads();
   const int o0 = blockIdx.x * 32 + warp * 4;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[4][kMaps];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int m = 0; m < kMaps; ++m) acc[r][m] = 0.f;
   const float* w[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) w[r] = W + (size_t)min(o0 + r, out - 1) * in;
@@ -859,31 +869,43 @@ __global__ void __launch_bounds__(256) reni_film_map_linear_kernel(const float* 
     float a[4], c[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) { a[r] = __ldg(w[r] + k); c[r] = __ldg(w[r] + k + 32); }
-    const float x0 = s_fx[k], x1 = s_fx[k + 32];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) acc[r] = fmaf(c[r], x1, fmaf(a[r], x0, acc[r]));
+    for (int m = 0; m < kMaps; ++m) {
+      const float x0 = s_fx[m * in + k], x1 = s_fx[m * in + k + 32];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r][m] = fmaf(c[r], x1, fmaf(a[r], x0, acc[r][m]));
+    }
   }
   for (; k < in; k += 32) {
-    const float x0 = s_fx[k];
+    float a[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) acc[r] = fmaf(__ldg(w[r] + k), x0, acc[r]);
+    for (int r = 0; r < 4; ++r) a[r] = __ldg(w[r] + k);
+#pragma unroll
+    for (int m = 0; m < kMaps; ++m) {
+      const float x0 = s_fx[m * in + k];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r][m] = fmaf(a[r], x0, acc[r][m]);
+    }
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    float v = acc[r];
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    if (lane == 0 && o0 + r < out) {
-      v += bias[o0 + r];
-      y[(size_t)b * out + o0 + r] = (leaky && v < 0.f) ? 0.2f * v : v;
+    for (int m = 0; m < kMaps; ++m) {
+      float v = acc[r][m];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+      if (lane == 0 && o0 + r < out && b0 + m < B) {
+        v += bias[o0 + r];
+        y[(size_t)(b0 + m) * out + o0 + r] = (leaky && v < 0.f) ? 0.2f * v : v;
+      }
     }
   }
 }
 
-// (A batched variant -- warp = output row, 32 per-map partial sums per lane against the maps' inputs staged in shared
-// memory, so that every weight is read once for 32 maps -- measured SLOWER than this per-map kernel for 8 and 32 maps
+// (A fully batched variant -- warp = output row, 32 per-map partial sums per lane against the maps' inputs staged in
+// shared memory in chunks, every weight read once for 32 maps -- measured SLOWER than the per-map kernel for 8 and 32 maps
 // (decode of 32 latents 211 -> 254 us): the first layer's 1332-column rows leave it only out / 8 = 32 blocks that each
-// walk six staged chunks in sequence.  Removed again.)
+// walk six staged chunks in sequence.  Removed again; kMaps = 4 above keeps the grid wide.)
 struct FilmMapFinishParams {
   const float* Z;    // (B, N, 3)
   const float* W0;   // (256, in0): in0 = 2 + N (SO2: [|d_xz|, d_y, innerprod]) or N (SO3)
