@@ -87,3 +87,34 @@ def test_null_arguments_return_error_codes_without_touching_the_gpu(lib):
     assert lib.reni_forward(C.byref(c), None, None, 0, None, None, 1, 128, None, None, None, 0, None, 0, 0, None) == -2
     assert lib.reni_prepare_weights(C.byref(c), None, None, None, 0, None) == -2
     assert lib.reni_selftest_umma(None, 0, None, 0, 0, 0, 0, 0, 0, 0, 0, 0, 16, 1, None, None) == -2
+
+
+def test_film_per_map_entry_points_host_side(lib):
+    """Sizes and argument checks of the FiLM additions that need no GPU: per-map weight images
+    (RENI_FLAG_FILM_PERMAP / reni_film_prepare_maps), the training per-map stage's activation buffer, overlap hook."""
+    c = cfg(hidden_layers=4, first_omega_0=1.0, hidden_omega_0=1.0)
+    FILM, SAVE, PERMAP = _lib.FLAG_FILM, _lib.FLAG_SAVE_FOR_BACKWARD, _lib.FLAG_FILM_PERMAP
+    B, P, L = 32, 8192, 4
+    plain = lib.reni_workspace_bytes(C.byref(c), B, P, FILM | SAVE)
+    permap = lib.reni_workspace_bytes(C.byref(c), B, P, FILM | SAVE | PERMAP)
+    # two fp16 weight images (forward and backward layout) + one bias block pair per map and layer
+    assert permap - plain >= B * L * (2 * 131072 + 2 * 4096)
+    assert permap - plain < B * L * (2 * 131072 + 2 * 4096) + 8192
+    # the per-map flag means nothing without the FiLM flag
+    assert lib.reni_workspace_bytes(C.byref(c), B, P, SAVE | PERMAP) == lib.reni_workspace_bytes(C.byref(c), B, P, SAVE)
+    # P must be a multiple of 512 (the four tiles of a CTA pair's unit share one map); NULLs are refused
+    dummy = (C.c_void_p * 6)()
+    one = C.c_void_p(1024)
+    assert lib.reni_film_prepare_maps(C.byref(c), one, dummy, dummy, 2, 640, one, 1 << 30, FILM, None) == -2
+    assert lib.reni_film_prepare_maps(C.byref(c), None, dummy, dummy, 2, 512, one, 1 << 30, FILM, None) == -2
+    dims = (C.c_int32 * 5)(36 * 36 + 36, 256, 256, 256, 2 * 5 * 256)
+    acts = lib.reni_film_map_acts_bytes(dims, 4, 32)
+    assert acts == 32 * 4 * sum(dims)  # every activation kept (each a multiple of 256 bytes here)
+    assert lib.reni_film_map_acts_bytes(dims, 0, 32) == -2
+    assert lib.reni_film_map_acts_bytes(dims, 4, 0) == -2
+    assert lib.reni_film_map_forward_train(C.byref(c), None, None, None, None, None, dims, 4, 32, None, None, None, 0,
+                                           None) == -2
+    assert lib.reni_film_map_backward(C.byref(c), None, None, None, None, dims, 4, 32, None, None, None, None, None,
+                                      None, None, None, None, 0, None) == -2
+    assert lib.reni_debug_set_overlap(-2, 0) == -2
+    assert lib.reni_debug_set_overlap(0, 0) == 0
