@@ -48,6 +48,11 @@ struct DwParams {
   // memory (l = L..1; g_y is behind the first bump), so hidden job l may pull the tile's blocks once
   // ready[tile] >= 8 * (L - l + 1) and the output job once it is >= 8.  Blocks are then taken in DESCENDING order,
   // interleaved over the job's slices -- the order the chain finishes them -- and arrive from L2 instead of HBM.
+  // FiLM, persistent mode (film_persistent = 1, grid = (SMs, 1)): the B * njobs * (2 tiles_per_map) stash blocks of all
+  // (map, job) items form one list that the CTAs share out evenly in contiguous ranges; a CTA flushes its accumulator
+  // whenever its range crosses into the next item (about two flushes per CTA instead of one per (map, job, slice) CTA,
+  // and no partially filled last round).
+  int film_persistent, B;
   const uint32_t* ready;
   uint32_t* stuck;  // set to 1 if a wait ran into its poll limit (the result is then wrong; the host checks in tests)
 };
@@ -55,7 +60,7 @@ struct DwParams {
 struct DwSmem {
   static constexpr int kRing = 0;
   static constexpr int kBars = kRing + kDwStages * kDwStageBytes;
-  static constexpr int kNumBars = 3 * kDwStages + 1;
+  static constexpr int kNumBars = 3 * kDwStages + 2;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemPtr + 16;
 };
@@ -74,6 +79,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
   uint64_t* empty = bars + kDwStages;
   uint64_t* conv = bars + 2 * kDwStages;  // converters -> MMA: operand images ready
   uint64_t* done = bars + 3 * kDwStages;
+  uint64_t* flushed = done + 1;  // converters -> MMA: the accumulator has been read out (segment boundary)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + DwSmem::kTmemPtr);
 
   const int L = p.L;
@@ -103,8 +109,29 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
   const int nst = overlap ? (total > slice ? (total - slice + nslices - 1) / nslices : 0) : s_end - s_begin;
   // i-th stash block of this CTA
   auto blk = [&](int i) { return overlap ? total - 1 - (slice + i * nslices) : s_begin + i; };
-  const bool is_out = (job == L);
-  const int layer = job + 1;
+  // Work of this CTA as a sequence of segments (job, map, first block, blocks): ONE for the grids above, one per
+  // (map, job) item touched by the CTA's range in the persistent FiLM mode.
+  struct Seg { int job, map, s0, n; };
+  const int nblk = p.tiles_per_map * 2;
+  const int64_t g_total = (int64_t)p.B * njobs * nblk;
+  const int64_t g_begin = p.film_persistent ? (int64_t)blockIdx.x * g_total / gridDim.x : 0;
+  const int64_t g_end = p.film_persistent ? (int64_t)(blockIdx.x + 1) * g_total / gridDim.x : 1;
+  auto next_seg = [&](int64_t& g, Seg& sg) -> bool {
+    if (g >= g_end) return false;
+    if (!p.film_persistent) {
+      sg = Seg{job, film ? (int)blockIdx.y : 0, s_begin, nst};
+      g = g_end;
+      return true;
+    }
+    const int64_t item = g / nblk;
+    const int64_t stop = (item + 1) * nblk < g_end ? (item + 1) * nblk : g_end;
+    sg.map = (int)(item / njobs);
+    sg.job = (int)(item % njobs);
+    sg.s0 = sg.map * nblk + (int)(g - item * nblk);
+    sg.n = (int)(stop - g);
+    g = stop;
+    return true;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kDwStages; ++i) {
@@ -113,6 +140,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
       mbar_init(&conv[i], 8);   // one arrival per converter warp
     }
     mbar_init(done, 1);
+    mbar_init(flushed, 8);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -123,84 +151,105 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
 
   // sources for stash block s (tile = s/2, half = s%2): the fp16 image that is used as it is, and the phase block
   // from which the h operand is rebuilt
-  auto img_src = [&](int s) -> const uint8_t* {
+  auto img_src = [&](int s, int job_) -> const uint8_t* {
     const int tile = s >> 1, half = s & 1;
+    const bool is_out = job_ == L;
+    const int layer = job_ + 1;
     if (is_out)
       return reinterpret_cast<const uint8_t*>(p.stash_gy) + (size_t)tile * kGyImageBytes +
              (size_t)half * (kHalfRows * kW6N * 2);
     return reinterpret_cast<const uint8_t*>(p.stash_d) + ((size_t)tile * (L + 1) + layer) * kTileImageBytes +
            (size_t)half * kHalfImageBytes;
   };
-  auto phase_src = [&](int s) -> const uint8_t* {
+  auto phase_src = [&](int s, int job_) -> const uint8_t* {
     const int tile = s >> 1, half = s & 1;
-    const int lh = is_out ? L : layer - 1;  // h_L for the output layer, h_{l-1} for hidden layer l
+    const int lh = job_ == L ? L : job_;  // h_L for the output layer, h_{l-1} for hidden layer l = job + 1
     return reinterpret_cast<const uint8_t*>(p.stash_u) + ((size_t)tile * (L + 1) + lh) * kTileImageBytes +
            (size_t)half * kHalfImageBytes;
   };
   // hidden job: A = delta_l (copied), B = h_{l-1} (converted).  output job: A = h_L (converted), B = g_y (copied)
-  const uint32_t img_off = is_out ? kHalfImageBytes : 0;
-  const uint32_t cvt_off = is_out ? 0 : kHalfImageBytes;
-  const uint32_t img_bytes = is_out ? (kHalfRows * kW6N * 2) : kHalfImageBytes;
+  auto img_off_of = [&](int job_) -> uint32_t { return job_ == L ? kHalfImageBytes : 0; };
+  auto cvt_off_of = [&](int job_) -> uint32_t { return job_ == L ? 0 : kHalfImageBytes; };
+  auto img_bytes_of = [&](int job_) -> uint32_t { return job_ == L ? (kHalfRows * kW6N * 2) : kHalfImageBytes; };
+
+  // block i of a segment (overlap mode has a single segment and walks its interleaved, descending order)
+  auto seg_blk = [&](const Seg& sg, int i) { return overlap ? blk(i) : sg.s0 + i; };
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
-      const uint32_t need = is_out ? 8u : 8u * (uint32_t)(L - layer + 1);
       int tile_ok = -1;
-      for (int i = 0; i < nst; ++i) {
-        const int s = blk(i);
-        if (overlap && (s >> 1) != tile_ok) {
-          const uint32_t* ctr = p.ready + (s >> 1);
-          uint32_t v, spins = 0;
-          for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-            if (v >= need) break;
-            if (++spins > (1u << 22)) {  // ~ seconds: never hang the device on a scheduling surprise
-              *p.stuck = 1u;
-              break;
+      int64_t g = g_begin;
+      Seg sg;
+      while (next_seg(g, sg)) {
+        const bool is_out = sg.job == L;
+        const uint32_t need = is_out ? 8u : 8u * (uint32_t)(L - sg.job);
+        const uint32_t img_off = img_off_of(sg.job), cvt_off = cvt_off_of(sg.job), img_bytes = img_bytes_of(sg.job);
+        for (int i = 0; i < sg.n; ++i) {
+          const int s = seg_blk(sg, i);
+          if (overlap && (s >> 1) != tile_ok) {
+            const uint32_t* ctr = p.ready + (s >> 1);
+            uint32_t v, spins = 0;
+            for (;;) {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+              if (v >= need) break;
+              if (++spins > (1u << 22)) {  // ~ seconds: never hang the device on a scheduling surprise
+                *p.stuck = 1u;
+                break;
+              }
+              __nanosleep(200);
             }
-            __nanosleep(200);
+            asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what was just acquired
+            tile_ok = s >> 1;
           }
-          asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what was just acquired
-          tile_ok = s >> 1;
-        }
-        mbar_wait(&empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&full[st], img_bytes + kHalfImageBytes);
-        uint8_t* dst = smem + DwSmem::kRing + st * kDwStageBytes;
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&full[st], img_bytes + kHalfImageBytes);
+          uint8_t* dst = smem + DwSmem::kRing + st * kDwStageBytes;
 #if RENI_DW_LOAD_HINT  // both stash blocks are read exactly once in this kernel: do not keep them in L2
-        bulk_g2s_stream(dst + img_off, img_src(s), img_bytes, &full[st]);
-        bulk_g2s_stream(dst + cvt_off, phase_src(s), kHalfImageBytes, &full[st]);
+          bulk_g2s_stream(dst + img_off, img_src(s, sg.job), img_bytes, &full[st]);
+          bulk_g2s_stream(dst + cvt_off, phase_src(s, sg.job), kHalfImageBytes, &full[st]);
 #else
-        bulk_g2s(dst + img_off, img_src(s), img_bytes, &full[st]);
-        bulk_g2s(dst + cvt_off, phase_src(s), kHalfImageBytes, &full[st]);
+          bulk_g2s(dst + img_off, img_src(s, sg.job), img_bytes, &full[st]);
+          bulk_g2s(dst + cvt_off, phase_src(s, sg.job), kHalfImageBytes, &full[st]);
 #endif
-        if (++st == kDwStages) { st = 0; ph ^= 1; }
+          if (++st == kDwStages) { st = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = is_out ? umma_idesc_f16(128, kW6N, 1, 1) : umma_idesc_f16(128, 256, 1, 1);
       const uint32_t ring_base = smem_u32(smem + DwSmem::kRing);
       uint32_t st = 0, ph = 0;
-      for (int i = 0; i < nst; ++i) {
-        mbar_wait(&conv[st], ph);
-        tc_fence_after();
-        const uint32_t sa = ring_base + st * kDwStageBytes;
-        const uint32_t sb = sa + kHalfImageBytes;
-#pragma unroll
-        for (int mh = 0; mh < 2; ++mh) {
-#pragma unroll
-          for (int ks = 0; ks < kHalfRows / 16; ++ks) {
-            // MN-major operands: 8-column groups are 64 rows x 16 B = 1024 B apart (SBO), 8-row groups 128 B (LBO)
-            const uint64_t da = umma_smem_desc(sa + mh * 16 * 1024 + ks * 256, 128, 1024);
-            const uint64_t db = umma_smem_desc(sb + ks * 256, 128, 1024);
-            umma_f16_ss(tmem_base + mh * 256, da, db, idesc, (i != 0) || (ks != 0));
-          }
+      int64_t g = g_begin;
+      Seg sg;
+      int seg_idx = 0;
+      while (next_seg(g, sg)) {
+        const uint32_t idesc = sg.job == L ? umma_idesc_f16(128, kW6N, 1, 1) : umma_idesc_f16(128, 256, 1, 1);
+        if (seg_idx > 0) {  // the previous segment's accumulator has been read out
+          mbar_wait(flushed, (uint32_t)(seg_idx - 1) & 1u);
+          tc_fence_after();
         }
-        umma_commit(&empty[st]);
-        if (++st == kDwStages) { st = 0; ph ^= 1; }
+        for (int i = 0; i < sg.n; ++i) {
+          mbar_wait(&conv[st], ph);
+          tc_fence_after();
+          const uint32_t sa = ring_base + st * kDwStageBytes;
+          const uint32_t sb = sa + kHalfImageBytes;
+#pragma unroll
+          for (int mh = 0; mh < 2; ++mh) {
+#pragma unroll
+            for (int ks = 0; ks < kHalfRows / 16; ++ks) {
+              // MN-major operands: 8-column groups are 64 rows x 16 B = 1024 B apart (SBO), 8-row groups 128 B (LBO)
+              const uint64_t da = umma_smem_desc(sa + mh * 16 * 1024 + ks * 256, 128, 1024);
+              const uint64_t db = umma_smem_desc(sb + ks * 256, 128, 1024);
+              umma_f16_ss(tmem_base + mh * 256, da, db, idesc, (i != 0) || (ks != 0));
+            }
+          }
+          umma_commit(&empty[st]);
+          if (++st == kDwStages) { st = 0; ph ^= 1; }
+        }
+        umma_commit(done);
+        ++seg_idx;
       }
-      umma_commit(done);
     }
   } else {
     // ---- converters; bias-gradient column sums straight from the smem operand: thread t owns the 8 columns of group
@@ -211,12 +260,18 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
     const uint32_t r = t & 63;            // conversion: row inside the 64-row block
     const uint32_t kset = t >> 6;         // conversion: 8-column groups kset*8 .. kset*8+7
     const uint32_t jg = t >> 3, rset = t & 7;
-    float acc[8];
+    uint32_t st = 0, ph = 0;
+    int64_t g = g_begin;
+    Seg sg;
+    int seg_idx = 0;
+    while (next_seg(g, sg)) {
+      const bool is_out = sg.job == L;
+      const int layer = sg.job + 1;
+      const uint32_t img_off = img_off_of(sg.job), cvt_off = cvt_off_of(sg.job);
+      float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    {
-      uint32_t st = 0, ph = 0;
-      for (int i = 0; i < nst; ++i) {
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int i = 0; i < sg.n; ++i) {
         mbar_wait(&full[st], ph);
         uint8_t* stage = smem + DwSmem::kRing + st * kDwStageBytes;
         // (1) phase block -> h = sin(angle) operand image, in place (same [k/8][64][8] geometry, 16 B per thread/group)
@@ -239,8 +294,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
         const uint8_t* base = stage + img_off;
         if (!is_out || jg == 0) {  // (g_y has 16 padded columns: only group 0 carries data)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint4 v = *reinterpret_cast<const uint4*>(base + (jg * kHalfRows + rset + 8 * i) * 16);
+          for (int q8 = 0; q8 < 8; ++q8) {
+            const uint4 v = *reinterpret_cast<const uint4*>(base + (jg * kHalfRows + rset + 8 * q8) * 16);
             const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
             const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
             const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
@@ -254,58 +309,63 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
         if (lane == 0) mbar_arrive(&conv[st]);
         if (++st == kDwStages) { st = 0; ph ^= 1; }
       }
-    }
 
-    // ---- flush: all MMAs done -> ring is free for the cross-row reduction, TMEM holds dW
-    mbar_wait(done, 0);
-    tc_fence_after();
-    const float inv_s = __ldg(p.scalars + 1) * (is_out ? p.out_scale : 1.f);
-    float* dW_dst = p.dW[layer];
-    float* db_dst = p.db[layer];
-    if (film && !is_out) {
-      dW_dst = p.film_S + ((size_t)blockIdx.y * L + job) * kH * kH;
-      db_dst = p.film_cs + ((size_t)blockIdx.y * L + job) * kH;
-    }
-    if (nst > 0) {
-      // column sums: add up the 8 row subsets (lanes that differ in their low 3 bits), one atomic per column
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float x = acc[i];
-        x += __shfl_xor_sync(0xffffffffu, x, 1);
-        x += __shfl_xor_sync(0xffffffffu, x, 2);
-        x += __shfl_xor_sync(0xffffffffu, x, 4);
-        acc[i] = x;
+      // ---- flush: all MMAs of the segment done -> TMEM holds its dW
+      mbar_wait(done, (uint32_t)seg_idx & 1u);
+      tc_fence_after();
+      const float inv_s = __ldg(p.scalars + 1) * (is_out ? p.out_scale : 1.f);
+      float* dW_dst = p.dW[layer];
+      float* db_dst = p.db[layer];
+      if (film && !is_out) {
+        dW_dst = p.film_S + ((size_t)sg.map * L + sg.job) * kH * kH;
+        db_dst = p.film_cs + ((size_t)sg.map * L + sg.job) * kH;
       }
-      if (rset == 0) {
-        const int ncol = is_out ? p.out_features : kH;
+      if (sg.n > 0) {
+        // column sums: add up the 8 row subsets (lanes that differ in their low 3 bits), one atomic per column
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if ((int)(jg * 8 + i) < ncol && (!is_out || jg == 0)) atomicAdd(db_dst + jg * 8 + i, acc[i] * inv_s);
-      }
-      const uint32_t q = warp & 3;
-      const uint32_t mh = (warp - 2) >> 2;
-      const uint32_t j = mh * 128 + q * 32 + lane;  // accumulator row
-      const uint32_t t_acc = tmem_base + ((q * 32) << 16) + mh * 256;
-      if (!is_out) {
-        float* dst = dW_dst + (size_t)j * kH;
+        for (int i = 0; i < 8; ++i) {
+          float x = acc[i];
+          x += __shfl_xor_sync(0xffffffffu, x, 1);
+          x += __shfl_xor_sync(0xffffffffu, x, 2);
+          x += __shfl_xor_sync(0xffffffffu, x, 4);
+          acc[i] = x;
+        }
+        if (rset == 0) {
+          const int ncol = is_out ? p.out_features : kH;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if ((int)(jg * 8 + i) < ncol && (!is_out || jg == 0)) atomicAdd(db_dst + jg * 8 + i, acc[i] * inv_s);
+        }
+        const uint32_t q = warp & 3;
+        const uint32_t mh = (warp - 2) >> 2;
+        const uint32_t j = mh * 128 + q * 32 + lane;  // accumulator row
+        const uint32_t t_acc = tmem_base + ((q * 32) << 16) + mh * 256;
+        if (!is_out) {
+          float* dst = dW_dst + (size_t)j * kH;
 #pragma unroll 1
-        for (int ch = 0; ch < kH / 32; ++ch) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + ch * 32, v);
+          for (int ch = 0; ch < kH / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(t_acc + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              red_add_v4(dst + ch * 32 + i, __uint_as_float(v[i]) * inv_s, __uint_as_float(v[i + 1]) * inv_s,
+                         __uint_as_float(v[i + 2]) * inv_s, __uint_as_float(v[i + 3]) * inv_s);
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld16(t_acc, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            red_add_v4(dst + ch * 32 + i, __uint_as_float(v[i]) * inv_s, __uint_as_float(v[i + 1]) * inv_s,
-                       __uint_as_float(v[i + 2]) * inv_s, __uint_as_float(v[i + 3]) * inv_s);
+          for (int c = 0; c < 3; ++c)
+            if (c < p.out_features) atomicAdd(dW_dst + (size_t)c * kH + j, __uint_as_float(v[c]) * inv_s);
         }
-      } else {
-        uint32_t v[16];
-        tmem_ld16(t_acc, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          if (c < p.out_features) atomicAdd(dW_dst + (size_t)c * kH + j, __uint_as_float(v[c]) * inv_s);
       }
+      // the accumulator may be overwritten by the next segment's first MMA
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(flushed);
+      ++seg_idx;
     }
   }
 
