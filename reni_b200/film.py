@@ -307,6 +307,10 @@ class _FilmDecoderBase(nn.Module):
         if Z.device.type != "cuda":
             raise RuntimeError("reni_b200 runs on CUDA (sm_100a) only and has no CPU fallback; got latent codes on "
                                f"{Z.device}.  Move the module and its inputs to a B200.")
+        if Z.shape[0] == 0 or (directions.dim() == 3 and directions.shape[1] == 0):
+            out = F_.empty_output(Z, directions, [p for n, p in self.named_parameters() if n not in ("Z", "mu", "log_var")],
+                                  self.out_features)
+            return torch.exp(out) if self.output_activation == "exp" else out
         differentiated = torch.is_grad_enabled() and (Z.requires_grad or any(p.requires_grad for p in self.parameters()))
         if not differentiated and Z.shape[0] <= self.NATIVE_MAP_LEVEL_MAX_BATCH and len(
                 [m for m in self.mapping_network.network if isinstance(m, nn.Linear)]) <= 8:

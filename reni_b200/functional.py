@@ -217,6 +217,21 @@ class _DecodeFunction(torch.autograd.Function):
         return (None, None, dZ if ctx.needs_input_grad[2] else None, None, *grads)
 
 
+def empty_output(Z: torch.Tensor, D: torch.Tensor, params: Sequence[torch.Tensor], out_features: int) -> torch.Tensor:
+    """Empty batch (B = 0) or empty direction set (P = 0): the reference's ops are shape-generic and return an empty
+    (B, P, out_features) tensor whose backward leaves zero gradients; no kernel runs (the C ABI refuses B < 1, P < 1)."""
+    _require_cuda(Z, D, *params)
+    out = torch.zeros(Z.shape[0], D.shape[1], out_features, device=Z.device, dtype=torch.float32)
+    if torch.is_grad_enabled():
+        tie = None
+        for t in (Z, *params):
+            if t.requires_grad:
+                tie = t.sum() * 0 if tie is None else tie + t.sum() * 0
+        if tie is not None:
+            out = out + tie
+    return out
+
+
 def decode(spec: DecoderSpec, inference_ws: Workspace, Z: torch.Tensor, D: torch.Tensor,
            params: Sequence[torch.Tensor]) -> torch.Tensor:
     """``params`` = [W0, b0, W1, b1, ..., W_out, b_out] (state_dict order of ``net``).
@@ -225,6 +240,8 @@ def decode(spec: DecoderSpec, inference_ws: Workspace, Z: torch.Tensor, D: torch
     differentiates either).  Under ``torch.no_grad()`` or with nothing requiring grad this is the
     inference kernel with no stash."""
     spec.validate()
+    if Z.dim() == 3 and D.dim() == 3 and (Z.shape[0] == 0 or D.shape[1] == 0):
+        return empty_output(Z, D, params, spec.out_features)
     if torch.is_grad_enabled() and (Z.requires_grad or any(p.requires_grad for p in params)):
         return _DecodeFunction.apply(spec, inference_ws, Z, D, *params)
     with torch.no_grad():

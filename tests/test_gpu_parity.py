@@ -487,3 +487,26 @@ def test_overlap_mode_matches_back_to_back_kernels(dev):
         assert lib.reni_debug_set_overlap(0, -1) != 0  # bad argument
     finally:
         lib.reni_debug_set_overlap(0, 0)
+
+
+@pytest.mark.gpu
+def test_empty_batch_and_empty_direction_set(dev):
+    """B = 0 and P = 0 behave like the reference's shape-generic ops: an empty (B, P, 3) radiance tensor, and a
+    backward through it that leaves zero gradients (no kernel runs; the C ABI itself refuses B < 1 / P < 1)."""
+    from reni_b200 import RENIAutoDecoder, RENIAutoDecoderFiLM
+
+    torch.manual_seed(3)
+    for m in (RENIAutoDecoder(4, 9, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev),
+              RENIAutoDecoderFiLM(4, 9, "SO2", 256, 5, 256, 3, 3, None, False).to(dev)):
+        D = torch.nn.functional.normalize(torch.randn(4, 128, 3, device=dev), dim=-1)
+        with torch.no_grad():
+            assert tuple(m(m.Z[:0], D[:0]).shape) == (0, 128, 3)
+            assert tuple(m(m.Z.detach(), D[:, :0]).shape) == (4, 0, 3)
+        Z = m.Z.detach()[:0].clone().requires_grad_(True)
+        out = m(Z, D[:0])
+        assert tuple(out.shape) == (0, 128, 3) and out.requires_grad
+        out.sum().backward()
+        assert tuple(Z.grad.shape) == (0, 9, 3)
+        for n, p in m.named_parameters():
+            if n != "Z":
+                assert p.grad is not None and float(p.grad.abs().max()) == 0.0
