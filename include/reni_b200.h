@@ -60,6 +60,8 @@ typedef struct {
 #define RENI_FLAG_NEED_DW 2           /* weight gradients wanted (otherwise latent gradients only)     */
 #define RENI_FLAG_LOSS 4              /* forward also produces per-map loss sums (target / sw given)   */
 #define RENI_FLAG_FILM 8              /* workspace query for the FiLM core (reni_film_forward/backward) */
+#define RENI_FLAG_PREPARE_WEIGHTS 32   /* reni_loss_forward_backward builds the weight images itself (what
+                                        * reni_prepare_weights does), on its side stream beside the per-map prologue */
 #define RENI_FLAG_FILM_PERMAP 16      /* FiLM core on per-map weight images (reni_film_prepare_maps), see below */
 
 int32_t reni_abi_version(void);

@@ -145,6 +145,7 @@ struct SideStream {
   cudaEvent_t step[kFilmMapMaxLinears + 1] = {};  // per-layer forks of reni_film_map_backward, created on first use
 };
 thread_local SideStream g_side;
+thread_local cudaEvent_t g_fwd_wait_event = nullptr;  // see reni_forward / RENI_FLAG_PREPARE_WEIGHTS
 bool side_stream(SideStream** out) {
   int dev = 0;
   if (note(cudaGetDevice(&dev)) != cudaSuccess) return false;
@@ -230,10 +231,18 @@ int64_t reni_workspace_bytes(const reni_config_t* c, int64_t B, int64_t P, int32
   return make_layout(c, B, P, flags).total;
 }
 
+static int32_t launch_prepare_weights(const reni_config_t* c, const float* const* host_weights,
+                                      const float* const* host_biases, void* ws, int64_t ws_bytes, cudaStream_t stream);
+
 int32_t reni_prepare_weights(const reni_config_t* c, const float* const* host_weights,
                              const float* const* host_biases, void* ws, int64_t ws_bytes, void* stream) {
   if (!config_ok(c)) return RENI_ERR_BAD_CONFIG;
   if (host_weights == nullptr || host_biases == nullptr || ws == nullptr) return RENI_ERR_BAD_ARGUMENT;
+  return launch_prepare_weights(c, host_weights, host_biases, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+static int32_t launch_prepare_weights(const reni_config_t* c, const float* const* host_weights,
+                                      const float* const* host_biases, void* ws, int64_t ws_bytes, cudaStream_t stream) {
   const WorkspaceLayout w = make_layout(c, 1, 1, 0);
   if (ws_bytes < w.scalars || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
   PrepParams p{};
@@ -256,7 +265,7 @@ int32_t reni_prepare_weights(const reni_config_t* c, const float* const* host_we
   p.last_sine = c->last_layer_linear ? 0 : 1;
   p.first_omega = c->first_omega_0;
   p.hidden_omega = c->hidden_omega_0;
-  reni_prep_weights_kernel<<<dim3(32, L + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  reni_prep_weights_kernel<<<dim3(32, L + 1), 256, 0, stream>>>(p);
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
@@ -298,6 +307,9 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
     if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   }
   mark_phase(1, stream);
+  if (g_fwd_wait_event != nullptr) {  // (set by reni_loss_forward_backward: weight images being built on the side stream)
+    if (note(cudaStreamWaitEvent(stream, g_fwd_wait_event, 0)) != cudaSuccess) return RENI_ERR_CUDA;
+  }
   return launch_forward(c, w, at<float>(ws, w.mc), nullptr, D, d_bstride, B, P, out, target, sw, sw_bstride, ws, flags,
                         stream, sms);
 }
@@ -758,8 +770,26 @@ int32_t reni_loss_forward_backward(const reni_config_t* c, const float* Z, const
   flags |= RENI_FLAG_SAVE_FOR_BACKWARD | RENI_FLAG_LOSS;
   if ((flags & RENI_FLAG_NEED_DW) && (host_dW == nullptr || host_db == nullptr)) return RENI_ERR_BAD_ARGUMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int32_t rc = reni_forward(c, Z, D, d_bstride, host_weights[0], host_biases[0], B, P, out, target, sw, sw_bstride, ws,
-                            ws_bytes, flags, stream_);
+  int32_t rc;
+  if ((flags & RENI_FLAG_PREPARE_WEIGHTS) && g_num_phase_events == 0 && !RENI_NO_FORK) {
+    // the fp16 weight images are built on the side stream while the per-map prologue runs on the caller's
+    SideStream* ps = nullptr;
+    if (!side_stream(&ps)) return RENI_ERR_CUDA;
+    if (ps->step[0] == nullptr && note(cudaEventCreateWithFlags(&ps->step[0], cudaEventDisableTiming)) != cudaSuccess)
+      return RENI_ERR_CUDA;
+    if (note(cudaEventRecord(ps->fork, stream)) != cudaSuccess) return RENI_ERR_CUDA;
+    if (note(cudaStreamWaitEvent(ps->stream, ps->fork, 0)) != cudaSuccess) return RENI_ERR_CUDA;
+    rc = launch_prepare_weights(c, host_weights, host_biases, ws, ws_bytes, ps->stream);
+    if (rc != RENI_OK) return rc;
+    if (note(cudaEventRecord(ps->step[0], ps->stream)) != cudaSuccess) return RENI_ERR_CUDA;
+    g_fwd_wait_event = ps->step[0];
+  } else if (flags & RENI_FLAG_PREPARE_WEIGHTS) {
+    rc = launch_prepare_weights(c, host_weights, host_biases, ws, ws_bytes, stream);
+    if (rc != RENI_OK) return rc;
+  }
+  rc = reni_forward(c, Z, D, d_bstride, host_weights[0], host_biases[0], B, P, out, target, sw, sw_bstride, ws,
+                    ws_bytes, flags, stream_);
+  g_fwd_wait_event = nullptr;
   if (rc != RENI_OK) return rc;
   const WorkspaceLayout w = make_layout(c, B, P, flags);
   // Without the cosine term the backward needs nothing from the loss reduction (S = 3P/2 is written by the prologue,

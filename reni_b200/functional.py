@@ -297,7 +297,14 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
     biases = [_f32c(b) for b in biases]
     flags = FLAG_SAVE_FOR_BACKWARD | FLAG_LOSS | (FLAG_NEED_DW if need_dw else 0)
     ws.ensure(workspace_bytes(cfg, B, P, flags), dev)
-    prepare_weights(cfg, weights, biases, ws, dev)
+    # changed parameters (every training step): the library rebuilds the fp16 weight images inside the fused call, on
+    # its side stream beside the per-map prologue, instead of in a launch of its own ahead of it
+    key = _params_key(weights, biases)
+    if ws.prepared_key != key:
+        if os.environ.get("RENI_PREPARE_IN_CALL", "0") == "1":
+            flags |= _lib.FLAG_PREPARE_WEIGHTS
+        else:
+            prepare_weights(cfg, weights, biases, ws, dev)
     out = torch.empty(B, P, 3, device=dev, dtype=torch.float32)
     loss = torch.empty(4, device=dev, dtype=torch.float32)
     dZ = torch.empty_like(Zc)
@@ -311,6 +318,7 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
         _ptr_array(dW) if need_dw else None, _ptr_array(db) if need_dw else None, _vp(ws.view), ws.nbytes, flags,
         _stream(dev))
     _lib.check(rc, "reni_loss_forward_backward")
+    ws.prepared_key = key
     return StepResult(loss[0], loss[1], loss[2], loss[3], out, dZ, dW, db)
 
 
