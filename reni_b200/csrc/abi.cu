@@ -1028,6 +1028,10 @@ int32_t reni_film_map_backward(const reni_config_t* c, const float* Z, const flo
     return RENI_ERR_BAD_ARGUMENT;
   const bool want_dw = dW0 != nullptr;  // (a frozen decoder only wants dZ)
   if (want_dw && (db0 == nullptr || host_map_dW == nullptr || host_map_db == nullptr)) return RENI_ERR_BAD_ARGUMENT;
+  for (int i = 0; i < n_linears; ++i) {  // (every pointer is checked before anything is forked onto the side stream)
+    if (host_map_weights[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+    if (want_dw && (host_map_dW[i] == nullptr || host_map_db[i] == nullptr)) return RENI_ERR_BAD_ARGUMENT;
+  }
   const int64_t acts_bytes = reni_film_map_acts_bytes(host_map_dims, n_linears, B);
   if (acts_bytes < 0) return (int32_t)acts_bytes;
   const int64_t dm_bytes = B * 4 * kH * (int64_t)sizeof(float);
@@ -1074,11 +1078,9 @@ int32_t reni_film_map_backward(const reni_config_t* c, const float* Z, const flo
     reni_film_map_bwd_w0_kernel<<<kH / 8, 256, 0, wstream>>>(q);
   }
   for (int i = n_linears - 1; i >= 0; --i) {
-    if (host_map_weights[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
     const int in = host_map_dims[i], out = host_map_dims[i + 1];
     const int leaky = i + 1 < n_linears ? 1 : 0;
     if (want_dw) {
-      if (host_map_dW[i] == nullptr || host_map_db[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
       if (i + 1 < n_linears && !fork_to_side(i + 1)) return RENI_ERR_CUDA;  // dact[i + 1] has just been produced
       reni_film_map_bwd_dw_kernel<<<dim3((unsigned)((in + 255) / 256), (unsigned)((out + kMapBwdRows - 1) / kMapBwdRows)),
                                     256, 0, wstream>>>(dact[i + 1], act[i + 1], act[i], host_map_dW[i], host_map_db[i],
