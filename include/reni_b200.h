@@ -63,6 +63,8 @@ typedef struct {
 #define RENI_FLAG_PREPARE_WEIGHTS 32   /* reni_loss_forward_backward builds the weight images itself (what
                                         * reni_prepare_weights does), on its side stream beside the per-map prologue */
 #define RENI_FLAG_FILM_PERMAP 16      /* FiLM core on per-map weight images (reni_film_prepare_maps), see below */
+#define RENI_FLAG_TILE_MAJOR_BWD 64   /* training backward of the Cond-by-Concat decoder through the tile-major delta chain +
+                                       * split-K weight-gradient GEMM instead of the layer-major kernels (A/B and fallback) */
 
 int32_t reni_abi_version(void);
 const char* reni_strerror(int32_t code);

@@ -128,6 +128,13 @@ CASES = {
     "so2_n9_h256": (16, 2, 128, 9, 256, 5, 3, "SO2", True, "tanh", 16, 1e-7, 1e-1, False),
     "so2_n36_h256": (17, 2, 512, 36, 256, 5, 3, "SO2", True, "tanh", 32, 1e-7, 1e-1, False),
     "so2_n36_h256_masked": (18, 3, 512, 36, 256, 5, 3, "SO2", True, "tanh", 32, 1e-7, 1e-4, False),
+    # BASELINE.json shapes (round 2): configs[0] itself (1 map, 64x128, N=36); N=49 (configs/experiment.yaml:7) and
+    # N=100 (configs[2]/[4]) on one 32x64 map -- the N=100 encoding of that map is 84 MB in fp32
+    "cfg1_so2_n36_64x128": (19, 1, 8192, 36, 256, 5, 3, "SO2", True, "tanh", 128, 1e-7, 1e-4, False),
+    "so2_n49_h256": (20, 1, 2048, 49, 256, 5, 3, "SO2", True, "tanh", 64, 1e-7, 1e-4, False),
+    "so2_n100_h256": (21, 1, 2048, 100, 256, 5, 3, "SO2", True, "tanh", 64, 1e-7, 1e-4, False),
+    "none_n9_h256": (22, 2, 512, 9, 256, 5, 3, "None", True, "tanh", 32, 1e-7, 1e-1, False),
+    "so3_n9_h256": (23, 2, 512, 9, 256, 5, 3, "SO3", True, "tanh", 32, 1e-7, 1e-1, False),
 }
 
 
@@ -141,12 +148,18 @@ def sub_dw(i, w):
 
 
 def main():
+    """``python oracle/make_golden.py [--only case1,case2]`` (--only: just those cases, geometry/module untouched)."""
     os.makedirs(GOLDEN, exist_ok=True)
     ref_model, ref_loss, ref_utils = _import_reference()
     import torch
 
+    only = None
+    if "--only" in sys.argv:
+        only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
     torch.set_num_threads(8)
     for name, (seed, B, P, N, H, L, out_f, eq, last_lin, act, grid, alpha, beta, full) in CASES.items():
+        if only is not None and name not in only:
+            continue
         p, Z, D, target, sw, mask = golden_inputs(seed, B, P, N, H, L, out_f, eq, grid_sidelen=grid)
         p.last_layer_linear = last_lin
         p.output_activation = act
@@ -175,6 +188,8 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), **store)
         print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in list(store.items())[:3]})
 
+    if only is not None:
+        return
     # ---- geometry helpers (utils.py:46-78) and reference constructor init statistics
     geo = {}
     for W in (16, 32, 128):

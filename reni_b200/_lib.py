@@ -19,6 +19,7 @@ FLAG_LOSS = 4
 FLAG_FILM = 8
 FLAG_FILM_PERMAP = 16
 FLAG_PREPARE_WEIGHTS = 32
+FLAG_TILE_MAJOR_BWD = 64
 
 EQUIVARIANCE = {"None": 0, "SO2": 1, "SO3": 2}
 

@@ -10,6 +10,7 @@
 #include "dw_kernel.cuh"
 #include "fwd_kernel.cuh"
 #include "layout.cuh"
+#include "lbwd_kernel.cuh"
 #include "small_kernels.cuh"
 
 #ifndef RENI_NO_FORK
@@ -28,6 +29,11 @@
 #define RENI_DW_BALANCE 0  // weight-gradient GEMM: 1 = CTAs per job in proportion to the job's stash bytes.  Measured
                            // slower (dW 328 vs 256 us at cfg 2): a CTA's throughput is set by its three stages in
                            // flight, not by its bytes, so the output-layer job needs as many CTAs as a hidden job
+#endif
+#ifndef RENI_LBWD
+#define RENI_LBWD 1  // training backward of the Cond-by-Concat decoder: 1 = layer-major (lbwd_kernel.cuh: delta chain and
+                     // weight gradients in one pass per layer), 0 = tile-major chain + split-K weight-gradient GEMM;
+                     // per call RENI_FLAG_TILE_MAJOR_BWD selects the latter
 #endif
 #ifndef RENI_FWD_PAIR
 #define RENI_FWD_PAIR 1  // forward on CTA pairs (0: one CTA per tile pair, grouped training / all-hands inference epilogue)
@@ -439,6 +445,71 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   if (cudaMemsetAsync(dmc, 0, (size_t)B * 5 * kH * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
   mark_phase(3, stream);
 
+  // ---- layer-major backward (lbwd_kernel.cuh): head + one launch per hidden layer, delta chain and dW together
+  const bool use_lbwd = RENI_LBWD && want_dw && film == nullptr && !(flags & RENI_FLAG_TILE_MAJOR_BWD) &&
+                        g_overlap_dw_ctas == 0;
+  if (use_lbwd) {
+    for (int i = 1; i <= L + 1; ++i)
+      if (host_dW[i] == nullptr || host_db[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+    LbwdHeadParams hp{};
+    hp.out = out;
+    hp.grad_out = grad_out;
+    hp.aout = at<float>(ws, w.aout);
+    hp.target = target;
+    hp.sw = sw;
+    hp.sw_bstride = sw_bstride;
+    hp.map_loss = at<float>(ws, w.map_loss);
+    hp.scalars = at<float>(ws, w.scalars);
+    hp.w6b = at<__half>(ws, w.w6b);
+    hp.stash_u = at<uint16_t>(ws, w.stash_c);
+    hp.stash_d = at<__half>(ws, w.stash_d);
+    hp.dW_out = host_dW[L + 1];
+    hp.db_out = host_db[L + 1];
+    hp.out_scale = c->last_layer_linear ? 1.f : c->hidden_omega_0;
+    hp.P = (int)P;
+    hp.tiles_per_map = (int)tiles_per_map(P);
+    hp.ntiles = ntiles;
+    hp.L = L;
+    hp.out_tanh = c->output_activation == 1;
+    hp.use_cos = use_cos;
+    hp.out_features = c->out_features;
+    if (note(cudaFuncSetAttribute(reni_lbwd_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  LbwdHeadSmem::kTotal)) != cudaSuccess)
+      return RENI_ERR_CUDA;
+    reni_lbwd_head_kernel<<<ntiles < sms ? ntiles : sms, kLbwdHeadThreads, LbwdHeadSmem::kTotal, stream>>>(hp);
+    if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
+    mark_phase(4, stream);
+    LbwdParams lp{};
+    lp.stash_u = hp.stash_u;
+    lp.stash_d = hp.stash_d;
+    lp.wb2 = at<__half>(ws, w.wb2);
+    lp.scalars = hp.scalars;
+    lp.D = D;
+    lp.d_bstride = d_bstride;
+    lp.dmc = dmc;
+    lp.P = (int)P;
+    lp.tiles_per_map = hp.tiles_per_map;
+    lp.ntiles = ntiles;
+    lp.L = L;
+    lp.so2 = c->equivariance == RENI_EQ_SO2;
+    const int npair = ntiles < sms / 2 ? ntiles : sms / 2;
+    if (note(cudaFuncSetAttribute(reni_lbwd_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  LbwdSmem::kTotal)) != cudaSuccess ||
+        note(cudaFuncSetAttribute(reni_lbwd_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  LbwdSmem::kTotal)) != cudaSuccess)
+      return RENI_ERR_CUDA;
+    for (int l = L; l >= 1; --l) {
+      lp.l = l;
+      lp.dW = host_dW[l];
+      lp.db = host_db[l];
+      lp.rev = (L - l + 1) & 1;  // each launch walks the tiles against the previous one: the newest deltas are in L2
+      if (l == 1) reni_lbwd_layer_kernel<true><<<2 * npair, kLbwdThreads, LbwdSmem::kTotal, stream>>>(lp);
+      else reni_lbwd_layer_kernel<false><<<2 * npair, kLbwdThreads, LbwdSmem::kTotal, stream>>>(lp);
+    }
+    if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
+    mark_phase(5, stream);
+  }
+
   BwdParams p{};
   p.out = out;
   p.grad_out = grad_out;
@@ -490,7 +561,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     if (note(cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return RENI_ERR_CUDA;
   }
   memset(&p.wmap, 0, sizeof(p.wmap));
-  {
+  if (!use_lbwd) {
     cudaLaunchConfig_t cfg{};
     if (pair_mode) {
       const int nquads = (ntiles + 3) / 4;
@@ -543,24 +614,34 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     }
   }
   if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
-  mark_phase(4, stream);
+  if (!use_lbwd) mark_phase(4, stream);
 
   // fork: the map-level backward below only needs dmc from the delta chain; with the per-kernel timing hook active
   // everything stays on the caller's stream so the phase events keep their meaning
   // (overlap mode: the fork happened before the chain, the weight-gradient kernel takes the side stream -- launched
   // AFTER the chain so that a tool that serialises kernels in launch order still terminates -- and the map-level
   // kernels follow the chain on the caller's stream while the weight-gradient CTAs drain)
-  cudaStream_t mstream = stream, dwstream = stream;
+  // (layer-major backward: dmc is complete only behind the last launch, so the two independent halves of the
+  // map-level backward -- dZ on the caller's stream, dW_0 / db_0 on the side stream -- run beside each other)
+  cudaStream_t mstream = stream, dwstream = stream, w0stream = stream;
   if (dw_ctas > 0) {
     dwstream = side->stream;
+  } else if (use_lbwd) {
+    if (g_num_phase_events == 0 && !RENI_NO_FORK && dZ != nullptr) {
+      if (side == nullptr && !side_stream(&side)) return RENI_ERR_CUDA;
+      if (note(cudaEventRecord(side->fork, stream)) != cudaSuccess) return RENI_ERR_CUDA;
+      if (note(cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return RENI_ERR_CUDA;
+      w0stream = side->stream;
+    }
   } else if (need_dw && film == nullptr && g_num_phase_events == 0 && !RENI_NO_FORK) {
     if (side == nullptr && !side_stream(&side)) return RENI_ERR_CUDA;
     if (note(cudaEventRecord(side->fork, stream)) != cudaSuccess) return RENI_ERR_CUDA;
     if (note(cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return RENI_ERR_CUDA;
     mstream = side->stream;
+    w0stream = mstream;
   }
 
-  if (need_dw) {
+  if (need_dw && !use_lbwd) {
     DwParams q{};
     q.stash_u = at<uint16_t>(ws, w.stash_c);
     q.stash_d = at<__half>(ws, w.stash_d);
@@ -665,7 +746,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     }
     if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   }
-  mark_phase(5, stream);
+  if (!use_lbwd) mark_phase(5, stream);
 
   {
     const int nin = (int)reni_in_features(c);
@@ -697,8 +778,8 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
       g.B = at<float>(ws, w.xc);
       g.C = host_dW[0];
       g.M = kH; g.N = nin; g.K = K5; g.a_sk = kH; g.a_sm = 1; g.ldb = nin; g.ldc = nin;
-      reni_small_gemm_kernel<<<dim3((nin + 63) / 64, kH / 64, (K5 + kSmallGemmK - 1) / kSmallGemmK), 256, 0, mstream>>>(g);
-      reni_db0_kernel<<<1, 256, 0, mstream>>>(at<float>(ws, w.dmc), host_db[0], (int)B);
+      reni_small_gemm_kernel<<<dim3((nin + 63) / 64, kH / 64, (K5 + kSmallGemmK - 1) / kSmallGemmK), 256, 0, w0stream>>>(g);
+      reni_db0_kernel<<<1, 256, 0, w0stream>>>(at<float>(ws, w.dmc), host_db[0], (int)B);
     }
     if (last_err() != cudaSuccess) return RENI_ERR_CUDA;
   }

@@ -169,6 +169,8 @@ class _DecodeFunction(torch.autograd.Function):
             flags |= FLAG_SAVE_FOR_BACKWARD
             if need_dw:
                 flags |= FLAG_NEED_DW
+                if os.environ.get("RENI_TILE_MAJOR_BWD", "0") == "1":
+                    flags |= _lib.FLAG_TILE_MAJOR_BWD
         nbytes = workspace_bytes(cfg, B, P, flags)
         # a forward that will be differentiated owns its stash until backward has run
         ws = Workspace() if flags else inference_ws
@@ -276,8 +278,12 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
                           sineweight: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
                           alpha: float = 0.0, beta: float = 0.0, use_cosine: bool = False, need_dw: bool = True,
                           grad_weights: Optional[Sequence[torch.Tensor]] = None,
-                          grad_biases: Optional[Sequence[torch.Tensor]] = None) -> StepResult:
+                          grad_biases: Optional[Sequence[torch.Tensor]] = None,
+                          tile_major_bwd: Optional[bool] = None) -> StepResult:
     """Fused forward + loss + backward (one training / latent-fit step without the optimiser).
+
+    ``tile_major_bwd`` selects the older tile-major delta chain + split-K weight-gradient GEMM instead of the
+    layer-major backward (A/B switch; default from ``RENI_TILE_MAJOR_BWD``, else layer-major).
 
     loss = WeightedMSE + alpha * sum Z^2 + beta * WeightedCosineSimilarity  (loss_functions.py:6-32,60-71);
     RENITrainLoss is alpha = beta = 0.  ``grad_weights`` / ``grad_biases`` (e.g. views into one flat
@@ -296,6 +302,10 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
     weights = [_f32c(w) for w in weights]
     biases = [_f32c(b) for b in biases]
     flags = FLAG_SAVE_FOR_BACKWARD | FLAG_LOSS | (FLAG_NEED_DW if need_dw else 0)
+    if tile_major_bwd is None:
+        tile_major_bwd = os.environ.get("RENI_TILE_MAJOR_BWD", "0") == "1"
+    if tile_major_bwd:
+        flags |= _lib.FLAG_TILE_MAJOR_BWD
     ws.ensure(workspace_bytes(cfg, B, P, flags), dev)
     # changed parameters (every training step): the library rebuilds the fp16 weight images inside the fused call, on
     # its side stream beside the per-map prologue, instead of in a launch of its own ahead of it

@@ -510,3 +510,34 @@ def test_empty_batch_and_empty_direction_set(dev):
         for n, p in m.named_parameters():
             if n != "Z":
                 assert p.grad is not None and float(p.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,P,N,L,last_lin,cosine", [(3, 8192, 9, 5, True, False), (2, 1000, 36, 5, True, True),
+                                                     (5, 300, 6, 3, False, True), (1, 128, 9, 1, True, False)])
+def test_layer_major_backward_matches_tile_major(dev, B, P, N, L, last_lin, cosine):
+    """The layer-major backward (lbwd_kernel.cuh: one launch per layer, delta chain and weight gradients together) and
+    the tile-major chain + split-K weight-gradient GEMM are two schedules of the same arithmetic: same fp16 operands,
+    fp32 accumulation, so every gradient agrees to summation-order noise.  Ragged tiles, 1..5 hidden layers, the sine
+    output layer and the cosine term included."""
+    torch.manual_seed(11)
+    from reni_b200 import RENIAutoDecoder
+    from reni_b200 import functional as F_
+
+    m = RENIAutoDecoder(B, N, "SO2", 256, L, 3, last_lin, "tanh", 30.0, 30.0, False).to(dev)
+    rng = np.random.default_rng(12)
+    D = rng.standard_normal((B, P, 3))
+    D = (D / np.linalg.norm(D, axis=-1, keepdims=True)).astype(np.float32)
+    tg = rng.uniform(-1, 1, (B, P, 3)).astype(np.float32)
+    sw = np.repeat(rng.uniform(0, 1, (B, P, 1)), 3, 2).astype(np.float32)
+    Z = m.Z.detach()
+    kw = dict(alpha=1e-3, beta=0.3 if cosine else 0.0, use_cosine=cosine, need_dw=True)
+    a = F_.loss_forward_backward(m.spec, F_.Workspace(), Z, t(D, dev), t(tg, dev), t(sw, dev), m.decoder_weights(),
+                                 m.decoder_biases(), tile_major_bwd=True, **kw)
+    b = F_.loss_forward_backward(m.spec, F_.Workspace(), Z, t(D, dev), t(tg, dev), t(sw, dev), m.decoder_weights(),
+                                 m.decoder_biases(), tile_major_bwd=False, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(a.out, b.out) and float(a.loss) == float(b.loss)
+    assert O.rel_l2(b.dZ.cpu().numpy(), a.dZ.cpu().numpy()) < 2e-3
+    for i in range(L + 2):
+        assert O.rel_l2(b.dW[i].cpu().numpy(), a.dW[i].cpu().numpy()) < 2e-3, f"dW{i}"
+        assert O.rel_l2(b.db[i].cpu().numpy(), a.db[i].cpu().numpy()) < 2e-3, f"db{i}"
