@@ -63,8 +63,12 @@ typedef struct {
 #define RENI_FLAG_PREPARE_WEIGHTS 32   /* reni_loss_forward_backward builds the weight images itself (what
                                         * reni_prepare_weights does), on its side stream beside the per-map prologue */
 #define RENI_FLAG_FILM_PERMAP 16      /* FiLM core on per-map weight images (reni_film_prepare_maps), see below */
-#define RENI_FLAG_TILE_MAJOR_BWD 64   /* training backward of the Cond-by-Concat decoder through the tile-major delta chain +
-                                       * split-K weight-gradient GEMM instead of the layer-major kernels (A/B and fallback) */
+#define RENI_FLAG_TILE_MAJOR_BWD 64   /* training backward of the Cond-by-Concat decoder: force the tile-major delta chain +
+                                       * split-K weight-gradient GEMM (the default schedule) */
+#define RENI_FLAG_FWD_SINGLE_TERM 256  /* forward hidden layers on one-term fp16 weights (fastest; radiance rel-L2 3e-4..1.3e-3) */
+#define RENI_FLAG_FWD_TWO_TERM 512     /* ... on two-term weights W_hi + W_lo (the library default; x 0.6..0.8 of that error) */
+#define RENI_FLAG_LAYER_MAJOR_BWD 128 /* ... force the layer-major schedule (one launch per hidden layer computes the delta chain
+                                       * and the weight gradients in one pass over the stash; same results up to summation order) */
 
 int32_t reni_abi_version(void);
 const char* reni_strerror(int32_t code);

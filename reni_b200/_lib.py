@@ -20,6 +20,9 @@ FLAG_FILM = 8
 FLAG_FILM_PERMAP = 16
 FLAG_PREPARE_WEIGHTS = 32
 FLAG_TILE_MAJOR_BWD = 64
+FLAG_LAYER_MAJOR_BWD = 128
+FLAG_FWD_SINGLE_TERM = 256
+FLAG_FWD_TWO_TERM = 512
 
 EQUIVARIANCE = {"None": 0, "SO2": 1, "SO3": 2}
 

@@ -31,9 +31,16 @@
                            // flight, not by its bytes, so the output-layer job needs as many CTAs as a hidden job
 #endif
 #ifndef RENI_LBWD
-#define RENI_LBWD 1  // training backward of the Cond-by-Concat decoder: 1 = layer-major (lbwd_kernel.cuh: delta chain and
-                     // weight gradients in one pass per layer), 0 = tile-major chain + split-K weight-gradient GEMM;
-                     // per call RENI_FLAG_TILE_MAJOR_BWD selects the latter
+#define RENI_LBWD 0  // default training backward of the Cond-by-Concat decoder: 0 = tile-major chain + split-K weight-gradient
+                     // GEMM, 1 = layer-major (lbwd_kernel.cuh: delta chain and weight gradients in one pass per layer).
+                     // Per call RENI_FLAG_LAYER_MAJOR_BWD / RENI_FLAG_TILE_MAJOR_BWD override it.  Measured at cfg 2:
+                     // layer-major 448 + 68 us against 293 + 248 us, but its map-level backward cannot hide under a
+                     // weight-gradient GEMM (+50 us exposed): no gain for the step, hence not the default.
+#endif
+#ifndef RENI_FWD_SPLIT_W
+#define RENI_FWD_SPLIT_W 1  // forward hidden layers on two-term fp16 weights (W' = W_hi + W_lo, two MMAs per K step): removes
+                            // the weight-rounding half of the fp16 operand error (radiance rel-L2 x 0.6..0.8) at twice the
+                            // forward tensor-core work; RENI_FLAG_FWD_SINGLE_TERM / RENI_FLAG_FWD_TWO_TERM override per call
 #endif
 #ifndef RENI_FWD_PAIR
 #define RENI_FWD_PAIR 1  // forward on CTA pairs (0: one CTA per tile pair, grouped training / all-hands inference epilogue)
@@ -71,6 +78,7 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   w.wf = take(L * kWImageBytes);
   w.wb = take(L * kWImageBytes);
   w.wf2 = take(L * kWImageBytes);
+  w.wf2lo = take(L * kWImageBytes);
   w.wb2 = take(L * kWImageBytes);
   w.wbias2 = take(L * 2 * kBiasBlockBytes);
   w.w6f = take(kW6ImageBytes);
@@ -85,9 +93,10 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   w.xc = take(B * 5 * nin * 4);   // xfull: input columns paired with [dM0..dM3, dc]
   w.dxc = take(B * 5 * nin * 4);  // E: gradient w.r.t. xfull
   w.dip = -1;
-  w.wf2m = w.wb2m = w.wbias2m = -1;
+  w.wf2m = w.wf2m_lo = w.wb2m = w.wbias2m = -1;
   if ((flags & RENI_FLAG_FILM) && (flags & RENI_FLAG_FILM_PERMAP)) {  // (placed ahead of everything the other flags size)
     w.wf2m = take(B * L * (int64_t)kWImageBytes);
+    w.wf2m_lo = take(B * L * (int64_t)kWImageBytes);
     w.wb2m = take(B * L * (int64_t)kWImageBytes);
     w.wbias2m = take(B * L * 2 * (int64_t)kBiasBlockBytes);
   }
@@ -261,6 +270,7 @@ static int32_t launch_prepare_weights(const reni_config_t* c, const float* const
   p.wf = at<__half>(ws, w.wf);
   p.wb = at<__half>(ws, w.wb);
   p.wf2 = at<__half>(ws, w.wf2);
+  p.wf2lo = at<__half>(ws, w.wf2lo);
   p.wb2 = at<__half>(ws, w.wb2);
   p.wbias2 = at<__half>(ws, w.wbias2);
   p.w6f = at<__half>(ws, w.w6f);
@@ -351,7 +361,9 @@ static int32_t launch_forward(const reni_config_t* c, const WorkspaceLayout& w, 
   p.so2 = c->equivariance == RENI_EQ_SO2;
   p.trace = g_trace;
   memset(&p.wmap, 0, sizeof(p.wmap));
+  memset(&p.wmap_lo, 0, sizeof(p.wmap_lo));
   memset(&p.bmap, 0, sizeof(p.bmap));
+  p.split = (flags & RENI_FLAG_FWD_SINGLE_TERM) ? 0 : ((flags & RENI_FLAG_FWD_TWO_TERM) ? 1 : RENI_FWD_SPLIT_W);
   const int npairs = (p.ntiles + 1) / 2;
   const bool train = (flags & RENI_FLAG_SAVE_FOR_BACKWARD) != 0;
   // CTA pairs (cluster of 2) share the weight stream: half the L2 -> SM weight traffic per SM
@@ -366,6 +378,8 @@ static int32_t launch_forward(const reni_config_t* c, const WorkspaceLayout& w, 
     p.b_map_rows = p.L * 2 * (kBiasBlockBytes / 256);
     if (!encode_rows256(&p.wmap, at<__half>(ws, w.wf2m), (uint64_t)B * p.L * kWImageBytes, kWChunkBytes / 256))
       return RENI_ERR_CUDA;
+    if (!encode_rows256(&p.wmap_lo, at<__half>(ws, w.wf2m_lo), (uint64_t)B * p.L * kWImageBytes, kWChunkBytes / 256))
+      return RENI_ERR_CUDA;
     if (!encode_rows256(&p.bmap, at<__half>(ws, w.wbias2m), (uint64_t)B * p.L * 2 * kBiasBlockBytes,
                         kBiasBlockBytes / 256))
       return RENI_ERR_CUDA;
@@ -374,6 +388,8 @@ static int32_t launch_forward(const reni_config_t* c, const WorkspaceLayout& w, 
     grid = 2 * nclusters;
   } else if (pair_mode) {  // one cluster of two CTAs per tile quad
     if (!encode_rows256(&p.wmap, p.wf2, (uint64_t)p.L * kWImageBytes, kWChunkBytes / 256)) return RENI_ERR_CUDA;
+    if (!encode_rows256(&p.wmap_lo, at<__half>(ws, w.wf2lo), (uint64_t)p.L * kWImageBytes, kWChunkBytes / 256))
+      return RENI_ERR_CUDA;
     if (!encode_rows256(&p.bmap, at<__half>(ws, w.wbias2), (uint64_t)p.L * 2 * kBiasBlockBytes, kBiasBlockBytes / 256))
       return RENI_ERR_CUDA;
     const int nquads = (p.ntiles + 3) / 4;
@@ -446,8 +462,8 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   mark_phase(3, stream);
 
   // ---- layer-major backward (lbwd_kernel.cuh): head + one launch per hidden layer, delta chain and dW together
-  const bool use_lbwd = RENI_LBWD && want_dw && film == nullptr && !(flags & RENI_FLAG_TILE_MAJOR_BWD) &&
-                        g_overlap_dw_ctas == 0;
+  const bool lbwd_wanted = (flags & RENI_FLAG_LAYER_MAJOR_BWD) != 0 || (RENI_LBWD && !(flags & RENI_FLAG_TILE_MAJOR_BWD));
+  const bool use_lbwd = lbwd_wanted && want_dw && film == nullptr && g_overlap_dw_ctas == 0;
   if (use_lbwd) {
     for (int i = 1; i <= L + 1; ++i)
       if (host_dW[i] == nullptr || host_db[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
@@ -492,6 +508,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     lp.ntiles = ntiles;
     lp.L = L;
     lp.so2 = c->equivariance == RENI_EQ_SO2;
+    lp.trace = nullptr;
     const int npair = ntiles < sms / 2 ? ntiles : sms / 2;
     if (note(cudaFuncSetAttribute(reni_lbwd_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   LbwdSmem::kTotal)) != cudaSuccess ||
@@ -502,6 +519,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
       lp.l = l;
       lp.dW = host_dW[l];
       lp.db = host_db[l];
+      lp.trace = (l == L - 1 || (L == 1 && l == 1)) ? g_trace : nullptr;  // (debug timeline of one mid-chain launch)
       lp.rev = (L - l + 1) & 1;  // each launch walks the tiles against the previous one: the newest deltas are in L2
       if (l == 1) reni_lbwd_layer_kernel<true><<<2 * npair, kLbwdThreads, LbwdSmem::kTotal, stream>>>(lp);
       else reni_lbwd_layer_kernel<false><<<2 * npair, kLbwdThreads, LbwdSmem::kTotal, stream>>>(lp);
@@ -1202,6 +1220,7 @@ int32_t reni_film_prepare_maps(const reni_config_t* c, const float* film, const 
   }
   q.film = film;
   q.wf2m = at<__half>(ws, w.wf2m);
+  q.wf2m_lo = at<__half>(ws, w.wf2m_lo);
   q.wb2m = at<__half>(ws, w.wb2m);
   q.wbias2m = at<__half>(ws, w.wbias2m);
   q.L = L;

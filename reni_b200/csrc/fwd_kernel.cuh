@@ -67,7 +67,11 @@ struct FwdParams {
   int w_map_rows, b_map_rows;  // per-map weight / bias images (FiLM on per-map images): rows of 256 B per map in wmap / bmap,
                                // 0 = one image shared by all maps
   unsigned long long* trace;  // debug: per-role clock64 timeline of CTA 0 (reni_debug_set_trace), else null
+  int split;                  // paired mode: 1 = two-term weights, every K chunk is followed by its fp16 residual chunk
+                              // (W' = W_hi + W_lo, acc = h W_hi^T + h W_lo^T): removes the weight-rounding half of the
+                              // fp16 operand error of the hidden layers at twice the tensor-core work
   alignas(64) CUtensorMap wmap;  // paired mode: wf2 as rows of 256 B, box = one 16 KB half chunk (TMA tile loads)
+  alignas(64) CUtensorMap wmap_lo;  // ... the residual images wf2lo, same geometry
   alignas(64) CUtensorMap bmap;  // paired mode: wbias2 as rows of 256 B, box = one 4 KB bias block
 };
 
@@ -159,6 +163,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
   auto clamp02 = [](int x) { return x < 0 ? 0 : (x > 2 ? 2 : x); };
   constexpr int kChunkBytes = kWChunkBytes;            // paired: [8 k-groups][128 n][8] = K 64 of this CTA's N half
   constexpr int kChunks = kPair ? 4 : kChunksPerLayer;
+  const int nsplit = (kPair && !kLayerResident && p.split) ? 2 : 1;
   uint64_t* a_ready_peer = acc_full + 2;  // [2] leader only: the peer's sub-tile g is ready (one arrival per warp)
   constexpr uint32_t kPeerWarps = kAllHands ? 16 : 8;
 
@@ -253,12 +258,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
               if (++st == kStages) { st = 0; ph ^= 1; }
             }
             for (int c = 0; c < kChunks; ++c) {
+              for (int sp = 0; sp < nsplit; ++sp) {  // the chunk of W_hi, then (two-term weights) the chunk of W_lo
               mbar_wait(&w_empty[st], ph ^ 1);
               if (kPair) {
                 // both halves complete on the LEADER's barrier (TMA tile load with .cta_group::2): no relay, one wait
                 if (crank == 0) mbar_arrive_expect_tx(&w_full[st], 2 * kChunkBytes);
                 const int32_t row = (int32_t)(((size_t)(l * 2 + crank) * (kWImageBytes / 2) + (size_t)c * kChunkBytes) / 256);
-                tma2_load_2d(smem + FwdSmem::kRing + st * kChunkBytes, &p.wmap, 0, wrow0 + row,
+                tma2_load_2d(smem + FwdSmem::kRing + st * kChunkBytes, sp ? &p.wmap_lo : &p.wmap, 0, wrow0 + row,
                              mapa_u32(smem_u32(&w_full[st]), 0));
               } else {
                 mbar_arrive_expect_tx(&w_full[st], kChunkBytes);
@@ -266,6 +272,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
                          kChunkBytes, &w_full[st]);
               }
               if (++st == kStages) { st = 0; ph ^= 1; }
+              }
             }
           }
         }
@@ -340,6 +347,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
                 if (++st == kStages) { st = 0; ph ^= 1; }
               }
               for (int c = 0; c < kChunks; ++c) {
+                for (int sp = 0; sp < nsplit; ++sp) {  // (two-term weights: the same A columns against W_hi, then W_lo)
                 mbar_wait(&w_full[st], ph);
                 tc_fence_after();
                 const uint32_t b_tile = ring_base + st * kChunkBytes;
@@ -355,6 +363,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
                 if (kPair) umma2_commit_multicast(&w_empty[st], 0x3);
                 else umma_commit(&w_empty[st]);
                 if (++st == kStages) { st = 0; ph ^= 1; }
+                }
               }
             } else {
 #pragma unroll
@@ -545,7 +554,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
             const float* bo = s_bias + L * kH;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              float y = __uint_as_float(v[c]) + bo[c];
+              float y = (__uint_as_float(v[c]) + __uint_as_float(v[c + 3])) + bo[c];  // (W_out hi + lo columns)
               if (p.last_sine) {
                 if (kTrain && rvalid) p.aout[((size_t)b * p.P + pix) * 3 + c] = y;
                 y = sinf(y);
@@ -741,7 +750,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
           const float* bo = s_bias + L * kH;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            float y = __uint_as_float(v[c]) + bo[c];
+            float y = (__uint_as_float(v[c]) + __uint_as_float(v[c + 3])) + bo[c];  // (W_out hi + lo columns)
             if (p.last_sine) {
               if (kTrain && rvalid) p.aout[((size_t)b * p.P + pix) * 3 + c] = y;
               y = sinf(y);

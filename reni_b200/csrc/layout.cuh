@@ -40,13 +40,13 @@ __host__ __device__ inline uint32_t stash_off(uint32_t r, uint32_t kg, uint32_t 
 
 struct WorkspaceLayout {
   // all offsets in bytes from the workspace base; 0-size regions are absent
-  int64_t wf, wb, wf2, wb2, wbias2, w6f, w6b, bias, mc;       // weight images + biases + per-map layer-0 (M_b, c_b)
+  int64_t wf, wb, wf2, wf2lo, wb2, wbias2, w6f, w6b, bias, mc;       // weight images + biases + per-map layer-0 (M_b, c_b)
   int64_t stash_h, stash_c, stash_d, stash_gy;   // per-tile activation / cos / delta stashes
   int64_t aout;                                  // output pre-activations (sine output layer only)
   int64_t loss_part, map_loss, dmc, scalars;     // loss partials, per-map loss coefficients, per-map dM/dc
   int64_t xc, dxc, dip;                          // per-map constant encoding columns and their gradients
   int64_t film_S, film_cs;                       // FiLM backward: per-map delta_l^T h_{l-1} and column sums of delta_l
-  int64_t wf2m, wb2m, wbias2m;                   // FiLM per-map weight / bias images (RENI_FLAG_FILM_PERMAP)
+  int64_t wf2m, wf2m_lo, wb2m, wbias2m;                   // FiLM per-map weight / bias images (RENI_FLAG_FILM_PERMAP)
   int64_t ready;                                 // overlap mode: per-tile "delta_l is out" counters (+ 1 word: stuck flag)
   int64_t total;
 };

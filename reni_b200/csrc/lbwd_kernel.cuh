@@ -30,6 +30,12 @@
 
 namespace reni {
 
+#ifndef RENI_LBWD_PF_DIST
+#define RENI_LBWD_PF_DIST 0  // L2 prefetch distance, in tiles ahead of the tile whose shared-memory load is being issued
+#endif
+#ifndef RENI_LBWD_STORE_HINT
+#define RENI_LBWD_STORE_HINT 0  // delta_{l-1} stores: 0 plain st.global (write-back: the next launch reads the newest tiles from L2), 1 st.cs
+#endif
 constexpr int kLbwdThreads = 576;  // warp 0 producer, warp 1 MMA issuer, warps 2..17 epilogue (row x 32 columns each)
 constexpr int kLbwdHalfCols = 128;
 constexpr int kLbwdHImageBytes = kTileRows * kLbwdHalfCols * 2;  // 32 KB: [16 k-groups][128 rows][8]
@@ -45,7 +51,16 @@ struct LbwdParams {
   int64_t d_bstride;
   float* dmc;               // kFirst: (B, 5, 256) dM_b rows 0..3, dc_b row 4 (atomics; caller zeroes)
   int P, tiles_per_map, ntiles, L, l, rev, so2;
+  unsigned long long* trace;  // debug: clock64 timeline of CTA 0 (reni_debug_set_trace), else null
 };
+
+// debug timeline: role 0 MMA issuer, 1 first epilogue warp, 2 producer; entry = code << 48 | clock
+DEVINL void lbwd_trace(const LbwdParams& p, int role, uint32_t& n, uint32_t code) {
+  if (p.trace != nullptr && blockIdx.x == 0 && n < 4096) {
+    p.trace[role * 4096 + n] = ((unsigned long long)code << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+    ++n;
+  }
+}
 
 struct LbwdSmem {
   static constexpr int kX = 0;                                  // 2 x 64 KB delta_l tiles
@@ -63,17 +78,28 @@ struct LbwdSmem {
 static_assert(LbwdSmem::kTotal <= 232448, "layer-major backward shared memory over budget");
 
 // One hidden layer l of the backward for all tiles.  Schedule per tile i (X = delta_l tile buffer i % 2):
-//   tensor pipe : chain(i) = X W -> acc ; wgrad(i) = X^T H -> dW      (issued back to back: H does not depend on chain)
-//   epilogue    : H(i) = sin(phase) as soon as wgrad(i-1) has read H ; next tile's phases requested ; bias sums from X ;
-//                 delta_{l-1} = acc * cos(phase) once chain(i) is complete
-// so a delta tile occupies its buffer for a load plus two GEMMs only, and the phase loads of tile i+1 are in flight
-// through the whole cos pass of tile i.
+//   tensor pipe : chain(i) = X W -> acc[i % 2] ; wgrad(i) = X^T H(i) -> dW   (H does not depend on chain(i): the two GEMMs
+//                 are issued back to back and the tile buffer is released behind them)
+//   epilogue    : H(i) = sin(phase(i)) as soon as wgrad(i-1) has read H (chain(i) runs underneath); bias sums of X(i);
+//                 delta_{l-1}(i) = acc * cos(phase(i)) once chain(i) is complete (wgrad(i) runs underneath)
+// The phase slice of tile i+1 is requested (registers) at the top of iteration i.
+// kFirst (l = 1): one chain accumulator (16 TMEM columns go to the layer-0 reduction); delta_0(i) takes the h buffer's
+// place behind wgrad(i) and is reduced against the feature rows before H(i+1) is written.
+//
+// Measured at cfg 2 (tools/step_phases.py, tools/trace_lbwd.py; profiles/r2_lbwd_*): this schedule 448 us for the five
+// launches (+ 68 us head) against 541 us for the tile-major chain + weight-gradient GEMM.  Variants that were built,
+// verified against the tile-major path and measured SLOWER, in this order: L2 prefetch of the next 1 / 2 / 3 tiles
+// (448 / 468 / 491 us); one chain accumulator + bias gradient on the tensor core + phases two tiles ahead (493 us);
+// sin pass one tile ahead of the cos pass (585 us); the same with delta_{l-1} leaving through the copy engine from the h
+// buffer instead of st.global (695 us).  The timeline shows why none of them helps: a 64 KB tile load takes 5000..6000
+// clk when all SMs stream (only one of the two buffers is ever in flight), and the 32 KB of delta stores drain at about
+// 13 B/clk/SM whichever engine issues them, blocking the epilogue's next shared-memory instruction for ~2500 clk.
 template <bool kFirst>
 __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const LbwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
-  constexpr int kNA = kFirst ? 1 : 2;  // chain accumulators (kFirst gives 16 TMEM columns to the layer-0 reduction)
+  constexpr int kNA = kFirst ? 1 : 2;  // chain accumulators
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LbwdSmem::kBars);
   uint64_t* w_full = bars;          // weight half landed
@@ -81,7 +107,7 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
   uint64_t* empty = bars + 3;       // [2] commit: both GEMMs have read X[b]
   uint64_t* acc_full = bars + 5;    // [2] commit: chain accumulator complete
   uint64_t* acc_free = bars + 7;    // [2] epilogue warps: accumulator has been read out (16 arrivals)
-  uint64_t* h_ready = bars + 9;     // epilogue warps: h image written (16 arrivals)
+  uint64_t* h_ready = bars + 9;     // epilogue warps: h image written, bias sums of the tile taken (16 arrivals)
   uint64_t* h_free = bars + 10;     // commit: the dW GEMM has read the h image
   uint64_t* d_ready = bars + 11;    // kFirst: delta_0 image + feature rows written (16 arrivals)
   uint64_t* hd_free = bars + 12;    // kFirst: commit: the layer-0 reduction has read them
@@ -132,7 +158,7 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
       mbar_arrive_expect_tx(w_full, kWImageBytes / 2);
       bulk_g2s(smem + LbwdSmem::kW, wsrc, kWImageBytes / 4, w_full);
       bulk_g2s(smem + LbwdSmem::kW + kWImageBytes / 4, wsrc + kWImageBytes / 4, kWImageBytes / 4, w_full);
-      auto prefetch = [&](int i) {  // delta tile + this CTA's half of the phase tile towards L2
+      auto prefetch = [&](int i) {  // delta tile + this CTA's half of the phase tile towards L2 (build switch, off)
         if (i >= ntl) return;
         const int t = tile_of(i);
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(stash_d + slot_off(t, l)), "r"(kTileImageBytes)
@@ -142,13 +168,13 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ph + kHalfImageBytes), "r"(16 * kHalfRows * 16)
                      : "memory");
       };
-      prefetch(0);
-      prefetch(1);
-      prefetch(2);
+      for (int d = 0; d < RENI_LBWD_PF_DIST; ++d) prefetch(d);
+      uint32_t tn = 0;
       for (int i = 0; i < ntl; ++i) {
         const int b = i & 1;
-        prefetch(i + 3);
+        if (RENI_LBWD_PF_DIST > 0) prefetch(i + RENI_LBWD_PF_DIST);
         if (i >= 2) mbar_wait(&empty[b], (uint32_t)(i / 2 - 1) & 1u);
+        lbwd_trace(p, 2, tn, 0x100 | (i & 0xff));  // load issued
         mbar_arrive_expect_tx(&full[b], kTileImageBytes);
         const uint8_t* src = stash_d + slot_off(tile_of(i), l);
         uint8_t* dst = smem + LbwdSmem::kX + b * kTileImageBytes;
@@ -166,10 +192,13 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
       const uint32_t w_base = smem_u32(smem + LbwdSmem::kW);
       const uint32_t h_base = smem_u32(smem + LbwdSmem::kHimg);
       mbar_wait(w_full, 0);
+      uint32_t tn = 0;
       auto chain = [&](int i) {
         const int b = i & 1, a = i % kNA;
         mbar_wait(&full[b], (uint32_t)(i / 2) & 1u);
+        lbwd_trace(p, 0, tn, 0x100 | (i & 0xff));  // tile landed
         if (i >= kNA) mbar_wait(&acc_free[a], (uint32_t)(i / kNA - 1) & 1u);
+        lbwd_trace(p, 0, tn, 0x200 | (i & 0xff));  // accumulator free: chain issued
         tc_fence_after();
         const uint32_t a_tile = x_base + b * kTileImageBytes;
 #pragma unroll
@@ -184,6 +213,7 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
       auto wgrad = [&](int j) {
         const int b = j & 1;
         mbar_wait(h_ready, (uint32_t)j & 1u);
+        lbwd_trace(p, 0, tn, 0x300 | (j & 0xff));  // h image ready: dW GEMM issued
         tc_fence_after();
         const uint32_t a_tile = x_base + b * kTileImageBytes;
 #pragma unroll
@@ -242,21 +272,22 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
       for (int i = 0; i < 5; ++i) atomicAdd(dst + i * kH, __uint_as_float(v[i]) * inv_s);
       tc_fence_before();
     };
-    auto load_phases = [&](int tile, uint4 (&ph)[4]) {
-      const uint8_t* ph_tile = stash_u + slot_off(tile, l - 1);
+    auto load_phases = [&](int i, uint4 (&ph)[4]) {
+      if (i >= ntl) return;
+      const uint8_t* ph_tile = stash_u + slot_off(tile_of(i), l - 1);
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         ph[g] = __ldcs(reinterpret_cast<const uint4*>(ph_tile + stash_off(row, r * 16 + cq * 4 + g, kH)));
     };
 
-    uint4 ph_next[4];
-    if (ntl > 0) load_phases(tile_of(0), ph_next);
-    for (int i = 0; i < ntl; ++i) {
+    uint32_t tn = 0;
+    const bool tr = (e == 0 && lane == 0);
+    // one tile: `ph` holds its phase slice, `nxt` (free now) takes the next tile's
+    auto body = [&](int i, const uint4 (&ph)[4], uint4 (&nxt)[4]) {
       const int b = i & 1, a = i % kNA;
       const int tile = tile_of(i);
-      uint4 ph[4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) ph[g] = ph_next[g];
+      if (tr) lbwd_trace(p, 1, tn, 0x100 | (i & 0xff));  // iteration start
+      load_phases(i + 1, nxt);
       // (A) h_{l-1} = sin(a_{l-1}) -> operand image, once the previous tile's GEMMs have read the buffer
       if (i >= 1) {
         if (kFirst) {
@@ -267,6 +298,7 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
           mbar_wait(h_free, (uint32_t)(i - 1) & 1u);
         }
       }
+      if (tr) lbwd_trace(p, 1, tn, 0x200 | (i & 0xff));  // h buffer free seen
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const uint4 hw = ph[g];
@@ -296,10 +328,10 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(h_ready);
-      // (C) the next tile's phase slice: in flight through the rest of this iteration
-      if (i + 1 < ntl) load_phases(tile_of(i + 1), ph_next);
-      // (D) delta_{l-1} = acc * cos(a_{l-1})
+      if (tr) lbwd_trace(p, 1, tn, 0x300 | (i & 0xff));  // h image written
+      // (C) delta_{l-1} = acc * cos(a_{l-1})
       mbar_wait(&acc_full[a], (uint32_t)(i / kNA) & 1u);
+      if (tr) lbwd_trace(p, 1, tn, 0x400 | (i & 0xff));  // accumulator seen
       tc_fence_after();
       uint4 dv[4];
 #pragma unroll
@@ -319,16 +351,20 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
                                __uint_as_float(v[g2 * 8 + 5]) * abl_cos(phase_angle_hi(hw.z)));
           dv[g].w = pack_half2(__uint_as_float(v[g2 * 8 + 6]) * abl_cos(phase_angle_lo(hw.w)),
                                __uint_as_float(v[g2 * 8 + 7]) * abl_cos(phase_angle_hi(hw.w)));
-          if (!kFirst)  // delta_{l-1} leaves for the next launch: a warp writes 512 contiguous bytes per group
-            *reinterpret_cast<uint4*>(stash_d + slot_off(tile, l - 1) +
-                                      tile_image_off(kTileRows, row, r * 16 + cq * 4 + g)) = dv[g];
+          if (!kFirst) {  // delta_{l-1} leaves for the next launch: a warp writes 512 contiguous bytes per group
+            uint4* dptr = reinterpret_cast<uint4*>(stash_d + slot_off(tile, l - 1) +
+                                                   tile_image_off(kTileRows, row, r * 16 + cq * 4 + g));
+            if (RENI_LBWD_STORE_HINT == 1) __stcs(dptr, dv[g]);
+            else *dptr = dv[g];
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_free[a]);
+      if (tr) lbwd_trace(p, 1, tn, 0x500 | (i & 0xff));  // cos pass done
       if (kFirst) {
-        // (E) delta_0 never leaves the SM: its image takes the h buffer's place once the dW GEMM has read h, with the
+        // (D) delta_0 never leaves the SM: its image takes the h buffer's place once the dW GEMM has read h, with the
         // feature rows [f0, f1, f2, f3, 1, 0, 0, 0] (zero for rows beyond P) beside it
         mbar_wait(h_free, (uint32_t)i & 1u);
 #pragma unroll
@@ -351,6 +387,15 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(d_ready);
+      }
+    };
+
+    {
+      uint4 pa[4], pb[4];
+      load_phases(0, pa);
+      for (int i = 0; i < ntl; i += 2) {
+        body(i, pa, pb);
+        if (i + 1 < ntl) body(i + 1, pb, pa);
       }
     }
 
@@ -403,7 +448,7 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
 //                                                     cosine folded in, exactly as reni_bwd_kernel does)
 //   delta_L = (g_y W_out'') * cos(a_L)               K = 3 on the CUDA cores, fp32 -> fp16 tile image in the stash
 //   dW_out += g_y^T h_L, db_out += sum g_y           h_L = sin(a_L) image in shared memory, N = 16 tcgen05.mma
-// warp 0: TMEM + MMA issuer; warps 1..8: workers, thread = (row, 128 columns).
+// warp 0: TMEM + MMA issuer; warps 1..16: workers, thread = (row, 64 columns), phase loads software-pipelined in halves.
 // ------------------------------------------------------------------------------------------------
 constexpr int kLbwdHeadThreads = 544;  // warp 0: TMEM + MMA issuer; warps 1..16: workers, thread = (row, 64 columns)
 

@@ -25,6 +25,7 @@ struct PrepParams {
   __half* wf;
   __half* wb;
   __half* wf2;
+  __half* wf2lo;   // residual of wf2: fp16(omega_l W_l - wf2), same geometry (two-term forward weights)
   __half* wb2;
   __half* wbias2;  // [l][n/128][2 k-groups][128][8]: column k=0 = hi, k=1 = lo fp16 halves of omega_l*b_l, rest 0
   __half* w6f;
@@ -45,13 +46,17 @@ __global__ void reni_prep_weights_kernel(const PrepParams p) {
     __half* wf = p.wf + (size_t)l * kH * kH;
     __half* wb = p.wb + (size_t)l * kH * kH;
     __half* wf2 = p.wf2 + (size_t)l * kH * kH;
+    __half* wf2lo = p.wf2lo + (size_t)l * kH * kH;
     __half* wb2 = p.wb2 + (size_t)l * kH * kH;
     for (int i = tid; i < kH * kH; i += nthreads) {
       const int n = i / kH, k = i % kH;  // W[n][k], coalesced read
       const float w = W[i];
       wf[((k >> 3) * kH + n) * 8 + (k & 7)] = __float2half_rn(om_f * w);
       wb[((n >> 3) * kH + k) * 8 + (n & 7)] = __float2half_rn(om_b * w);
-      wf2[(((n >> 7) * (kH / 8) + (k >> 3)) * 128 + (n & 127)) * 8 + (k & 7)] = __float2half_rn(om_f * w);
+      const __half whi = __float2half_rn(om_f * w);
+      wf2[(((n >> 7) * (kH / 8) + (k >> 3)) * 128 + (n & 127)) * 8 + (k & 7)] = whi;
+      wf2lo[(((n >> 7) * (kH / 8) + (k >> 3)) * 128 + (n & 127)) * 8 + (k & 7)] =
+          __float2half_rn(om_f * w - __half2float(whi));
       wb2[(((k >> 7) * (kH / 8) + (n >> 3)) * 128 + (k & 127)) * 8 + (n & 7)] = __float2half_rn(om_b * w);
     }
     for (int i = tid; i < kH; i += nthreads) {
@@ -75,7 +80,13 @@ __global__ void reni_prep_weights_kernel(const PrepParams p) {
     for (int i = tid; i < kW6N * kH; i += nthreads) {
       const int n = i / kH, k = i % kH;
       const float w = (n < p.out_features) ? s * W[n * kH + k] : 0.f;
-      p.w6f[((k >> 3) * kW6N + n) * 8 + (k & 7)] = __float2half_rn(w);
+      // forward image: rows 0..2 = fp16(W_out), rows 3..5 = the fp16 residual (the epilogue adds columns c and c + 3)
+      float wfwd = w;
+      if (n >= 3 && n < 3 + p.out_features) {
+        const float w0 = s * W[(n - 3) * kH + k];
+        wfwd = w0 - __half2float(__float2half_rn(w0));
+      }
+      p.w6f[((k >> 3) * kW6N + n) * 8 + (k & 7)] = __float2half_rn(wfwd);
       p.w6b[((n >> 3) * kH + k) * 8 + (n & 7)] = __float2half_rn(om_b * w);
     }
     for (int i = tid; i < kW6N; i += nthreads)
@@ -97,6 +108,7 @@ struct FilmPrepParams {
   const float* b[kMaxHiddenLayers + 2];
   const float* film;                     // (B, L, 2, 256)
   __half* wf2m;
+  __half* wf2m_lo;  // residual images of wf2m (two-term forward weights)
   __half* wb2m;
   __half* wbias2m;
   int L;
@@ -111,6 +123,7 @@ __global__ void __launch_bounds__(256) reni_film_prep_maps_kernel(const FilmPrep
   s_freq[threadIdx.x] = freq[threadIdx.x];
   __syncthreads();
   uint4* wf = reinterpret_cast<uint4*>(p.wf2m + ((size_t)b * p.L + l) * kH * kH);
+  uint4* wflo = reinterpret_cast<uint4*>(p.wf2m_lo + ((size_t)b * p.L + l) * kH * kH);
   uint4* wb = reinterpret_cast<uint4*>(p.wb2m + ((size_t)b * p.L + l) * kH * kH);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
@@ -121,12 +134,20 @@ __global__ void __launch_bounds__(256) reni_film_prep_maps_kernel(const FilmPrep
       const float f = s_freq[n];
       const float4 a = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * kH + kg * 8));
       const float4 c = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * kH + kg * 8 + 4));
+      const float x[8] = {f * a.x, f * a.y, f * a.z, f * a.w, f * c.x, f * c.y, f * c.z, f * c.w};
       uint4 v;
-      v.x = pack_half2(f * a.x, f * a.y);
-      v.y = pack_half2(f * a.z, f * a.w);
-      v.z = pack_half2(f * c.x, f * c.y);
-      v.w = pack_half2(f * c.z, f * c.w);
+      v.x = pack_half2(x[0], x[1]);
+      v.y = pack_half2(x[2], x[3]);
+      v.z = pack_half2(x[4], x[5]);
+      v.w = pack_half2(x[6], x[7]);
       wf[((n >> 7) * (kH / 8) + kg) * 128 + (n & 127)] = v;
+      const __half2* hv = reinterpret_cast<const __half2*>(&v);
+      uint4 lo;  // residuals of the four rounded pairs
+      lo.x = pack_half2(x[0] - __low2float(hv[0]), x[1] - __high2float(hv[0]));
+      lo.y = pack_half2(x[2] - __low2float(hv[1]), x[3] - __high2float(hv[1]));
+      lo.z = pack_half2(x[4] - __low2float(hv[2]), x[5] - __high2float(hv[2]));
+      lo.w = pack_half2(x[6] - __low2float(hv[3]), x[7] - __high2float(hv[3]));
+      wflo[((n >> 7) * (kH / 8) + kg) * 128 + (n & 127)] = lo;
     }
     {  // backward image: thread = (8 consecutive n, k)
       const int k = i & (kH - 1), ng = i >> 8;

@@ -128,6 +128,26 @@ def workspace_bytes(cfg: RENIConfig, B: int, P: int, flags: int) -> int:
     return int(n)
 
 
+def _bwd_schedule_flag(tile_major: Optional[bool]) -> int:
+    """RENI_FLAG_TILE_MAJOR_BWD / RENI_FLAG_LAYER_MAJOR_BWD from an explicit choice or the RENI_TILE_MAJOR_BWD variable."""
+    if tile_major is None:
+        env = os.environ.get("RENI_TILE_MAJOR_BWD")
+        if env is None:
+            return 0
+        tile_major = env == "1"
+    return _lib.FLAG_TILE_MAJOR_BWD if tile_major else _lib.FLAG_LAYER_MAJOR_BWD
+
+
+def _fwd_terms_flag() -> int:
+    """RENI_FWD_TERMS=1 / 2 forces one- / two-term forward weights (A/B switch; default: the library's, two-term)."""
+    env = os.environ.get("RENI_FWD_TERMS")
+    if env == "1":
+        return _lib.FLAG_FWD_SINGLE_TERM
+    if env == "2":
+        return _lib.FLAG_FWD_TWO_TERM
+    return 0
+
+
 def _params_key(weights, biases):
     return tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases))
 
@@ -164,23 +184,22 @@ class _DecodeFunction(torch.autograd.Function):
         P = Dc.shape[1]
         need_dz = ctx.needs_input_grad[2]
         need_dw = any(ctx.needs_input_grad[4:])
-        flags = 0
+        flags = _fwd_terms_flag()
         if need_dz or need_dw:
             flags |= FLAG_SAVE_FOR_BACKWARD
             if need_dw:
                 flags |= FLAG_NEED_DW
-                if os.environ.get("RENI_TILE_MAJOR_BWD", "0") == "1":
-                    flags |= _lib.FLAG_TILE_MAJOR_BWD
+                flags |= _bwd_schedule_flag(None)
         nbytes = workspace_bytes(cfg, B, P, flags)
         # a forward that will be differentiated owns its stash until backward has run
-        ws = Workspace() if flags else inference_ws
+        ws = Workspace() if (flags & FLAG_SAVE_FOR_BACKWARD) else inference_ws
         ws.ensure(nbytes, dev)
         prepare_weights(cfg, weights, biases, ws, dev)
         out = torch.empty(B, P, 3, device=dev, dtype=torch.float32)
         rc = lib.reni_forward(C.byref(cfg), _vp(Zc), _vp(Dc), d_bs, _vp(weights[0]), _vp(biases[0]), B, P, _vp(out),
                               None, None, 0, _vp(ws.view), ws.nbytes, flags, _stream(dev))
         _lib.check(rc, "reni_forward")
-        if flags:
+        if flags & FLAG_SAVE_FOR_BACKWARD:
             ctx.spec, ctx.ws, ctx.flags, ctx.d_bs = spec, ws, flags, d_bs
             ctx.save_for_backward(Zc, Dc, out, *weights, *biases)
         if spec.out_features != 3:
@@ -282,8 +301,8 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
                           tile_major_bwd: Optional[bool] = None) -> StepResult:
     """Fused forward + loss + backward (one training / latent-fit step without the optimiser).
 
-    ``tile_major_bwd`` selects the older tile-major delta chain + split-K weight-gradient GEMM instead of the
-    layer-major backward (A/B switch; default from ``RENI_TILE_MAJOR_BWD``, else layer-major).
+    ``tile_major_bwd``: True forces the tile-major delta chain + split-K weight-gradient GEMM, False the layer-major
+    backward (one launch per layer); None takes ``RENI_TILE_MAJOR_BWD`` (0/1) or else the library default (tile-major).
 
     loss = WeightedMSE + alpha * sum Z^2 + beta * WeightedCosineSimilarity  (loss_functions.py:6-32,60-71);
     RENITrainLoss is alpha = beta = 0.  ``grad_weights`` / ``grad_biases`` (e.g. views into one flat
@@ -302,10 +321,7 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
     weights = [_f32c(w) for w in weights]
     biases = [_f32c(b) for b in biases]
     flags = FLAG_SAVE_FOR_BACKWARD | FLAG_LOSS | (FLAG_NEED_DW if need_dw else 0)
-    if tile_major_bwd is None:
-        tile_major_bwd = os.environ.get("RENI_TILE_MAJOR_BWD", "0") == "1"
-    if tile_major_bwd:
-        flags |= _lib.FLAG_TILE_MAJOR_BWD
+    flags |= _bwd_schedule_flag(tile_major_bwd) | _fwd_terms_flag()
     ws.ensure(workspace_bytes(cfg, B, P, flags), dev)
     # changed parameters (every training step): the library rebuilds the fp16 weight images inside the fused call, on
     # its side stream beside the per-map prologue, instead of in a launch of its own ahead of it

@@ -97,9 +97,9 @@ def test_film_per_map_entry_points_host_side(lib):
     B, P, L = 32, 8192, 4
     plain = lib.reni_workspace_bytes(C.byref(c), B, P, FILM | SAVE)
     permap = lib.reni_workspace_bytes(C.byref(c), B, P, FILM | SAVE | PERMAP)
-    # two fp16 weight images (forward and backward layout) + one bias block pair per map and layer
-    assert permap - plain >= B * L * (2 * 131072 + 2 * 4096)
-    assert permap - plain < B * L * (2 * 131072 + 2 * 4096) + 8192
+    # three fp16 weight images (forward hi + residual, backward layout) + one bias block pair per map and layer
+    assert permap - plain >= B * L * (3 * 131072 + 2 * 4096)
+    assert permap - plain < B * L * (3 * 131072 + 2 * 4096) + 8192
     # the per-map flag means nothing without the FiLM flag
     assert lib.reni_workspace_bytes(C.byref(c), B, P, SAVE | PERMAP) == lib.reni_workspace_bytes(C.byref(c), B, P, SAVE)
     # P must be a multiple of 512 (the four tiles of a CTA pair's unit share one map); NULLs are refused

@@ -13,7 +13,10 @@ from helpers import (O, TOL_GRAD, TOL_RADIANCE, TOL_RADIANCE_MAX, load_case, mod
 
 pytestmark = pytest.mark.gpu
 
-H256_CASES = ["so2_n9_h256", "so2_n36_h256", "so2_n36_h256_masked"]
+# reference-generated fixtures at hidden width 256; the last five are BASELINE.json shapes / the other encodings:
+# configs[0] itself (1 map 64x128, N=36), N=49 and N=100 (one 32x64 map each), and None / SO3 training gradients
+H256_CASES = ["so2_n9_h256", "so2_n36_h256", "so2_n36_h256_masked", "cfg1_so2_n36_64x128", "so2_n49_h256",
+              "so2_n100_h256", "none_n9_h256", "so3_n9_h256"]
 
 
 @pytest.fixture(scope="module")
@@ -297,12 +300,10 @@ def test_full_size_properties_config2(dev):
     outs, refs = np.concatenate(outs), np.concatenate(refs)
     print("config-2 radiance over 8 maps: rel-L2", O.rel_l2(outs, refs), "rel-max", O.rel_max(outs, refs),
           "max abs err", np.abs(outs - refs).max())
-    # A random-init decoder at this size emits |o| ~ 0.02 RMS (little more than its output bias); the fp16 rounding of
-    # the weights then gives 1.15e-3 here (reproduced bit-for-bit by a numpy emulation, DESIGN.md "Precision"), with
-    # an absolute radiance error of 1.2e-4.  The bar for THIS draw is therefore 1.5e-3; the reference-generated golden
-    # cases above are held to 1e-3.
+    # (one-term fp16 weights measured 1.15e-3 on this draw -- a random-init decoder emits |o| ~ 0.02 RMS, little more
+    # than its output bias; the two-term forward weights, now the default, bring it under the stated 1e-3)
     assert np.abs(outs - refs).max() < 2.5e-4
-    assert O.rel_l2(outs, refs) < 1.5 * TOL_RADIANCE
+    assert O.rel_l2(outs, refs) < TOL_RADIANCE
     assert O.rel_max(outs, refs) < TOL_RADIANCE_MAX
 
 
@@ -536,7 +537,8 @@ def test_layer_major_backward_matches_tile_major(dev, B, P, N, L, last_lin, cosi
     b = F_.loss_forward_backward(m.spec, F_.Workspace(), Z, t(D, dev), t(tg, dev), t(sw, dev), m.decoder_weights(),
                                  m.decoder_biases(), tile_major_bwd=False, **kw)
     torch.cuda.synchronize()
-    assert torch.equal(a.out, b.out) and float(a.loss) == float(b.loss)
+    # (the loss is a sum of per-map atomics: equal up to their order)
+    assert torch.equal(a.out, b.out) and abs(float(a.loss) - float(b.loss)) <= 1e-6 * abs(float(a.loss))
     assert O.rel_l2(b.dZ.cpu().numpy(), a.dZ.cpu().numpy()) < 2e-3
     for i in range(L + 2):
         assert O.rel_l2(b.dW[i].cpu().numpy(), a.dW[i].cpu().numpy()) < 2e-3, f"dW{i}"

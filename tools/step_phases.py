@@ -35,7 +35,7 @@ torch.cuda.synchronize()
 handles = (C.c_void_p * n_ev)(*[e.cuda_event for e in evs])
 names = {False: ["prologue", "fwd", "loss", "lbwd_head", "lbwd_layers", "map_level"],
          True: ["prologue", "fwd", "loss", "bwd_chain", "dw", "map_level"]}
-for tile_major in (False, True):
+for tile_major in (((os.environ.get("RENI_TILE_MAJOR_BWD") == "1"),) if os.environ.get("RENI_ONLY_LBWD") else (False, True)):
     ws = F_.Workspace()
     step = lambda: F_.loss_forward_backward(m.spec, ws, Z, D, tg, sw, m.decoder_weights(), m.decoder_biases(),
                                             tile_major_bwd=tile_major)
