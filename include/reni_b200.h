@@ -14,7 +14,11 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
  *   - the caller owns every buffer including the workspace (size from reni_workspace_bytes);
- *     the library allocates nothing, keeps no state between calls and is re-entrant;
+ *     the library allocates no device memory and keeps no per-call state.  What it does keep: one side stream and a
+ *     few events per host thread and device (created on first use, for the fork/join of independent kernels inside
+ *     a step; legal under CUDA-graph capture), and the process-wide reni_debug_* hooks below, which exist for
+ *     measurement and must only be changed while no call is in flight.  Compute calls are re-entrant across
+ *     threads on different workspaces;
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*), no host synchronisation;
  *   - return value: 0 on success, negative reni_status_t otherwise (reni_strerror for text);
  *   - fp32 tensors are dense row-major exactly as the reference's torch tensors:
@@ -229,6 +233,35 @@ typedef struct {
 } reni_adam_segment_t;
 int32_t reni_adam_step(const reni_adam_segment_t* host_segments, int32_t nseg, int32_t* step, double lr, double beta1,
                        double beta2, double eps, void* stream);
+
+/* Variational auto-decoder latents (RENIVariationalAutoDecoder.sample_latent, src/models/RENI.py:329-335; KLD,
+ * src/utils/loss_functions.py:16-22; RENIVADTrainLoss as training_step builds it, src/lightning/RENI_module.py:312-315).
+ *   reni_vad_sample   : Z[b] = mu[idx[b]] + eps[b] * exp(0.5 * log_var[idx[b]]); eps (B, N, 3) ~ N(0,1) from the caller
+ *   reni_vad_backward : dmu / dlog_var (whole tables, ACCUMULATED) from dLoss/dZ plus the KLD term's own gradient, all
+ *                       times grad_scale (1 / world size under data parallelism: DDP averages the replicated tables'
+ *                       gradients); kld_out (1 float, ACCUMULATED) += kld_weight / Z_dims * sum_b KLD_b
+ *   idx : (B) int64 rows of the tables; nz = 3 N floats per row */
+int32_t reni_vad_sample(const float* mu, const float* log_var, const int64_t* idx, const float* eps, int64_t B,
+                        int64_t nz, float* Z, void* stream);
+int32_t reni_vad_backward(const float* mu, const float* log_var, const int64_t* idx, const float* eps, const float* dZ,
+                          int64_t B, int64_t nz, float kld_weight_over_zdims, float grad_scale, float* dmu,
+                          float* dlog_var, float* kld_out, void* stream);
+
+/* In-place mean (or scaled sum) of one fp32 buffer over the W ranks of a node, through NVLink peer memory: the one
+ * exchange step of data-parallel training (Lightning's DDPStrategy averages every gradient, run.py:97), as a plain
+ * kernel that can be captured in the step's CUDA graph directly behind the gradient kernels.
+ *   dev_buf_ptrs  : DEVICE array of W pointers to the ranks' buffers (the same symmetric allocation on every rank,
+ *                   e.g. torch.distributed._symmetric_memory's buffer_ptrs_dev)
+ *   dev_flag_ptrs : DEVICE array of W pointers to the ranks' flag blocks, reni_allreduce_flag_bytes() each, zeroed once
+ *   multicast_ptr : multicast address aliasing the W buffers (NVSwitch, multimem.ld_reduce / multimem.st), or NULL for
+ *                   the two-shot exchange over the peer pointers
+ *   numel         : fp32 elements, a multiple of 4;  scale: 1 / W for the mean
+ *   epoch         : DEVICE word, incremented on the stream by this call (orders the flag values across calls/replays)
+ *   status        : DEVICE word, set to 1 if a rank gave up waiting for a peer (bounded spin; the result is then wrong)
+ * Every rank must make the same sequence of calls. */
+int64_t reni_allreduce_flag_bytes(void);
+int32_t reni_allreduce(void* dev_buf_ptrs, void* dev_flag_ptrs, void* multicast_ptr, int64_t numel, int32_t rank,
+                       int32_t world, float scale, uint32_t* epoch, uint32_t* status, void* stream);
 
 /* Debug / measurement hook: register up to 16 CUDA events (cudaEvent_t handles, HOST array) that the
  * calling thread's subsequent reni_forward / reni_backward / reni_loss_forward_backward calls record on

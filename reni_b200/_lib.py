@@ -87,6 +87,10 @@ SIGNATURES = {
                                                _vp, _i64, C.c_float, _i32, _vp, _vp, _vp, _vp, C.POINTER(_vp),
                                                C.POINTER(_vp), _vp, _i64, _i32, _vp]),
     "reni_adam_step": (_i32, [C.POINTER(AdamSegment), _i32, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp]),
+    "reni_vad_sample": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "reni_vad_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
+    "reni_allreduce_flag_bytes": (_i64, []),
+    "reni_allreduce": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, C.c_float, _vp, _vp, _vp]),
     "reni_debug_set_phase_events": (_i32, [C.POINTER(_vp), _i32]),
     "reni_debug_last_cuda_error": (C.c_char_p, []),
     "reni_debug_set_trace": (_i32, [_vp]),

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include "allreduce_kernel.cuh"
 #include "bwd_kernel.cuh"
 #include "dw_kernel.cuh"
 #include "fwd_kernel.cuh"
@@ -1002,6 +1003,58 @@ int32_t reni_adam_step(const reni_adam_segment_t* host_segments, int32_t nseg, i
     reni_adam_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
   }
   reni_adam_advance_kernel<<<1, 1, 0, stream>>>(step);
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+int32_t reni_vad_sample(const float* mu, const float* log_var, const int64_t* idx, const float* eps, int64_t B,
+                        int64_t nz, float* Z, void* stream_) {
+  if (mu == nullptr || log_var == nullptr || idx == nullptr || eps == nullptr || Z == nullptr || B < 1 || nz < 1)
+    return RENI_ERR_BAD_ARGUMENT;
+  VadParams p{};
+  p.mu = mu; p.log_var = log_var; p.idx = idx; p.eps = eps; p.Z = Z;
+  p.B = (int)B; p.nz = (int)nz;
+  reni_vad_sample_kernel<<<(unsigned)B, 128, 0, static_cast<cudaStream_t>(stream_)>>>(p);
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+int32_t reni_vad_backward(const float* mu, const float* log_var, const int64_t* idx, const float* eps, const float* dZ,
+                          int64_t B, int64_t nz, float kld_weight_over_zdims, float grad_scale, float* dmu,
+                          float* dlog_var, float* kld_out, void* stream_) {
+  if (mu == nullptr || log_var == nullptr || idx == nullptr || eps == nullptr || dZ == nullptr || dmu == nullptr ||
+      dlog_var == nullptr || kld_out == nullptr || B < 1 || nz < 1)
+    return RENI_ERR_BAD_ARGUMENT;
+  VadParams p{};
+  p.mu = mu; p.log_var = log_var; p.idx = idx; p.eps = eps; p.dZ = dZ;
+  p.dmu = dmu; p.dlog_var = dlog_var; p.kld_out = kld_out;
+  p.B = (int)B; p.nz = (int)nz; p.kw = kld_weight_over_zdims; p.grad_scale = grad_scale;
+  reni_vad_backward_kernel<<<(unsigned)B, 128, 0, static_cast<cudaStream_t>(stream_)>>>(p);
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+int64_t reni_allreduce_flag_bytes(void) { return (int64_t)kArMaxBlocks * kArMaxWorld * sizeof(uint32_t); }
+
+int32_t reni_allreduce(void* dev_buf_ptrs, void* dev_flag_ptrs, void* multicast_ptr, int64_t numel, int32_t rank,
+                       int32_t world, float scale, uint32_t* epoch, uint32_t* status, void* stream_) {
+  if (dev_buf_ptrs == nullptr || dev_flag_ptrs == nullptr || epoch == nullptr || status == nullptr || numel < 4 ||
+      (numel & 3) != 0 || world < 1 || world > kArMaxWorld || rank < 0 || rank >= world)
+    return RENI_ERR_BAD_ARGUMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  AllReduceParams p{};
+  p.bufs = static_cast<float* const*>(dev_buf_ptrs);
+  p.flags = static_cast<uint32_t* const*>(dev_flag_ptrs);
+  p.mc = static_cast<float*>(multicast_ptr);
+  p.n4 = numel / 4;
+  p.rank = rank;
+  p.world = world;
+  p.scale = scale;
+  p.epoch = epoch;
+  p.status = status;
+  reni_allreduce_epoch_kernel<<<1, 1, 0, stream>>>(epoch);
+  const int64_t per = (p.n4 + world - 1) / world;
+  int blocks = (int)((per + kArThreads - 1) / kArThreads);
+  if (blocks < 1) blocks = 1;
+  if (blocks > kArMaxBlocks) blocks = kArMaxBlocks;
+  reni_allreduce_kernel<<<blocks, kArThreads, 0, stream>>>(p);
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 

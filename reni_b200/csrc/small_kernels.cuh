@@ -786,6 +786,61 @@ __global__ void __launch_bounds__(256) reni_film_dw_kernel(const FilmReduceParam
 }
 
 // ------------------------------------------------------------------------------------------------
+// Variational auto-decoder latents (RENIVariationalAutoDecoder, RENI.py:329-335; KLD, loss_functions.py:16-22;
+// RENIVADTrainLoss with beta = KLD_WEIGHTING and Z_dims = 3N, RENI_module.py:312-315):
+//   sample   : Z[b] = mu[idx[b]] + eps[b] * exp(0.5 * log_var[idx[b]])          (eps ~ N(0,1) drawn by the caller)
+//   backward : given dLoss/dZ of the decoder step,
+//                dmu[idx[b]]      += s * (dZ + kw * mu)
+//                dlog_var[idx[b]] += s * (dZ * eps * 0.5 * exp(0.5 log_var) - 0.5 * kw * (1 - exp(log_var)))
+//              kld_out            += kw * sum(-0.5 * (1 + log_var - mu^2 - exp(log_var)))       kw = beta / Z_dims
+//              (s = 1 / world size: DDP averages the whole gradient of the replicated tables)
+// One block per map; accumulation with atomics (an index may repeat inside a batch, as with index_add_).
+// ------------------------------------------------------------------------------------------------
+struct VadParams {
+  const float* mu;
+  const float* log_var;
+  const int64_t* idx;
+  const float* eps;    // (B, nz)
+  float* Z;            // (B, nz) sample
+  const float* dZ;     // (B, nz)
+  float* dmu;          // (dataset, nz), accumulated
+  float* dlog_var;     // (dataset, nz), accumulated
+  float* kld_out;      // scalar, accumulated
+  int B, nz;
+  float kw, grad_scale;
+};
+
+__global__ void __launch_bounds__(128) reni_vad_sample_kernel(const VadParams p) {
+  const int b = blockIdx.x;
+  const int64_t row = p.idx[b];
+  for (int i = threadIdx.x; i < p.nz; i += blockDim.x) {
+    const float m = p.mu[row * p.nz + i], lv = p.log_var[row * p.nz + i];
+    p.Z[(size_t)b * p.nz + i] = fmaf(p.eps[(size_t)b * p.nz + i], expf(0.5f * lv), m);
+  }
+}
+
+__global__ void __launch_bounds__(128) reni_vad_backward_kernel(const VadParams p) {
+  const int b = blockIdx.x;
+  const int64_t row = p.idx[b];
+  float part = 0.f;
+  for (int i = threadIdx.x; i < p.nz; i += blockDim.x) {
+    const float m = p.mu[row * p.nz + i], lv = p.log_var[row * p.nz + i];
+    const float ev = expf(lv), sd = expf(0.5f * lv);
+    const float g = p.dZ[(size_t)b * p.nz + i];
+    atomicAdd(p.dmu + row * p.nz + i, p.grad_scale * fmaf(p.kw, m, g));
+    atomicAdd(p.dlog_var + row * p.nz + i,
+              p.grad_scale * (g * p.eps[(size_t)b * p.nz + i] * 0.5f * sd - 0.5f * p.kw * (1.f - ev)));
+    part += -0.5f * (1.f + lv - m * m - ev);
+  }
+  __shared__ float s_part[4];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(0xffffffffu, part, s);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(p.kld_out, p.kw * (s_part[0] + s_part[1] + s_part[2] + s_part[3]));
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused Adam over a list of fp32 segments (the flat decoder-weight buffer, the latent table, ...): ONE launch
 // replaces the ~12 foreach kernels x tensors of torch.optim.Adam.  Same arithmetic as torch's default
 // (non-amsgrad, no weight decay) single-tensor Adam, the optimiser the reference constructs

@@ -67,6 +67,16 @@ def _ptr_array(ts: Sequence[Optional[torch.Tensor]]):
     return (C.c_void_p * len(ts))(*[(t.data_ptr() if t is not None else 0) for t in ts])
 
 
+def _call(dev: torch.device, fn, *args):
+    """Library call with ``dev`` as the current CUDA device: the library sizes its grids, and creates its side stream,
+    for the current device, while the kernels run on the tensors' stream -- the two must agree (a model on cuda:1
+    with cuda:0 current would otherwise fork onto a stream of the wrong device)."""
+    if dev.index is not None and torch.cuda.current_device() != dev.index:
+        with torch.cuda.device(dev):
+            return fn(*args)
+    return fn(*args)
+
+
 def _stream(device: torch.device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -154,11 +164,12 @@ def _params_key(weights, biases):
 
 def prepare_weights(cfg: RENIConfig, weights, biases, ws: Workspace, device) -> None:
     """fp32 parameters -> fp16 operand images inside the workspace (skipped if unchanged)."""
+    dev = device
     key = _params_key(weights, biases)
     if ws.prepared_key == key:
         return
     lib = _lib.load()
-    rc = lib.reni_prepare_weights(C.byref(cfg), _ptr_array(weights), _ptr_array(biases), _vp(ws.view), ws.nbytes,
+    rc = _call(dev, lib.reni_prepare_weights, C.byref(cfg), _ptr_array(weights), _ptr_array(biases), _vp(ws.view), ws.nbytes,
                                   _stream(device))
     _lib.check(rc, "reni_prepare_weights")
     ws.prepared_key = key
@@ -196,7 +207,7 @@ class _DecodeFunction(torch.autograd.Function):
         ws.ensure(nbytes, dev)
         prepare_weights(cfg, weights, biases, ws, dev)
         out = torch.empty(B, P, 3, device=dev, dtype=torch.float32)
-        rc = lib.reni_forward(C.byref(cfg), _vp(Zc), _vp(Dc), d_bs, _vp(weights[0]), _vp(biases[0]), B, P, _vp(out),
+        rc = _call(dev, lib.reni_forward, C.byref(cfg), _vp(Zc), _vp(Dc), d_bs, _vp(weights[0]), _vp(biases[0]), B, P, _vp(out),
                               None, None, 0, _vp(ws.view), ws.nbytes, flags, _stream(dev))
         _lib.check(rc, "reni_forward")
         if flags & FLAG_SAVE_FOR_BACKWARD:
@@ -226,7 +237,7 @@ class _DecodeFunction(torch.autograd.Function):
         dZ = torch.empty_like(Zc)
         dW = [torch.zeros_like(w) for w in weights] if need_dw else None
         db = [torch.zeros_like(b) for b in biases] if need_dw else None
-        rc = lib.reni_backward(C.byref(cfg), _vp(Zc), _vp(Dc), ctx.d_bs, _ptr_array(weights), B, P, _vp(out), _vp(g),
+        rc = _call(dev, lib.reni_backward, C.byref(cfg), _vp(Zc), _vp(Dc), ctx.d_bs, _ptr_array(weights), B, P, _vp(out), _vp(g),
                                _vp(dZ), _ptr_array(dW) if need_dw else None, _ptr_array(db) if need_dw else None,
                                _vp(ctx.ws.view), ctx.ws.nbytes, ctx.flags, _stream(dev))
         _lib.check(rc, "reni_backward")
@@ -338,7 +349,7 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
     if need_dw:
         dW = list(grad_weights) if grad_weights is not None else [torch.zeros_like(w) for w in weights]
         db = list(grad_biases) if grad_biases is not None else [torch.zeros_like(b) for b in biases]
-    rc = lib.reni_loss_forward_backward(
+    rc = _call(dev, lib.reni_loss_forward_backward, 
         C.byref(cfg), _vp(Zc), _vp(Dc), d_bs, _ptr_array(weights), _ptr_array(biases), B, P, _vp(tc), _vp(swc), sw_bs,
         float(alpha), float(beta), 1 if use_cosine else 0, _vp(out), _vp(loss), _vp(dZ),
         _ptr_array(dW) if need_dw else None, _ptr_array(db) if need_dw else None, _vp(ws.view), ws.nbytes, flags,
@@ -399,7 +410,7 @@ def _film_permap_flag(P: int) -> int:
 
 def _film_prepare_maps(lib, cfg, filmc, weights, biases, B: int, P: int, ws: "Workspace", flags: int, dev) -> None:
     if flags & _lib.FLAG_FILM_PERMAP:
-        rc = lib.reni_film_prepare_maps(C.byref(cfg), _vp(filmc), _ptr_array([weights[0]] + weights),
+        rc = _call(dev, lib.reni_film_prepare_maps, C.byref(cfg), _vp(filmc), _ptr_array([weights[0]] + weights),
                                         _ptr_array([biases[0]] + biases), B, P, _vp(ws.view), ws.nbytes, flags,
                                         _stream(dev))
         _lib.check(rc, "reni_film_prepare_maps")
@@ -434,7 +445,7 @@ class _FilmCoreFunction(torch.autograd.Function):
         prepare_weights(cfg, [weights[0]] + weights, [biases[0]] + biases, ws, dev)
         _film_prepare_maps(lib, cfg, filmc, weights, biases, B, P, ws, flags, dev)
         out = torch.empty(B, P, 3, device=dev, dtype=torch.float32)
-        rc = lib.reni_film_forward(C.byref(cfg), _vp(mcc), _vp(filmc), _vp(Dc), d_bs, B, P, _vp(out), _vp(ws.view),
+        rc = _call(dev, lib.reni_film_forward, C.byref(cfg), _vp(mcc), _vp(filmc), _vp(Dc), d_bs, B, P, _vp(out), _vp(ws.view),
                                    ws.nbytes, flags, _stream(dev))
         _lib.check(rc, "reni_film_forward")
         if flags & FLAG_SAVE_FOR_BACKWARD:
@@ -465,7 +476,7 @@ class _FilmCoreFunction(torch.autograd.Function):
         d_film = torch.empty_like(filmc)
         dW = [torch.zeros_like(w) for w in weights] if need_dw else None
         db = [torch.zeros_like(b) for b in biases] if need_dw else None
-        rc = lib.reni_film_backward(
+        rc = _call(dev, lib.reni_film_backward, 
             C.byref(cfg), _vp(filmc), _vp(Dc), ctx.d_bs, _ptr_array([weights[0]] + weights),
             _ptr_array([biases[0]] + biases), B, P, _vp(out), _vp(g), _vp(d_mc), _vp(d_film),
             _ptr_array([None] + dW) if need_dw else None, _ptr_array([None] + db) if need_dw else None,
@@ -544,7 +555,7 @@ def film_loss_forward_backward(spec: FilmSpec, ws: Workspace, mc: torch.Tensor, 
     if need_dw:
         dW = list(grad_weights) if grad_weights is not None else [torch.zeros_like(w) for w in weights]
         db = list(grad_biases) if grad_biases is not None else [torch.zeros_like(b) for b in biases]
-    rc = lib.reni_film_loss_forward_backward(
+    rc = _call(dev, lib.reni_film_loss_forward_backward, 
         C.byref(cfg), _vp(mcc), _vp(filmc), _vp(Dc), d_bs, _ptr_array([weights[0]] + weights),
         _ptr_array([biases[0]] + biases), B, P, _vp(tc), _vp(swc), sw_bs, float(beta), 1 if use_cosine else 0, _vp(out),
         _vp(loss), _vp(d_mc), _vp(d_film), _ptr_array([None] + dW) if need_dw else None,

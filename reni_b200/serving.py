@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 
 from .film import _FilmDecoderBase
+from .functional import Workspace
 
 
 class GraphedDecoder:
@@ -27,18 +28,28 @@ class GraphedDecoder:
         if self.directions.shape[0] == 1 and batch > 1:
             self.directions = self.directions.expand(batch, -1, -1)  # one grid shared by all maps (stride 0)
         self._film = isinstance(model, _FilmDecoderBase)
+        # the captured graph holds raw pointers into its workspace, so it owns one: the model's own inference workspace
+        # may be replaced (grown) by a later eager call with a larger batch
+        self._ws = Workspace()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():  # warm-up outside capture: workspace, lazy initialisation
             for _ in range(2):
                 self._decode()
         torch.cuda.current_stream(dev).wait_stream(side)
-        model._ws.prepared_key = None  # rebuild the weight images INSIDE the graph: replays follow weight updates
+        self._ws.prepared_key = None  # rebuild the weight images INSIDE the graph: replays follow weight updates
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.out = self._decode()
 
     def _decode(self) -> torch.Tensor:
+        saved_ws, self.model._ws = self.model._ws, self._ws
+        try:
+            return self._decode_inner()
+        finally:
+            self.model._ws = saved_ws
+
+    def _decode_inner(self) -> torch.Tensor:
         if self._film:  # the one-launch native per-map stage (reni_film_map_forward) instead of ~25 torch launches
             saved = self.model.NATIVE_MAP_LEVEL_MAX_BATCH
             self.model.NATIVE_MAP_LEVEL_MAX_BATCH = max(saved, self.Z.shape[0])

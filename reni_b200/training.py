@@ -15,6 +15,7 @@ latent gradients stay on the rank that owns the maps.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -38,18 +39,77 @@ def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
 
 class FlatGradBuffer:
     """One contiguous fp32 buffer holding every decoder-weight gradient (680 707 floats at N=36), with
-    per-parameter views used both as the kernels' accumulation targets and as ``param.grad``."""
+    per-parameter views used both as the kernels' accumulation targets and as ``param.grad``.
 
-    def __init__(self, params: Sequence[torch.Tensor]):
+    Exchange (DDP semantics, run.py:97: average over ranks of the per-rank batch-summed gradients), chosen once:
+      * ``"multicast"`` / ``"p2p"``: the buffer lives in symmetric memory (torch.distributed._symmetric_memory does the
+        peer mapping) and ``reni_allreduce`` reduces it in place through NVLink -- multimem.ld_reduce / multimem.st on
+        the NVSwitch multicast address, or a two-shot exchange over the peer pointers.  A plain kernel on the
+        caller's stream: it can be captured in the step graph right behind the gradient kernels (``capturable``).
+      * ``"nccl"``: one ``ncclAllReduce`` (gloo: sum + divide) -- the fallback and the CPU-test path.
+    ``RENI_EXCHANGE=nccl|p2p|multicast`` forces a choice."""
+
+    def __init__(self, params: Sequence[torch.Tensor], group=None, symmetric: Optional[bool] = None):
         self.params = list(params)
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.group = group
+        self.exchange = "none"
+        self.capturable = True  # (nothing to exchange at world size 1)
+        self._symm = None
+        self.flat = None
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if world > 1:
+            self.exchange, self.capturable = "nccl", False
+            want = os.environ.get("RENI_EXCHANGE", "")
+            if symmetric is not False and want != "nccl" and dev.type == "cuda" and dist.get_backend(group) == "nccl":
+                try:
+                    self._setup_symmetric(n, dev, group, world, want)
+                except Exception as e:  # symmetric memory unavailable (driver, topology, torch build): NCCL does it
+                    self._symm = None
+                    self.flat = None
+                    self.symmetric_error = repr(e)
+                    if symmetric is True or want in ("p2p", "multicast"):
+                        raise
+        if self.flat is None:
+            self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.views: List[torch.Tensor] = []
         off = 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+
+    def _setup_symmetric(self, n: int, dev, group, world: int, want: str) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+
+        lib = _lib.load()
+        pg = group if group is not None else dist.group.WORLD
+        n4 = (n + 3) // 4 * 4
+        buf = symm_mem.empty(n4, dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(buf, pg)
+        nflag = int(lib.reni_allreduce_flag_bytes()) // 4
+        flags = symm_mem.empty(nflag, dtype=torch.int32, device=dev)
+        flags.zero_()
+        fh = symm_mem.rendezvous(flags, pg)
+        if getattr(hdl, "offset", 0) or getattr(fh, "offset", 0):
+            raise RuntimeError("symmetric allocation at a non-zero offset")
+        buf.zero_()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)  # every rank's flag block is zero before anybody signals
+        try:
+            mc = int(hdl.multicast_ptr) if want != "p2p" else 0
+        except Exception:
+            mc = 0
+        if want == "multicast" and not mc:
+            raise RuntimeError("no multicast address for the symmetric gradient buffer")
+        self._symm = dict(buf=buf, hdl=hdl, flags=flags, fh=fh, mc=mc, n4=n4, world=world, rank=dist.get_rank(group),
+                          epoch=torch.zeros(1, dtype=torch.int32, device=dev),
+                          status=torch.zeros(1, dtype=torch.int32, device=dev))
+        self.flat = buf[:n]
+        self.exchange = "multicast" if mc else "p2p"
+        self.capturable = True
 
     def zero_(self) -> None:
         self.flat.zero_()
@@ -60,7 +120,23 @@ class FlatGradBuffer:
 
     def all_reduce_mean(self, group=None) -> None:
         """DDP semantics (run.py:97): average over ranks of the per-rank batch-summed gradients."""
-        if not (dist.is_available() and dist.is_initialized()):
+        if self.exchange == "none" or not (dist.is_available() and dist.is_initialized()):
+            return
+        group = group if group is not None else self.group
+        if self._symm is not None:
+            import ctypes as C
+
+            from . import _lib
+
+            sm = self._symm
+            dev = self.flat.device
+            with torch.cuda.device(dev):
+                rc = _lib.load().reni_allreduce(
+                    C.c_void_p(int(sm["hdl"].buffer_ptrs_dev)), C.c_void_p(int(sm["fh"].buffer_ptrs_dev)),
+                    C.c_void_p(sm["mc"]), sm["n4"], sm["rank"], sm["world"], 1.0 / sm["world"],
+                    C.c_void_p(sm["epoch"].data_ptr()), C.c_void_p(sm["status"].data_ptr()),
+                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _lib.check(rc, "reni_allreduce")
             return
         world = dist.get_world_size(group)
         if world == 1:
@@ -70,6 +146,10 @@ class FlatGradBuffer:
         else:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             self.flat.div_(world)
+
+    def exchange_failed(self) -> bool:
+        """True if a rank gave up waiting for a peer inside reni_allreduce (host sync; for tests and diagnostics)."""
+        return self._symm is not None and bool(int(self._symm["status"].item()))
 
 
 class RENITrainer:
@@ -81,7 +161,7 @@ class RENITrainer:
     def __init__(self, model: _DecoderBase, task: str, sidelen: int, lr: float = 1e-5,
                  prior_loss_weight: float = 1e-7, cosine_similarity_weight: float = 1e-4,
                  kld_weighting: float = 1e-4, mask: Optional[torch.Tensor] = None, process_group=None,
-                 ddp_latent_scaling: bool = True, cuda_graph: bool = False):
+                 ddp_latent_scaling: bool = True, cuda_graph: bool = False, latent_sync: str = "local"):
         if task not in ("FIT_DECODER", "FIT_LATENT"):
             raise NotImplementedError("FIT_INVERSE needs the PyTorch3D renderer and is out of scope for this path")
         self.model = model
@@ -89,6 +169,13 @@ class RENITrainer:
         self.group = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.ddp_latent_scaling = ddp_latent_scaling
+        # Latent tables under data parallelism.  "local" (default): maps are sharded, a rank only ever updates the rows
+        # of the maps it owns (shard_range) and the tables are NOT kept identical across ranks -- feed each rank its
+        # own shard and use gather_latents() for a checkpoint.  "replicated": the reference's DDP behaviour, the dense
+        # table gradient is all-reduced too, every rank holds the same table and any sampler works.
+        if latent_sync not in ("local", "replicated"):
+            raise ValueError("latent_sync must be 'local' or 'replicated'")
+        self.latent_sync = latent_sync
         dev = next(model.parameters()).device
         self.device = dev
         self.set_resolution(sidelen)
@@ -120,7 +207,7 @@ class RENITrainer:
             opt_params = list(model.parameters())
             latents = {id(p) for p in (getattr(model, n, None) for n in ("Z", "mu", "log_var")) if p is not None}
             self.flat = FlatGradBuffer([p for p in model.parameters() if id(p) not in latents] if self.is_film
-                                       else model.decoder_parameters())
+                                       else model.decoder_parameters(), group=process_group)
         self.optimizer = FusedAdam(opt_params, lr=lr)  # one launch; same arithmetic as torch.optim.Adam(params, lr)
 
     # -- multi-resolution curriculum hook (callbacks.py:11-29 doubles the resolution at curriculum epochs)
@@ -156,7 +243,7 @@ class RENITrainer:
         """Same inputs and returned keys as RENI_module.training_step; gradients are left in ``.grad``."""
         if self.is_film:
             return self._film_step(batch)
-        if self.cuda_graph and not (self.is_vad and not self.fixed):  # (the VAD sampler draws from torch's RNG: eager)
+        if self.cuda_graph:  # (the VAD sampler's noise is a torch.randn inside the capture: graph-safe Philox offsets)
             return self._graphed_step(batch)
         return self._eager_step(batch)
 
@@ -182,19 +269,24 @@ class RENITrainer:
                 s_idx = torch.empty(idx.shape, dtype=torch.long, device=self.device)
                 s_imgs.copy_(imgs)
                 s_idx.copy_(idx)
+                # a captured graph holds raw pointers into its workspace: each graph owns one (a shared, growing
+                # workspace would be freed under it by a later, larger batch shape)
+                gws = Workspace()
                 side = torch.cuda.Stream(device=self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):  # warm-up outside capture (lazy initialisation, cuBLAS workspaces)
                     for _ in range(3):
-                        self._film_body(s_imgs, s_idx)
+                        gws.prepared_key = None
+                        self._film_body(s_imgs, s_idx, ws=gws)
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 graph = torch.cuda.CUDAGraph()
+                gws.prepared_key = None  # the fp32 -> fp16 weight images are rebuilt inside every replayed step
                 with torch.cuda.graph(graph):
-                    log = self._film_body(s_imgs, s_idx)
+                    log = self._film_body(s_imgs, s_idx, ws=gws)
                 grads = [(p, p.grad) for p in self.model.parameters()]
-                entry = (graph, s_imgs, s_idx, log, grads, self.last_output)
+                entry = (graph, s_imgs, s_idx, log, grads, self.last_output, gws)
                 self._graphs[key] = entry
-            graph, s_imgs, s_idx, log, grads, last_out = entry
+            graph, s_imgs, s_idx, log, grads, last_out, _gws = entry
             src_imgs, src_idx = (slot["imgs"], slot["idx"]) if slot is not None else (imgs, idx)
             s_imgs.copy_(src_imgs, non_blocking=True)
             s_idx.copy_(src_idx, non_blocking=True)
@@ -210,9 +302,11 @@ class RENITrainer:
                     p.grad.div_(self.world_size)
         if self.flat is not None:
             self.flat.all_reduce_mean(self.group)
+        self._sync_latent_grads()
         return log
 
-    def _film_body(self, imgs: torch.Tensor, idx: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def _film_body(self, imgs: torch.Tensor, idx: torch.Tensor, ws: Optional[Workspace] = None) -> Dict[str, torch.Tensor]:
+        ws = ws if ws is not None else self._ws
         B = imgs.shape[0]
         imgs = imgs.permute(0, 2, 3, 1).reshape(B, -1, 3)
         sw = self.sineweight if self.mask is None else self.sineweight * self.mask
@@ -245,7 +339,7 @@ class RENITrainer:
                 views = [by_id[id(p)] for p in core]
             fit_latent = self.task == "FIT_LATENT"
             res = F_.film_loss_forward_backward(
-                model.spec, self._ws, mc.detach(), film.detach(), self.directions, imgs,
+                model.spec, ws, mc.detach(), film.detach(), self.directions, imgs,
                 self.sineweight if self.mask is None else self.sineweight * self.mask, core,
                 beta=self.beta if fit_latent else 0.0, use_cosine=fit_latent, need_dw=need_dw,
                 grad_weights=views[0::2] if need_dw else None, grad_biases=views[1::2] if need_dw else None)
@@ -321,27 +415,36 @@ class RENITrainer:
         slot = self._take_prefetched(batch)
         imgs, idx = batch
         idx = torch.as_tensor(idx, dtype=torch.long)
+        self._check_shard(idx)
         key = (tuple(imgs.shape), imgs.dtype, int(idx.numel()))
         entry = self._graphs.get(key)
+        # the gradient exchange is part of the graph when it is a plain kernel (reni_allreduce over symmetric memory);
+        # an NCCL all-reduce is launched behind each replay instead
+        in_graph = self.flat is None or self.flat.capturable
         if entry is None:
             s_imgs = torch.empty(imgs.shape, dtype=imgs.dtype, device=self.device)
             s_idx = torch.empty(idx.shape, dtype=torch.long, device=self.device)
             s_imgs.copy_(imgs)
             s_idx.copy_(idx)
+            # a captured graph holds raw pointers into its workspace: each graph owns one (a shared, growing workspace
+            # would be freed under it by a later, larger batch shape)
+            gws = Workspace()
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):  # warm-up outside capture: lazy allocations, function attributes
                 for _ in range(2):
-                    self._ws.prepared_key = None
-                    self._eager_step((s_imgs, s_idx), exchange=False)
+                    gws.prepared_key = None
+                    self._eager_step((s_imgs, s_idx), exchange=in_graph, ws=gws)
             torch.cuda.current_stream(self.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            self._ws.prepared_key = None  # the fp32 -> fp16 weight conversion is part of every replayed step
-            with torch.cuda.graph(graph):  # compute only: the NCCL exchange is launched behind each replay
-                log = self._eager_step((s_imgs, s_idx), exchange=False)
-            entry = (graph, s_imgs, s_idx, log, self._latent_table().grad)
+            gws.prepared_key = None  # the fp32 -> fp16 weight conversion is part of every replayed step
+            with torch.cuda.graph(graph):
+                log = self._eager_step((s_imgs, s_idx), exchange=in_graph, ws=gws)
+            grads = [(p, p.grad) for p in (getattr(self.model, n, None) for n in ("Z", "mu", "log_var"))
+                     if p is not None and p.grad is not None]
+            entry = (graph, s_imgs, s_idx, log, grads, gws)
             self._graphs[key] = entry
-        graph, s_imgs, s_idx, log, table_grad = entry
+        graph, s_imgs, s_idx, log, grads, _gws = entry
         if slot is not None:  # staged by prefetch(): device -> device into the graph's static inputs
             s_imgs.copy_(slot["imgs"], non_blocking=True)
             s_idx.copy_(slot["idx"], non_blocking=True)
@@ -351,18 +454,23 @@ class RENITrainer:
             s_idx.copy_(idx, non_blocking=True)
         graph.replay()
         # the replay refreshed the captured gradient tensors in place; make sure the parameters still point at them
-        self._latent_table().grad = table_grad
+        for p, g in grads:
+            p.grad = g
         if self.flat is not None:
-            self.flat.all_reduce_mean(self.group)  # the ONE exchange step of data-parallel training
+            if not in_graph:
+                self.flat.all_reduce_mean(self.group)  # the ONE exchange step of data-parallel training
             self.flat.attach()
         return log
 
-    def _eager_step(self, batch, exchange: bool = True) -> Dict[str, torch.Tensor]:
+    def _eager_step(self, batch, exchange: bool = True, ws: Optional[Workspace] = None) -> Dict[str, torch.Tensor]:
+        ws = ws if ws is not None else self._ws
         slot = self._take_prefetched(batch)
         imgs, idx = batch
         if slot is not None:
             imgs, idx = slot["imgs"].clone(), slot["idx"].clone()
             slot["free"].record(torch.cuda.current_stream(self.device))
+        else:
+            self._check_shard(idx)
         imgs = imgs.to(self.device, non_blocking=True)
         B = imgs.shape[0]
         imgs = imgs.permute(0, 2, 3, 1).reshape(B, -1, 3)  # (B,C,H,W) -> (B,P,3)   RENI_module.py:83-84
@@ -371,9 +479,13 @@ class RENITrainer:
         model = self.model
         table = self._latent_table()
         sampled = self.is_vad and not self.fixed
+        latent_scale = 1.0 / self.world_size if (self.world_size > 1 and self.ddp_latent_scaling) else 1.0
         if sampled:
-            Z, mu, log_var = model.sample_latent(idx)  # RENI_module.py:100-101 (torch RNG, autograd graph)
-            Zin = Z.detach()
+            # RENI_module.py:100-101 -> sample_latent (RENI.py:329-335): the noise is torch's (same generator use as
+            # randn_like(std)), the sample itself one library call; nothing here needs an autograd graph
+            eps = torch.randn(B, model.ndims, 3, device=self.device, dtype=torch.float32)
+            Zin = torch.empty_like(eps)
+            self._vad_call("reni_vad_sample", model.mu, model.log_var, idx, eps, B, model.ndims * 3, Zin)
         else:
             Zin = table.detach()[idx]  # :98,:103
         need_dw = not self.fixed
@@ -384,22 +496,25 @@ class RENITrainer:
         else:
             alpha, beta, use_cos = 0.0, 0.0, False                  # RENITrainLoss (:117)
         res = F_.loss_forward_backward(
-            model.spec, self._ws, Zin, self.directions, imgs, sw, model.decoder_weights(), model.decoder_biases(),
+            model.spec, ws, Zin, self.directions, imgs, sw, model.decoder_weights(), model.decoder_biases(),
             alpha=alpha, beta=beta, use_cosine=use_cos, need_dw=need_dw,
             grad_weights=self.flat.views[0::2] if need_dw else None,
             grad_biases=self.flat.views[1::2] if need_dw else None)
-        dZ = res.dZ
-        if self.world_size > 1 and self.ddp_latent_scaling:
-            # the reference replicates the latent table and DDP averages its (mostly zero) gradient over ranks
-            dZ = dZ / self.world_size
         log: Dict[str, torch.Tensor] = {"loss": res.loss}
         if sampled:
-            kld = self.kld_weighting * KLD(mu, log_var, Z_dims=model.ndims * 3)  # :312-315
-            model.mu.grad = None
-            model.log_var.grad = None
-            torch.autograd.backward([Z, kld], [dZ, torch.ones_like(kld)])
-            log = {"loss": res.loss + kld.detach(), "mse_loss": res.mse_loss, "kld_loss": kld.detach()}
+            # RENIVADTrainLoss (loss_functions.py:47-58, beta = KLD_WEIGHTING, Z_dims = 3N: RENI_module.py:312-315): the KLD
+            # value and BOTH terms' gradients for mu / log_var in one launch; the reference's DDP averages the whole
+            # gradient of the replicated tables, so the KLD part is divided by the world size like the MSE part
+            model.mu.grad = torch.zeros_like(model.mu)
+            model.log_var.grad = torch.zeros_like(model.log_var)
+            kld = torch.zeros((), device=self.device, dtype=torch.float32)
+            nz = model.ndims * 3
+            self._vad_call("reni_vad_backward", model.mu, model.log_var, idx, eps, res.dZ, B, nz,
+                           float(self.kld_weighting) / nz, float(latent_scale), model.mu.grad, model.log_var.grad, kld)
+            log = {"loss": res.loss + kld, "mse_loss": res.mse_loss, "kld_loss": kld}
         else:
+            # the reference replicates the latent table and DDP averages its (mostly zero) gradient over ranks
+            dZ = res.dZ * latent_scale if latent_scale != 1.0 else res.dZ
             g = torch.zeros_like(table)
             g.index_add_(0, idx, dZ)
             table.grad = g
@@ -409,8 +524,78 @@ class RENITrainer:
             if exchange:
                 self.flat.all_reduce_mean(self.group)  # the ONE exchange step of data-parallel training
             self.flat.attach()
+        if exchange:
+            self._sync_latent_grads()
         self.last_output = res.out
         return log
+
+    def _vad_call(self, name: str, mu, log_var, idx, eps, *rest) -> None:
+        import ctypes as C
+
+        from . import _lib
+
+        def arg(a):
+            if isinstance(a, torch.Tensor):
+                return C.c_void_p(a.data_ptr())
+            return a
+
+        with torch.cuda.device(self.device):
+            rc = getattr(_lib.load(), name)(arg(mu.detach()), arg(log_var.detach()), arg(idx), arg(eps),
+                                            *[arg(a) for a in rest],
+                                            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        _lib.check(rc, name)
+
+    # -- latent tables under data parallelism -------------------------------------------------------------------
+    def _latent_params(self):
+        return [p for p in (getattr(self.model, n, None) for n in ("Z", "mu", "log_var")) if p is not None]
+
+    def _sync_latent_grads(self) -> None:
+        """latent_sync="replicated": sum the dense table gradients over the ranks (each rank's is already divided by the
+        world size), as the reference's DDP does for the replicated table."""
+        if self.world_size == 1 or self.latent_sync != "replicated":
+            return
+        for p in self._latent_params():
+            if p.grad is not None and p.requires_grad:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group)
+                if not self.ddp_latent_scaling:
+                    p.grad.div_(self.world_size)
+
+    def _check_shard(self, idx) -> None:
+        """latent_sync="local": a rank may only touch the latents of its own maps.  Checked when the indices are host
+        tensors / lists (no device sync); a DistributedSampler that shuffles across ranks trips this."""
+        if self.world_size == 1 or self.latent_sync != "local":
+            return
+        t = torch.as_tensor(idx)
+        if t.device.type != "cpu" or t.numel() == 0:
+            return
+        rank = dist.get_rank(self.group)
+        lo, hi = shard_range(self._latent_table().shape[0], rank, self.world_size)
+        if int(t.min()) < lo or int(t.max()) >= hi:
+            raise ValueError(
+                f"rank {rank} owns latent rows [{lo}, {hi}) (shard_range) but the batch indexes "
+                f"[{int(t.min())}, {int(t.max())}]: with latent_sync='local' every rank must be fed its own shard of "
+                "maps; use latent_sync='replicated' for the reference's replicated-table behaviour")
+
+    @torch.no_grad()
+    def gather_latents(self) -> Dict[str, torch.Tensor]:
+        """Full latent tables for a checkpoint: with latent_sync="local" every rank holds trained rows only for its own
+        shard (shard_range), so the tables are assembled from the owners' rows.  Collective: call on every rank."""
+        out = {}
+        for name in ("Z", "mu", "log_var"):
+            p = getattr(self.model, name, None)
+            if p is None:
+                continue
+            full = p.detach().clone()
+            if self.world_size > 1 and self.latent_sync == "local":
+                n = full.shape[0]
+                rank = dist.get_rank(self.group)
+                lo, hi = shard_range(n, rank, self.world_size)
+                mine = torch.zeros_like(full)
+                mine[lo:hi] = full[lo:hi]
+                dist.all_reduce(mine, op=dist.ReduceOp.SUM, group=self.group)  # disjoint shards: the sum assembles them
+                full = mine
+            out[name] = full
+        return out
 
     def step(self, batch) -> Dict[str, torch.Tensor]:
         """training_step + optimiser step (what trainer.fit does per iteration)."""
