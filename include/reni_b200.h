@@ -256,7 +256,8 @@ int32_t reni_vad_backward(const float* mu, const float* log_var, const int64_t* 
  *   multicast_ptr : multicast address aliasing the W buffers (NVSwitch, multimem.ld_reduce / multimem.st), or NULL for
  *                   the two-shot exchange over the peer pointers
  *   numel         : fp32 elements, a multiple of 4;  scale: 1 / W for the mean
- *   epoch         : DEVICE word, incremented on the stream by this call (orders the flag values across calls/replays)
+ *   epoch         : DEVICE block of reni_allreduce_flag_bytes() / 64 words, zeroed once: per-block call counters kept by
+ *                   the kernel itself (order the flag values across calls and graph replays)
  *   status        : DEVICE word, set to 1 if a rank gave up waiting for a peer (bounded spin; the result is then wrong)
  * Every rank must make the same sequence of calls. */
 int64_t reni_allreduce_flag_bytes(void);

@@ -131,7 +131,10 @@ CASES = {
     # BASELINE.json shapes (round 2): configs[0] itself (1 map, 64x128, N=36); N=49 (configs/experiment.yaml:7) and
     # N=100 (configs[2]/[4]) on one 32x64 map -- the N=100 encoding of that map is 84 MB in fp32
     "cfg1_so2_n36_64x128": (19, 1, 8192, 36, 256, 5, 3, "SO2", True, "tanh", 128, 1e-7, 1e-4, False),
-    "so2_n49_h256": (20, 1, 2048, 49, 256, 5, 3, "SO2", True, "tanh", 64, 1e-7, 1e-4, False),
+    "so2_n49_h256": (24, 1, 2048, 49, 256, 5, 3, "SO2", True, "tanh", 64, 1e-7, 1e-4, False),
+    # a draw whose random-init decoder emits almost nothing but a small output bias (radiance RMS 0.010): the RELATIVE
+    # radiance error of fp16 operands is inflated accordingly (the tests hold it to an absolute bound instead)
+    "so2_n49_h256_lowrms": (20, 1, 2048, 49, 256, 5, 3, "SO2", True, "tanh", 64, 1e-7, 1e-4, False),
     "so2_n100_h256": (21, 1, 2048, 100, 256, 5, 3, "SO2", True, "tanh", 64, 1e-7, 1e-4, False),
     "none_n9_h256": (22, 2, 512, 9, 256, 5, 3, "None", True, "tanh", 32, 1e-7, 1e-1, False),
     "so3_n9_h256": (23, 2, 512, 9, 256, 5, 3, "SO3", True, "tanh", 32, 1e-7, 1e-1, False),

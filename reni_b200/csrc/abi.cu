@@ -1049,11 +1049,14 @@ int32_t reni_allreduce(void* dev_buf_ptrs, void* dev_flag_ptrs, void* multicast_
   p.scale = scale;
   p.epoch = epoch;
   p.status = status;
-  reni_allreduce_epoch_kernel<<<1, 1, 0, stream>>>(epoch);
+  // one block per SM at most, each thread with kArUnroll 16-byte elements in flight (the grid only depends on numel
+  // and world, so every rank -- and every replay of a captured call -- launches the same blocks)
   const int64_t per = (p.n4 + world - 1) / world;
-  int blocks = (int)((per + kArThreads - 1) / kArThreads);
+  int blocks = (int)((per + (int64_t)kArThreads * kArUnroll - 1) / ((int64_t)kArThreads * kArUnroll));
   if (blocks < 1) blocks = 1;
-  if (blocks > kArMaxBlocks) blocks = kArMaxBlocks;
+  const int sms = num_sms();
+  const int cap = sms > 0 && sms < kArMaxBlocks ? sms : kArMaxBlocks;
+  if (blocks > cap) blocks = cap;
   reni_allreduce_kernel<<<blocks, kArThreads, 0, stream>>>(p);
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }

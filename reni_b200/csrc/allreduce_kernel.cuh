@@ -12,9 +12,11 @@
 //                             multimem.st [mc + i], v * scale       (the switch writes all W copies)
 //                 peer ptrs : v = sum_p ld [buf_p + i] ; st [buf_p + i], v * scale for every p   (two-shot over P2P)
 //   barrier B   every rank's slice has been written everywhere
-// Flags are monotone: the caller bumps a device-side epoch before each call (reni_allreduce_epoch_kernel, captured in
-// the same graph), block b of rank r signals slot [b][r] of every peer with 2 * epoch + 1 (+ 2 for barrier B) and waits
-// for its own slots.  All waits are bounded: a missing peer sets *status instead of hanging the device.
+// Flags are monotone: every block keeps its own call counter (epoch[b], incremented by the block itself, so a captured
+// graph replays correctly); block b of rank r signals slot [b][r] of every peer with 2 * epoch + 1 (+ 2 for barrier B)
+// and waits for its own slots.  All waits are bounded: a missing peer sets *status instead of hanging the device.
+// One launch; up to one block per SM with four 16-byte multimem / peer loads in flight per thread (the first version
+// -- 32 blocks, one load in flight -- took 66 us for 2.7 MB on two GPUs, latency-bound; NCCL takes 53 us).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -22,8 +24,9 @@
 namespace reni {
 
 constexpr int kArThreads = 512;
-constexpr int kArMaxBlocks = 32;
+constexpr int kArMaxBlocks = 160;
 constexpr int kArMaxWorld = 16;
+constexpr int kArUnroll = 4;
 
 struct AllReduceParams {
   float* const* bufs;        // device array of W pointers to the ranks' buffers (own buffer at [rank])
@@ -32,11 +35,9 @@ struct AllReduceParams {
   int64_t n4;                // float4 elements
   int rank, world;
   float scale;               // 1 / world for the mean
-  const uint32_t* epoch;     // device word, bumped before the call
+  uint32_t* epoch;           // kArMaxBlocks device words: per-block call counters
   uint32_t* status;          // set to 1 if a wait gave up
 };
-
-__global__ void reni_allreduce_epoch_kernel(uint32_t* epoch) { *epoch += 1; }
 
 __device__ __forceinline__ void ar_signal(uint32_t* addr, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
@@ -60,34 +61,44 @@ __device__ __forceinline__ void ar_barrier(const AllReduceParams& p, uint32_t ta
         *p.status = 1u;
         break;
       }
-      __nanosleep(64);
+      if (spins > 64) __nanosleep(32);
     }
   }
   __syncthreads();
 }
 
 __global__ void __launch_bounds__(kArThreads) reni_allreduce_kernel(const AllReduceParams p) {
-  const uint32_t e = *p.epoch;
+  const uint32_t e = p.epoch[blockIdx.x] + 1;  // this block's call number (every rank launches the same grid)
   ar_barrier(p, 2 * e + 1);
   const int64_t per = (p.n4 + p.world - 1) / p.world;
   const int64_t lo = (int64_t)p.rank * per;
   const int64_t hi = lo + per < p.n4 ? lo + per : p.n4;
   const int64_t stride = (int64_t)gridDim.x * kArThreads;
   if (p.mc != nullptr) {
-    for (int64_t i = lo + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i < hi; i += stride) {
-      float4 v;
-      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                   : "l"(p.mc + 4 * i)
-                   : "memory");
-      v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
-      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.mc + 4 * i), "f"(v.x),
-                   "f"(v.y), "f"(v.z), "f"(v.w)
-                   : "memory");
+    for (int64_t i0 = lo + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i0 < hi; i0 += kArUnroll * stride) {
+      float4 v[kArUnroll];
+#pragma unroll
+      for (int u = 0; u < kArUnroll; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < hi)
+          asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                       : "l"(p.mc + 4 * i)
+                       : "memory");
+      }
+#pragma unroll
+      for (int u = 0; u < kArUnroll; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < hi)
+          asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.mc + 4 * i),
+                       "f"(v[u].x * p.scale), "f"(v[u].y * p.scale), "f"(v[u].z * p.scale), "f"(v[u].w * p.scale)
+                       : "memory");
+      }
     }
   } else {
     for (int64_t i = lo + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i < hi; i += stride) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
       for (int q = 0; q < p.world; ++q) {
         float4 v;  // (peer memory, written by another device before barrier A: bypass L1)
         asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -100,8 +111,8 @@ __global__ void __launch_bounds__(kArThreads) reni_allreduce_kernel(const AllRed
       for (int q = 0; q < p.world; ++q) reinterpret_cast<float4*>(p.bufs[q])[i] = acc;
     }
   }
-  __threadfence_system();
-  ar_barrier(p, 2 * e + 2);
+  ar_barrier(p, 2 * e + 2);  // (bar.sync + one system-scope fence per signalling thread publish the block's stores)
+  if (threadIdx.x == 0) p.epoch[blockIdx.x] = e;
 }
 
 }  // namespace reni

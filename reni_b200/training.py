@@ -105,7 +105,7 @@ class FlatGradBuffer:
         if want == "multicast" and not mc:
             raise RuntimeError("no multicast address for the symmetric gradient buffer")
         self._symm = dict(buf=buf, hdl=hdl, flags=flags, fh=fh, mc=mc, n4=n4, world=world, rank=dist.get_rank(group),
-                          epoch=torch.zeros(1, dtype=torch.int32, device=dev),
+                          epoch=torch.zeros(nflag, dtype=torch.int32, device=dev),
                           status=torch.zeros(1, dtype=torch.int32, device=dev))
         self.flat = buf[:n]
         self.exchange = "multicast" if mc else "p2p"

@@ -78,6 +78,29 @@ def test_forward_matches_reference_golden(dev, name):
     assert O.rel_max(out, ref) < TOL_RADIANCE_MAX
 
 
+def test_low_output_draw_absolute_error(dev):
+    """so2_n49_h256_lowrms: a random-init draw whose decoder emits radiance of RMS 0.010 (a small output bias and little
+    else).  The absolute radiance error is the same ~1.5e-5 as on every other draw (fp16 operand rounding through five
+    omega = 30 layers), which is 1.3e-3 of THIS output; gradients stay well inside their bar.  Recorded, not hidden:
+    DESIGN.md "Precision" has the distribution over draws."""
+    from reni_b200 import functional as F_
+
+    c = load_case("so2_n49_h256_lowrms")
+    g = c["g"]
+    m = model_from_params(c["p"], c["N"], dev)
+    Z, D, tg, sw = (t(c[k], dev) for k in ("Z", "D", "target", "sw"))
+    r = F_.loss_forward_backward(m.spec, F_.Workspace(), Z, D, tg, sw, m.decoder_weights(), m.decoder_biases(), need_dw=True)
+    torch.cuda.synchronize()
+    out, ref = r.out.cpu().numpy(), g["out_f32"]
+    print("low-output draw: radiance rel-L2", O.rel_l2(out, ref), "max abs err", np.abs(out - ref).max(),
+          "radiance RMS", float(np.sqrt((ref.astype(np.float64) ** 2).mean())))
+    assert np.abs(out - ref).max() < 6e-5
+    assert O.rel_l2(out, ref) < 2e-3
+    assert O.rel_l2(r.dZ.cpu().numpy(), g["train_dZ_f32"]) < TOL_GRAD
+    for i in range(c["L"] + 2):
+        assert O.rel_l2(sub_dw(i, r.dW[i].cpu().numpy()), g[f"train_dW{i}_f32"]) < TOL_GRAD, f"dW{i}"
+
+
 @pytest.mark.parametrize("name", H256_CASES)
 def test_fused_training_step_matches_reference_golden(dev, name):
     """FIT_DECODER: RENITrainLoss + all gradients; FIT_LATENT: RENITestLoss (prior + cosine [+ mask]) + dZ."""

@@ -82,7 +82,7 @@ def _worker(rank, world, port, q):
             dist.all_reduce(loss, op=dist.ReduceOp.SUM)
             # single-rank reference on this rank's GPU (no process group inside: world_size forced to 1)
             m1 = RENIAutoDecoder(total, 9, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
-            m1.load_state_dict(m.state_dict())
+            m1.load_state_dict({"model." + k: v for k, v in m.state_dict().items()})  # (Lightning-prefixed keys, RENI.py:190-203)
             tr1 = RENITrainer(m1, "FIT_DECODER", W, lr=1e-4)
             tr1.world_size = 1
             tr1.flat.exchange = "none"

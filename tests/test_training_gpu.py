@@ -101,7 +101,7 @@ def test_graphed_trainer_follows_optimizer_steps(dev, W, film):
         (lambda: RENIAutoDecoder(8, N, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False))
     a = mk().to(dev)
     b = mk().to(dev)
-    b.load_state_dict(a.state_dict())
+    b.load_state_dict({"model." + k: v for k, v in a.state_dict().items()})  # (Lightning-prefixed keys, RENI.py:190-203)
     imgs = torch.rand(B, 3, W // 2, W, device=dev) * 2 - 1
     idx = torch.tensor([0, 3, 4, 6], device=dev)
     te = RENITrainer(a, "FIT_DECODER", W, lr=3e-4)
