@@ -71,6 +71,11 @@ typedef struct {
                                        * split-K weight-gradient GEMM (the default schedule) */
 #define RENI_FLAG_FWD_SINGLE_TERM 256  /* forward hidden layers on one-term fp16 weights (fastest; radiance rel-L2 3e-4..1.3e-3) */
 #define RENI_FLAG_FWD_TWO_TERM 512     /* ... on two-term weights W_hi + W_lo (the library default; x 0.6..0.8 of that error) */
+#define RENI_FLAG_GRID_DIRECTIONS 1024  /* the directions are the equirectangular grid get_directions(W) (src/utils/utils.py:46-65)
+                                        * with P = W * W / 2: computed in the kernels from the pixel index, D may be NULL */
+#define RENI_FLAG_GRID_SINEWEIGHT 2048  /* the sine weights are get_sineweight(W) (utils.py:68-78) times a binary mask
+                                        * (RENI_module.py:92-94): computed in the kernels; the `sw` argument is then NOT a float
+                                        * tensor but NULL (no mask) or a `const uint32_t*` of P bits, bit p = pixel p is kept */
 #define RENI_FLAG_LAYER_MAJOR_BWD 128 /* ... force the layer-major schedule (one launch per hidden layer computes the delta chain
                                        * and the weight gradients in one pass over the stash; same results up to summation order) */
 

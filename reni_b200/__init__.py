@@ -10,7 +10,7 @@ training / latent-optimisation step around it (src/lightning/RENI_module.py:80-1
 All decoder arithmetic runs in the hand-written CUDA library ``reni_b200/lib/libreni_b200.so``
 (C ABI: include/reni_b200.h), built by ``__graft_entry__.build()``.  There is no CPU fallback.
 """
-from .geometry import get_directions, get_mask, get_sineweight, rectangle_mask
+from .geometry import get_directions, get_mask, get_sineweight, pack_mask_bits, rectangle_mask
 from .losses import (KLD, CosineSimilarity, RENITestLoss, RENITrainLoss, RENIVADTrainLoss, WeightedCosineSimilarity,
                      WeightedMSE)
 from .film import CustomMappingNetwork, FiLMLayer, RENIAutoDecoderFiLM, RENIVariationalAutoDecoderFiLM
@@ -24,6 +24,6 @@ __all__ = [
     "RENIAutoDecoderFiLM", "RENIVariationalAutoDecoderFiLM", "FiLMLayer", "CustomMappingNetwork",
     "WeightedMSE", "KLD", "WeightedCosineSimilarity", "CosineSimilarity",
     "RENITrainLoss", "RENIVADTrainLoss", "RENITestLoss",
-    "get_directions", "get_sineweight", "get_mask", "rectangle_mask",
+    "get_directions", "get_sineweight", "get_mask", "rectangle_mask", "pack_mask_bits",
     "RENITrainer", "FlatGradBuffer", "shard_range", "FusedAdam", "GraphedDecoder",
 ]

@@ -23,6 +23,8 @@ FLAG_TILE_MAJOR_BWD = 64
 FLAG_LAYER_MAJOR_BWD = 128
 FLAG_FWD_SINGLE_TERM = 256
 FLAG_FWD_TWO_TERM = 512
+FLAG_GRID_DIRECTIONS = 1024
+FLAG_GRID_SINEWEIGHT = 2048
 
 EQUIVARIANCE = {"None": 0, "SO2": 1, "SO3": 2}
 

@@ -66,6 +66,13 @@ bool config_ok(const reni_config_t* c) {
 
 int64_t tiles_per_map(int64_t P) { return (P + kTileRows - 1) / kTileRows; }
 
+// side length W of the equirectangular grid with P = W * W / 2 directions (get_directions(W), utils.py:46-65); 0 if none
+int grid_sidelen(int64_t P) {
+  int64_t w = 2;
+  while (w * w / 2 < P) w += 2;
+  return (w * w / 2 == P) ? (int)w : 0;
+}
+
 WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_t flags) {
   WorkspaceLayout w{};
   const int64_t L = c->hidden_layers;
@@ -123,6 +130,24 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
 
 // RENI_FLAG_FILM_PERMAP needs every unit of four tiles inside one map
 bool permap_ok(int64_t P) { return P % kTileRows == 0 && (P / kTileRows) % 4 == 0; }
+
+// RENI_FLAG_GRID_DIRECTIONS / RENI_FLAG_GRID_SINEWEIGHT: directions and sine weights in closed form from the pixel index
+// (utils.py:46-78); the sw argument then carries the mask as one bit per pixel (or null)
+struct GridArgs {
+  int w = 0, dir = 0, sw = 0;
+  const uint32_t* mask = nullptr;
+};
+bool grid_args(int32_t flags, int64_t P, const float* D, const float* sw, GridArgs* g) {
+  g->dir = (flags & RENI_FLAG_GRID_DIRECTIONS) ? 1 : 0;
+  g->sw = (flags & RENI_FLAG_GRID_SINEWEIGHT) ? 1 : 0;
+  if (g->dir || g->sw) {
+    g->w = grid_sidelen(P);
+    if (g->w == 0) return false;  // P is not W * W / 2
+  }
+  if (!g->dir && D == nullptr) return false;
+  g->mask = g->sw ? reinterpret_cast<const uint32_t*>(sw) : nullptr;
+  return true;
+}
 
 template <class T>
 T* at(void* ws, int64_t off) {
@@ -291,10 +316,11 @@ int32_t reni_forward(const reni_config_t* c, const float* Z, const float* D, int
                      const float* target, const float* sw, int64_t sw_bstride, void* ws, int64_t ws_bytes,
                      int32_t flags, void* stream_) {
   if (!config_ok(c)) return RENI_ERR_BAD_CONFIG;
-  if (Z == nullptr || D == nullptr || weight0 == nullptr || bias0 == nullptr || out == nullptr || ws == nullptr ||
-      B < 1 || P < 1)
+  if (Z == nullptr || (D == nullptr && !(flags & RENI_FLAG_GRID_DIRECTIONS)) || weight0 == nullptr || bias0 == nullptr ||
+      out == nullptr || ws == nullptr || B < 1 || P < 1)
     return RENI_ERR_BAD_ARGUMENT;
-  if ((flags & RENI_FLAG_LOSS) && (target == nullptr || sw == nullptr)) return RENI_ERR_BAD_ARGUMENT;
+  if ((flags & RENI_FLAG_LOSS) && (target == nullptr || (sw == nullptr && !(flags & RENI_FLAG_GRID_SINEWEIGHT))))
+    return RENI_ERR_BAD_ARGUMENT;
   const WorkspaceLayout w = make_layout(c, B, P, flags);
   if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return RENI_ERR_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -350,6 +376,12 @@ static int32_t launch_forward(const reni_config_t* c, const WorkspaceLayout& w, 
   p.target = (flags & RENI_FLAG_LOSS) ? target : nullptr;
   p.sw = sw;
   p.sw_bstride = sw_bstride;
+  GridArgs ga;
+  if (!grid_args(flags, P, D, sw, &ga)) return RENI_ERR_BAD_ARGUMENT;
+  p.grid_w = ga.w;
+  p.dir_grid = ga.dir;
+  p.sw_grid = ga.sw;
+  p.mask_bits = ga.mask;
   p.loss_part = (flags & RENI_FLAG_LOSS) ? at<float>(ws, w.loss_part) : nullptr;
   p.aout = at<float>(ws, w.aout);
   p.B = (int)B;
@@ -462,6 +494,8 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   if (cudaMemsetAsync(dmc, 0, (size_t)B * 5 * kH * 4, stream) != cudaSuccess) return RENI_ERR_CUDA;
   mark_phase(3, stream);
 
+  GridArgs ga;
+  if (!grid_args(flags, P, D, sw, &ga)) return RENI_ERR_BAD_ARGUMENT;
   // ---- layer-major backward (lbwd_kernel.cuh): head + one launch per hidden layer, delta chain and dW together
   const bool lbwd_wanted = (flags & RENI_FLAG_LAYER_MAJOR_BWD) != 0 || (RENI_LBWD && !(flags & RENI_FLAG_TILE_MAJOR_BWD));
   const bool use_lbwd = lbwd_wanted && want_dw && film == nullptr && g_overlap_dw_ctas == 0;
@@ -490,6 +524,9 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     hp.out_tanh = c->output_activation == 1;
     hp.use_cos = use_cos;
     hp.out_features = c->out_features;
+    hp.grid_w = ga.w;
+    hp.sw_grid = ga.sw;
+    hp.mask_bits = ga.mask;
     if (note(cudaFuncSetAttribute(reni_lbwd_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   LbwdHeadSmem::kTotal)) != cudaSuccess)
       return RENI_ERR_CUDA;
@@ -509,6 +546,8 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
     lp.ntiles = ntiles;
     lp.L = L;
     lp.so2 = c->equivariance == RENI_EQ_SO2;
+    lp.grid_w = ga.w;
+    lp.dir_grid = ga.dir;
     lp.trace = nullptr;
     const int npair = ntiles < sms / 2 ? ntiles : sms / 2;
     if (note(cudaFuncSetAttribute(reni_lbwd_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -546,6 +585,10 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   p.stash_gy = at<__half>(ws, w.stash_gy);
   p.D = D;
   p.d_bstride = d_bstride;
+  p.grid_w = ga.w;
+  p.dir_grid = ga.dir;
+  p.sw_grid = ga.sw;
+  p.mask_bits = ga.mask;
   p.dmc = dmc;
   const bool permap = film != nullptr && (flags & RENI_FLAG_FILM_PERMAP) != 0;  // modulation folded into per-map images
   p.film = (film != nullptr && !permap) ? film->film : nullptr;
@@ -836,9 +879,10 @@ int32_t reni_backward(const reni_config_t* c, const float* Z, const float* D, in
                       const float* grad_out, float* dZ, float* const* host_dW, float* const* host_db, void* ws,
                       int64_t ws_bytes, int32_t flags, void* stream_) {
   if (!config_ok(c)) return RENI_ERR_BAD_CONFIG;
-  if (Z == nullptr || D == nullptr || host_weights == nullptr || host_weights[0] == nullptr || out == nullptr ||
-      grad_out == nullptr || ws == nullptr || B < 1 || P < 1)
+  if (Z == nullptr || (D == nullptr && !(flags & RENI_FLAG_GRID_DIRECTIONS)) || host_weights == nullptr ||
+      host_weights[0] == nullptr || out == nullptr || grad_out == nullptr || ws == nullptr || B < 1 || P < 1)
     return RENI_ERR_BAD_ARGUMENT;
+  flags &= ~RENI_FLAG_GRID_SINEWEIGHT;  // (no sine weights on this path: the gradient comes from the caller)
   if (!(flags & RENI_FLAG_SAVE_FOR_BACKWARD)) return RENI_ERR_BAD_ARGUMENT;
   if ((flags & RENI_FLAG_NEED_DW) && (host_dW == nullptr || host_db == nullptr)) return RENI_ERR_BAD_ARGUMENT;
   const WorkspaceLayout w = make_layout(c, B, P, flags);
@@ -865,7 +909,8 @@ int32_t reni_loss_forward_backward(const reni_config_t* c, const float* Z, const
                                    int32_t flags, void* stream_) {
   if (!config_ok(c)) return RENI_ERR_BAD_CONFIG;
   if (host_weights == nullptr || host_biases == nullptr || host_weights[0] == nullptr || host_biases[0] == nullptr ||
-      target == nullptr || sw == nullptr || out == nullptr || loss_out == nullptr)
+      target == nullptr || (sw == nullptr && !(flags & RENI_FLAG_GRID_SINEWEIGHT)) || out == nullptr ||
+      loss_out == nullptr)
     return RENI_ERR_BAD_ARGUMENT;
   flags |= RENI_FLAG_SAVE_FOR_BACKWARD | RENI_FLAG_LOSS;
   if ((flags & RENI_FLAG_NEED_DW) && (host_dW == nullptr || host_db == nullptr)) return RENI_ERR_BAD_ARGUMENT;
@@ -907,6 +952,13 @@ int32_t reni_loss_forward_backward(const reni_config_t* c, const float* Z, const
   f.loss_part = at<float>(ws, w.loss_part);
   f.sw = sw;
   f.sw_bstride = sw_bstride;
+  {
+    GridArgs ga;
+    if (!grid_args(flags, P, D, sw, &ga)) return RENI_ERR_BAD_ARGUMENT;
+    f.grid_w = ga.w;
+    f.sw_grid = ga.sw;
+    f.mask_bits = ga.mask;
+  }
   f.Z = (alpha != 0.f) ? Z : nullptr;
   f.map_loss = at<float>(ws, w.map_loss);
   f.loss_out = loss_out;

@@ -57,6 +57,8 @@ struct BwdParams {
   int B, P, tiles_per_map, ntiles, L;
   int out_tanh, d_slots, so2;
   int use_cos;            // fused loss: 0 = no cosine term (map_loss is not read, it may still be in flight)
+  int grid_w, dir_grid, sw_grid;  // analytic grid (RENI_FLAG_GRID_DIRECTIONS / RENI_FLAG_GRID_SINEWEIGHT), see fwd_kernel.cuh
+  const uint32_t* mask_bits;
   int w_map_rows;         // per-map backward images (FiLM on per-map images): rows of 256 B per map in wmap, 0 = shared
   uint32_t* ready;        // overlap mode (weight-gradient kernel co-resident on the other SMs): per-tile counter, +1 per
                           // epilogue warp each time a stashed delta_l of the tile is complete in global memory
@@ -435,14 +437,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
             gy[c] = gg;
           }
         } else {
-          const float* wp = p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+          const float* wp = p.sw_grid ? nullptr : p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+          const float wg = p.sw_grid ? grid_sineweight(pix, p.grid_w, p.mask_bits) : 0.f;
           const float* ml = p.map_loss + (size_t)b * 32;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const float o = __ldg(p.out + e + c);
             const float t = __ldg(p.target + e + c);
             // S*g_o = (o-t)*sw + coefA*t + coefB*o   with S = 3P/2
-            float gg = (o - t) * __ldg(wp + c);
+            float gg = (o - t) * (p.sw_grid ? wg : __ldg(wp + c));
             if (p.use_cos) gg += __ldg(ml + 16 + c) * t + __ldg(ml + 19 + c) * o;
             if (p.out_tanh) gg *= (1.f - o * o);
             if (p.aout != nullptr) gg *= cosf(__ldg(p.aout + e + c));
@@ -454,8 +457,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
         // feature row [f0, f1, f2, f3, 1, 0, ...] for the layer-0 reduction GEMM (zero for rows beyond P)
         float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, one = 0.f;
         if (rvalid) {
-          const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
-          const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+          float dx, dy, dz;
+          if (p.dir_grid) {
+            float sp_;
+            grid_point(pix, p.grid_w, dx, dy, dz, sp_);
+          } else {
+            const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
+            dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
+          }
           if (p.so2) { f0 = dx; f1 = dz; f2 = sqrtf(dx * dx + dz * dz); f3 = dy; }
           else       { f0 = dx; f1 = dy; f2 = dz; }
           one = 1.f;

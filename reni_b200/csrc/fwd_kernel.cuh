@@ -67,6 +67,10 @@ struct FwdParams {
   int w_map_rows, b_map_rows;  // per-map weight / bias images (FiLM on per-map images): rows of 256 B per map in wmap / bmap,
                                // 0 = one image shared by all maps
   unsigned long long* trace;  // debug: per-role clock64 timeline of CTA 0 (reni_debug_set_trace), else null
+  int grid_w;                 // side length W of the analytic equirectangular grid (P = W * W / 2), used by:
+  int dir_grid;               // 1: D is not read, directions come from grid_point(pix, grid_w) (RENI_FLAG_GRID_DIRECTIONS)
+  int sw_grid;                // 1: sw is not read, sine weights come from grid_sineweight (RENI_FLAG_GRID_SINEWEIGHT)
+  const uint32_t* mask_bits;  // sw_grid: one bit per pixel (1 = kept), or null
   int split;                  // paired mode: 1 = two-term weights, every K chunk is followed by its fp16 residual chunk
                               // (W' = W_hi + W_lo, acc = h W_hi^T + h W_lo^T): removes the weight-rounding half of the
                               // fp16 operand error of the hidden layers at twice the tensor-core work
@@ -416,8 +420,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
         // invariant direction features, registers only (RENI.py:37-49)
         float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
         if (pix < p.P) {
-          const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
-          const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+          float dx, dy, dz;
+          if (p.dir_grid) {
+            float sp_;
+            grid_point(pix, p.grid_w, dx, dy, dz, sp_);
+          } else {
+            const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
+            dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
+          }
           if (p.so2) {
             f0 = dx;
             f1 = dz;
@@ -575,10 +585,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
             for (int i = 0; i < kLossPartials; ++i) part[i] = 0.f;
             if (rvalid) {
               const float* tp = p.target + ((size_t)b * p.P + pix) * 3;
-              const float* wp = p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+              const float* wp = p.sw_grid ? nullptr : p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+              const float wg = p.sw_grid ? grid_sineweight(pix, p.grid_w, p.mask_bits) : 0.f;
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
-                const float t = __ldg(tp + c), w = __ldg(wp + c);
+                const float t = __ldg(tp + c), w = p.sw_grid ? wg : __ldg(wp + c);
                 const float er = o[c] - t;
                 part[0] = fmaf(er * er, w, part[0]);
                 part[1 + c] = o[c] * t;
@@ -638,8 +649,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
       // ---- invariant direction features, registers only (RENI.py:37-49)
       float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
       if (rvalid) {
-        const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
-        const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+        float dx, dy, dz;
+        if (p.dir_grid) {
+          float sp_;
+          grid_point(pix, p.grid_w, dx, dy, dz, sp_);
+        } else {
+          const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
+          dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
+        }
         if (p.so2) {
           f0 = dx;
           f1 = dz;
@@ -771,10 +788,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
           for (int i = 0; i < kLossPartials; ++i) part[i] = 0.f;
           if (rvalid) {
             const float* tp = p.target + ((size_t)b * p.P + pix) * 3;
-            const float* wp = p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+            const float* wp = p.sw_grid ? nullptr : p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+            const float wg = p.sw_grid ? grid_sineweight(pix, p.grid_w, p.mask_bits) : 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const float t = __ldg(tp + c), w = __ldg(wp + c);
+              const float t = __ldg(tp + c), w = p.sw_grid ? wg : __ldg(wp + c);
               const float er = o[c] - t;
               part[0] = fmaf(er * er, w, part[0]);
               part[1 + c] = o[c] * t;

@@ -51,6 +51,7 @@ struct LbwdParams {
   int64_t d_bstride;
   float* dmc;               // kFirst: (B, 5, 256) dM_b rows 0..3, dc_b row 4 (atomics; caller zeroes)
   int P, tiles_per_map, ntiles, L, l, rev, so2;
+  int grid_w, dir_grid;     // analytic directions (RENI_FLAG_GRID_DIRECTIONS): grid_point(pix, grid_w) instead of D
   unsigned long long* trace;  // debug: clock64 timeline of CTA 0 (reni_debug_set_trace), else null
 };
 
@@ -375,8 +376,14 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
           const int pix = (tile - bm * p.tiles_per_map) * kTileRows + (int)row;
           float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, one = 0.f;
           if (pix < p.P) {
-            const float* d = p.D + (size_t)bm * p.d_bstride + (size_t)pix * 3;
-            const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+            float dx, dy, dz;
+            if (p.dir_grid) {
+              float sp_;
+              grid_point(pix, p.grid_w, dx, dy, dz, sp_);
+            } else {
+              const float* d = p.D + (size_t)bm * p.d_bstride + (size_t)pix * 3;
+              dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
+            }
             if (p.so2) { f0 = dx; f1 = dz; f2 = sqrtf(dx * dx + dz * dz); f3 = dy; }
             else       { f0 = dx; f1 = dy; f2 = dz; }
             one = 1.f;
@@ -468,6 +475,8 @@ struct LbwdHeadParams {
   float* db_out;
   float out_scale;
   int P, tiles_per_map, ntiles, L, out_tanh, use_cos, out_features;
+  int grid_w, sw_grid;      // analytic sine weights (RENI_FLAG_GRID_SINEWEIGHT)
+  const uint32_t* mask_bits;
 };
 
 struct LbwdHeadSmem {
@@ -570,13 +579,14 @@ __global__ void __launch_bounds__(kLbwdHeadThreads, 1) reni_lbwd_head_kernel(con
           gy[c] = gg;
         }
       } else {
-        const float* wp = p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+        const float* wp = p.sw_grid ? nullptr : p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+        const float wg = p.sw_grid ? grid_sineweight(pix, p.grid_w, p.mask_bits) : 0.f;
         const float* ml = p.map_loss + (size_t)b * 32;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float o = __ldg(p.out + eo + c);
           const float t = __ldg(p.target + eo + c);
-          float gg = (o - t) * __ldg(wp + c);  // S * g_o = (o - t) * sw + coefA * t + coefB * o  with S = 3P/2
+          float gg = (o - t) * (p.sw_grid ? wg : __ldg(wp + c));  // S * g_o = (o - t) * sw + coefA * t + coefB * o  with S = 3P/2
           if (p.use_cos) gg += __ldg(ml + 16 + c) * t + __ldg(ml + 19 + c) * o;
           if (p.out_tanh) gg *= (1.f - o * o);
           if (p.aout != nullptr) gg *= cosf(__ldg(p.aout + eo + c));

@@ -322,6 +322,29 @@ DEVINL float phase_angle_hi(uint32_t w) {  // angle of the high 16-bit phase of 
   return fmaf(f, kPhaseToAngle, -8388608.f * kPhaseToAngle);
 }
 
+// ------------------------------------------------------------------ analytic equirectangular grid
+// get_directions / get_sineweight (src/utils/utils.py:46-78) in closed form from the pixel index: u = (i + 1/2) / (W/2),
+// v = (j + 1/2) / (W/2), theta = pi (u - 1), phi = pi v, d = (sin phi sin theta, cos phi, -sin phi cos theta), sw = sin phi.
+// With RENI_FLAG_GRID_DIRECTIONS / RENI_FLAG_GRID_SINEWEIGHT the kernels call this instead of loading D / sw, and the
+// mask (RENI_module.py:92-94) is one bit per pixel.
+DEVINL void grid_point(int pix, int W, float& dx, float& dy, float& dz, float& sinphi) {
+  const int j = pix / W, i = pix - j * W;
+  const float inv = 2.f / (float)W;
+  float st, ct, sp, cp;
+  sincospif(((float)i + 0.5f) * inv - 1.f, &st, &ct);
+  sincospif(((float)j + 0.5f) * inv, &sp, &cp);
+  dx = sp * st;
+  dy = cp;
+  dz = -sp * ct;
+  sinphi = sp;
+}
+DEVINL float grid_sineweight(int pix, int W, const uint32_t* mask_bits) {
+  float sp, cp;
+  sincospif(((float)(pix / W) + 0.5f) * (2.f / (float)W), &sp, &cp);
+  if (mask_bits != nullptr && !((__ldg(mask_bits + (pix >> 5)) >> (pix & 31)) & 1u)) sp = 0.f;
+  return sp;
+}
+
 DEVINL float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -488,6 +488,8 @@ struct LossFinishParams {
   int B, P, tiles_per_map, nz;  // nz = N*3
   float alpha, beta;
   int use_cos;
+  int grid_w, sw_grid;           // analytic sine weights (RENI_FLAG_GRID_SINEWEIGHT)
+  const uint32_t* mask_bits;
 };
 
 __global__ void __launch_bounds__(128) reni_loss_finish_kernel(const LossFinishParams p) {
@@ -531,7 +533,8 @@ __global__ void __launch_bounds__(128) reni_loss_finish_kernel(const LossFinishP
       float cA = 0.f, cB = 0.f;
       if (p.use_cos) {
         const float no = fmaxf(sqrtf(t[4 + c]), 1e-20f), nt = fmaxf(sqrtf(t[7 + c]), 1e-20f);
-        const float w0 = p.sw[(size_t)b * p.sw_bstride + c];  // sine weight (x mask) of pixel 0
+        const float w0 = p.sw_grid ? grid_sineweight(0, p.grid_w, p.mask_bits)
+                                   : p.sw[(size_t)b * p.sw_bstride + c];  // sine weight (x mask) of pixel 0
         const float cs = t[1 + c] / (no * nt);
         cosl += cs * w0;
         const float k = S * p.beta * (-w0 / 3.f);

@@ -304,13 +304,18 @@ class StepResult:
     db: Optional[List[torch.Tensor]]
 
 
-def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: torch.Tensor, target: torch.Tensor,
-                          sineweight: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: Optional[torch.Tensor],
+                          target: torch.Tensor, sineweight: Optional[torch.Tensor], weights: Sequence[torch.Tensor],
+                          biases: Sequence[torch.Tensor],
                           alpha: float = 0.0, beta: float = 0.0, use_cosine: bool = False, need_dw: bool = True,
                           grad_weights: Optional[Sequence[torch.Tensor]] = None,
                           grad_biases: Optional[Sequence[torch.Tensor]] = None,
-                          tile_major_bwd: Optional[bool] = None) -> StepResult:
+                          tile_major_bwd: Optional[bool] = None, mask_bits: Optional[torch.Tensor] = None) -> StepResult:
     """Fused forward + loss + backward (one training / latent-fit step without the optimiser).
+
+    Analytic grid (the reference's callers always pass ``get_directions(W)`` / ``get_sineweight(W) [* mask]``,
+    RENI_module.py:89-94): ``D=None`` makes the kernels compute the equirectangular directions from the pixel index
+    (P = W * W / 2), ``sineweight=None`` the sine weights, times ``mask_bits`` (``geometry.pack_mask_bits``) if given.
 
     ``tile_major_bwd``: True forces the tile-major delta chain + split-K weight-gradient GEMM, False the layer-major
     backward (one launch per layer); None takes ``RENI_TILE_MAJOR_BWD`` (0/1) or else the library default (tile-major).
@@ -320,18 +325,39 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
     all-reduce buffer) are ACCUMULATED into; fresh zero tensors are used when omitted."""
     lib = _lib.load()
     cfg = spec.c_config()
-    dev = _require_cuda(Z, D, target, sineweight, *weights, *biases)
+    dev = _require_cuda(Z, target, *[t for t in (D, sineweight, mask_bits) if t is not None], *weights, *biases)
     Zc = _f32c(Z)
     B = Zc.shape[0]
-    Dc, d_bs = _batch_stride(D, B, "directions")
-    swc, sw_bs = _batch_stride(sineweight, B, "sineweight")
-    P = Dc.shape[1]
+    P = target.shape[1]
+    grid_flags = 0
+    if D is None:
+        Dc, d_bs = None, 0
+        grid_flags |= _lib.FLAG_GRID_DIRECTIONS
+    else:
+        Dc, d_bs = _batch_stride(D, B, "directions")
+        if Dc.shape[1] != P:
+            raise ValueError(f"directions have {Dc.shape[1]} pixels, target {P}")
+    if sineweight is None:
+        swc, sw_bs = None, 0
+        grid_flags |= _lib.FLAG_GRID_SINEWEIGHT
+        if mask_bits is not None:
+            if mask_bits.dtype != torch.int32 or mask_bits.numel() * 32 < P:
+                raise ValueError("mask_bits must be int32 words with one bit per pixel (geometry.pack_mask_bits)")
+            swc = mask_bits.contiguous()
+    else:
+        if mask_bits is not None:
+            raise ValueError("mask_bits goes with sineweight=None (analytic sine weights); multiply a sineweight tensor by the mask instead")
+        swc, sw_bs = _batch_stride(sineweight, B, "sineweight")
+    if grid_flags:
+        side = int(round((2 * P) ** 0.5))
+        if side * side // 2 != P or side % 2:
+            raise ValueError(f"the analytic grid needs P = W * W / 2 directions, got {P}")
     tc = _f32c(target)
     if tuple(tc.shape) != (B, P, 3):
         raise ValueError(f"target must have shape {(B, P, 3)}, got {tuple(tc.shape)}")
     weights = [_f32c(w) for w in weights]
     biases = [_f32c(b) for b in biases]
-    flags = FLAG_SAVE_FOR_BACKWARD | FLAG_LOSS | (FLAG_NEED_DW if need_dw else 0)
+    flags = FLAG_SAVE_FOR_BACKWARD | FLAG_LOSS | (FLAG_NEED_DW if need_dw else 0) | grid_flags
     flags |= _bwd_schedule_flag(tile_major_bwd) | _fwd_terms_flag()
     ws.ensure(workspace_bytes(cfg, B, P, flags), dev)
     # changed parameters (every training step): the library rebuilds the fp16 weight images inside the fused call, on

@@ -54,3 +54,21 @@ def rectangle_mask(sidelen: int, row0: int, row1: int, col0: int, col1: int) -> 
     m = torch.zeros(sidelen // 2, sidelen)
     m[row0:row1, col0:col1] = 1
     return m.reshape(-1, 1).repeat(1, 3).unsqueeze(0)
+
+
+def pack_mask_bits(mask: torch.Tensor) -> torch.Tensor:
+    """Binary (1, P, 3) / (P, 3) / (P,) mask -> int32 words with one bit per pixel (bit p & 31 of word p >> 5), the form
+    the kernels take with RENI_FLAG_GRID_SINEWEIGHT (the mask of RENI_module.py:92-94 applied inside the kernels).
+    Raises if the mask is not binary or differs between the channels of a pixel (get_mask's PNGs do neither)."""
+    m = mask.reshape(-1, mask.shape[-1]) if mask.dim() > 1 else mask.reshape(-1, 1)
+    if not bool(((m == 0) | (m == 1)).all()) or not bool((m == m[:, :1]).all()):
+        raise ValueError("in-kernel masks must be binary and equal on the three channels of a pixel")
+    bits = (m[:, 0] != 0).to(torch.int64)
+    P = bits.numel()
+    pad = (-P) % 32
+    if pad:
+        bits = torch.cat([bits, bits.new_zeros(pad)])
+    weights = (1 << torch.arange(32, dtype=torch.int64, device=bits.device))
+    words = (bits.reshape(-1, 32) * weights).sum(dim=1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)  # two's complement into int32
+    return words.to(torch.int32).contiguous()

@@ -161,7 +161,8 @@ class RENITrainer:
     def __init__(self, model: _DecoderBase, task: str, sidelen: int, lr: float = 1e-5,
                  prior_loss_weight: float = 1e-7, cosine_similarity_weight: float = 1e-4,
                  kld_weighting: float = 1e-4, mask: Optional[torch.Tensor] = None, process_group=None,
-                 ddp_latent_scaling: bool = True, cuda_graph: bool = False, latent_sync: str = "local"):
+                 ddp_latent_scaling: bool = True, cuda_graph: bool = False, latent_sync: str = "local",
+                 analytic_grid: bool = False):
         if task not in ("FIT_DECODER", "FIT_LATENT"):
             raise NotImplementedError("FIT_INVERSE needs the PyTorch3D renderer and is out of scope for this path")
         self.model = model
@@ -178,6 +179,10 @@ class RENITrainer:
         self.latent_sync = latent_sync
         dev = next(model.parameters()).device
         self.device = dev
+        # analytic_grid=True: the kernels compute get_directions / get_sineweight from the pixel index and take the mask
+        # as one bit per pixel, instead of reading the (1, P, 3) arrays and a torch `sineweight * mask` per step
+        # (Cond-by-Concat decoders; utils.py:46-78, RENI_module.py:89-94)
+        self.analytic_grid = bool(analytic_grid)
         self.set_resolution(sidelen)
         self.mask = mask.to(dev) if mask is not None else None
         self.alpha = prior_loss_weight
@@ -495,9 +500,19 @@ class RENITrainer:
             alpha, beta, use_cos = self.alpha, self.beta, True      # RENITestLoss  (:126-128)
         else:
             alpha, beta, use_cos = 0.0, 0.0, False                  # RENITrainLoss (:117)
+        grid_kw = {}
+        D_arg, sw_arg = self.directions, sw
+        if self.analytic_grid:
+            from .geometry import pack_mask_bits
+
+            D_arg, sw_arg = None, None
+            if self.mask is not None:
+                if getattr(self, "_mask_bits_for", None) is not self.mask:
+                    self._mask_bits, self._mask_bits_for = pack_mask_bits(self.mask), self.mask
+                grid_kw["mask_bits"] = self._mask_bits
         res = F_.loss_forward_backward(
-            model.spec, ws, Zin, self.directions, imgs, sw, model.decoder_weights(), model.decoder_biases(),
-            alpha=alpha, beta=beta, use_cosine=use_cos, need_dw=need_dw,
+            model.spec, ws, Zin, D_arg, imgs, sw_arg, model.decoder_weights(), model.decoder_biases(),
+            alpha=alpha, beta=beta, use_cosine=use_cos, need_dw=need_dw, **grid_kw,
             grad_weights=self.flat.views[0::2] if need_dw else None,
             grad_biases=self.flat.views[1::2] if need_dw else None)
         log: Dict[str, torch.Tensor] = {"loss": res.loss}

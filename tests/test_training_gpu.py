@@ -152,3 +152,46 @@ def test_graphs_keep_their_own_workspace(dev):
     with torch.no_grad():
         m(torch.randn(12, N, 3, device=dev), D.expand(12, -1, -1))  # a larger eager decode in between
     assert torch.equal(gd(Z2), ref)
+
+
+@pytest.mark.parametrize("masked,cosine", [(False, False), (True, True)])
+@pytest.mark.parametrize("tile_major", [True, False])
+def test_analytic_grid_and_bitmask_match_arrays(dev, masked, cosine, tile_major):
+    """RENI_FLAG_GRID_DIRECTIONS / RENI_FLAG_GRID_SINEWEIGHT: directions and sine weights computed in the kernels from
+    the pixel index (utils.py:46-78) and the mask as one bit per pixel (RENI_module.py:92-94) give the step computed from
+    the get_directions / get_sineweight * mask arrays; both backward schedules; the trainer option too."""
+    from reni_b200 import RENIAutoDecoder, RENITrainer, get_directions, get_sineweight, pack_mask_bits, rectangle_mask
+    from reni_b200 import functional as F_
+
+    torch.manual_seed(4)
+    W, B, N = 64, 3, 9
+    P = W * W // 2
+    m = RENIAutoDecoder(B, N, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+    D, sw = get_directions(W).to(dev), get_sineweight(W).to(dev)
+    mask = rectangle_mask(W, 5, 23, 20, 41).to(dev) if masked else None
+    tg = torch.rand(B, P, 3, device=dev) * 2 - 1
+    Z = m.Z.detach()
+    kw = dict(alpha=1e-3 if cosine else 0.0, beta=0.3 if cosine else 0.0, use_cosine=cosine, need_dw=True,
+              tile_major_bwd=tile_major)
+    a = F_.loss_forward_backward(m.spec, F_.Workspace(), Z, D, tg, sw if mask is None else sw * mask,
+                                 m.decoder_weights(), m.decoder_biases(), **kw)
+    b = F_.loss_forward_backward(m.spec, F_.Workspace(), Z, None, tg, None, m.decoder_weights(), m.decoder_biases(),
+                                 mask_bits=pack_mask_bits(mask) if masked else None, **kw)
+    torch.cuda.synchronize()
+    # the grid in closed form (sincospi) and the arrays (torch.sin of a rounded pi * x) differ in the last bits, which
+    # flips the fp16 rounding of an activation here and there: compare at that level
+    assert float((a.out - b.out).norm() / a.out.norm()) < 1e-4 and float((a.out - b.out).abs().max()) < 2e-4
+    assert abs(float(a.loss) - float(b.loss)) < 1e-4 * abs(float(a.loss))
+    assert float((a.dZ - b.dZ).norm() / a.dZ.norm()) < 2e-3
+    for x, y in zip(a.dW + a.db, b.dW + b.db):
+        assert float((x - y).norm() / x.norm()) < 2e-3
+    imgs = tg.reshape(B, W // 2, W, 3).permute(0, 3, 1, 2).contiguous()
+    idx = torch.arange(B, device=dev)
+    t0 = RENITrainer(m, "FIT_LATENT" if cosine else "FIT_DECODER", W, mask=mask, analytic_grid=False)
+    t1 = RENITrainer(m, "FIT_LATENT" if cosine else "FIT_DECODER", W, mask=mask, analytic_grid=True)
+    l0 = t0.training_step((imgs, idx))
+    g0 = m.Z.grad.clone()
+    l1 = t1.training_step((imgs, idx))
+    torch.cuda.synchronize()
+    assert abs(float(l0["loss"]) - float(l1["loss"])) < 1e-4 * abs(float(l0["loss"]))
+    assert float((g0 - m.Z.grad).norm() / g0.norm()) < 2e-3
