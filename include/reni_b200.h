@@ -252,6 +252,22 @@ int32_t reni_vad_backward(const float* mu, const float* log_var, const int64_t* 
                           int64_t B, int64_t nz, float kld_weight_over_zdims, float grad_scale, float* dmu,
                           float* dlog_var, float* kld_out, void* stream);
 
+/* Blinn-Phong shading of a surface by every texel of the environment map -- what the FIT_INVERSE task does with the
+ * decoder output (blinn_phong_shading_env_map, src/utils/pytorch3d_envmap_shader.py:85-119, reached from
+ * RENI_module.get_render, :386-396): with unit surface normals n_p and unit view directions v_p per render pixel,
+ *   colors[b, p, :] = sum_j ( kd * clamp(n_p . l_j) + c * ks * clamp(n_p . normalize(v_p + l_j))^shininess ) * light[b, j, :]
+ *   c = (shininess + 2) / (4 (2 - exp(-shininess / 2)));   light = environment map x sine weight (EnvironmentMap, :33-44)
+ * and its adjoint with respect to the light colours, d_light[b, j, :] = sum_p (same weight) * grad_colors[b, p, :].
+ * The (B, H, W, J[, 3]) tensors the reference materialises are never formed.
+ *   normals, view_dirs : (n_pix, 3);  D : (B or 1, J, 3), d_batch_stride 0 = one grid for all maps
+ *   light / d_light : (B, J, 3);  colors / grad_colors : (B, n_pix, 3), all overwritten where written */
+int32_t reni_envmap_shade_forward(const float* normals, const float* view_dirs, int64_t n_pix, const float* D,
+                                  int64_t d_batch_stride, const float* light, int64_t B, int64_t J, float kd, float ks,
+                                  float shininess, float* colors, void* stream);
+int32_t reni_envmap_shade_backward(const float* normals, const float* view_dirs, int64_t n_pix, const float* D,
+                                   int64_t d_batch_stride, const float* grad_colors, int64_t B, int64_t J, float kd,
+                                   float ks, float shininess, float* d_light, void* stream);
+
 /* In-place mean (or scaled sum) of one fp32 buffer over the W ranks of a node, through NVLink peer memory: the one
  * exchange step of data-parallel training (Lightning's DDPStrategy averages every gradient, run.py:97), as a plain
  * kernel that can be captured in the step's CUDA graph directly behind the gradient kernels.

@@ -16,6 +16,7 @@ from .losses import (KLD, CosineSimilarity, RENITestLoss, RENITrainLoss, RENIVAD
 from .film import CustomMappingNetwork, FiLMLayer, RENIAutoDecoderFiLM, RENIVariationalAutoDecoderFiLM
 from .models import RENIAutoDecoder, RENIVariationalAutoDecoder, SineLayer, get_model
 from .optim import FusedAdam
+from .render import EnvironmentMap, blinn_phong_shading_env_map
 from .serving import GraphedDecoder
 from .training import FlatGradBuffer, RENITrainer, shard_range
 
@@ -26,4 +27,5 @@ __all__ = [
     "RENITrainLoss", "RENIVADTrainLoss", "RENITestLoss",
     "get_directions", "get_sineweight", "get_mask", "rectangle_mask", "pack_mask_bits",
     "RENITrainer", "FlatGradBuffer", "shard_range", "FusedAdam", "GraphedDecoder",
+    "EnvironmentMap", "blinn_phong_shading_env_map",
 ]

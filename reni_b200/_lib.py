@@ -91,6 +91,8 @@ SIGNATURES = {
     "reni_adam_step": (_i32, [C.POINTER(AdamSegment), _i32, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp]),
     "reni_vad_sample": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "reni_vad_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
+    "reni_envmap_shade_forward": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, C.c_float, C.c_float, C.c_float, _vp, _vp]),
+    "reni_envmap_shade_backward": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, C.c_float, C.c_float, C.c_float, _vp, _vp]),
     "reni_allreduce_flag_bytes": (_i64, []),
     "reni_allreduce": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, C.c_float, _vp, _vp, _vp]),
     "reni_debug_set_phase_events": (_i32, [C.POINTER(_vp), _i32]),

@@ -12,6 +12,7 @@
 #include "fwd_kernel.cuh"
 #include "layout.cuh"
 #include "lbwd_kernel.cuh"
+#include "shade_kernel.cuh"
 #include "small_kernels.cuh"
 
 #ifndef RENI_NO_FORK
@@ -1081,6 +1082,50 @@ int32_t reni_vad_backward(const float* mu, const float* log_var, const int64_t* 
   p.B = (int)B; p.nz = (int)nz; p.kw = kld_weight_over_zdims; p.grad_scale = grad_scale;
   reni_vad_backward_kernel<<<(unsigned)B, 128, 0, static_cast<cudaStream_t>(stream_)>>>(p);
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+static int32_t launch_shade(bool backward, const float* normals, const float* view, int64_t n_pix, const float* D,
+                            int64_t d_bstride, const float* light, const float* grad, int64_t B, int64_t J, float kd,
+                            float ks, float shininess, float* colors, float* d_light, cudaStream_t stream) {
+  if (normals == nullptr || view == nullptr || D == nullptr || n_pix < 1 || B < 1 || J < 1 || B > 65535 ||
+      !(shininess >= 0.f))
+    return RENI_ERR_BAD_ARGUMENT;
+  ShadeParams p{};
+  p.normals = normals; p.view = view; p.D = D; p.d_bstride = d_bstride;
+  p.light = light; p.grad = grad; p.colors = colors; p.d_light = d_light;
+  p.B = (int)B; p.J = (int)J; p.n_pix = (int)n_pix;
+  p.kd = kd;
+  // Blinn-Phong normalisation of the specular lobe (pytorch3d_envmap_shader.py:113-115)
+  p.cks = ks * (shininess + 2.f) / (4.f * (2.f - expf(-shininess / 2.f)));
+  p.shininess = shininess;
+  const bool shared = d_bstride == 0;
+  const unsigned chunks = (unsigned)(shared ? (B + kShadeMaps - 1) / kShadeMaps : B);
+  const int64_t n = backward ? J : n_pix;
+  const dim3 grid((unsigned)((n + kShadeThreads - 1) / kShadeThreads), chunks);
+  if (backward) {
+    if (shared) reni_shade_bwd_kernel<true><<<grid, kShadeThreads, 0, stream>>>(p);
+    else reni_shade_bwd_kernel<false><<<grid, kShadeThreads, 0, stream>>>(p);
+  } else {
+    if (shared) reni_shade_fwd_kernel<true><<<grid, kShadeThreads, 0, stream>>>(p);
+    else reni_shade_fwd_kernel<false><<<grid, kShadeThreads, 0, stream>>>(p);
+  }
+  return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+
+int32_t reni_envmap_shade_forward(const float* normals, const float* view_dirs, int64_t n_pix, const float* D,
+                                  int64_t d_bstride, const float* light, int64_t B, int64_t J, float kd, float ks,
+                                  float shininess, float* colors, void* stream_) {
+  if (light == nullptr || colors == nullptr) return RENI_ERR_BAD_ARGUMENT;
+  return launch_shade(false, normals, view_dirs, n_pix, D, d_bstride, light, nullptr, B, J, kd, ks, shininess, colors,
+                      nullptr, static_cast<cudaStream_t>(stream_));
+}
+
+int32_t reni_envmap_shade_backward(const float* normals, const float* view_dirs, int64_t n_pix, const float* D,
+                                   int64_t d_bstride, const float* grad_colors, int64_t B, int64_t J, float kd, float ks,
+                                   float shininess, float* d_light, void* stream_) {
+  if (grad_colors == nullptr || d_light == nullptr) return RENI_ERR_BAD_ARGUMENT;
+  return launch_shade(true, normals, view_dirs, n_pix, D, d_bstride, nullptr, grad_colors, B, J, kd, ks, shininess,
+                      nullptr, d_light, static_cast<cudaStream_t>(stream_));
 }
 
 int64_t reni_allreduce_flag_bytes(void) { return (int64_t)kArMaxBlocks * kArMaxWorld * sizeof(uint32_t); }

@@ -359,12 +359,20 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
     biases = [_f32c(b) for b in biases]
     flags = FLAG_SAVE_FOR_BACKWARD | FLAG_LOSS | (FLAG_NEED_DW if need_dw else 0) | grid_flags
     flags |= _bwd_schedule_flag(tile_major_bwd) | _fwd_terms_flag()
-    ws.ensure(workspace_bytes(cfg, B, P, flags), dev)
+    # Maps are independent units and every gradient buffer is accumulated into, so a batch whose stash would not fit the
+    # workspace budget is walked in chunks of maps through the same workspace (BASELINE configs[3] at full size: 4096
+    # maps would need 97 GiB in one call).  RENI_MAX_WORKSPACE_GB (default 48) sets the budget.
+    budget = int(float(os.environ.get("RENI_MAX_WORKSPACE_GB", "48")) * 2 ** 30)
+    chunk = B
+    if workspace_bytes(cfg, B, P, flags) > budget and B > 1:
+        per_map = max(1, (workspace_bytes(cfg, min(B, 64), P, flags) - workspace_bytes(cfg, 1, P, flags)) // max(1, min(B, 64) - 1))
+        chunk = max(1, min(B, (budget - workspace_bytes(cfg, 1, P, flags)) // per_map))
+    ws.ensure(workspace_bytes(cfg, chunk, P, flags), dev)
     # changed parameters (every training step): the library rebuilds the fp16 weight images inside the fused call, on
     # its side stream beside the per-map prologue, instead of in a launch of its own ahead of it
     key = _params_key(weights, biases)
     if ws.prepared_key != key:
-        if os.environ.get("RENI_PREPARE_IN_CALL", "0") == "1":
+        if os.environ.get("RENI_PREPARE_IN_CALL", "0") == "1" and chunk == B:
             flags |= _lib.FLAG_PREPARE_WEIGHTS
         else:
             prepare_weights(cfg, weights, biases, ws, dev)
@@ -375,12 +383,22 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
     if need_dw:
         dW = list(grad_weights) if grad_weights is not None else [torch.zeros_like(w) for w in weights]
         db = list(grad_biases) if grad_biases is not None else [torch.zeros_like(b) for b in biases]
-    rc = _call(dev, lib.reni_loss_forward_backward, 
-        C.byref(cfg), _vp(Zc), _vp(Dc), d_bs, _ptr_array(weights), _ptr_array(biases), B, P, _vp(tc), _vp(swc), sw_bs,
-        float(alpha), float(beta), 1 if use_cosine else 0, _vp(out), _vp(loss), _vp(dZ),
-        _ptr_array(dW) if need_dw else None, _ptr_array(db) if need_dw else None, _vp(ws.view), ws.nbytes, flags,
-        _stream(dev))
-    _lib.check(rc, "reni_loss_forward_backward")
+    total = None
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        part = loss if chunk == B else torch.empty(4, device=dev, dtype=torch.float32)
+        rc = _call(dev, lib.reni_loss_forward_backward,
+                   C.byref(cfg), _vp(Zc[lo:hi]), _vp(Dc if d_bs == 0 or Dc is None else Dc[lo:hi]), d_bs,
+                   _ptr_array(weights), _ptr_array(biases), hi - lo, P, _vp(tc[lo:hi]),
+                   _vp(swc if sw_bs == 0 or swc is None else swc[lo:hi]), sw_bs,
+                   float(alpha), float(beta), 1 if use_cosine else 0, _vp(out[lo:hi]), _vp(part), _vp(dZ[lo:hi]),
+                   _ptr_array(dW) if need_dw else None, _ptr_array(db) if need_dw else None, _vp(ws.view), ws.nbytes,
+                   flags, _stream(dev))
+        _lib.check(rc, "reni_loss_forward_backward")
+        if chunk != B:
+            total = part if total is None else total + part
+    if total is not None:
+        loss = total
     ws.prepared_key = key
     return StepResult(loss[0], loss[1], loss[2], loss[3], out, dZ, dW, db)
 

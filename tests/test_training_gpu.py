@@ -195,3 +195,32 @@ def test_analytic_grid_and_bitmask_match_arrays(dev, masked, cosine, tile_major)
     torch.cuda.synchronize()
     assert abs(float(l0["loss"]) - float(l1["loss"])) < 1e-4 * abs(float(l0["loss"]))
     assert float((g0 - m.Z.grad).norm() / g0.norm()) < 2e-3
+
+
+def test_large_batches_are_walked_in_chunks_of_maps(dev, monkeypatch):
+    """A batch whose stash exceeds the workspace budget is processed in chunks of maps through one workspace (maps are
+    independent units, gradients accumulate): same loss, outputs and gradients as the single call."""
+    from reni_b200 import RENIAutoDecoder, get_directions, get_sineweight
+    from reni_b200 import functional as F_
+
+    torch.manual_seed(2)
+    W, B, N = 32, 11, 9
+    P = W * W // 2
+    m = RENIAutoDecoder(B, N, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
+    D, sw = get_directions(W).to(dev), get_sineweight(W).to(dev)
+    tg = torch.rand(B, P, 3, device=dev) * 2 - 1
+    kw = dict(alpha=1e-3, beta=0.2, use_cosine=True, need_dw=True)
+    a = F_.loss_forward_backward(m.spec, F_.Workspace(), m.Z.detach(), D, tg, sw, m.decoder_weights(), m.decoder_biases(), **kw)
+    ws = F_.Workspace()
+    flags = 1 | 2 | 4  # SAVE_FOR_BACKWARD | NEED_DW | LOSS
+    room = F_.workspace_bytes(m.spec.c_config(), 4, P, flags)  # room for four maps of this size
+    monkeypatch.setenv("RENI_MAX_WORKSPACE_GB", repr(room / 2 ** 30))
+    b = F_.loss_forward_backward(m.spec, ws, m.Z.detach(), D, tg, sw, m.decoder_weights(), m.decoder_biases(), **kw)
+    torch.cuda.synchronize()
+    assert ws.nbytes <= room < F_.workspace_bytes(m.spec.c_config(), B, P, flags)
+    assert torch.equal(a.out, b.out)
+    for x, y in zip((a.loss, a.mse_loss, a.prior_loss, a.cosine_loss), (b.loss, b.mse_loss, b.prior_loss, b.cosine_loss)):
+        assert abs(float(x) - float(y)) <= 1e-5 * abs(float(x)) + 1e-9
+    assert float((a.dZ - b.dZ).abs().max()) <= 1e-5 * float(a.dZ.abs().max())
+    for x, y in zip(a.dW + a.db, b.dW + b.db):
+        assert float((x - y).norm() / x.norm()) < 1e-4
