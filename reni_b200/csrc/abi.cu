@@ -1100,8 +1100,22 @@ static int32_t launch_shade(bool backward, const float* normals, const float* vi
   p.shininess = shininess;
   const bool shared = d_bstride == 0;
   const unsigned chunks = (unsigned)(shared ? (B + kShadeMaps - 1) / kShadeMaps : B);
-  const int64_t n = backward ? J : n_pix;
-  const dim3 grid((unsigned)((n + kShadeThreads - 1) / kShadeThreads), chunks);
+  const int64_t n = backward ? J : n_pix;           // one thread per output row
+  const int64_t red = backward ? n_pix : J;         // reduction axis
+  const int64_t rows = (n + kShadeThreads - 1) / kShadeThreads * chunks;
+  // enough blocks for ~8 per SM, each with at least two tiles of the reduction axis
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  int64_t split = (8LL * sms + rows - 1) / rows;
+  const int64_t max_split = (red + 2 * kShadeTile - 1) / (2 * kShadeTile);
+  if (split > max_split) split = max_split;
+  if (split < 1) split = 1;
+  p.split = (int)split;
+  if (split > 1) {
+    float* outp = backward ? d_light : colors;
+    if (cudaMemsetAsync(outp, 0, (size_t)B * n * 3 * sizeof(float), stream) != cudaSuccess) return RENI_ERR_CUDA;
+  }
+  const dim3 grid((unsigned)((n + kShadeThreads - 1) / kShadeThreads), chunks, (unsigned)split);
   if (backward) {
     if (shared) reni_shade_bwd_kernel<true><<<grid, kShadeThreads, 0, stream>>>(p);
     else reni_shade_bwd_kernel<false><<<grid, kShadeThreads, 0, stream>>>(p);

@@ -330,6 +330,18 @@ def test_full_size_properties_config2(dev):
     assert O.rel_max(outs, refs) < TOL_RADIANCE_MAX
 
 
+def _oracle_radiance_spot_check(m, Z_row, D, out_row, stride, what):
+    """Radiance of ONE map on every `stride`-th direction against the fp64 oracle (the radiance of a direction does not
+    depend on the other directions, so a subset keeps the N^2-wide encoding of N = 100 small enough to build)."""
+    p64 = params_from_model(m)
+    Dsub = D[:, ::stride].cpu().numpy().astype(np.float64)
+    ref = O.decoder_forward(Z_row.cpu().numpy().astype(np.float64), Dsub, p64)
+    got = out_row[:, ::stride].cpu().numpy()
+    e = O.rel_l2(got, ref)
+    print(f"{what}: radiance rel-L2 vs oracle on {Dsub.shape[1]} directions = {e:.2e} (RMS {np.sqrt((ref ** 2).mean()):.3f})")
+    assert e < TOL_RADIANCE, what
+
+
 def test_full_size_properties_configs_3_4_5(dev):
     """The other BASELINE shapes through size-independent properties:
     cfg 3 (N=100, 128x256): per-map results do not depend on which other maps share the batch; the fused step's dZ equals
@@ -366,6 +378,8 @@ def test_full_size_properties_configs_3_4_5(dev):
     with torch.no_grad():
         o_rot = m(Z[:2] @ R.T, D @ R.T)
     assert float((o_rot - full.out[:2]).norm() / full.out[:2].norm()) < TOL_RADIANCE
+    # the N = 100 prologue (a 10 202-column GEMV per map) against the oracle, at the full 128x256 grid
+    _oracle_radiance_spot_check(m, Z[[5]], D, full.out[[5]], 16, "cfg 3, N=100, map 5")
     del full, sub, out, ws
     # ---- cfg 4: latent-only, masked
     B, N, W = 64, 36, 128
@@ -396,7 +410,8 @@ def test_full_size_properties_configs_3_4_5(dev):
     W = 512
     P = W * W // 2
     D = get_directions(W).to(dev)
-    for N in (9, 49):
+    for N in (9, 36, 49, 100):
+        torch.manual_seed(30 + N)
         mi = RENIAutoDecoder(4, N, "SO2", 256, 5, 3, True, "tanh", 30.0, 30.0, False).to(dev)
         Z = mi.Z.detach()
         with torch.no_grad():
@@ -404,6 +419,7 @@ def test_full_size_properties_configs_3_4_5(dev):
             assert torch.equal(o, mi(Z, D))
             perm = torch.tensor([2, 0, 3, 1], device=dev)
             assert torch.equal(mi(Z[perm], D), o[perm])
+        _oracle_radiance_spot_check(mi, Z[[1]], D, o[[1]], 64 if N == 100 else 16, f"cfg 5, N={N}, map 1")
         tgt = torch.zeros(4, P, 3, device=dev)
         swf = get_sineweight(W).to(dev)
         r = F_.loss_forward_backward(mi.spec, F_.Workspace(), Z, D, tgt, swf, mi.decoder_weights(), mi.decoder_biases(),
