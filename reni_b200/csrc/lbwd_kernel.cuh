@@ -33,6 +33,10 @@ namespace reni {
 #ifndef RENI_LBWD_PF_DIST
 #define RENI_LBWD_PF_DIST 0  // L2 prefetch distance, in tiles ahead of the tile whose shared-memory load is being issued
 #endif
+#ifndef RENI_LBWD_STAGGER
+#define RENI_LBWD_STAGGER 0  // start CTA pair c after (c % 8) * RENI_LBWD_STAGGER clocks: de-synchronises the load / compute
+                             // phases of the SMs (all of them otherwise hit HBM at the same moments)
+#endif
 #ifndef RENI_LBWD_STORE_HINT
 #define RENI_LBWD_STORE_HINT 0  // delta_{l-1} stores: 0 plain st.global (write-back: the next launch reads the newest tiles from L2), 1 st.cs
 #endif
@@ -151,6 +155,11 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
   // TMEM columns: chain accumulators [0,128) [128,256) (kFirst: one, and the layer-0 reduction at [128,144));
   // dW accumulator rows j < 128 at [256,384), rows j >= 128 at [384,512)
   constexpr uint32_t kColRed = 128, kColDw = 256;
+  if (RENI_LBWD_STAGGER > 0) {
+    const long long t0 = clock64(), wait = (long long)(c % 8) * RENI_LBWD_STAGGER;
+    while (clock64() - t0 < wait) {
+    }
+  }
 
   if (warp == 0) {
     // ============================================================ producer: weight half once, one delta tile per step

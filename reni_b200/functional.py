@@ -43,20 +43,55 @@ class DecoderSpec:
             raise AttributeError("module 'torch.nn' has no attribute 'Exp'")
         if self.output_activation not in (None, "tanh"):
             raise ValueError(f"unsupported output_activation {self.output_activation!r}")
-        if self.hidden_features != HIDDEN_FEATURES:
+        if not 1 <= self.hidden_features <= HIDDEN_FEATURES:
             raise NotImplementedError(
-                f"reni_b200 kernels are built for hidden_features={HIDDEN_FEATURES}, got {self.hidden_features}")
+                f"reni_b200 kernels are built for hidden_features <= {HIDDEN_FEATURES} (narrower decoders run zero-padded "
+                f"to {HIDDEN_FEATURES}), got {self.hidden_features}")
         if not 1 <= self.hidden_layers <= 6:
             raise NotImplementedError("reni_b200 kernels support 1..6 hidden layers")
         if not 1 <= self.out_features <= 3:
             raise NotImplementedError("reni_b200 kernels support out_features <= 3")
 
+    def padded(self) -> "DecoderSpec":
+        """The spec the kernels run: hidden width 256.  A narrower decoder is embedded exactly -- zero rows / columns give
+        sin(0) = 0 activations that feed nothing, and zero gradients outside the real block (``pad_parameters``)."""
+        if self.hidden_features == HIDDEN_FEATURES:
+            return self
+        import dataclasses
+
+        return dataclasses.replace(self, hidden_features=HIDDEN_FEATURES)
+
     def c_config(self) -> RENIConfig:
         self.validate()
+        if self.hidden_features != HIDDEN_FEATURES:
+            return self.padded().c_config()
         return RENIConfig(
             self.ndims, _lib.EQUIVARIANCE[self.equivariance], self.hidden_features, self.hidden_layers,
             self.out_features, 1 if self.last_layer_linear else 0, 1 if self.output_activation == "tanh" else 0,
             float(self.first_omega_0), float(self.hidden_omega_0))
+
+
+def pad_parameters(spec: DecoderSpec, params: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """[W0, b0, ..., W_out, b_out] of a decoder with hidden width H < 256 zero-padded to the kernels' width (differentiable:
+    ``F.pad``'s backward slices the gradients back).  Identity at H = 256."""
+    H = spec.hidden_features
+    if H == HIDDEN_FEATURES:
+        return list(params)
+    pad = HIDDEN_FEATURES - H
+    n = len(params) // 2
+    out: List[torch.Tensor] = []
+    for i in range(n):
+        W, b = params[2 * i], params[2 * i + 1]
+        last = i == n - 1
+        if i == 0:
+            Wp = torch.nn.functional.pad(W, (0, 0, 0, pad))            # (H, in) -> (256, in)
+        elif last:
+            Wp = torch.nn.functional.pad(W, (0, pad))                  # (out, H) -> (out, 256)
+        else:
+            Wp = torch.nn.functional.pad(W, (0, pad, 0, pad))          # (H, H) -> (256, 256)
+        bp = b if last else torch.nn.functional.pad(b, (0, pad))
+        out += [Wp, bp]
+    return out
 
 
 def _vp(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -275,9 +310,10 @@ def decode(spec: DecoderSpec, inference_ws: Workspace, Z: torch.Tensor, D: torch
     if Z.dim() == 3 and D.dim() == 3 and (Z.shape[0] == 0 or D.shape[1] == 0):
         return empty_output(Z, D, params, spec.out_features)
     if torch.is_grad_enabled() and (Z.requires_grad or any(p.requires_grad for p in params)):
-        return _DecodeFunction.apply(spec, inference_ws, Z, D, *params)
+        return _DecodeFunction.apply(spec.padded(), inference_ws, Z, D, *pad_parameters(spec, params))
     with torch.no_grad():
-        return _DecodeFunction.forward(_NoGradCtx(len(params)), spec, inference_ws, Z, D, *params)
+        return _DecodeFunction.forward(_NoGradCtx(len(params)), spec.padded(), inference_ws, Z, D,
+                                       *pad_parameters(spec, params))
 
 
 class _NoGradCtx:
@@ -323,6 +359,9 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
     loss = WeightedMSE + alpha * sum Z^2 + beta * WeightedCosineSimilarity  (loss_functions.py:6-32,60-71);
     RENITrainLoss is alpha = beta = 0.  ``grad_weights`` / ``grad_biases`` (e.g. views into one flat
     all-reduce buffer) are ACCUMULATED into; fresh zero tensors are used when omitted."""
+    if spec.hidden_features != HIDDEN_FEATURES:
+        return _narrow_loss_forward_backward(spec, ws, Z, D, target, sineweight, weights, biases, alpha, beta, use_cosine,
+                                             need_dw, grad_weights, grad_biases, tile_major_bwd, mask_bits)
     lib = _lib.load()
     cfg = spec.c_config()
     dev = _require_cuda(Z, target, *[t for t in (D, sineweight, mask_bits) if t is not None], *weights, *biases)
@@ -401,6 +440,35 @@ def loss_forward_backward(spec: DecoderSpec, ws: Workspace, Z: torch.Tensor, D: 
         loss = total
     ws.prepared_key = key
     return StepResult(loss[0], loss[1], loss[2], loss[3], out, dZ, dW, db)
+
+
+def _narrow_loss_forward_backward(spec, ws, Z, D, target, sineweight, weights, biases, alpha, beta, use_cosine, need_dw,
+                                  grad_weights, grad_biases, tile_major_bwd, mask_bits) -> StepResult:
+    """Fused step of a decoder narrower than the kernels' 256 features: run the zero-padded decoder, hand back the real
+    blocks of the gradients (accumulated into ``grad_weights`` / ``grad_biases`` like the full-width path)."""
+    with torch.no_grad():
+        flat = []
+        for wt, bt in zip(weights, biases):
+            flat += [wt, bt]
+        padded = pad_parameters(spec, flat)
+    r = loss_forward_backward(spec.padded(), ws, Z, D, target, sineweight, padded[0::2], padded[1::2], alpha=alpha,
+                              beta=beta, use_cosine=use_cosine, need_dw=need_dw, tile_major_bwd=tile_major_bwd,
+                              mask_bits=mask_bits)
+    if not need_dw:
+        return r
+    dW, db = [], []
+    for i, (wt, bt) in enumerate(zip(weights, biases)):
+        gw = r.dW[i][: wt.shape[0], : wt.shape[1]]
+        gb = r.db[i][: bt.shape[0]]
+        if grad_weights is not None:
+            grad_weights[i].add_(gw)
+            grad_biases[i].add_(gb)
+            dW.append(grad_weights[i])
+            db.append(grad_biases[i])
+        else:
+            dW.append(gw.contiguous())
+            db.append(gb.contiguous())
+    return StepResult(r.loss, r.mse_loss, r.prior_loss, r.cosine_loss, r.out, r.dZ, dW, db)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -80,7 +80,9 @@ def test_forward_validation_mirrors_reference():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(2, 4, 3), D)
     with pytest.raises(NotImplementedError):
-        make(N=4, hidden_features=64)(torch.zeros(2, 4, 3), D)
+        make(N=4, hidden_features=512)(torch.zeros(2, 4, 3), D)  # wider than the kernels' 256 features
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        make(N=4, hidden_features=64)(torch.zeros(2, 4, 3), D)   # narrower decoders run zero-padded (on the GPU)
 
 
 def test_vad_sample_latent_is_reparameterised():
