@@ -393,7 +393,7 @@ static int32_t launch_forward(const reni_config_t* c, const WorkspaceLayout& w, 
   p.out_tanh = c->output_activation == 1;
   p.last_sine = c->last_layer_linear ? 0 : 1;
   p.so2 = c->equivariance == RENI_EQ_SO2;
-  p.trace = g_trace;
+  p.trace = RENI_BWD_TRACE ? nullptr : g_trace;
   memset(&p.wmap, 0, sizeof(p.wmap));
   memset(&p.wmap_lo, 0, sizeof(p.wmap_lo));
   memset(&p.bmap, 0, sizeof(p.bmap));
@@ -570,6 +570,7 @@ static int32_t launch_backward(const reni_config_t* c, const WorkspaceLayout& w,
   }
 
   BwdParams p{};
+  p.trace = RENI_BWD_TRACE ? g_trace : nullptr;  // (debug builds: the timeline hook follows the delta chain instead)
   p.out = out;
   p.grad_out = grad_out;
   p.aout = at<float>(ws, w.aout);

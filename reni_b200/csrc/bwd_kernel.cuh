@@ -62,8 +62,19 @@ struct BwdParams {
   int w_map_rows;         // per-map backward images (FiLM on per-map images): rows of 256 B per map in wmap, 0 = shared
   uint32_t* ready;        // overlap mode (weight-gradient kernel co-resident on the other SMs): per-tile counter, +1 per
                           // epilogue warp each time a stashed delta_l of the tile is complete in global memory
+  unsigned long long* trace;  // debug builds (-DRENI_BWD_TRACE=1): clock64 timeline of CTA 0, see tools/trace_bwd.py
   alignas(64) CUtensorMap wmap;  // wb2 as rows of 256 B, box = one 16 KB half chunk
 };
+
+#ifndef RENI_BWD_TRACE
+#define RENI_BWD_TRACE 0
+#endif
+DEVINL void btrace_ev(const BwdParams& p, int role, uint32_t& n, uint32_t code) {
+  if (RENI_BWD_TRACE && p.trace != nullptr && blockIdx.x == 0 && n < 4096) {
+    p.trace[role * 4096 + n] = ((unsigned long long)code << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+    ++n;
+  }
+}
 
 struct BwdSmem {
   static constexpr int kA = 0;
@@ -147,6 +158,12 @@ DEVINL uint4 phase_load(const uint4* p) {
                                  // 0 off, 1 latent-only chain (225 -> 213 us at cfg 2), 2 also with weight gradients
                                  // (293 -> 307 us: that kernel is short of bandwidth, early requests hurt it); also
                                  // prefetching the unit's out / target rows changed nothing
+#endif
+#ifndef RENI_BWD_SIGNAL_FIRST
+#define RENI_BWD_SIGNAL_FIRST 0  // sub-tile handed to the MMA issuer before (1) / after (0) its stash copies are queued:
+                                 // 1 removes a ~3900 clk wait from the issuer's timeline and the kernel gets SLOWER
+                                 // (295 -> 304 us): the layer step is bound by its 256 KB of HBM traffic per SM
+                                 // (tools/ubench/sm_traffic.cu: 11.0 K clk for the copies alone, 10.8 K measured here)
 #endif
 #ifndef RENI_BWD_BULK_STASH
 #define RENI_BWD_BULK_STASH 1  // 1: delta stash written by per-warp bulk copies of the finished smem pieces; 0: st.global
@@ -331,6 +348,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
       const uint32_t w6_base = smem_u32(smem + BwdSmem::kW6);
       uint32_t st = 0, ph = 0;
       uint32_t a_ph = 0, ap_ph = 0;  // bit g: parity of a_ready[g] / a_ready_peer[g]
+      uint32_t tn = 0;
       for (int it = 0; it < iters; ++it) {
         const int ubase = unit_base(it);
         const int nsub = clamp02(p.ntiles - ubase);           // live sub-tiles of the leader
@@ -339,11 +357,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
           for (int g = 0; g < nsub; ++g) {
             mbar_wait(&a_ready[g], (a_ph >> g) & 1);
             a_ph ^= 1u << g;
+            btrace_ev(p, 0, tn, 0x700 | ((uint32_t)l << 4) | g);  // own epilogue group seen
             if (g < nsub_peer) {
               mbar_wait(&a_ready_peer[g], (ap_ph >> g) & 1);
               ap_ph ^= 1u << g;
             }
             tc_fence_after();
+            btrace_ev(p, 0, tn, 0x100 | ((uint32_t)l << 4) | g);  // operand ready seen
             const uint32_t a_tile = a_base + g * kTileImageBytes;
             const uint32_t d_tmem = tmem_base + g * 256;
             if (l == L + 1) {
@@ -398,6 +418,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
               }
             }
             commit(&acc_full[g], (g < nsub_peer) ? 0x3 : 0x1);
+            btrace_ev(p, 0, tn, 0x200 | ((uint32_t)l << 4) | g);  // pass issued
           }
         }
       }
@@ -412,6 +433,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
     uint8_t* a_tile = smem + BwdSmem::kA + g * kTileImageBytes;
     const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256 + chalf * 128;
     uint32_t acc_ph = 0;
+    uint32_t tn = 0;
+    const bool tracer = e == 0 && lane == 0;
     const float S = __ldg(p.scalars);
 
     for (int it = 0; it < iters; ++it) {
@@ -503,9 +526,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
         for (int k = 0; k < 16; ++k)
           hh[k] = (RENI_ABL & 8) ? make_uint4(k, row, l, g)
                                  : phase_load(reinterpret_cast<const uint4*>(hl + stash_off(row, chalf * 16 + k, kH)));
+        if (tracer) btrace_ev(p, 1 + g, tn, 0x300 | ((uint32_t)l << 4) | g);  // phase loads issued, waiting for the accumulator
         mbar_wait(&acc_full[g], acc_ph);
         acc_ph ^= 1;
         tc_fence_after();
+        if (tracer) btrace_ev(p, 1 + g, tn, 0x400 | ((uint32_t)l << 4) | g);  // accumulator seen
         const float* fl = nullptr;  // this map's freq_l (hidden layers only; layer 0 is modulated by the caller)
         if (kFilm && l > 0) fl = p.film + ((size_t)b * L + (l - 1)) * 2 * kH;
         if (kNeedDW && p.ready != nullptr && l < L) {
@@ -521,6 +546,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
           if (lane < 16) bulk_wait_read0();
           __syncwarp();
         }
+        if (tracer) btrace_ev(p, 1 + g, tn, 0x600 | ((uint32_t)l << 4) | g);  // previous stash copies have left the tile
         auto process16 = [&](const uint32_t (&v)[16], int it) {
 #pragma unroll
           for (int q8 = 0; q8 < 2; ++q8) {
@@ -574,6 +600,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
         }
         tc_fence_before();
         fence_proxy_async_smem();
+        if (tracer) btrace_ev(p, 1 + g, tn, 0x500 | ((uint32_t)l << 4) | g);  // this warp's epilogue done
+        else if (lane == 0) btrace_ev(p, 1 + warp, tn, 0x500 | ((uint32_t)l << 4) | g);  // (roles 3..18: the other warps)
+#if RENI_BWD_SIGNAL_FIRST
+        // the next GEMM only READS the tile, like the stash copies below, so the issuer may be told before they are queued
+        // (the copy engine drains ~28 B/clk and the issue of a copy blocks behind its queue, profiles/r2_ubench_s2g.txt)
+        signal_ready(g);
+#endif
         if (kBulk && dl != nullptr && !(RENI_ABL & 1)) {
           // this warp's block of the finished tile image (32 rows x 16 column groups) goes to the stash as 16 bulk
           // copies of 512 B, one per lane: no st.global in the epilogue, the copy engine reads while the tensor core does
@@ -585,7 +618,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
             bulk_commit();
           }
         }
+#if !RENI_BWD_SIGNAL_FIRST
         signal_ready(g);
+#endif
       }
       // ---- layer-0 reduction result: D[j, 0..4] for j = row (columns 0..15) and j = 128 + row (columns 16..31)
       mbar_wait(&acc_full[g], acc_ph);

@@ -22,6 +22,10 @@ constexpr int kDwStages = 3;
 constexpr int kDwStageBytes = 2 * kHalfImageBytes;  // 64 KB: A operand + B operand; the phase block lands in the
                                                     // operand slot of h and is converted in place
 
+#ifndef RENI_DW_INTERLEAVE
+#define RENI_DW_INTERLEAVE 1  // 1: a CTA walks blocks slice, slice+nslices, ... (ascending) instead of one contiguous range: the
+                              // delta chain walks the units downwards, so every CTA starts on the tiles it wrote last (L2)
+#endif
 #ifndef RENI_DW_LOAD_HINT
 #define RENI_DW_LOAD_HINT 1  // stash blocks loaded with an L2 evict-first policy (258 -> 252 us at cfg 2)
 #endif
@@ -106,7 +110,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
   const bool overlap = p.ready != nullptr;
   const int s_begin = s_base + (int)((int64_t)slice * total / nslices);
   const int s_end = s_base + (int)((int64_t)(slice + 1) * total / nslices);
-  const int nst = overlap ? (total > slice ? (total - slice + nslices - 1) / nslices : 0) : s_end - s_begin;
+  const bool inter = RENI_DW_INTERLEAVE && !overlap && !p.film_persistent;
+  const int nst = (overlap || inter) ? (total > slice ? (total - slice + nslices - 1) / nslices : 0) : s_end - s_begin;
   // i-th stash block of this CTA
   auto blk = [&](int i) { return overlap ? total - 1 - (slice + i * nslices) : s_begin + i; };
   // Work of this CTA as a sequence of segments (job, map, first block, blocks): ONE for the grids above, one per
@@ -173,7 +178,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
   auto img_bytes_of = [&](int job_) -> uint32_t { return job_ == L ? (kHalfRows * kW6N * 2) : kHalfImageBytes; };
 
   // block i of a segment (overlap mode has a single segment and walks its interleaved, descending order)
-  auto seg_blk = [&](const Seg& sg, int i) { return overlap ? blk(i) : sg.s0 + i; };
+  auto seg_blk = [&](const Seg& sg, int i) {
+    return overlap ? blk(i) : (inter ? s_base + slice + i * nslices : sg.s0 + i);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
