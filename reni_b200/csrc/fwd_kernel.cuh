@@ -104,6 +104,10 @@ DEVINL void trace_ev(const FwdParams& p, int role, uint32_t& n, uint32_t code) {
   }
 }
 
+#ifndef RENI_FWD_PIPE_L0
+#define RENI_FWD_PIPE_L0 2  // all-hands epilogue: 1 = layer 0 of the next unit ahead of the current unit's output epilogue,
+                           // 2 = and the output epilogue finished behind the next unit's first hidden epilogue
+#endif
 #ifndef RENI_FWD_STASH_HINT
 #define RENI_FWD_STASH_HINT 1  // phase-stash stores: 0 plain st.global, 1 st.global.cs (streaming: fwd 214 -> 207 us), 2 st.global.wt (no change)
 #endif
@@ -394,82 +398,169 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
     const uint32_t etid = threadIdx.x - 64;         // 0..511
     float* s_mc_all = reinterpret_cast<float*>(smem + FwdSmem::kMc);
     uint32_t acc_ph = 0;  // bit g = phase parity of acc_full[g]
+    auto unit_tbase = [&](int it) { return (worker + it * nworkers) * unit_tiles + 2 * (int)crank; };  // this CTA's first tile
+    auto tile_of = [&](int tb, int g) { return g ? min(tb + 1, p.ntiles - 1) : tb; };
 
-    for (int it = 0; it < iters; ++it) {
-      const int tbase = (worker + it * nworkers) * unit_tiles + 2 * (int)crank;  // this CTA's first tile
-      const int nsub = clamp02(p.ntiles - tbase);
-      if (nsub == 0) break;
-      const int tile0 = tbase, tile1 = min(tbase + 1, p.ntiles - 1);
-      const int bmap0 = tile0 / p.tiles_per_map, bmap1 = tile1 / p.tiles_per_map;
-      const int pix0 = (tile0 - bmap0 * p.tiles_per_map) * kTileRows + row;
-      const int pix1 = (tile1 - bmap1 * p.tiles_per_map) * kTileRows + row;
-
-      // ---- per-map layer-0 operands of both sub-tiles -> smem
-      named_bar_sync(1, kEpiThreads);
+    // per-map layer-0 operands of a unit's sub-tiles -> smem
+    auto load_mc = [&](int tb) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        const float4* src = reinterpret_cast<const float4*>(p.mc + (size_t)(g ? bmap1 : bmap0) * 5 * kH);
+        const float4* src = reinterpret_cast<const float4*>(p.mc + (size_t)(tile_of(tb, g) / p.tiles_per_map) * 5 * kH);
         float4* dst = reinterpret_cast<float4*>(s_mc_all + g * 5 * kH);
         for (int i = etid; i < 5 * kH / 4; i += kEpiThreads) dst[i] = __ldg(src + i);
       }
-      named_bar_sync(1, kEpiThreads);
-
-      // ---- layer 0: h0 = sin(f . M' + c')  (omega folded into M', c'); this warp's 64 columns of each sub-tile
-      for (int g = 0; g < nsub; ++g) {
-        const int b = g ? bmap1 : bmap0, pix = g ? pix1 : pix0;
-        // invariant direction features, registers only (RENI.py:37-49)
-        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-        if (pix < p.P) {
-          float dx, dy, dz;
-          if (p.dir_grid) {
-            float sp_;
-            grid_point(pix, p.grid_w, dx, dy, dz, sp_);
-          } else {
-            const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
-            dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
-          }
-          if (p.so2) {
-            f0 = dx;
-            f1 = dz;
-            f2 = sqrtf(dx * dx + dz * dz);
-            f3 = dy;
-          } else {  // SO3 / None: the three inner-product columns (RENI.py:25,57)
-            f0 = dx;
-            f1 = dy;
-            f2 = dz;
-          }
+    };
+    // layer 0 of sub-tile g of the unit at tb: h0 = sin(f . M' + c')  (omega folded into M', c'); this warp's 64 columns
+    auto layer0 = [&](int tb, int g) {
+      const int tile = tile_of(tb, g);
+      const int b = tile / p.tiles_per_map;
+      const int pix = (tile - b * p.tiles_per_map) * kTileRows + row;
+      // invariant direction features, registers only (RENI.py:37-49)
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+      if (pix < p.P) {
+        float dx, dy, dz;
+        if (p.dir_grid) {
+          float sp_;
+          grid_point(pix, p.grid_w, dx, dy, dz, sp_);
+        } else {
+          const float* d = p.D + (size_t)b * p.d_bstride + (size_t)pix * 3;
+          dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
         }
-        uint8_t* a_tile = smem + FwdSmem::kA + g * kTileImageBytes;
-        const float* s_mc = s_mc_all + g * 5 * kH;
-        uint8_t* st_u = nullptr;
-        if (kTrain) st_u = reinterpret_cast<uint8_t*>(p.stash_u) + (size_t)(tbase + g) * (L + 1) * kTileImageBytes;
-#pragma unroll 2
-        for (int k8 = 0; k8 < 8; ++k8) {
-          const int kg = cq * 8 + k8;
-          float a[8];
-          {
-            const float4* m = reinterpret_cast<const float4*>(s_mc + kg * 8);
-            const float4 c0 = m[4 * (kH / 4)], c1 = m[4 * (kH / 4) + 1];
-            a[0] = c0.x; a[1] = c0.y; a[2] = c0.z; a[3] = c0.w;
-            a[4] = c1.x; a[5] = c1.y; a[6] = c1.z; a[7] = c1.w;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float fi = (i == 0) ? f0 : (i == 1) ? f1 : (i == 2) ? f2 : f3;
-              const float4 m0 = m[i * (kH / 4)], m1 = m[i * (kH / 4) + 1];
-              a[0] = fmaf(fi, m0.x, a[0]); a[1] = fmaf(fi, m0.y, a[1]);
-              a[2] = fmaf(fi, m0.z, a[2]); a[3] = fmaf(fi, m0.w, a[3]);
-              a[4] = fmaf(fi, m1.x, a[4]); a[5] = fmaf(fi, m1.y, a[5]);
-              a[6] = fmaf(fi, m1.z, a[6]); a[7] = fmaf(fi, m1.w, a[7]);
-            }
-          }
-          uint4 hv, uv;
-          sin8<kTrain>(a, hv, uv);
-          *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
-          if (kTrain && !(RENI_ABL & 1)) stash_store(st_u + stash_off(row, kg, kH), uv);
+        if (p.so2) {
+          f0 = dx;
+          f1 = dz;
+          f2 = sqrtf(dx * dx + dz * dz);
+          f3 = dy;
+        } else {  // SO3 / None: the three inner-product columns (RENI.py:25,57)
+          f0 = dx;
+          f1 = dy;
+          f2 = dz;
         }
-        fence_proxy_async_smem();
-        signal_ready(g);
       }
+      uint8_t* a_tile = smem + FwdSmem::kA + g * kTileImageBytes;
+      const float* s_mc = s_mc_all + g * 5 * kH;
+      uint8_t* st_u = nullptr;
+      if (kTrain) st_u = reinterpret_cast<uint8_t*>(p.stash_u) + (size_t)(tb + g) * (L + 1) * kTileImageBytes;
+#pragma unroll 2
+      for (int k8 = 0; k8 < 8; ++k8) {
+        const int kg = cq * 8 + k8;
+        float a[8];
+        {
+          const float4* m = reinterpret_cast<const float4*>(s_mc + kg * 8);
+          const float4 c0 = m[4 * (kH / 4)], c1 = m[4 * (kH / 4) + 1];
+          a[0] = c0.x; a[1] = c0.y; a[2] = c0.z; a[3] = c0.w;
+          a[4] = c1.x; a[5] = c1.y; a[6] = c1.z; a[7] = c1.w;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float fi = (i == 0) ? f0 : (i == 1) ? f1 : (i == 2) ? f2 : f3;
+            const float4 m0 = m[i * (kH / 4)], m1 = m[i * (kH / 4) + 1];
+            a[0] = fmaf(fi, m0.x, a[0]); a[1] = fmaf(fi, m0.y, a[1]);
+            a[2] = fmaf(fi, m0.z, a[2]); a[3] = fmaf(fi, m0.w, a[3]);
+            a[4] = fmaf(fi, m1.x, a[4]); a[5] = fmaf(fi, m1.y, a[5]);
+            a[6] = fmaf(fi, m1.z, a[6]); a[7] = fmaf(fi, m1.w, a[7]);
+          }
+        }
+        uint4 hv, uv;
+        sin8<kTrain>(a, hv, uv);
+        *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
+        if (kTrain && !(RENI_ABL & 1)) stash_store(st_u + stash_off(row, kg, kH), uv);
+      }
+      fence_proxy_async_smem();
+      signal_ready(g);
+    };
+    // output layer (N = 16 padded), first half: wait for the accumulator and take the three pre-activations out of TMEM
+    auto read_out = [&](int g, float (&y)[3]) {
+      mbar_wait(&acc_full[g], (acc_ph >> g) & 1);
+      acc_ph ^= 1u << g;
+      tc_fence_after();
+      if (cq == 0) {
+        const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256;
+        uint32_t v[16];
+        tmem_ld16(t_acc, v);
+        tmem_ld_wait();
+        const float* bo = s_bias + L * kH;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          y[c] = (__uint_as_float(v[c]) + __uint_as_float(v[c + 3])) + bo[c];  // (W_out hi + lo columns)
+      }
+      tc_fence_before();
+    };
+    // ... second half: optional sin, optional tanh, store, fused loss partials
+    auto finish_out = [&](int tb, int g, const float (&y)[3]) {
+      if (cq != 0) return;
+      const int tile = tb + g;
+      const int b = tile_of(tb, g) / p.tiles_per_map;
+      const int pix = (tile_of(tb, g) - b * p.tiles_per_map) * kTileRows + row;
+      const bool rvalid = pix < p.P;
+      float o[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float yy = y[c];
+        if (p.last_sine) {
+          if (kTrain && rvalid) p.aout[((size_t)b * p.P + pix) * 3 + c] = yy;
+          yy = sinf(yy);
+        }
+        if (p.out_tanh) yy = tanhf(yy);
+        o[c] = yy;
+      }
+      if (rvalid) {
+        float* op = p.out + ((size_t)b * p.P + pix) * 3;
+        op[0] = o[0];
+        op[1] = o[1];
+        op[2] = o[2];
+      }
+      if (p.loss_part != nullptr) {
+        float part[kLossPartials];
+#pragma unroll
+        for (int i = 0; i < kLossPartials; ++i) part[i] = 0.f;
+        if (rvalid) {
+          const float* tp = p.target + ((size_t)b * p.P + pix) * 3;
+          const float* wp = p.sw_grid ? nullptr : p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
+          const float wg = p.sw_grid ? grid_sineweight(pix, p.grid_w, p.mask_bits) : 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float t = __ldg(tp + c), w = p.sw_grid ? wg : __ldg(wp + c);
+            const float er = o[c] - t;
+            part[0] = fmaf(er * er, w, part[0]);
+            part[1 + c] = o[c] * t;
+            part[4 + c] = o[c] * o[c];
+            part[7 + c] = t * t;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kLossPartials; ++i) {
+          float x = part[i];
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+          part[i] = x;
+        }
+        if (lane == 0) {
+          float* lp = p.loss_part + ((size_t)tile * 4 + q) * kLossPartials;
+#pragma unroll
+          for (int i = 0; i < kLossPartials; ++i) lp[i] = part[i];
+        }
+      }
+    };
+
+    // Layer 0 of unit it+1 is computed at the END of unit it, between reading the output accumulator of a sub-tile and
+    // finishing its outputs (RENI_FWD_PIPE_L0): the activation tile of sub-tile g is free as soon as its output GEMM
+    // has completed, so the first hidden GEMM of the next unit starts ~7 K clk earlier than when the whole output
+    // epilogue of both sub-tiles came first (timeline: the tensor pipe idled ~10 K of 69 K clk at every unit boundary).
+    if (iters > 0 && clamp02(p.ntiles - unit_tbase(0)) > 0) {
+      const int tb = unit_tbase(0), ns = clamp02(p.ntiles - tb);
+      load_mc(tb);
+      named_bar_sync(1, kEpiThreads);
+      for (int g = 0; g < ns; ++g) layer0(tb, g);
+    }
+    // outputs of the previous unit that are still to be finished (behind the first hidden epilogue of this unit, where
+    // the epilogue warps have slack: the tensor pipe is busy with the other sub-tile's first GEMM)
+    float y0[3] = {0.f, 0.f, 0.f}, y1[3] = {0.f, 0.f, 0.f};
+    int pend_tb = 0, pend_n = 0;
+    for (int it = 0; it < iters; ++it) {
+      const int tbase = unit_tbase(it);
+      const int nsub = clamp02(p.ntiles - tbase);
+      if (nsub == 0) break;
+      const int bmap0 = tile_of(tbase, 0) / p.tiles_per_map, bmap1 = tile_of(tbase, 1) / p.tiles_per_map;
 
       // ---- hidden layers: bias + sin epilogue, TMEM -> registers -> smem tile image (in place); the sub-tiles alternate
       for (int l = 1; l <= L; ++l) {
@@ -543,76 +634,42 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
           tc_fence_before();
           fence_proxy_async_smem();
           signal_ready(g);
+          if (pend_n > 0) {
+            finish_out(pend_tb, 0, y0);
+            if (pend_n > 1) finish_out(pend_tb, 1, y1);
+            pend_n = 0;
+          }
         }
       }
 
-      // ---- output layer (N = 16 padded): bias, optional sin, optional tanh, store, fused loss partials
-      for (int g = 0; g < nsub; ++g) {
-        mbar_wait(&acc_full[g], (acc_ph >> g) & 1);
-        acc_ph ^= 1u << g;
-        tc_fence_after();
-        if (cq == 0) {
-          const int tile = tbase + g;
-          const int b = g ? bmap1 : bmap0, pix = g ? pix1 : pix0;
-          const bool rvalid = pix < p.P;
-          const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256;
-          float o[3];
-          {
-            uint32_t v[16];
-            tmem_ld16(t_acc, v);
-            tmem_ld_wait();
-            const float* bo = s_bias + L * kH;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float y = (__uint_as_float(v[c]) + __uint_as_float(v[c + 3])) + bo[c];  // (W_out hi + lo columns)
-              if (p.last_sine) {
-                if (kTrain && rvalid) p.aout[((size_t)b * p.P + pix) * 3 + c] = y;
-                y = sinf(y);
-              }
-              if (p.out_tanh) y = tanhf(y);
-              o[c] = y;
-            }
-          }
-          if (rvalid) {
-            float* op = p.out + ((size_t)b * p.P + pix) * 3;
-            op[0] = o[0];
-            op[1] = o[1];
-            op[2] = o[2];
-          }
-          if (p.loss_part != nullptr) {
-            float part[kLossPartials];
-#pragma unroll
-            for (int i = 0; i < kLossPartials; ++i) part[i] = 0.f;
-            if (rvalid) {
-              const float* tp = p.target + ((size_t)b * p.P + pix) * 3;
-              const float* wp = p.sw_grid ? nullptr : p.sw + (size_t)b * p.sw_bstride + (size_t)pix * 3;
-              const float wg = p.sw_grid ? grid_sineweight(pix, p.grid_w, p.mask_bits) : 0.f;
-#pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                const float t = __ldg(tp + c), w = p.sw_grid ? wg : __ldg(wp + c);
-                const float er = o[c] - t;
-                part[0] = fmaf(er * er, w, part[0]);
-                part[1 + c] = o[c] * t;
-                part[4 + c] = o[c] * o[c];
-                part[7 + c] = t * t;
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < kLossPartials; ++i) {
-              float x = part[i];
-#pragma unroll
-              for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
-              part[i] = x;
-            }
-            if (lane == 0) {
-              float* lp = p.loss_part + ((size_t)tile * 4 + q) * kLossPartials;
-#pragma unroll
-              for (int i = 0; i < kLossPartials; ++i) lp[i] = part[i];
-            }
-          }
-        }
-        tc_fence_before();
+      // ---- unit boundary: output layer of this unit, layer 0 of the next one
+      const int tb_next = unit_tbase(it + 1);
+      const int ns_next = (it + 1 < iters) ? clamp02(p.ntiles - tb_next) : 0;
+      if (ns_next > 0) {
+        // (every warp has seen a hidden-layer accumulator of each live sub-tile, i.e. all of them are past this unit's
+        // layer 0: its operands can be replaced.  L = 0 has no such guarantee: the barrier in front covers it.)
+        if (L == 0 || nsub < 2) named_bar_sync(1, kEpiThreads);
+        load_mc(tb_next);
+        named_bar_sync(1, kEpiThreads);
       }
+      if (pend_n > 0) {  // (L = 0: nothing ran in between)
+        finish_out(pend_tb, 0, y0);
+        if (pend_n > 1) finish_out(pend_tb, 1, y1);
+        pend_n = 0;
+      }
+      read_out(0, y0);
+      if (RENI_FWD_PIPE_L0 && ns_next > 0) layer0(tb_next, 0);
+      if (nsub > 1) read_out(1, y1);
+      if (RENI_FWD_PIPE_L0 && ns_next > 1) layer0(tb_next, 1);
+      if (RENI_FWD_PIPE_L0 == 2 && ns_next > 0) {
+        pend_tb = tbase;
+        pend_n = nsub;
+      } else {
+        finish_out(tbase, 0, y0);
+        if (nsub > 1) finish_out(tbase, 1, y1);
+      }
+      if (!RENI_FWD_PIPE_L0)
+        for (int g = 0; g < ns_next; ++g) layer0(tb_next, g);
     }
   } else {
     // ============================================================ epilogue groups
