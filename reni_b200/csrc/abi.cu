@@ -14,6 +14,7 @@
 #include "lbwd_kernel.cuh"
 #include "shade_kernel.cuh"
 #include "small_kernels.cuh"
+#include "film_map_fused.cuh"
 
 #ifndef RENI_NO_FORK
 #define RENI_NO_FORK 0  // 1: keep every kernel of the step on the caller's stream (A/B switch for the fork/join)
@@ -1173,6 +1174,35 @@ int32_t reni_allreduce(void* dev_buf_ptrs, void* dev_flag_ptrs, void* multicast_
   return last_err() == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
 }
 
+#ifndef RENI_FILM_MAP_FUSED
+#define RENI_FILM_MAP_FUSED 0  // 1: per-map stage as one cooperative launch per direction (film_map_fused.cuh) instead of
+                               // the staged launches -- measured SLOWER at 32 maps (forward 60 vs 47 us, forward +
+                               // backward 190 vs 154 us in a replayed graph): its stages are bound by the same L2 latency
+                               // per k-step as the staged kernels and the barriers cost what the launches did
+#endif
+constexpr int64_t kFilmMapSyncBytes = 256;
+
+// cooperative launch of a fused per-map kernel on at most kMapFusedMaxCtas CTAs; `sync` = its two barrier words
+extern "C++" {
+template <typename P>
+static int32_t launch_map_fused(void (*kernel)(P), const P& p, unsigned int* sync, cudaStream_t stream) {
+  const int sms = num_sms();
+  if (sms <= 0) return RENI_ERR_NO_DEVICE;
+  if (cudaMemsetAsync(sync, 0, 8, stream) != cudaSuccess) return RENI_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(sms < kMapFusedMaxCtas ? sms : kMapFusedMaxCtas));
+  cfg.blockDim = dim3(kMapFusedThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return note(cudaLaunchKernelEx(&cfg, kernel, p)) == cudaSuccess ? RENI_OK : RENI_ERR_CUDA;
+}
+}  // extern "C++"
+
 int64_t reni_film_map_scratch_bytes(const int32_t* host_map_dims, int32_t n_linears, int64_t B) {
   if (host_map_dims == nullptr || n_linears < 1 || n_linears > kFilmMapMaxLinears || B < 1) return RENI_ERR_BAD_ARGUMENT;
   int64_t widest = 0;
@@ -1180,17 +1210,36 @@ int64_t reni_film_map_scratch_bytes(const int32_t* host_map_dims, int32_t n_line
     if (host_map_dims[i] < 1) return RENI_ERR_BAD_ARGUMENT;
     if (host_map_dims[i] > widest) widest = host_map_dims[i];
   }
-  return 2 * B * widest * (int64_t)sizeof(float);  // two ping-pong activation buffers
+  // two ping-pong activation buffers + the grid-barrier words of the fused launch
+  return 2 * align_up(B * widest * (int64_t)sizeof(float), 256) + kFilmMapSyncBytes;
 }
 
 // Shared body of the two per-map forwards: act[i] = input of linear i (act[0] = mapping input), act[n] = raw output
 static int32_t film_map_forward_impl(const reni_config_t* c, const float* Z, const float* weight0, const float* bias0,
                                      const float* const* host_map_weights, const float* const* host_map_biases,
                                      const int32_t* host_map_dims, int32_t n_linears, int64_t B, float* mc, float* film,
-                                     float* const* act, cudaStream_t stream) {
+                                     float* const* act, unsigned int* sync, cudaStream_t stream) {
   const int N = c->ndims, Lf = c->hidden_layers + 1;
   const int mn_in = c->equivariance == RENI_EQ_SO2 ? N * N + N : N * N;
   const int so2 = c->equivariance == RENI_EQ_SO2;
+  if (RENI_FILM_MAP_FUSED) {
+    FilmMapFusedParams q{};
+    q.Z = Z; q.W0 = weight0; q.b0 = bias0;
+    for (int i = 0; i < n_linears; ++i) {
+      if (host_map_weights[i] == nullptr || host_map_biases[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
+      q.W[i] = host_map_weights[i];
+      q.bias[i] = host_map_biases[i];
+    }
+    for (int i = 0; i <= n_linears; ++i) {
+      q.act[i] = act[i];
+      q.dims[i] = host_map_dims[i];
+    }
+    q.n_linears = n_linears;
+    q.mc = mc; q.film = film;
+    q.B = (int)B; q.N = N; q.so2 = so2; q.Lf = Lf;
+    q.sync = sync;
+    return launch_map_fused(reni_film_map_fused_fwd_kernel, q, sync, stream);
+  }
   reni_film_map_input_kernel<<<(unsigned)B, 256, 3 * N * sizeof(float), stream>>>(Z, act[0], N, so2, mn_in);
   for (int i = 0; i < n_linears; ++i) {
     if (host_map_weights[i] == nullptr || host_map_biases[i] == nullptr) return RENI_ERR_BAD_ARGUMENT;
@@ -1241,10 +1290,12 @@ int32_t reni_film_map_forward(const reni_config_t* c, const float* Z, const floa
   if (need < 0) return (int32_t)need;
   if (scratch_bytes < need) return RENI_ERR_WORKSPACE;
   float* act[kFilmMapMaxLinears + 1];  // two ping-pong buffers
+  const int64_t half = (need - kFilmMapSyncBytes) / 2;
   for (int i = 0; i <= n_linears; ++i)
-    act[i] = static_cast<float*>(scratch) + (i & 1) * (need / (2 * sizeof(float)));
+    act[i] = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + (i & 1) * half);
   return film_map_forward_impl(c, Z, weight0, bias0, host_map_weights, host_map_biases, host_map_dims, n_linears, B, mc,
-                               film, act, static_cast<cudaStream_t>(stream_));
+                               film, act, reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(scratch) + 2 * half),
+                               static_cast<cudaStream_t>(stream_));
 }
 
 int64_t reni_film_map_acts_bytes(const int32_t* host_map_dims, int32_t n_linears, int64_t B) {
@@ -1254,7 +1305,7 @@ int64_t reni_film_map_acts_bytes(const int32_t* host_map_dims, int32_t n_linears
     if (host_map_dims[i] < 1) return RENI_ERR_BAD_ARGUMENT;
     total += align_up(B * host_map_dims[i] * (int64_t)sizeof(float), 256);
   }
-  return total;
+  return total + kFilmMapSyncBytes;  // (+ the grid-barrier words of the fused launches, behind the last activation)
 }
 
 static void film_map_act_ptrs(float* base, const int32_t* dims, int32_t n_linears, int64_t B, float** act) {
@@ -1280,7 +1331,9 @@ int32_t reni_film_map_forward_train(const reni_config_t* c, const float* Z, cons
   float* act[kFilmMapMaxLinears + 1];
   film_map_act_ptrs(static_cast<float*>(acts), host_map_dims, n_linears, B, act);
   return film_map_forward_impl(c, Z, weight0, bias0, host_map_weights, host_map_biases, host_map_dims, n_linears, B, mc,
-                               film, act, static_cast<cudaStream_t>(stream_));
+                               film, act,
+                               reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(acts) + need - kFilmMapSyncBytes),
+                               static_cast<cudaStream_t>(stream_));
 }
 
 int32_t reni_film_map_backward(const reni_config_t* c, const float* Z, const float* weight0, const float* bias0,
@@ -1312,9 +1365,30 @@ int32_t reni_film_map_backward(const reni_config_t* c, const float* Z, const flo
   film_map_act_ptrs(static_cast<float*>(scratch), host_map_dims, n_linears, B, dact);
   float* dM = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + acts_bytes);
   // the dX kernels add their output-row slices with atomics
-  if (cudaMemsetAsync(scratch, 0, (size_t)(acts_bytes - align_up(B * host_map_dims[n_linears] * 4, 256)), stream) !=
-      cudaSuccess)
+  if (cudaMemsetAsync(scratch, 0,
+                      (size_t)(acts_bytes - kFilmMapSyncBytes - align_up(B * host_map_dims[n_linears] * 4, 256)),
+                      stream) != cudaSuccess)
     return RENI_ERR_CUDA;
+  if (RENI_FILM_MAP_FUSED) {
+    FilmMapFusedBwdParams q{};
+    q.Z = Z; q.W0 = weight0; q.b0 = bias0;
+    for (int i = 0; i < n_linears; ++i) {
+      q.W[i] = host_map_weights[i];
+      q.dW[i] = want_dw ? host_map_dW[i] : nullptr;
+      q.db[i] = want_dw ? host_map_db[i] : nullptr;
+    }
+    for (int i = 0; i <= n_linears; ++i) {
+      q.act[i] = act[i];
+      q.dact[i] = dact[i];
+      q.dims[i] = host_map_dims[i];
+    }
+    q.n_linears = n_linears;
+    q.d_mc = d_mc; q.d_film = d_film; q.dM = dM; q.dZ = dZ;
+    q.dW0 = want_dw ? dW0 : nullptr; q.db0 = want_dw ? db0 : nullptr;
+    q.B = (int)B; q.N = N; q.so2 = so2; q.Lf = Lf;
+    q.sync = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(scratch) + acts_bytes - kFilmMapSyncBytes);
+    return launch_map_fused(reni_film_map_fused_bwd_kernel, q, q.sync, stream);
+  }
   {
     FilmMapBwdHeadParams h{};
     h.Z = Z; h.W0 = weight0; h.b0 = bias0; h.raw = act[n_linears]; h.d_mc = d_mc; h.d_film = d_film;

@@ -109,7 +109,7 @@ def test_film_per_map_entry_points_host_side(lib):
     assert lib.reni_film_prepare_maps(C.byref(c), None, dummy, dummy, 2, 512, one, 1 << 30, FILM, None) == -2
     dims = (C.c_int32 * 5)(36 * 36 + 36, 256, 256, 256, 2 * 5 * 256)
     acts = lib.reni_film_map_acts_bytes(dims, 4, 32)
-    assert acts == 32 * 4 * sum(dims)  # every activation kept (each a multiple of 256 bytes here)
+    assert acts == 32 * 4 * sum(dims) + 256  # every activation kept (multiples of 256 bytes here) + the barrier words
     assert lib.reni_film_map_acts_bytes(dims, 0, 32) == -2
     assert lib.reni_film_map_acts_bytes(dims, 4, 0) == -2
     assert lib.reni_film_map_forward_train(C.byref(c), None, None, None, None, None, dims, 4, 32, None, None, None, 0,
