@@ -96,6 +96,16 @@ struct FwdSmem {
 };
 static_assert(FwdSmem::kTotal <= 232448, "forward kernel shared memory over budget");
 
+// (debug timeline) wall-clock stamp: the same record with the low 48 bits of %globaltimer (ns) instead of clock64 --
+// two such pairs give the SM clock the kernel actually ran at
+DEVINL void trace_wall(const FwdParams& p, int role, uint32_t& n, uint32_t code) {
+  if (p.trace != nullptr && blockIdx.x == 0 && n < 4096) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[role * 4096 + n] = ((unsigned long long)code << 48) | (t & 0xFFFFFFFFFFFFull);
+    ++n;
+  }
+}
 // debug timeline: role r (0 MMA issuer, 1/2 epilogue group 0/1) appends (code << 48 | clock) to its 4096-entry lane
 DEVINL void trace_ev(const FwdParams& p, int role, uint32_t& n, uint32_t code) {
   if (p.trace != nullptr && blockIdx.x == 0 && n < 4096) {
@@ -300,6 +310,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
       uint32_t st = 0, ph = 0;
       uint32_t a_ph = 0, ap_ph = 0;  // bit g: parity of a_ready[g] / a_ready_peer[g]
       uint32_t tn = 0;
+      trace_ev(p, 0, tn, 0x900);    // issuer starts (clock64) ...
+      trace_wall(p, 0, tn, 0xA00);  // ... and the wall clock at the same moment
       for (int it = 0; it < iters; ++it) {
         const int ubase = (worker + it * nworkers) * unit_tiles;
         const int nsub = clamp02(p.ntiles - ubase);                      // live sub-tiles of this (the leader) CTA
@@ -388,6 +400,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
           }
         }
       }
+      trace_ev(p, 0, tn, 0x900);
+      trace_wall(p, 0, tn, 0xA00);
     }
   } else if (kAllHands) {
     // ============================================================ epilogue warps

@@ -27,13 +27,14 @@ step()
 torch.cuda.synchronize()
 lib.reni_debug_set_trace(None)
 ev = buf.cpu().numpy().astype(np.uint64).reshape(3, 4096)
-names = {1: "A_seen", 2: "issued", 3: "wait_acc", 4: "acc_seen", 5: "epi_done", 6: "w_wait", 7: "w_own", 8: "w_all"}
-rows = []
+names = {9: "clk_mark", 10: "wall_ns", 1: "A_seen", 2: "issued", 3: "wait_acc", 4: "acc_seen", 5: "epi_done", 6: "w_wait", 7: "w_own", 8: "w_all"}
+rows, walls = [], []
 for r in range(3):
     for x in ev[r]:
         if x == 0: continue
         code, clk = int(x >> np.uint64(48)), int(x & np.uint64(0xFFFFFFFFFFFF))
-        rows.append((clk, r, names.get(code >> 8, "?"), (code >> 4) & 15, code & 15))
+        if (code >> 8) == 10: walls.append(clk)
+        else: rows.append((clk, r, names.get(code >> 8, "?"), (code >> 4) & 15, code & 15))
 rows.sort()
 t0 = rows[0][0]
 lo, hi = int(os.environ.get("LO", "200")), int(os.environ.get("HI", "420"))
@@ -41,3 +42,7 @@ prev = {}
 for clk, r, nm, l, g in rows[lo:hi]:
     role = ["mma ", "epi0", "epi1"][r]
     print(f"{clk - t0:9d}  {role} {nm:9s} l={l} g={g}")
+
+ck = sorted(c for c, r, nm, l, g in rows if nm == "clk_mark"); wl = sorted(walls)
+if len(ck) >= 2 and len(wl) >= 2:
+    print(f"issuer span: {ck[-1] - ck[0]} clk in {(wl[-1] - wl[0]) / 1e3:.1f} us -> SM clock {(ck[-1] - ck[0]) / (wl[-1] - wl[0]) * 1e3:.0f} MHz")
