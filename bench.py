@@ -340,6 +340,25 @@ def run_gpu_arm(args):
                   "p90": step_ms[(len(step_ms) * 9) // 10], "max": step_ms[-1]}
     clocks = sampler.stop() if sampler else None
 
+    # ---- per-kernel breakdown, directly behind the timed region (the same clock regime): the same step launched
+    # eagerly with CUDA events recorded between its kernels on the launching stream (library debug hook; the map-level
+    # backward then stays on the main stream instead of overlapping the weight-gradient GEMM, so the parts add up to
+    # slightly more than the graph-replayed step)
+    n_ev = 7
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
+    for e in evs:
+        e.record()  # forces creation of the cudaEvent_t handles
+    torch.cuda.synchronize()
+    handles = (C.c_void_p * n_ev)(*[e.cuda_event for e in evs])
+    phase_ms = [[] for _ in range(n_ev - 1)]
+    _lib.check(lib.reni_debug_set_phase_events(handles, n_ev))
+    for i in range(min(args.steps, 50)):
+        flush.zero_()
+        step_compute()
+        torch.cuda.synchronize()
+        for k in range(n_ev - 1):
+            phase_ms[k].append(evs[k].elapsed_time(evs[k + 1]))
+    _lib.check(lib.reni_debug_set_phase_events(None, 0))
     # ---- sustained regime (informational): the SM clock steps down after ~50 back-to-back steps of this load
     # (sw_power_cap); the mean over the last 100 of 200 further steps is what a long training run sees
     sustained_ms = None
@@ -362,24 +381,6 @@ def run_gpu_arm(args):
         finally:
             os.environ.pop("RENI_FWD_TERMS", None)
 
-    # ---- per-kernel breakdown: the same step launched eagerly with CUDA events recorded between its kernels on the
-    # launching stream (library debug hook; the map-level backward then stays on the main stream instead of
-    # overlapping the weight-gradient GEMM, so the parts add up to slightly more than the graph-replayed step)
-    n_ev = 7
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
-    for e in evs:
-        e.record()  # forces creation of the cudaEvent_t handles
-    torch.cuda.synchronize()
-    handles = (C.c_void_p * n_ev)(*[e.cuda_event for e in evs])
-    phase_ms = [[] for _ in range(n_ev - 1)]
-    _lib.check(lib.reni_debug_set_phase_events(handles, n_ev))
-    for i in range(min(args.steps, 50)):
-        flush.zero_()
-        step_compute()
-        torch.cuda.synchronize()
-        for k in range(n_ev - 1):
-            phase_ms[k].append(evs[k].elapsed_time(evs[k + 1]))
-    _lib.check(lib.reni_debug_set_phase_events(None, 0))
     barrier()
     # the exchange alone (device time of the call on this rank, all ranks launching together)
     exch_ms = None
