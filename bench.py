@@ -161,21 +161,36 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi in loop mode (5 ms), started well before the timed region (its start-up takes longer than a short
+    region lasts); `begin()` / `end()` bracket the region and only samples stamped inside it (else the nearest ones) count."""
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "5", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def begin(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.t1 is None:
+            self.end()
+        time.sleep(0.03)  # (let the sample that covers the end of the region be written)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -183,26 +198,36 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, pw, reasons = [], [], [], set()
+        rows = []
         for ln in self.f.read().splitlines():
             parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 10:
                 continue
             try:
-                sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(parts[2]), float(parts[3]), float(parts[4]), parts[6:10]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        inside = [r for r in rows if self.t0 is None or self.t0 <= r[0] <= self.t1]
+        where = "inside the timed region"
+        if not inside:  # a region shorter than the sampling period: the samples nearest to it
+            mid = self.t0 + (self.t1 - self.t0) / 2
+            inside = sorted(rows, key=lambda r: abs((r[0] - mid).total_seconds()))[:3]
+            where = "nearest to the timed region"
+        sm, mx, pw = [r[1] for r in inside], [r[2] for r in inside], [r[3] for r in inside]
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.f.name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         # "under load": samples drawing more than half of the maximum observed power
         thr = 0.5 * max(pw)
-        load = [s for s, w in zip(sm, pw) if w >= thr] or sm
+        load = [s_ for s_, w in zip(sm, pw) if w >= thr] or sm
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(inside), "sampled": where, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -307,6 +332,8 @@ def run_gpu_arm(args):
         if not in_graph:
             flat.all_reduce_mean()
 
+    # (nvidia-smi needs longer to start than a 20-step region lasts: started here, its samples are filtered by time stamp)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(3, args.warmup)):
         step_graphed()
     torch.cuda.synchronize()
@@ -327,10 +354,13 @@ def run_gpu_arm(args):
         barrier()
         return [a.elapsed_time(b) for a, b in zip(e0, e1)]
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
+    if sampler:
+        sampler.begin()
     # ---- timed region: exactly K steps, device-timed, L2 flushed between steps (flush outside the event pairs)
     step_ms = timed(step_graphed, args.steps)
+    if sampler:
+        sampler.end()
     if os.environ.get("RENI_BENCH_TRACE"):
         print("step times in order (ms):", " ".join(f"{t:.3f}" for t in step_ms), file=sys.stderr)
     step_ms.sort()
