@@ -47,8 +47,13 @@ def main():
     lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "reni_b200", "lib", "libreni_b200.so")
     counts = census(lib)
     names = demangle(list(counts))
-    sha = hashlib.sha256(open(lib, "rb").read()).hexdigest()[:16]
-    print(f"# SASS census of {os.path.relpath(lib, ROOT)} (sha256[:16] {sha}); cuobjdump -sass, counts of instructions per kernel")
+    # (keyed by the hash of the kernel SOURCES, as profiles/ncu_traffic.json is: the built .so differs from build to build)
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "reni_b200", "csrc")
+    for f in sorted(os.listdir(csrc)) + [os.path.join("..", "..", "include", "reni_b200.h")]:
+        h.update(open(os.path.join(csrc, f), "rb").read())
+    print(f"# SASS census of {os.path.relpath(lib, ROOT)} (kernel sources sha256[:16] {h.hexdigest()[:16]}); "
+          "cuobjdump -sass, counts of instructions per kernel")
     cols = [n for n, _ in PATTERNS]
     print("| kernel | " + " | ".join(cols) + " |")
     print("|---|" + "---|" * len(cols))
