@@ -112,7 +112,7 @@ WorkspaceLayout make_layout(const reni_config_t* c, int64_t B, int64_t P, int32_
   }
   if (flags & RENI_FLAG_SAVE_FOR_BACKWARD) {
     const bool dw = (flags & (RENI_FLAG_NEED_DW | RENI_FLAG_FILM)) != 0;  // (FiLM: dfreq / dphase need the delta stash)
-    w.stash_c = take(ntiles * (L + 1) * (int64_t)kTileImageBytes);  // 16-bit phase stash (rebuilds both h and cos)
+    w.stash_c = take(ntiles * (L + 1) * (int64_t)kPhaseTileBytes);  // phase stash (rebuilds both h and cos), phase.cuh
     w.stash_h = -1;
     w.stash_d = dw ? take(ntiles * (L + 1) * (int64_t)kTileImageBytes) : -1;  // slot 0 unused (delta_0 stays on chip)
     w.stash_gy = take(ntiles * (int64_t)kGyImageBytes);

@@ -5,7 +5,7 @@
 //                                           or an external grad_out, times tanh' = 1 - o^2; scaled by S into fp16 range
 //     d_L   = (g_y  W_out'') * cos(a_L)     tcgen05.mma K = 16
 //     d_l-1 = (d_l  W_l'')   * cos(a_l-1)   tcgen05.mma 128 x 256 x 256, l = L..1; cos rebuilt (MUFU) from the forward's
-//                                           16-bit phase stash; omega of the consuming layer folded into W''
+//                                           phase stash (phase.cuh); omega of the consuming layer folded into W''
 //     dM_b, dc_b += [f | 1]^T d_0           tcgen05.mma N = 16 with d_0 read as an MN-major operand (contraction over the
 //                                           tile's rows): the per-map layer-0 reduction costs 16 tiny MMAs per tile
 //   d_l tiles stay in shared memory for the next GEMM; when weight gradients are wanted d_1..d_L are also stashed as
@@ -24,6 +24,7 @@
 #include <cuda.h>  // CUtensorMap
 
 #include "layout.cuh"
+#include "phase.cuh"
 #include "ptx.cuh"
 
 namespace reni {
@@ -47,7 +48,7 @@ struct BwdParams {
   const __half* wb;       // L backward weight images [j/8][k][8] (unpaired mode)
   const __half* wb2;      // ... split for CTA pairs: [l][k half][j/8][128][8]
   const __half* w6b;      // [2][256][8]
-  const uint16_t* stash_u;  // 16-bit phases of a_l, per tile (L+1) tile images
+  const uint16_t* stash_u;  // phases of a_l (12 or 16 bits each, phase.cuh), per tile (L+1) tile-layer images
   __half* stash_d;        // delta stash: per tile nslots images (nslots = L+1 or 1)
   __half* stash_gy;       // per tile [2 halves][2][64][8]
   const float* D;         // directions (for the layer-0 feature columns f)
@@ -138,15 +139,6 @@ DEVINL void ready_signal(uint32_t* ctr) {
 #ifndef RENI_BWD_PHASE_HINT
 #define RENI_BWD_PHASE_HINT 1  // phase-stash loads: 0 ld.global.nc, 1 ld.global.cs (streaming), 2 ld.global.lu (293 -> 289..291 us)
 #endif
-DEVINL uint4 phase_load(const uint4* p) {
-#if RENI_BWD_PHASE_HINT == 1
-  return __ldcs(p);
-#elif RENI_BWD_PHASE_HINT == 2
-  return __ldlu(p);
-#else
-  return __ldg(p);
-#endif
-}
 #ifndef RENI_BWD_PF_DIST
 #define RENI_BWD_PF_DIST 1
 #endif
@@ -269,8 +261,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
           for (int g = 0; g < nsub; ++g)
             for (int d = 0; d < kPfDist && L - d >= 0; ++d)
               bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
-                                   ((size_t)(tbase + g) * (L + 1) + (L - d)) * kTileImageBytes,
-                               kTileImageBytes);
+                                   ((size_t)(tbase + g) * (L + 1) + (L - d)) * kPhaseTileBytes,
+                               kPhaseTileBytes);
         auto prefetch_next_unit = [&]() {
           if (!kPfNext || it + 1 >= iters) return;
           const int tnext = unit_base(it + 1) + 2 * (int)crank;
@@ -278,8 +270,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
           for (int g = 0; g < nnext; ++g) {
             for (int d = 0; d < kPfDist && L - d >= 0; ++d)
               bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
-                                   ((size_t)(tnext + g) * (L + 1) + (L - d)) * kTileImageBytes,
-                               kTileImageBytes);
+                                   ((size_t)(tnext + g) * (L + 1) + (L - d)) * kPhaseTileBytes,
+                               kPhaseTileBytes);
           }
         };
         if (kPair && kBwdLayerResident) {
@@ -288,8 +280,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
             for (int g = 0; g < nsub; ++g)
               if (kPfDist > 0 && l - kPfDist >= 0)
                 bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
-                                     ((size_t)(tbase + g) * (L + 1) + (l - kPfDist)) * kTileImageBytes,
-                                 kTileImageBytes);
+                                     ((size_t)(tbase + g) * (L + 1) + (l - kPfDist)) * kPhaseTileBytes,
+                                 kPhaseTileBytes);
             if (l == 1) prefetch_next_unit();
             for (int c = 0; c < kChunks; ++c) {
               mbar_wait(&w_empty[c], ph ^ 1);
@@ -305,8 +297,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
           for (int g = 0; g < nstream; ++g) {
             if (kPfDist > 0 && g < nsub && l - kPfDist >= 0)
               bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.stash_u) +
-                                   ((size_t)(tbase + g) * (L + 1) + (l - kPfDist)) * kTileImageBytes,
-                               kTileImageBytes);
+                                   ((size_t)(tbase + g) * (L + 1) + (l - kPfDist)) * kPhaseTileBytes,
+                               kPhaseTileBytes);
             if (l == 1 && g == 0) prefetch_next_unit();
             for (int c = 0; c < kChunks; ++c) {
               mbar_wait(&w_empty[st], ph ^ 1);
@@ -443,7 +435,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
       const int b = tile / p.tiles_per_map;
       const int pix = (tile - b * p.tiles_per_map) * kTileRows + row;
       const bool rvalid = pix < p.P;
-      const uint8_t* st_u = reinterpret_cast<const uint8_t*>(p.stash_u) + (size_t)tile * (L + 1) * kTileImageBytes;
+      const uint8_t* st_u = reinterpret_cast<const uint8_t*>(p.stash_u) + (size_t)tile * (L + 1) * kPhaseTileBytes;
       uint8_t* st_d = reinterpret_cast<uint8_t*>(p.stash_d) + (size_t)tile * p.d_slots * kTileImageBytes;
 
       // ---- g_y (scaled by S) -> fp16 [128 x 16] operand at the head of the tile image
@@ -517,15 +509,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
 
       // ---- delta_l = acc * cos(a_l), l = L..0 ; this thread: (row, columns chalf*128 .. +127)
       for (int l = L; l >= 0; --l) {
-        const uint8_t* hl = st_u + (size_t)l * kTileImageBytes;
+        const uint8_t* hl = st_u + (size_t)l * kPhaseTileBytes;
         uint8_t* dl = nullptr;
         if (kNeedDW && l > 0) dl = st_d + (size_t)l * kTileImageBytes;
-        // the whole layer slice of the phase stash (16 x 16 B) is requested before waiting for the GEMM
-        uint4 hh[16];
+        // the whole layer slice of the phase stash (16 records of 8 columns) is requested before waiting for the GEMM
+        PhaseRec hh[4][4];
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          hh[k] = (RENI_ABL & 8) ? make_uint4(k, row, l, g)
-                                 : phase_load(reinterpret_cast<const uint4*>(hl + stash_off(row, chalf * 16 + k, kH)));
+        for (int k = 0; k < 4; ++k) phase_fetch4<RENI_BWD_PHASE_HINT>(hl, row, chalf * 4 + k, hh[k]);
         if (tracer) btrace_ev(p, 1 + g, tn, 0x300 | ((uint32_t)l << 4) | g);  // phase loads issued, waiting for the accumulator
         mbar_wait(&acc_full[g], acc_ph);
         acc_ph ^= 1;
@@ -552,16 +542,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) reni_bwd_kernel(const __grid_c
           for (int q8 = 0; q8 < 2; ++q8) {
             const int kl = it * 2 + q8;
             const int kg = chalf * 16 + kl;
-            const uint4 hw = hh[kl];
-            float d[8];  // delta = acc * cos(a), cos rebuilt from the 16-bit phases
-            d[0] = __uint_as_float(v[q8 * 8 + 0]) * abl_cos(phase_angle_lo(hw.x));
-            d[1] = __uint_as_float(v[q8 * 8 + 1]) * abl_cos(phase_angle_hi(hw.x));
-            d[2] = __uint_as_float(v[q8 * 8 + 2]) * abl_cos(phase_angle_lo(hw.y));
-            d[3] = __uint_as_float(v[q8 * 8 + 3]) * abl_cos(phase_angle_hi(hw.y));
-            d[4] = __uint_as_float(v[q8 * 8 + 4]) * abl_cos(phase_angle_lo(hw.z));
-            d[5] = __uint_as_float(v[q8 * 8 + 5]) * abl_cos(phase_angle_hi(hw.z));
-            d[6] = __uint_as_float(v[q8 * 8 + 6]) * abl_cos(phase_angle_lo(hw.w));
-            d[7] = __uint_as_float(v[q8 * 8 + 7]) * abl_cos(phase_angle_hi(hw.w));
+            const PhaseRec& hw = hh[kl >> 2][kl & 3];
+            float d[8];  // delta = acc * cos(a), cos rebuilt from the stashed phases
+            d[0] = __uint_as_float(v[q8 * 8 + 0]) * abl_cos(phase_angle_of<0>(hw));
+            d[1] = __uint_as_float(v[q8 * 8 + 1]) * abl_cos(phase_angle_of<1>(hw));
+            d[2] = __uint_as_float(v[q8 * 8 + 2]) * abl_cos(phase_angle_of<2>(hw));
+            d[3] = __uint_as_float(v[q8 * 8 + 3]) * abl_cos(phase_angle_of<3>(hw));
+            d[4] = __uint_as_float(v[q8 * 8 + 4]) * abl_cos(phase_angle_of<4>(hw));
+            d[5] = __uint_as_float(v[q8 * 8 + 5]) * abl_cos(phase_angle_of<5>(hw));
+            d[6] = __uint_as_float(v[q8 * 8 + 6]) * abl_cos(phase_angle_of<6>(hw));
+            d[7] = __uint_as_float(v[q8 * 8 + 7]) * abl_cos(phase_angle_of<7>(hw));
             uint4 dv;
             dv.x = pack_half2(d[0], d[1]);
             dv.y = pack_half2(d[2], d[3]);

@@ -5,7 +5,7 @@
 //   dW_out[c,k] = sum_r g_y[r,c] * h_L[r,k] ,  db_out[c] = sum_r g_y[r,c]
 //
 // delta_l / g_y are the fp16 tile images the delta-chain kernel stashed ([k/8][64 rows][8]); h_l is rebuilt here from
-// the forward's 16-bit phase stash (sin via MUFU on the otherwise idle CUDA cores, written straight into the operand
+// the forward's phase stash (phase.cuh) (sin via MUFU on the otherwise idle CUDA cores, written straight into the operand
 // image).  Read as MN-major UMMA operands the contraction runs over the rows, so no transpose is ever materialised.
 // CTA i works on layer job (i mod (L+1)) and a contiguous slice of the 64-row stash blocks; the 256 x 256 fp32
 // accumulator lives in TMEM (2 x 256 columns) for the whole slice and is flushed once with vector reductions.
@@ -13,12 +13,14 @@
 //   warps 2..9 : phase -> h operand image (in place), column sums for the bias gradient, then the TMEM -> HBM flush
 #pragma once
 #include "layout.cuh"
+#include "phase.cuh"
 #include "ptx.cuh"
 
 namespace reni {
 
 constexpr int kDwThreads = 320;
 constexpr int kDwStages = 3;
+constexpr int kPhaseLand = kHalfImageBytes - kPhaseHalfBytes;  // where a phase block lands inside its operand region
 constexpr int kDwStageBytes = 2 * kHalfImageBytes;  // 64 KB: A operand + B operand; the phase block lands in the
                                                     // operand slot of h and is converted in place
 
@@ -169,8 +171,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
   auto phase_src = [&](int s, int job_) -> const uint8_t* {
     const int tile = s >> 1, half = s & 1;
     const int lh = job_ == L ? L : job_;  // h_L for the output layer, h_{l-1} for hidden layer l = job + 1
-    return reinterpret_cast<const uint8_t*>(p.stash_u) + ((size_t)tile * (L + 1) + lh) * kTileImageBytes +
-           (size_t)half * kHalfImageBytes;
+    return reinterpret_cast<const uint8_t*>(p.stash_u) + ((size_t)tile * (L + 1) + lh) * kPhaseTileBytes +
+           (size_t)half * kPhaseHalfBytes;
   };
   // hidden job: A = delta_l (copied), B = h_{l-1} (converted).  output job: A = h_L (converted), B = g_y (copied)
   auto img_off_of = [&](int job_) -> uint32_t { return job_ == L ? kHalfImageBytes : 0; };
@@ -210,14 +212,28 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
             tile_ok = s >> 1;
           }
           mbar_wait(&empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&full[st], img_bytes + kHalfImageBytes);
+          mbar_arrive_expect_tx(&full[st], img_bytes + kPhaseHalfBytes);
           uint8_t* dst = smem + DwSmem::kRing + st * kDwStageBytes;
 #if RENI_DW_LOAD_HINT  // both stash blocks are read exactly once in this kernel: do not keep them in L2
           bulk_g2s_stream(dst + img_off, img_src(s, sg.job), img_bytes, &full[st]);
-          bulk_g2s_stream(dst + cvt_off, phase_src(s, sg.job), kHalfImageBytes, &full[st]);
+          if (kPhaseLand == 0) {
+            bulk_g2s_stream(dst + cvt_off, phase_src(s, sg.job), kPhaseHalfBytes, &full[st]);
+          } else {
+            // 12-bit phases: the quarter of the block that converter column set c turns into its 8 KB of the operand
+            // image lands at the END of those 8 KB, so a converter thread only ever overwrites its own input
+            for (int c = 0; c < 4; ++c)
+              bulk_g2s_stream(dst + cvt_off + c * (kHalfImageBytes / 4) + kPhaseLand / 4,
+                              phase_src(s, sg.job) + c * (kPhaseHalfBytes / 4), kPhaseHalfBytes / 4, &full[st]);
+          }
 #else
           bulk_g2s(dst + img_off, img_src(s, sg.job), img_bytes, &full[st]);
-          bulk_g2s(dst + cvt_off, phase_src(s, sg.job), kHalfImageBytes, &full[st]);
+          if (kPhaseLand == 0) {
+            bulk_g2s(dst + cvt_off, phase_src(s, sg.job), kPhaseHalfBytes, &full[st]);
+          } else {
+            for (int c = 0; c < 4; ++c)
+              bulk_g2s(dst + cvt_off + c * (kHalfImageBytes / 4) + kPhaseLand / 4,
+                       phase_src(s, sg.job) + c * (kPhaseHalfBytes / 4), kPhaseHalfBytes / 4, &full[st]);
+          }
 #endif
           if (++st == kDwStages) { st = 0; ph ^= 1; }
         }
@@ -281,19 +297,27 @@ __global__ void __launch_bounds__(kDwThreads, 1) reni_dw_kernel(const DwParams p
       for (int i = 0; i < sg.n; ++i) {
         mbar_wait(&full[st], ph);
         uint8_t* stage = smem + DwSmem::kRing + st * kDwStageBytes;
-        // (1) phase block -> h = sin(angle) operand image, in place (same [k/8][64][8] geometry, 16 B per thread/group)
+        // (1) phase block -> h = sin(angle) operand image [k/8][64][8].  16-bit phases: in place, group by group.
+        // 12-bit phases: this thread's two 32-column groups sit at the end of its column set's 8 KB of the operand region
+        // (see the producer); it takes them into registers, then writes its eight 16-byte pieces over that region.
         {
           uint8_t* hd = stage + cvt_off;
-          const uint8_t* us = hd;
+          PhaseRec u[2][4];
+          if (kPhaseLand != 0) {
+            const uint8_t* us = hd + kset * (kHalfImageBytes / 4) + kPhaseLand / 4;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) phase_fetch4_smem(us, r, kk, u[kk]);
+          }
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const uint32_t off = ((kset * 8 + kk) * kHalfRows + r) * 16;
-            const uint4 u = *reinterpret_cast<const uint4*>(us + off);
+            if (kPhaseLand == 0 && (kk & 3) == 0) phase_fetch4_smem(hd, r, kset * 2 + (kk >> 2), u[kk >> 2]);
+            const PhaseRec& uw = u[kk >> 2][kk & 3];
             uint4 h;
-            h.x = pack_half2(abl_sin(phase_angle_lo(u.x)), abl_sin(phase_angle_hi(u.x)));
-            h.y = pack_half2(abl_sin(phase_angle_lo(u.y)), abl_sin(phase_angle_hi(u.y)));
-            h.z = pack_half2(abl_sin(phase_angle_lo(u.z)), abl_sin(phase_angle_hi(u.z)));
-            h.w = pack_half2(abl_sin(phase_angle_lo(u.w)), abl_sin(phase_angle_hi(u.w)));
+            h.x = pack_half2(abl_sin(phase_angle_of<0>(uw)), abl_sin(phase_angle_of<1>(uw)));
+            h.y = pack_half2(abl_sin(phase_angle_of<2>(uw)), abl_sin(phase_angle_of<3>(uw)));
+            h.z = pack_half2(abl_sin(phase_angle_of<4>(uw)), abl_sin(phase_angle_of<5>(uw)));
+            h.w = pack_half2(abl_sin(phase_angle_of<6>(uw)), abl_sin(phase_angle_of<7>(uw)));
             *reinterpret_cast<uint4*>(hd + off) = h;
           }
         }

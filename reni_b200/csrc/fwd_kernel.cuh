@@ -18,7 +18,7 @@
 //                   without stash stores (63.5 % vs 61 % of the bf16 peak at cfg 5), grouped wins with them
 //                   (234 vs 262 us at cfg 2) -- hence one mode per use.
 // Activations never leave the SM (smem tile image, overwritten in place).
-// With kTrain the 16-bit phase of every pre-activation (ptx.cuh: phase_encode2) is additionally stashed in the
+// With kTrain the phase of every pre-activation (12 bits by default, phase.cuh) is additionally stashed in the
 // tile-image geometry: the backward kernels rebuild cos(a_l) (delta chain) and h_l = sin(a_l) (weight-gradient GEMM
 // operand) from it to ~5e-5, so one 2-byte stash replaces an h stash plus a cos stash and costs no second MUFU here.
 // (Rebuilding cos as +-sqrt(1 - h^2) from an fp16 h was tried and measured: gradient error 0.6-1.6e-2, rejected.)
@@ -28,6 +28,7 @@
 #include <cuda.h>  // CUtensorMap
 
 #include "layout.cuh"
+#include "phase.cuh"
 #include "ptx.cuh"
 
 namespace reni {
@@ -55,7 +56,7 @@ struct FwdParams {
   const __half* w6f;     // [k/8 32][n 16][8] final-layer image
   const float* bias;     // L*256 (omega_l * b_l) then 16 (final bias, zero padded)
   float* out;            // (B, P, 3)
-  uint16_t* stash_u;     // kTrain: per tile (L+1) tile images of the 16-bit phases of a_l
+  uint16_t* stash_u;     // kTrain: per tile (L+1) tile-layer images of the phases of a_l (phase.cuh)
   const float* target;   // fused loss partial sums (optional, may be null)
   const float* sw;       // (B or 1, P, 3)
   int64_t sw_bstride;
@@ -121,30 +122,14 @@ DEVINL void trace_ev(const FwdParams& p, int role, uint32_t& n, uint32_t code) {
 #ifndef RENI_FWD_STASH_HINT
 #define RENI_FWD_STASH_HINT 1  // phase-stash stores: 0 plain st.global, 1 st.global.cs (streaming: fwd 214 -> 207 us), 2 st.global.wt (no change)
 #endif
-// 16-byte phase-stash store (the stash is written once here and not read before the backward kernels)
-DEVINL void stash_store(uint8_t* dst, const uint4& v) {
-#if RENI_FWD_STASH_HINT == 1
-  __stcs(reinterpret_cast<uint4*>(dst), v);
-#elif RENI_FWD_STASH_HINT == 2
-  __stwt(reinterpret_cast<uint4*>(dst), v);
-#else
-  *reinterpret_cast<uint4*>(dst) = v;
-#endif
-}
-
-// sin of 8 pre-activations -> packed fp16 and, if kPhase, their packed 16-bit phases
+// sin of 8 pre-activations -> packed fp16 and, if kPhase, their packed phases
 template <bool kPhase>
-DEVINL void sin8(const float (&a)[8], uint4& hv, uint4& uv) {
+DEVINL void sin8(const float (&a)[8], uint4& hv, PhaseRec& uv) {
   hv.x = pack_half2(epi_sin<0>(a[0]), epi_sin<1>(a[1]));
   hv.y = pack_half2(epi_sin<2>(a[2]), epi_sin<3>(a[3]));
   hv.z = pack_half2(epi_sin<4>(a[4]), epi_sin<5>(a[5]));
   hv.w = pack_half2(epi_sin<6>(a[6]), epi_sin<7>(a[7]));
-  if (kPhase) {
-    uv.x = phase_encode2(a[0], a[1]);
-    uv.y = phase_encode2(a[2], a[3]);
-    uv.z = phase_encode2(a[4], a[5]);
-    uv.w = phase_encode2(a[6], a[7]);
-  }
+  if (kPhase) uv = phase_encode8(a);
 }
 
 // kFilm (FiLM conditioning, RENI.py:515-524,666-678): the hidden layers compute sin(freq_l[b] * (W_l h + b_l) + phase_l[b])
@@ -454,8 +439,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
       uint8_t* a_tile = smem + FwdSmem::kA + g * kTileImageBytes;
       const float* s_mc = s_mc_all + g * 5 * kH;
       uint8_t* st_u = nullptr;
-      if (kTrain) st_u = reinterpret_cast<uint8_t*>(p.stash_u) + (size_t)(tb + g) * (L + 1) * kTileImageBytes;
+      if (kTrain) st_u = reinterpret_cast<uint8_t*>(p.stash_u) + (size_t)(tb + g) * (L + 1) * kPhaseTileBytes;
+      PhaseRec ubuf[4];
+#if RENI_PHASE_BITS == 16
 #pragma unroll 2
+#else
+#pragma unroll 4
+#endif
       for (int k8 = 0; k8 < 8; ++k8) {
         const int kg = cq * 8 + k8;
         float a[8];
@@ -474,10 +464,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
             a[6] = fmaf(fi, m1.z, a[6]); a[7] = fmaf(fi, m1.w, a[7]);
           }
         }
-        uint4 hv, uv;
+        uint4 hv;
+        PhaseRec uv;
         sin8<kTrain>(a, hv, uv);
         *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
-        if (kTrain && !(RENI_ABL & 1)) stash_store(st_u + stash_off(row, kg, kH), uv);
+        if (kTrain && !(RENI_ABL & 1)) phase_put<RENI_FWD_STASH_HINT>(ubuf, k8 & 3, st_u, row, kg, uv);
       }
       fence_proxy_async_smem();
       signal_ready(g);
@@ -583,7 +574,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
           uint8_t* a_tile = smem + FwdSmem::kA + g * kTileImageBytes;
           uint8_t* su = nullptr;
           if (kTrain)
-            su = reinterpret_cast<uint8_t*>(p.stash_u) + ((size_t)(tbase + g) * (L + 1) + l) * kTileImageBytes;
+            su = reinterpret_cast<uint8_t*>(p.stash_u) + ((size_t)(tbase + g) * (L + 1) + l) * kPhaseTileBytes;
           const uint32_t t_acc = tmem_base + ((q * 32) << 16) + g * 256 + cq * 64;
           const float* fl = nullptr;  // this map's (freq_l, phase_l)
           if (kFilm) fl = p.film + ((size_t)(g ? bmap1 : bmap0) * L + (l - 1)) * 2 * kH;
@@ -592,6 +583,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
           tc_fence_after();
           // TMEM -> registers in 16-column slices, double buffered: the next tcgen05.ld is in flight while this
           // slice goes through bias + sin + pack + store
+          PhaseRec ubuf[4];  // (12-bit phases leave as groups of 32 columns: phase.cuh)
           auto process16 = [&](const uint32_t (&v)[16], int it) {
 #pragma unroll
             for (int q8 = 0; q8 < 2; ++q8) {
@@ -626,10 +618,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
                 a[6] = __uint_as_float(v[q8 * 8 + 6]) + b1.z;
                 a[7] = __uint_as_float(v[q8 * 8 + 7]) + b1.w;
               }
-              uint4 hv, uv;
+              uint4 hv;
+              PhaseRec uv;
               sin8<kTrain>(a, hv, uv);
               *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
-              if (kTrain && !(RENI_ABL & 1)) stash_store(su + stash_off(row, kg, kH), uv);
+              if (kTrain && !(RENI_ABL & 1)) phase_put<RENI_FWD_STASH_HINT>(ubuf, kl & 3, su, row, kg, uv);
             }
           };
           {
@@ -706,7 +699,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
       const int pix = (tile - b * p.tiles_per_map) * kTileRows + row;
       const bool rvalid = pix < p.P;
       uint8_t* st_u = nullptr;
-      if (kTrain) st_u = reinterpret_cast<uint8_t*>(p.stash_u) + (size_t)tile * (L + 1) * kTileImageBytes;
+      if (kTrain) st_u = reinterpret_cast<uint8_t*>(p.stash_u) + (size_t)tile * (L + 1) * kPhaseTileBytes;
 
       // ---- per-map layer-0 operands -> smem (group-private)
       named_bar_sync(1 + g, kGroupThreads);
@@ -741,7 +734,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
       }
 
       // ---- layer 0: h0 = sin(f . M' + c')  (omega folded into M', c'); this warp's 128 columns
+      PhaseRec ubuf0[4];
+#if RENI_PHASE_BITS == 16
 #pragma unroll 2
+#else
+#pragma unroll 4
+#endif
       for (int k8 = 0; k8 < 16; ++k8) {
         const int kg = chalf * 16 + k8;
         float a[8];
@@ -760,10 +758,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
             a[6] = fmaf(fi, m1.z, a[6]); a[7] = fmaf(fi, m1.w, a[7]);
           }
         }
-        uint4 hv, uv;
+        uint4 hv;
+        PhaseRec uv;
         sin8<kTrain>(a, hv, uv);
         *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
-        if (kTrain && !(RENI_ABL & 1)) stash_store(st_u + stash_off(row, kg, kH), uv);
+        if (kTrain && !(RENI_ABL & 1)) phase_put<RENI_FWD_STASH_HINT>(ubuf0, k8 & 3, st_u, row, kg, uv);
       }
       fence_proxy_async_smem();
       signal_ready(g);
@@ -771,7 +770,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
       // ---- hidden layers: bias + sin epilogue, TMEM -> registers -> smem tile image (in place)
       for (int l = 1; l <= L; ++l) {
         const float* bl = s_bias + (l - 1) * kH + chalf * 128;
-        uint8_t* su = kTrain ? st_u + (size_t)l * kTileImageBytes : nullptr;
+        uint8_t* su = kTrain ? st_u + (size_t)l * kPhaseTileBytes : nullptr;
         if (e == 0 && lane == 0) trace_ev(p, 1 + g, tn, 0x300 | (l << 4) | g);  // waiting for the accumulator
         mbar_wait(&acc_full[g], acc_ph);
         acc_ph ^= 1;
@@ -779,6 +778,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
         if (e == 0 && lane == 0) trace_ev(p, 1 + g, tn, 0x400 | (l << 4) | g);  // accumulator seen
         // TMEM -> registers in 16-column slices, double buffered: the next tcgen05.ld is in flight while this
         // slice goes through bias + sin + pack + store
+        PhaseRec ubuf[4];
         auto process16 = [&](const uint32_t (&v)[16], int it) {
 #pragma unroll
           for (int q8 = 0; q8 < 2; ++q8) {
@@ -800,10 +800,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) reni_fwd_kernel(const __grid_c
               a[6] = __uint_as_float(v[q8 * 8 + 6]) + b1.z;
               a[7] = __uint_as_float(v[q8 * 8 + 7]) + b1.w;
             }
-            uint4 hv, uv;
+            uint4 hv;
+            PhaseRec uv;
             sin8<kTrain>(a, hv, uv);
             *reinterpret_cast<uint4*>(a_tile + tile_image_off(kTileRows, row, kg)) = hv;
-            if (kTrain && !(RENI_ABL & 1)) stash_store(su + stash_off(row, kg, kH), uv);
+            if (kTrain && !(RENI_ABL & 1)) phase_put<RENI_FWD_STASH_HINT>(ubuf, kl & 3, su, row, kg, uv);
           }
         };
         {

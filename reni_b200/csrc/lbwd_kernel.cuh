@@ -26,6 +26,7 @@
 #pragma once
 #include "dw_kernel.cuh"
 #include "layout.cuh"
+#include "phase.cuh"
 #include "ptx.cuh"
 
 namespace reni {
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
   const uint8_t* stash_u = reinterpret_cast<const uint8_t*>(p.stash_u);
   uint8_t* stash_d = reinterpret_cast<uint8_t*>(p.stash_d);
   auto slot_off = [&](int tile, int layer) { return ((size_t)tile * (L + 1) + layer) * kTileImageBytes; };
+  auto pslot_off = [&](int tile, int layer) { return ((size_t)tile * (L + 1) + layer) * kPhaseTileBytes; };
 
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
@@ -173,9 +175,10 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
         const int t = tile_of(i);
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(stash_d + slot_off(t, l)), "r"(kTileImageBytes)
                      : "memory");
-        const uint8_t* ph = stash_u + slot_off(t, l - 1) + (size_t)r * 16 * (kHalfRows * 16);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ph), "r"(16 * kHalfRows * 16) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ph + kHalfImageBytes), "r"(16 * kHalfRows * 16)
+        const uint8_t* ph = stash_u + pslot_off(t, l - 1) + (size_t)r * 16 * (kHalfRows * kPhaseRecBytes);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ph), "r"(16 * kHalfRows * kPhaseRecBytes) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ph + kPhaseHalfBytes),
+                     "r"(16 * kHalfRows * kPhaseRecBytes)
                      : "memory");
       };
       for (int d = 0; d < RENI_LBWD_PF_DIST; ++d) prefetch(d);
@@ -282,18 +285,16 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
       for (int i = 0; i < 5; ++i) atomicAdd(dst + i * kH, __uint_as_float(v[i]) * inv_s);
       tc_fence_before();
     };
-    auto load_phases = [&](int i, uint4 (&ph)[4]) {
+    auto load_phases = [&](int i, PhaseRec (&ph)[4]) {
       if (i >= ntl) return;
-      const uint8_t* ph_tile = stash_u + slot_off(tile_of(i), l - 1);
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        ph[g] = __ldcs(reinterpret_cast<const uint4*>(ph_tile + stash_off(row, r * 16 + cq * 4 + g, kH)));
+      const uint8_t* ph_tile = stash_u + pslot_off(tile_of(i), l - 1);
+      phase_fetch4<1>(ph_tile, row, r * 4 + cq, ph);
     };
 
     uint32_t tn = 0;
     const bool tr = (e == 0 && lane == 0);
     // one tile: `ph` holds its phase slice, `nxt` (free now) takes the next tile's
-    auto body = [&](int i, const uint4 (&ph)[4], uint4 (&nxt)[4]) {
+    auto body = [&](int i, const PhaseRec (&ph)[4], PhaseRec (&nxt)[4]) {
       const int b = i & 1, a = i % kNA;
       const int tile = tile_of(i);
       if (tr) lbwd_trace(p, 1, tn, 0x100 | (i & 0xff));  // iteration start
@@ -311,12 +312,12 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
       if (tr) lbwd_trace(p, 1, tn, 0x200 | (i & 0xff));  // h buffer free seen
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const uint4 hw = ph[g];
+        const PhaseRec& hw = ph[g];
         uint4 hv;
-        hv.x = pack_half2(abl_sin(phase_angle_lo(hw.x)), abl_sin(phase_angle_hi(hw.x)));
-        hv.y = pack_half2(abl_sin(phase_angle_lo(hw.y)), abl_sin(phase_angle_hi(hw.y)));
-        hv.z = pack_half2(abl_sin(phase_angle_lo(hw.z)), abl_sin(phase_angle_hi(hw.z)));
-        hv.w = pack_half2(abl_sin(phase_angle_lo(hw.w)), abl_sin(phase_angle_hi(hw.w)));
+        hv.x = pack_half2(abl_sin(phase_angle_of<0>(hw)), abl_sin(phase_angle_of<1>(hw)));
+        hv.y = pack_half2(abl_sin(phase_angle_of<2>(hw)), abl_sin(phase_angle_of<3>(hw)));
+        hv.z = pack_half2(abl_sin(phase_angle_of<4>(hw)), abl_sin(phase_angle_of<5>(hw)));
+        hv.w = pack_half2(abl_sin(phase_angle_of<6>(hw)), abl_sin(phase_angle_of<7>(hw)));
         *reinterpret_cast<uint4*>(smem + LbwdSmem::kHimg + tile_image_off(kTileRows, row, cq * 4 + g)) = hv;
       }
       fence_proxy_async_smem();
@@ -352,15 +353,15 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
 #pragma unroll
         for (int g2 = 0; g2 < 2; ++g2) {
           const int g = hf * 2 + g2;
-          const uint4 hw = ph[g];
-          dv[g].x = pack_half2(__uint_as_float(v[g2 * 8 + 0]) * abl_cos(phase_angle_lo(hw.x)),
-                               __uint_as_float(v[g2 * 8 + 1]) * abl_cos(phase_angle_hi(hw.x)));
-          dv[g].y = pack_half2(__uint_as_float(v[g2 * 8 + 2]) * abl_cos(phase_angle_lo(hw.y)),
-                               __uint_as_float(v[g2 * 8 + 3]) * abl_cos(phase_angle_hi(hw.y)));
-          dv[g].z = pack_half2(__uint_as_float(v[g2 * 8 + 4]) * abl_cos(phase_angle_lo(hw.z)),
-                               __uint_as_float(v[g2 * 8 + 5]) * abl_cos(phase_angle_hi(hw.z)));
-          dv[g].w = pack_half2(__uint_as_float(v[g2 * 8 + 6]) * abl_cos(phase_angle_lo(hw.w)),
-                               __uint_as_float(v[g2 * 8 + 7]) * abl_cos(phase_angle_hi(hw.w)));
+          const PhaseRec& hw = ph[g];
+          dv[g].x = pack_half2(__uint_as_float(v[g2 * 8 + 0]) * abl_cos(phase_angle_of<0>(hw)),
+                               __uint_as_float(v[g2 * 8 + 1]) * abl_cos(phase_angle_of<1>(hw)));
+          dv[g].y = pack_half2(__uint_as_float(v[g2 * 8 + 2]) * abl_cos(phase_angle_of<2>(hw)),
+                               __uint_as_float(v[g2 * 8 + 3]) * abl_cos(phase_angle_of<3>(hw)));
+          dv[g].z = pack_half2(__uint_as_float(v[g2 * 8 + 4]) * abl_cos(phase_angle_of<4>(hw)),
+                               __uint_as_float(v[g2 * 8 + 5]) * abl_cos(phase_angle_of<5>(hw)));
+          dv[g].w = pack_half2(__uint_as_float(v[g2 * 8 + 6]) * abl_cos(phase_angle_of<6>(hw)),
+                               __uint_as_float(v[g2 * 8 + 7]) * abl_cos(phase_angle_of<7>(hw)));
           if (!kFirst) {  // delta_{l-1} leaves for the next launch: a warp writes 512 contiguous bytes per group
             uint4* dptr = reinterpret_cast<uint4*>(stash_d + slot_off(tile, l - 1) +
                                                    tile_image_off(kTileRows, row, r * 16 + cq * 4 + g));
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(kLbwdThreads, 1) reni_lbwd_layer_kernel(const 
     };
 
     {
-      uint4 pa[4], pb[4];
+      PhaseRec pa[4], pb[4];
       load_phases(0, pa);
       for (int i = 0; i < ntl; i += 2) {
         body(i, pa, pb);
@@ -538,8 +539,8 @@ __global__ void __launch_bounds__(kLbwdHeadThreads, 1) reni_lbwd_head_kernel(con
         const int b = i & 1;
         if (i + 2 < ntl)  // a later tile's phases towards L2
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
-                           stash_u + ((size_t)tile_of(i + 2) * (L + 1) + L) * kTileImageBytes),
-                       "r"(kTileImageBytes)
+                           stash_u + ((size_t)tile_of(i + 2) * (L + 1) + L) * kPhaseTileBytes),
+                       "r"(kPhaseTileBytes)
                        : "memory");
         mbar_wait(&h_ready[b], (uint32_t)(i >> 1) & 1u);
         tc_fence_after();
@@ -565,11 +566,9 @@ __global__ void __launch_bounds__(kLbwdHeadThreads, 1) reni_lbwd_head_kernel(con
     const uint32_t row = rq * 32 + lane;
     const float S = __ldg(p.scalars);
     float dbo[3] = {0.f, 0.f, 0.f};
-    auto load_phases = [&](int tile, int half, uint4 (&ph)[4]) {
-      const uint8_t* ph_tile = stash_u + ((size_t)tile * (L + 1) + L) * kTileImageBytes;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        ph[g] = __ldcs(reinterpret_cast<const uint4*>(ph_tile + stash_off(row, cq * 8 + half * 4 + g, kH)));
+    auto load_phases = [&](int tile, int half, PhaseRec (&ph)[4]) {
+      const uint8_t* ph_tile = stash_u + ((size_t)tile * (L + 1) + L) * kPhaseTileBytes;
+      phase_fetch4<1>(ph_tile, row, cq * 2 + half, ph);
     };
     // per-row loss inputs of a tile -> S * dLoss/dy (zero for rows beyond P)
     auto row_gy = [&](int tile, float (&gy)[3]) {
@@ -608,7 +607,7 @@ __global__ void __launch_bounds__(kLbwdHeadThreads, 1) reni_lbwd_head_kernel(con
       for (int c = 0; c < 3; ++c) gy[c] = __half2float(__float2half_rn(gy[c]));
     };
 
-    uint4 pa[4], pb[4];
+    PhaseRec pa[4], pb[4];
     float gy[3], gy_next[3];
     if (ntl > 0) {
       load_phases(tile_of(0), 0, pa);
@@ -633,14 +632,12 @@ __global__ void __launch_bounds__(kLbwdHeadThreads, 1) reni_lbwd_head_kernel(con
             make_uint4(pack_half2(gy[0], gy[1]), pack_half2(gy[2], 0.f), 0u, 0u);
         *reinterpret_cast<uint4*>(g_tile + tile_image_off(kTileRows, row, 1)) = make_uint4(0u, 0u, 0u, 0u);
       }
-      auto half_pass = [&](const uint4 (&ph)[4], int half) {
+      auto half_pass = [&](const PhaseRec (&ph)[4], int half) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int kg = cq * 8 + half * 4 + g;
-          const uint4 hw = ph[g];
           float a[8];
-          a[0] = phase_angle_lo(hw.x); a[1] = phase_angle_hi(hw.x); a[2] = phase_angle_lo(hw.y); a[3] = phase_angle_hi(hw.y);
-          a[4] = phase_angle_lo(hw.z); a[5] = phase_angle_hi(hw.z); a[6] = phase_angle_lo(hw.w); a[7] = phase_angle_hi(hw.w);
+          phase_decode8(ph[g], a);
           float d[8], h[8];
 #pragma unroll
           for (int x = 0; x < 8; ++x) {

@@ -62,9 +62,10 @@ def test_workspace_sizes(lib):
     full = lib.reni_workspace_bytes(C.byref(c), 32, 8192, 3)
     assert 0 < inf < lat < full
     ntiles = 32 * 64
-    # latent-only: 16-bit phase stash (6 images) per tile; full: phase + delta (6 each) + g_y
-    assert lat - inf >= ntiles * 6 * 65536
-    assert full - inf >= ntiles * 12 * 65536
+    # latent-only: phase stash (6 images of 64 KB at 16 bits per phase, 48 KB at 12) per tile; full: phase + delta
+    # (6 images of 64 KB) + g_y
+    assert lat - inf >= ntiles * 6 * 49152
+    assert full - inf >= ntiles * 6 * (49152 + 65536)
     assert full < 2.0e9
     # ragged P rounds up to whole 128-direction tiles
     assert lib.reni_workspace_bytes(C.byref(c), 1, 129, 1) > lib.reni_workspace_bytes(C.byref(c), 1, 128, 1)
