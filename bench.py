@@ -514,8 +514,10 @@ def run_gpu_arm(args):
             if n in gemm_flops:
                 kernels[n]["tflops"] = round(gemm_flops[n] / (ms * 1e-3) / 1e12, 1)
         if not layer_major:
-            # stash traffic of the weight-gradient GEMM: it re-reads h_{l-1} and delta_l (fp16) for 5 layers + h_L, g_y
-            kernels["reni_dw_kernel"]["hbm_gbs"] = round((5 * 1024 + 512 + 32) * d / (kms["reni_dw_kernel"] * 1e-3) / 1e9, 1)
+            # stash traffic of the weight-gradient GEMM per direction: delta_l (fp16, 512 B) and the phases of h_{l-1}
+            # (256 x reni_phase_bits / 8 B) for the 5 hidden layers, the phases of h_L, g_y (32 B)
+            pb = 256 * int(lib.reni_phase_bits()) // 8
+            kernels["reni_dw_kernel"]["hbm_gbs"] = round((5 * (512 + pb) + pb + 32) * d / (kms["reni_dw_kernel"] * 1e-3) / 1e9, 1)
         dom = max(gemm_flops, key=lambda n: kms[n])
         achieved = gemm_flops[dom] / (kms[dom] * 1e-3) / 1e12
         step_tflops = FLOPS_TRAIN * dirs_step / world / (total_ms / args.steps * 1e-3) / 1e12

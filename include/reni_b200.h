@@ -88,6 +88,11 @@ int64_t reni_in_features(const reni_config_t* cfg);
 /* Bytes of workspace needed for a batch of B maps x P directions under `flags`. */
 int64_t reni_workspace_bytes(const reni_config_t* cfg, int64_t B, int64_t P, int32_t flags);
 
+/* Width of one entry of the training forward's phase stash in this build (12, or 16 with -DRENI_PHASE_BITS=16): the
+ * stash holds one such number per hidden pre-activation and is what reni_workspace_bytes is dominated by; callers that
+ * account for the step's HBM traffic (bench.py) ask here. */
+int32_t reni_phase_bits(void);
+
 /* Convert the decoder parameters into the fp16 operand images the kernels stream.
  * weights[i] / biases[i], i = 0 .. hidden_layers + 1, are HOST arrays of DEVICE pointers in
  * the order of net.0.linear, ..., net.L.linear, net.(L+1) (state_dict order of the reference).

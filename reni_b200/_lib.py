@@ -97,6 +97,7 @@ SIGNATURES = {
     "reni_allreduce": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, C.c_float, _vp, _vp, _vp]),
     "reni_debug_set_phase_events": (_i32, [C.POINTER(_vp), _i32]),
     "reni_debug_last_cuda_error": (C.c_char_p, []),
+    "reni_phase_bits": (_i32, []),
     "reni_debug_set_trace": (_i32, [_vp]),
     "reni_debug_set_overlap": (_i32, [_i32, _i32]),
     "reni_probe_remote_tx": (_i32, [_vp, _u32, _vp, _i32, _vp]),

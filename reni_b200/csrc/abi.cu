@@ -11,6 +11,7 @@
 #include "dw_kernel.cuh"
 #include "fwd_kernel.cuh"
 #include "layout.cuh"
+#include "phase.cuh"
 #include "lbwd_kernel.cuh"
 #include "shade_kernel.cuh"
 #include "small_kernels.cuh"
@@ -862,6 +863,8 @@ int32_t reni_debug_set_trace(void* device_buffer) {
 }
 
 const char* reni_debug_last_cuda_error(void) { return cudaGetErrorString(g_last_cuda); }
+
+int32_t reni_phase_bits(void) { return RENI_PHASE_BITS; }
 
 int32_t reni_debug_set_overlap(int32_t dw_ctas, int32_t out_ctas) {
   if (dw_ctas < -1 || out_ctas < 0) return RENI_ERR_BAD_ARGUMENT;
