@@ -305,6 +305,9 @@ def run_gpu_arm(args):
         flat.all_reduce_mean()  # the one exchange step (no-op at world size 1)
         return r
 
+    # (nvidia-smi needs longer to start than a 20-step region lasts: started here, hundreds of ms ahead; its samples are
+    # filtered by time stamp)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(3, args.warmup)):
         step_resident()
     torch.cuda.synchronize()
@@ -332,8 +335,6 @@ def run_gpu_arm(args):
         if not in_graph:
             flat.all_reduce_mean()
 
-    # (nvidia-smi needs longer to start than a 20-step region lasts: started here, its samples are filtered by time stamp)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(3, args.warmup)):
         step_graphed()
     torch.cuda.synchronize()
