@@ -152,10 +152,11 @@ DEVINL void ready_signal(uint32_t* ctr) {
                                  // prefetching the unit's out / target rows changed nothing
 #endif
 #ifndef RENI_BWD_SIGNAL_FIRST
-#define RENI_BWD_SIGNAL_FIRST 0  // sub-tile handed to the MMA issuer before (1) / after (0) its stash copies are queued:
-                                 // 1 removes a ~3900 clk wait from the issuer's timeline and the kernel gets SLOWER
-                                 // (295 -> 304 us): the layer step is bound by its 256 KB of HBM traffic per SM
-                                 // (tools/ubench/sm_traffic.cu: 11.0 K clk for the copies alone, 10.8 K measured here)
+#define RENI_BWD_SIGNAL_FIRST 1  // sub-tile handed to the MMA issuer before (1) / after (0) its stash copies are queued.
+                                 // 1 removes a ~3900 clk wait from the issuer's timeline.  With the 16-bit phase stash
+                                 // the kernel got SLOWER for it (295 -> 304 us: the layer step was bound by its 256 KB of
+                                 // HBM traffic per SM, tools/ubench/sm_traffic.cu); with 12-bit phases it is no longer
+                                 // purely HBM-bound and gains (264 -> 260 us)
 #endif
 #ifndef RENI_BWD_BULK_STASH
 #define RENI_BWD_BULK_STASH 1  // 1: delta stash written by per-warp bulk copies of the finished smem pieces; 0: st.global
