@@ -546,6 +546,7 @@ def run_gpu_arm(args):
                                (f" + all-reduce(mean) of {flat.flat.numel()} fp32 [{flat.exchange}" +
                                 (", inside the graph]" if in_graph else ", launched behind each replay]") if world > 1 else ""),
                        "backward": "layer-major" if layer_major else "tile-major",
+                       "stash": f"{int(lib.reni_phase_bits())}-bit phase per hidden pre-activation + fp16 deltas (backward rebuilds sin / cos from the phase)",
                        "optimizer": "excluded on both arms", "parallelism": f"dp{world} (maps sharded, latents local)"},
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_note": traffic_note,
